@@ -1,0 +1,162 @@
+/* texpose_b200 -- C ABI of the B200 (sm_100a) kernels behind TexPose's per-ray NeRF render hot path.
+ *
+ * The reference (HanzhiC/TexPose) is pure Python/PyTorch and has no FFI of its own:
+ * the drop-in boundary is its Python call surface, and every entry point below replaces the aten-op
+ * sequence of one reference function (cited per declaration, paths relative to the reference checkout).
+ * INTEGRATION.md shows the ctypes binding and the reference-side patch.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers into caller-owned memory unless marked "host"; the library never
+ *     allocates or frees device memory and keeps no mutable global state;
+ *   - tensors are dense row-major fp32 unless a leading dimension (`ld*`, in elements) is given;
+ *   - every call takes the caller's cudaStream_t as `void* stream`, enqueues asynchronously and never
+ *     synchronises;
+ *   - return value: 0 ok; <0 argument/shape/alignment/arch/workspace error (TP_ERR_*); >0 a cudaError_t;
+ *   - no CPU fallback and no backend dispatch: a device that is not sm_100 yields TP_ERR_ARCH from the
+ *     tensor-core entry points.
+ */
+#ifndef TEXPOSE_B200_H_
+#define TEXPOSE_B200_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TP_VERSION 100
+
+/* epilogues of tp_linear_forward */
+#define TP_ACT_NONE 0
+#define TP_ACT_RELU 1
+#define TP_ACT_TRUNK_LAST_STL 2   /* row 0 -> softplus -> aux0 = density[S,2] col 0; rows 1.. -> relu -> Y[:, n-1] */
+#define TP_ACT_TRUNK_LAST_PLAIN 3 /* same with aux0 = density[S] */
+#define TP_ACT_RGB_STATIC 4       /* sigmoid -> Y = rgb[S,3,2] slot 0 */
+#define TP_ACT_TRANS_OUT 5        /* rows 0-2 sigmoid -> Y = rgb[S,3,2] slot 1; row 3 softplus -> aux0 = density[S,2] col 1;
+                                     row 4 softplus -> aux1 = uncert[S] */
+#define TP_ACT_SIGMOID 6
+
+int tp_version(void);
+/* 1 when the current device is compute capability 10.x (tcgen05/TMEM available), else 0. */
+int tp_device_is_sm100(void);
+
+/* ---- rays / sampling (K1) ------------------------------------------------------------------------------- */
+
+/* camera.get_center_and_ray (camera.py:292-314) + Graph.ray_batch_sample (model/nerf_adapt_st_gan.py:702-710).
+ * kinv [B,3,3] = intr.inverse(), pose_inv [B,3,4] = Pose().invert(pose) (host-side torch calls, a1 in SURVEY 8a).
+ * ray_idx: NULL -> all H*W pixels (R must equal H*W); else int64 [B,R] pixel indices.  pix_offset 0.5. */
+int tp_raygen(const float* kinv, const float* pose_inv, int B, int H, int W, float pix_offset, const int64_t* ray_idx,
+              int R, float* center, float* ray, void* stream);
+
+/* RaySampler.get_rays (tools/ray_sampler.py:39-69): coords [B,P,2] in [-1,1] (x,y), bilinear ramp lookup, no +0.5. */
+int tp_patch_rays(const float* kinv, const float* pose_inv, const float* coords, int B, int P, int H, int W,
+                  float* center, float* ray, void* stream);
+
+/* F.grid_sample(image[B,C,H,W], coords[B,P,2], bilinear, zeros, align_corners=True) -> out [B,C,P]
+ * (RaySampler.get_bounds / get_image, tools/ray_sampler.py:12-37). */
+int tp_grid_sample_bilinear(const float* image, const float* coords, int B, int C, int H, int W, int P, float* out,
+                            void* stream);
+
+/* Graph.ray_batch_sample on an arbitrary [B,HW,C] tensor (model/nerf_adapt_st_gan.py:702-710). */
+int tp_gather_rows(const float* src, const int64_t* idx, int B, int64_t HW, int C, int R, float* out, void* stream);
+
+/* camera.aabb_ray_intersection (camera.py:415-433; compute_box.py:69-87).  aabb_* [3] or, if aabb_batched, [B,3].
+ * Bit-exact incl. NaN propagation for axis-parallel rays.  valid: uint8 [B,n]. */
+int tp_aabb_intersect(const float* aabb_min, const float* aabb_max, int aabb_batched, const float* ray_o,
+                      const float* ray_d, int B, int64_t n_per_batch, float* t_near, float* t_far, uint8_t* valid,
+                      void* stream);
+
+/* Graph.sample_depth, metric parametrisation (model/nerf_adapt_st_gan.py:682-700).
+ * mode 0: rand [n_rays,N] supplied (the torch.rand draw); 1: midpoint 0.5 (sample_stratified false);
+ * 2: in-kernel Philox4x32-10 jitter keyed by (seed, sample index).  out [n_rays,N]. */
+int tp_sample_depth(const float* z_near, const float* z_far, const float* rand, int64_t n_rays, int N, int mode,
+                    uint64_t seed, float* out, void* stream);
+
+/* compute_box.py:266-271 + data/lm.py:349-350 fused: full-frame rays -> slab test -> misses zeroed ->
+ * zeros replaced by the background range.  z_near/z_far [B,H*W]; valid may be NULL. */
+int tp_box_range(const float* kinv, const float* pose_inv, int B, int H, int W, const float* aabb_min,
+                 const float* aabb_max, int aabb_batched, float bg_near, float bg_far, float* z_near, float* z_far,
+                 uint8_t* valid, void* stream);
+
+/* 'render' range source: 0.8/1.2 x depth, zeros -> background (data/lm.py:352-356). */
+int tp_depth_guided_range(const float* depth, int64_t n, float bg_near, float bg_far, float* z_near, float* z_far,
+                          void* stream);
+
+/* compute_surfelinfo.normal_from_depth (compute_surfelinfo.py:37-55).  depth [B,H,W] -> normal [B,3,H,W]. */
+int tp_normal_from_depth(const float* kinv, const float* pose_inv, const float* depth, int B, int H, int W,
+                         float* normal, void* stream);
+
+/* ---- compositing (K3) ----------------------------------------------------------------------------------- */
+
+/* NeRF.composite, static/transient/joint chains (layers/nerf_static_transient_light.py:168-212).
+ * ray [R,3]; rgb [R,N,3,2]; density [R,N,2]; depth [R,N]; uncert [R,N].
+ * outputs: rgb, rgb_static, rgb_transient [R,3]; depth, opacity(3x), uncert [R]; prob, alpha_static, alpha_transient [R,N]. */
+int tp_composite_stl_forward(const float* ray, const float* rgb, const float* density, const float* depth,
+                             const float* uncert, int64_t R, int N, float min_uncert, float* o_rgb,
+                             float* o_rgb_static, float* o_rgb_transient, float* o_depth, float* o_opacity,
+                             float* o_opacity_static, float* o_opacity_transient, float* o_prob, float* o_uncert,
+                             float* o_alpha_static, float* o_alpha_transient, void* stream);
+
+/* Backward of the above w.r.t. rgb, density, uncert samples.  Any g_* may be NULL (= zero gradient).
+ * depth/ray receive no gradient (they come from no_grad rays + rand in the reference). */
+int tp_composite_stl_backward(const float* ray, const float* rgb, const float* density, const float* depth,
+                              const float* uncert, int64_t R, int N, const float* g_rgb, const float* g_rgb_static,
+                              const float* g_rgb_transient, const float* g_depth, const float* g_opacity,
+                              const float* g_opacity_static, const float* g_opacity_transient, const float* g_prob,
+                              const float* g_uncert, const float* g_alpha_static, const float* g_alpha_transient,
+                              float* d_rgb, float* d_density, float* d_uncert, void* stream);
+
+/* NeRF.composite of the plain model (layers/nerf.py:117-136).  rgb [R,N,3]; density [R,N]. */
+int tp_composite_plain_forward(const float* ray, const float* rgb, const float* density, const float* depth,
+                               int64_t R, int N, int use_bg, float bgcolor, float* o_rgb, float* o_depth,
+                               float* o_opacity, float* o_prob, void* stream);
+int tp_composite_plain_backward(const float* ray, const float* rgb, const float* density, const float* depth,
+                                int64_t R, int N, int use_bg, float bgcolor, const float* g_rgb, const float* g_depth,
+                                const float* g_opacity, const float* g_prob, float* d_rgb, float* d_density,
+                                void* stream);
+
+/* ---- MLP, fp32 SIMT parity path + generic layer backward (K2 fp32 / K2b) ---------------------------------- */
+
+/* NeRF.positional_encoding with the raw coordinates prepended (layers/nerf_static_transient_light.py:81-82,217-223):
+ * enc[s, 0:3+6L] for x = center[s/N] + ray[s/N] * depth[s] (camera.py:317-322). */
+int tp_points_encode(const float* center, const float* ray, const float* depth, int64_t S, int N, int L, float* enc,
+                     int64_t ld, void* stream);
+/* same for explicit points x [S,3]. */
+int tp_positional_encode(const float* x, int64_t S, int L, float* enc, int64_t ld, void* stream);
+/* per-ray view direction encoding; normalize!=0 applies F.normalize first (nerf_static_transient_light.py:155-157). */
+int tp_view_encode(const float* ray, int64_t R, int L, int normalize, float* enc, int64_t ld, void* stream);
+
+/* One nn.Linear (+ activation) on a segmented input: row s of X is the concatenation of nseg (<=4) segments,
+ * segment i contributing seg_cols[i] columns read at seg_ptr[i][(s / seg_group[i]) * seg_ld[i] + c].
+ * seg_* are HOST arrays.  W [Nout, Ktot] with leading dimension ldw; bias [Nout] or NULL.  See TP_ACT_*. */
+int tp_linear_forward(const float* const* seg_ptr, const int64_t* seg_ld, const int64_t* seg_group,
+                      const int32_t* seg_cols, int nseg, const float* W, int64_t ldw, const float* bias, int64_t S,
+                      int Nout, int act, float* Y, int64_t ldy, float* aux0, float* aux1, void* stream);
+
+/* dX[:, 0:K1] = (dY W[:, 0:K1]) masked by xact > 0 (xact NULL = no mask). */
+int tp_linear_backward_input(const float* dY, int64_t lddy, const float* W, int64_t ldw, int64_t S, int Nout, int K1,
+                             const float* xact, int64_t ldx, float* dX, int64_t lddx, void* stream);
+
+/* dW [Nout,Ktot] (=/+=) dY^T X, db [Nout] (=/+=) colsum(dY); split-K with a fixed-order second stage. */
+int64_t tp_linear_backward_weight_workspace(int64_t S, int Nout, int Ktot);
+int tp_linear_backward_weight(const float* dY, int64_t lddy, const float* const* seg_ptr, const int64_t* seg_ld,
+                              const int64_t* seg_group, const int32_t* seg_cols, int nseg, int64_t S, int Nout,
+                              float* dW, float* db, int accumulate, float* workspace, int64_t workspace_floats,
+                              void* stream);
+
+/* out[g, :] = sum of dY rows of group g (rows g*group .. ); workspace >= 32 * ceil(S/group) * Nout floats. */
+int tp_group_colsum(const float* dY, int64_t lddy, int64_t S, int64_t group, int Nout, float* out, float* workspace,
+                    int64_t workspace_floats, void* stream);
+
+/* gradients w.r.t. the output layers' pre-activations from the stored outputs (sigmoid / softplus). */
+int tp_stl_output_grad(const float* rgb, const float* density, const float* uncert, const float* g_rgb,
+                       const float* g_density, const float* g_uncert, int64_t S, float* dz_rgb, float* dz_trans,
+                       float* dz_sigma, void* stream);
+int tp_plain_output_grad(const float* rgb, const float* density, const float* g_rgb, const float* g_density, int64_t S,
+                         float* dz_rgb, float* dz_sigma, void* stream);
+int tp_trunk_last_grad(const float* dz_sigma, const float* d_feat, int64_t ldd, const float* feat, int64_t ldf,
+                       int64_t S, int F, float* dz, int64_t ldz, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TEXPOSE_B200_H_ */

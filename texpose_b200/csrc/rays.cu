@@ -1,0 +1,391 @@
+// K1: pixel->ray generation, AABB slab test, stratified sample placement, patch (grid_sample)
+// rays/bounds, ray gather, fused on-the-fly box bounds, normals-from-depth.
+//
+// All of these are HBM-bound elementwise/stencil kernels: grid-stride loops, grids sized as a
+// multiple of the SM count, coalesced (SoA-per-thread) accesses.  Arithmetic follows the reference
+// operation by operation with explicit rounding intrinsics (no FMA contraction where the reference
+// has none) so ray/AABB/sample results are bit-exact:
+//   camera.py:292-314 (get_center_and_ray), camera.py:415-433 (aabb_ray_intersection),
+//   tools/ray_sampler.py:23-69, model/nerf_adapt_st_gan.py:682-710, compute_surfelinfo.py:37-55,
+//   compute_box.py:266-271 + data/lm.py:349-356.
+#include "common.cuh"
+#include "../../include/texpose_b200.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+// [u,v,1] @ Kinv^T then [cam,1] @ pose_inv^T, ray = grid - center.  The reference evaluates both
+// products with torch.matmul; its fp32 result equals a sequential mul,fma,fma(,fma) chain over k
+// (verified bit-for-bit against the reference on CPU, tests/golden/rays.npz).
+__device__ __forceinline__ void unproject(const float* __restrict__ kinv, const float* __restrict__ pinv,
+                                          float u, float v, float c[3], float d[3]) {
+  float cam[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    float acc = __fmul_rn(u, kinv[j * 3 + 0]);
+    acc = __fmaf_rn(v, kinv[j * 3 + 1], acc);
+    cam[j] = __fmaf_rn(1.0f, kinv[j * 3 + 2], acc);
+  }
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    float acc = __fmul_rn(cam[0], pinv[j * 4 + 0]);
+    acc = __fmaf_rn(cam[1], pinv[j * 4 + 1], acc);
+    acc = __fmaf_rn(cam[2], pinv[j * 4 + 2], acc);
+    acc = __fmaf_rn(1.0f, pinv[j * 4 + 3], acc);
+    c[j] = pinv[j * 4 + 3];  // 0*R + 1*t == t exactly
+    d[j] = __fsub_rn(acc, c[j]);
+  }
+}
+
+__global__ void raygen_kernel(const float* __restrict__ kinv, const float* __restrict__ pinv, int B, int H, int W,
+                              float pix_offset, const long long* __restrict__ ray_idx, int R,
+                              float* __restrict__ center, float* __restrict__ ray) {
+  const long long total = (long long)B * R;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / R);
+    const long long p = ray_idx ? ray_idx[i] : (i - (long long)b * R);
+    const float u = __fadd_rn((float)(p % W), pix_offset);
+    const float v = __fadd_rn((float)(p / W), pix_offset);
+    float c[3], d[3];
+    unproject(kinv + b * 9, pinv + b * 12, u, v, c, d);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      center[i * 3 + j] = c[j];
+      ray[i * 3 + j] = d[j];
+    }
+  }
+}
+
+// F.grid_sample(mode='bilinear', padding_mode='zeros', align_corners=True) coordinate + weights.
+struct Bilin {
+  int x0, y0;
+  float wnw, wne, wsw, wse;
+};
+__device__ __forceinline__ Bilin bilin_setup(float gx, float gy, int H, int W) {
+  const float ix = __fmul_rn(__fmul_rn(__fadd_rn(gx, 1.f), 0.5f), (float)(W - 1));
+  const float iy = __fmul_rn(__fmul_rn(__fadd_rn(gy, 1.f), 0.5f), (float)(H - 1));
+  const float fx = floorf(ix), fy = floorf(iy);
+  Bilin s;
+  s.x0 = (int)fx;
+  s.y0 = (int)fy;
+  const float ex = __fsub_rn(__fadd_rn(fx, 1.f), ix), wx = __fsub_rn(ix, fx);
+  const float ey = __fsub_rn(__fadd_rn(fy, 1.f), iy), wy = __fsub_rn(iy, fy);
+  s.wnw = __fmul_rn(ex, ey);
+  s.wne = __fmul_rn(wx, ey);
+  s.wsw = __fmul_rn(ex, wy);
+  s.wse = __fmul_rn(wx, wy);
+  return s;
+}
+template <class F>
+__device__ __forceinline__ float bilin_apply(const Bilin& s, int H, int W, F val) {
+  float acc = 0.f;
+  const bool xl = s.x0 >= 0 && s.x0 < W, xr = s.x0 + 1 >= 0 && s.x0 + 1 < W;
+  const bool yt = s.y0 >= 0 && s.y0 < H, yb = s.y0 + 1 >= 0 && s.y0 + 1 < H;
+  if (xl && yt) acc = __fmaf_rn(val(s.y0, s.x0), s.wnw, acc);
+  if (xr && yt) acc = __fmaf_rn(val(s.y0, s.x0 + 1), s.wne, acc);
+  if (xl && yb) acc = __fmaf_rn(val(s.y0 + 1, s.x0), s.wsw, acc);
+  if (xr && yb) acc = __fmaf_rn(val(s.y0 + 1, s.x0 + 1), s.wse, acc);
+  return acc;
+}
+
+__global__ void patch_rays_kernel(const float* __restrict__ kinv, const float* __restrict__ pinv,
+                                  const float* __restrict__ coords, int B, int P, int H, int W,
+                                  float* __restrict__ center, float* __restrict__ ray) {
+  const long long total = (long long)B * P;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / P);
+    const Bilin s = bilin_setup(coords[i * 2 + 0], coords[i * 2 + 1], H, W);
+    // bilinear lookup of the integer index ramps X[y][x]=x, Y[y][x]=y (tools/ray_sampler.py:48-56)
+    const float u = bilin_apply(s, H, W, [](int, int x) { return (float)x; });
+    const float v = bilin_apply(s, H, W, [](int y, int) { return (float)y; });
+    float c[3], d[3];
+    unproject(kinv + b * 9, pinv + b * 12, u, v, c, d);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      center[i * 3 + j] = c[j];
+      ray[i * 3 + j] = d[j];
+    }
+  }
+}
+
+__global__ void grid_sample_kernel(const float* __restrict__ img, const float* __restrict__ coords, int B, int C,
+                                   int H, int W, int P, float* __restrict__ out) {
+  const long long total = (long long)B * C * P;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(i % P);
+    const int c = (int)((i / P) % C);
+    const int b = (int)(i / ((long long)P * C));
+    const float* g = coords + ((long long)b * P + p) * 2;
+    const Bilin s = bilin_setup(g[0], g[1], H, W);
+    const float* plane = img + ((long long)b * C + c) * H * W;
+    out[i] = bilin_apply(s, H, W, [&](int y, int x) { return plane[(long long)y * W + x]; });
+  }
+}
+
+__global__ void gather_rows_kernel(const float* __restrict__ src, const long long* __restrict__ idx, int B,
+                                   long long HW, int C, int R, float* __restrict__ out) {
+  const long long total = (long long)B * R * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long br = i / C;
+    const int b = (int)(br / R);
+    out[i] = src[((long long)b * HW + idx[br]) * C + c];
+  }
+}
+
+// torch.minimum/maximum and max/min reductions propagate NaN (0*inf for axis-parallel rays).
+__device__ __forceinline__ float nan_min(float a, float b) { return (a != a || b != b) ? __int_as_float(0x7fc00000) : fminf(a, b); }
+__device__ __forceinline__ float nan_max(float a, float b) { return (a != a || b != b) ? __int_as_float(0x7fc00000) : fmaxf(a, b); }
+
+__device__ __forceinline__ void slab(const float lo[3], const float hi[3], const float o[3], const float d[3],
+                                     float& t_near, float& t_far, bool& valid) {
+  float t0[3], t1[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const float inv = __frcp_rn(d[j]);
+    const float a = __fmul_rn(__fsub_rn(lo[j], o[j]), inv);
+    const float b = __fmul_rn(__fsub_rn(hi[j], o[j]), inv);
+    t0[j] = nan_min(a, b);
+    t1[j] = nan_max(a, b);
+  }
+  t_near = nan_max(nan_max(t0[0], t0[1]), t0[2]);
+  t_far = nan_min(nan_min(t1[0], t1[1]), t1[2]);
+  valid = (t_far > 0.f) && (t_far > t_near);
+}
+
+__global__ void aabb_kernel(const float* __restrict__ amin, const float* __restrict__ amax, int aabb_stride,
+                            const float* __restrict__ ro, const float* __restrict__ rd, long long n_per_batch,
+                            long long total, float* __restrict__ t_near, float* __restrict__ t_far,
+                            unsigned char* __restrict__ valid) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / n_per_batch;
+    float lo[3], hi[3], o[3], d[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      lo[j] = amin[b * aabb_stride + j];
+      hi[j] = amax[b * aabb_stride + j];
+      o[j] = ro[i * 3 + j];
+      d[j] = rd[i * 3 + j];
+    }
+    float tn, tf;
+    bool ok;
+    slab(lo, hi, o, d, tn, tf, ok);
+    t_near[i] = tn;
+    t_far[i] = tf;
+    valid[i] = ok ? 1 : 0;
+  }
+}
+
+// d_i = (u_i + i) * (1/N) * (far - near) + near, one rounding per reference op
+// (model/nerf_adapt_st_gan.py:690-697; torch divides by a Python scalar as a multiply by 1/N).
+__global__ void sample_depth_kernel(const float* __restrict__ z_near, const float* __restrict__ z_far,
+                                    const float* __restrict__ rand, long long n_rays, int N, int mode,
+                                    unsigned long long seed, float* __restrict__ out) {
+  const long long total = n_rays * N;
+  const float inv_n = 1.0f / (float)N;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / N;
+    const int k = (int)(i - r * N);
+    float u;
+    if (mode == 0) u = rand[i];
+    else if (mode == 1) u = 0.5f;
+    else {
+      const uint4 x = tp_philox((uint32_t)(i >> 2), (uint32_t)((i >> 2) >> 32), (uint32_t)seed, (uint32_t)(seed >> 32));
+      const uint32_t w = (i & 3) == 0 ? x.x : (i & 3) == 1 ? x.y : (i & 3) == 2 ? x.z : x.w;
+      u = tp_u01(w);
+    }
+    const float lo = z_near[r], hi = z_far[r];
+    const float t = __fmul_rn(__fadd_rn(u, (float)k), inv_n);
+    out[i] = __fadd_rn(__fmul_rn(t, __fsub_rn(hi, lo)), lo);
+  }
+}
+
+// Fused: full-frame rays -> slab test -> zero the misses -> zeros become the background range.
+__global__ void box_range_kernel(const float* __restrict__ kinv, const float* __restrict__ pinv, int B, int H, int W,
+                                 const float* __restrict__ amin, const float* __restrict__ amax, int aabb_stride,
+                                 float bg_near, float bg_far, float* __restrict__ z_near, float* __restrict__ z_far,
+                                 unsigned char* __restrict__ valid) {
+  const long long HW = (long long)H * W, total = HW * B;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / HW);
+    const long long p = i - (long long)b * HW;
+    float c[3], d[3], lo[3], hi[3];
+    unproject(kinv + b * 9, pinv + b * 12, __fadd_rn((float)(p % W), 0.5f), __fadd_rn((float)(p / W), 0.5f), c, d);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      lo[j] = amin[b * aabb_stride + j];
+      hi[j] = amax[b * aabb_stride + j];
+    }
+    float tn, tf;
+    bool ok;
+    slab(lo, hi, c, d, tn, tf, ok);
+    tn = ok ? tn : 0.f;
+    tf = ok ? tf : 0.f;
+    z_near[i] = tn > 0.f ? tn : bg_near;
+    z_far[i] = tf > 0.f ? tf : bg_far;
+    if (valid) valid[i] = ok ? 1 : 0;
+  }
+}
+
+__global__ void guided_range_kernel(const float* __restrict__ depth, long long n, float bg_near, float bg_far,
+                                    float* __restrict__ z_near, float* __restrict__ z_far) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float zn = __fmul_rn(depth[i], 0.8f), zf = __fmul_rn(depth[i], 1.2f);
+    z_near[i] = zn > 0.f ? zn : bg_near;
+    z_far[i] = zf > 0.f ? zf : bg_far;
+  }
+}
+
+// compute_surfelinfo.py:37-55.  One thread per pixel; the 4 neighbour points are recomputed from the
+// depth map (4 B in, 12 B out per pixel; neighbour depth reads hit L1/L2).
+__device__ __forceinline__ void backproject(const float* kinv, const float* pinv, const float* depth, int W, int x, int y,
+                                            float P[3]) {
+  float c[3], d[3];
+  unproject(kinv, pinv, __fadd_rn((float)x, 0.5f), __fadd_rn((float)y, 0.5f), c, d);
+  const float z = depth[(long long)y * W + x];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) P[j] = __fadd_rn(c[j], __fmul_rn(d[j], z));
+}
+
+__global__ void normal_kernel(const float* __restrict__ kinv, const float* __restrict__ pinv,
+                              const float* __restrict__ depth, int B, int H, int W, float* __restrict__ out) {
+  const long long HW = (long long)H * W, total = HW * B;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / HW);
+    const long long p = i - (long long)b * HW;
+    const int x = (int)(p % W), y = (int)(p / W);
+    const float* dm = depth + (long long)b * HW;
+    float n[3] = {0.f, 0.f, 0.f};
+    if (x > 0 && x < W - 1 && y > 0 && y < H - 1) {
+      float pe[3], pw[3], ps[3], pn[3], tu[3], tv[3];
+      backproject(kinv + b * 9, pinv + b * 12, dm, W, x + 1, y, pe);
+      backproject(kinv + b * 9, pinv + b * 12, dm, W, x - 1, y, pw);
+      backproject(kinv + b * 9, pinv + b * 12, dm, W, x, y + 1, ps);
+      backproject(kinv + b * 9, pinv + b * 12, dm, W, x, y - 1, pn);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        tu[j] = __fsub_rn(pe[j], pw[j]);
+        tv[j] = __fsub_rn(ps[j], pn[j]);
+      }
+      n[0] = __fsub_rn(__fmul_rn(tu[1], tv[2]), __fmul_rn(tu[2], tv[1]));
+      n[1] = __fsub_rn(__fmul_rn(tu[2], tv[0]), __fmul_rn(tu[0], tv[2]));
+      n[2] = __fsub_rn(__fmul_rn(tu[0], tv[1]), __fmul_rn(tu[1], tv[0]));
+      const float len = fmaxf(sqrtf(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]), 1e-12f);  // F.normalize eps
+      n[0] /= len;
+      n[1] /= len;
+      n[2] = -(n[2] / len);
+    }
+    const float m = dm[p] > 0.f ? 1.f : 0.f;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) out[((long long)b * 3 + j) * HW + p] = n[j] * m;
+  }
+}
+
+}  // namespace
+
+#define TP_CHECK(cond, code) \
+  do {                       \
+    if (!(cond)) return (code); \
+  } while (0)
+
+TP_API int tp_raygen(const float* kinv, const float* pose_inv, int B, int H, int W, float pix_offset,
+                     const int64_t* ray_idx, int R, float* center, float* ray, void* stream) {
+  TP_CHECK(kinv && pose_inv && center && ray, TP_ERR_BAD_ARG);
+  TP_CHECK(B > 0 && H > 0 && W > 0 && R >= 0, TP_ERR_BAD_SHAPE);
+  TP_CHECK(ray_idx || R == H * W, TP_ERR_BAD_SHAPE);
+  if ((long long)B * R == 0) return TP_OK;
+  raygen_kernel<<<tp_grid_for((long long)B * R, kThreads, 8), kThreads, 0, (cudaStream_t)stream>>>(
+      kinv, pose_inv, B, H, W, pix_offset, (const long long*)ray_idx, R, center, ray);
+  return tp_launch_status();
+}
+
+TP_API int tp_patch_rays(const float* kinv, const float* pose_inv, const float* coords, int B, int P, int H, int W,
+                         float* center, float* ray, void* stream) {
+  TP_CHECK(kinv && pose_inv && coords && center && ray, TP_ERR_BAD_ARG);
+  TP_CHECK(B > 0 && H > 1 && W > 1 && P >= 0, TP_ERR_BAD_SHAPE);
+  if ((long long)B * P == 0) return TP_OK;
+  patch_rays_kernel<<<tp_grid_for((long long)B * P, kThreads, 8), kThreads, 0, (cudaStream_t)stream>>>(
+      kinv, pose_inv, coords, B, P, H, W, center, ray);
+  return tp_launch_status();
+}
+
+TP_API int tp_grid_sample_bilinear(const float* image, const float* coords, int B, int C, int H, int W, int P,
+                                   float* out, void* stream) {
+  TP_CHECK(image && coords && out, TP_ERR_BAD_ARG);
+  TP_CHECK(B > 0 && C > 0 && H > 1 && W > 1 && P >= 0, TP_ERR_BAD_SHAPE);
+  if (P == 0) return TP_OK;
+  grid_sample_kernel<<<tp_grid_for((long long)B * C * P, kThreads, 8), kThreads, 0, (cudaStream_t)stream>>>(
+      image, coords, B, C, H, W, P, out);
+  return tp_launch_status();
+}
+
+TP_API int tp_gather_rows(const float* src, const int64_t* idx, int B, int64_t HW, int C, int R, float* out,
+                          void* stream) {
+  TP_CHECK(src && idx && out, TP_ERR_BAD_ARG);
+  TP_CHECK(B > 0 && HW > 0 && C > 0 && R >= 0, TP_ERR_BAD_SHAPE);
+  if (R == 0) return TP_OK;
+  gather_rows_kernel<<<tp_grid_for((long long)B * R * C, kThreads, 8), kThreads, 0, (cudaStream_t)stream>>>(
+      src, (const long long*)idx, B, HW, C, R, out);
+  return tp_launch_status();
+}
+
+TP_API int tp_aabb_intersect(const float* aabb_min, const float* aabb_max, int aabb_batched, const float* ray_o,
+                             const float* ray_d, int B, int64_t n_per_batch, float* t_near, float* t_far,
+                             uint8_t* valid, void* stream) {
+  TP_CHECK(aabb_min && aabb_max && ray_o && ray_d && t_near && t_far && valid, TP_ERR_BAD_ARG);
+  TP_CHECK(B > 0 && n_per_batch >= 0, TP_ERR_BAD_SHAPE);
+  const long long total = (long long)B * n_per_batch;
+  if (total == 0) return TP_OK;
+  aabb_kernel<<<tp_grid_for(total, kThreads, 8), kThreads, 0, (cudaStream_t)stream>>>(
+      aabb_min, aabb_max, aabb_batched ? 3 : 0, ray_o, ray_d, n_per_batch, total, t_near, t_far, valid);
+  return tp_launch_status();
+}
+
+TP_API int tp_sample_depth(const float* z_near, const float* z_far, const float* rand, int64_t n_rays, int N,
+                           int mode, uint64_t seed, float* out, void* stream) {
+  TP_CHECK(z_near && z_far && out, TP_ERR_BAD_ARG);
+  TP_CHECK(n_rays >= 0 && N > 0, TP_ERR_BAD_SHAPE);
+  TP_CHECK(mode >= 0 && mode <= 2 && (mode != 0 || rand), TP_ERR_BAD_ARG);
+  if (n_rays == 0) return TP_OK;
+  sample_depth_kernel<<<tp_grid_for(n_rays * N, kThreads, 8), kThreads, 0, (cudaStream_t)stream>>>(
+      z_near, z_far, rand, n_rays, N, mode, seed, out);
+  return tp_launch_status();
+}
+
+TP_API int tp_box_range(const float* kinv, const float* pose_inv, int B, int H, int W, const float* aabb_min,
+                        const float* aabb_max, int aabb_batched, float bg_near, float bg_far, float* z_near,
+                        float* z_far, uint8_t* valid, void* stream) {
+  TP_CHECK(kinv && pose_inv && aabb_min && aabb_max && z_near && z_far, TP_ERR_BAD_ARG);
+  TP_CHECK(B > 0 && H > 0 && W > 0, TP_ERR_BAD_SHAPE);
+  box_range_kernel<<<tp_grid_for((long long)B * H * W, kThreads, 8), kThreads, 0, (cudaStream_t)stream>>>(
+      kinv, pose_inv, B, H, W, aabb_min, aabb_max, aabb_batched ? 3 : 0, bg_near, bg_far, z_near, z_far, valid);
+  return tp_launch_status();
+}
+
+TP_API int tp_depth_guided_range(const float* depth, int64_t n, float bg_near, float bg_far, float* z_near,
+                                 float* z_far, void* stream) {
+  TP_CHECK(depth && z_near && z_far, TP_ERR_BAD_ARG);
+  TP_CHECK(n >= 0, TP_ERR_BAD_SHAPE);
+  if (n == 0) return TP_OK;
+  guided_range_kernel<<<tp_grid_for(n, kThreads, 8), kThreads, 0, (cudaStream_t)stream>>>(depth, n, bg_near, bg_far,
+                                                                                       z_near, z_far);
+  return tp_launch_status();
+}
+
+TP_API int tp_normal_from_depth(const float* kinv, const float* pose_inv, const float* depth, int B, int H, int W,
+                                float* normal, void* stream) {
+  TP_CHECK(kinv && pose_inv && depth && normal, TP_ERR_BAD_ARG);
+  TP_CHECK(B > 0 && H > 2 && W > 2, TP_ERR_BAD_SHAPE);
+  normal_kernel<<<tp_grid_for((long long)B * H * W, kThreads, 8), kThreads, 0, (cudaStream_t)stream>>>(
+      kinv, pose_inv, depth, B, H, W, normal);
+  return tp_launch_status();
+}

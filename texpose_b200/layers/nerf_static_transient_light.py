@@ -1,0 +1,114 @@
+"""Drop-in for layers/nerf_static_transient_light.py: the static / transient / light NeRF of the texture learner.
+
+Same constructor, parameter containers (`mlp_feat`, `mlp_rgb`, `mlp_trans` ModuleLists of nn.Linear, `progress`)
+and method signatures as the reference class, so checkpoints (state-dict keys `nerf.mlp_feat.{i}.weight` ...)
+load unchanged; the arithmetic runs in the sm_100a kernels behind the C-ABI.
+"""
+from __future__ import annotations
+
+import torch
+
+from .. import ops
+from . import _common
+from ._mlp import MLPConfig, NerfMLP
+
+
+class NeRF(torch.nn.Module):
+
+    def __init__(self, opt):
+        super().__init__()
+        # layer shapes: layers/nerf_static_transient_light.py:15-61
+        d3 = 3 + 6 * opt.arch.posenc.L_3D if opt.arch.posenc else 3
+        dview = (3 + 6 * opt.arch.posenc.L_view if opt.arch.posenc.L_view else 3) if opt.nerf.view_dep else 0
+        tf = opt.arch.tf_init
+        self.mlp_feat = torch.nn.ModuleList()
+        dims = _common.layer_dims(opt.arch.layers_feat)
+        for li, (k_in, k_out) in enumerate(dims):
+            k_in = d3 if li == 0 else k_in
+            k_in = k_in + d3 if li in opt.arch.skip else k_in
+            last = li == len(dims) - 1
+            lin = torch.nn.Linear(k_in, k_out + 1 if last else k_out)
+            if tf:
+                _common.tf_init_(lin, out="first" if last else None)
+            self.mlp_feat.append(lin)
+        for p in self.mlp_feat.parameters():      # static scene is frozen (:34, :236-239)
+            p.requires_grad = False
+
+        feat_dim = opt.arch.layers_feat[-1]
+        self.mlp_rgb = torch.nn.ModuleList()
+        dims = _common.layer_dims(opt.arch.layers_rgb)
+        for li, (k_in, k_out) in enumerate(dims):
+            if li == 0:
+                k_in = feat_dim + dview + 3 + opt.nerf.N_latent_light
+            lin = torch.nn.Linear(k_in, k_out)
+            if tf:
+                _common.tf_init_(lin, out="all" if li == len(dims) - 1 else None)
+            self.mlp_rgb.append(lin)
+
+        if opt.arch.layers_trans:
+            self.mlp_trans = torch.nn.ModuleList()
+            dims = _common.layer_dims(opt.arch.layers_trans)
+            for li, (k_in, k_out) in enumerate(dims):
+                if li == 0:
+                    k_in = feat_dim + opt.nerf.N_latent_trans
+                lin = torch.nn.Linear(k_in, k_out)
+                if tf:
+                    _common.tf_init_(lin, out="all" if li == len(dims) - 1 else None)
+                self.mlp_trans.append(lin)
+        if opt.c2f is not None:
+            self.progress = torch.nn.Parameter(torch.tensor(0.))
+        self._packed = None     # (version key, packed bf16 weight image) for the tcgen05 kernel
+
+    # ------------------------------------------------------------------ helpers
+    def _config(self, opt, mode) -> MLPConfig:
+        if opt.arch.density_activ != "softplus":
+            raise NotImplementedError("texpose_b200 implements density_activ: softplus (the reference yaml setting)")
+        if opt.nerf.density_noise_reg and mode == "train":
+            raise NotImplementedError("density_noise_reg is null in every reference yaml; not implemented")
+        if opt.c2f is not None and opt.c2f.range is not None:
+            raise NotImplementedError("coarse-to-fine windowing (c2f.range) is off in the reference yaml; not implemented")
+        if not opt.arch.layers_trans:
+            raise NotImplementedError("static/transient NeRF requires arch.layers_trans")
+        return MLPConfig(L_3D=opt.arch.posenc.L_3D, L_view=opt.arch.posenc.L_view or 0, skip=tuple(opt.arch.skip),
+                         view_dep=bool(opt.nerf.view_dep), n_feat=len(self.mlp_feat), n_rgb=len(self.mlp_rgb),
+                         n_trans=len(self.mlp_trans), n_latent_light=opt.nerf.N_latent_light,
+                         n_latent_trans=opt.nerf.N_latent_trans, precision=_common.mlp_precision(opt),
+                         save_for_backward=torch.is_grad_enabled(), packed=self)
+
+    def _run(self, cfg, geom, latent_variable_trans, latent_variable_light):
+        params = _common.flat_params(self.mlp_feat, self.mlp_rgb, self.mlp_trans)
+        return NerfMLP.apply(cfg, geom, latent_variable_trans, latent_variable_light, *params)
+
+    # ------------------------------------------------------------------ reference interface
+    def forward(self, opt, points_3D, ray_unit=None, latent_variable_trans=None, latent_variable_light=None, mode=None):
+        """layers/nerf_static_transient_light.py:76-145 -> rgb [B,HW,N,3,2], density [B,HW,N,2], uncert [B,HW,N,1]."""
+        assert points_3D.dim() == 4, "points_3D must be [B,HW,N,3] (reference :78)"
+        cfg = self._config(opt, mode)
+        if cfg.view_dep:
+            assert ray_unit is not None
+        cfg.precision = "fp32"      # explicit-points entry: the fused bf16 kernel is ray-parameterised
+        geom = _common.point_geometry(cfg, points_3D, ray_unit)
+        return self._run(cfg, geom, latent_variable_trans, latent_variable_light)
+
+    def forward_samples(self, opt, center, ray, depth_samples, latent_variable_trans=None, latent_variable_light=None,
+                        mode=None):
+        """layers/nerf_static_transient_light.py:147-166."""
+        cfg = self._config(opt, mode)
+        geom = _common.ray_geometry(cfg, center, ray, depth_samples)
+        return self._run(cfg, geom, latent_variable_trans, latent_variable_light)
+
+    @staticmethod
+    def composite(opt, ray, rgb_samples, density_samples, depth_samples, uncert_samples=None):
+        """layers/nerf_static_transient_light.py:168-212; returns the reference's 11-tuple."""
+        return ops.CompositeSTL.apply(ray, rgb_samples, density_samples, depth_samples, uncert_samples,
+                                      float(opt.nerf.min_uncert))
+
+    def positional_encoding(self, opt, x, L, c2f=False):
+        """layers/nerf_static_transient_light.py:217-234 for [...,3] inputs (c2f window off)."""
+        if opt.c2f is not None and opt.c2f.range is not None and c2f:
+            raise NotImplementedError("c2f windowing is off in the reference yaml; not implemented")
+        if x.shape[-1] != 3:
+            raise NotImplementedError("positional_encoding kernel handles 3-vectors (points / view directions)")
+        flat = ops._f32(x.detach()).reshape(-1, 3)
+        enc = ops.positional_encode(flat, L)
+        return enc[:, 3:3 + 6 * L].reshape(*x.shape[:-1], 6 * L)

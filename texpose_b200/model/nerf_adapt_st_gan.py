@@ -1,0 +1,197 @@
+"""Drop-in for the render path of model/nerf_adapt_st_gan.py `Graph` (reference lines :464-514, :547-710).
+
+Only the hot path is mirrored: nerf_forward / render / render_by_slices / sample_depth / ray_batch_sample.
+The engine around it (Model, discriminator, perceptual losses, visualisation) is out of scope
+and keeps calling these methods unchanged -- see INTEGRATION.md for the patch point.
+
+Differences that are deliberate (B200-first, results identical):
+  * eval/val modes generate only the requested rays (the reference rebuilds the full frame for every
+    2048-ray chunk, :568) and render a whole frame per launch instead of ~150 Python chunks;
+  * the host-syncing NaN retry loop (:554,:569) is dropped (opt.b200.nan_guard restores it);
+  * no hard-coded .cuda(): tensors follow `opt.device`.
+"""
+from __future__ import annotations
+
+import torch
+
+from .. import camera, ops
+from ..config import AttrDict
+from ..layers.nerf_static_transient_light import NeRF
+from ..layers import _common
+from ..tools.ray_sampler import RaySampler
+
+
+def rotation_distance(R1, R2, eps=1e-7):
+    """camera.rotation_distance (camera.py:345-350): geodesic angle, used once per eval frame (host logic)."""
+    R_diff = R1 @ R2.transpose(-2, -1)
+    trace = R_diff[..., 0, 0] + R_diff[..., 1, 1] + R_diff[..., 2, 2]
+    return ((trace - 1) / 2).clamp(-1 + eps, 1 - eps).acos_()
+
+
+class Graph(torch.nn.Module):
+
+    def __init__(self, opt, n_train_images=None):
+        super().__init__()
+        self.nerf = NeRF(opt)
+        self.ray_sampler = RaySampler(opt)
+        if n_train_images is not None:      # the reference attaches these in Model.build_networks (:56-59)
+            self.latent_vars_trans = torch.nn.Embedding(n_train_images, opt.nerf.N_latent_trans)
+            torch.nn.init.normal_(self.latent_vars_trans.weight)
+            self.latent_vars_light = torch.nn.Embedding(n_train_images, opt.nerf.N_latent_light)
+            torch.nn.init.normal_(self.latent_vars_light.weight)
+
+    # ---------------------------------------------------------------- small host-side helpers
+    @staticmethod
+    def get_pose(opt, var, mode=None):
+        source = dict(gt=var.pose, predicted=var.pose_init if "pose_init" in var else var.pose)
+        return source[opt.data.pose_source] if mode == "train" else source["gt"]
+
+    @staticmethod
+    def _b200(opt, key, default=None):
+        b = opt.get("b200") if hasattr(opt, "get") else None
+        return b.get(key, default) if b else default
+
+    # ---------------------------------------------------------------- reference interface
+    def forward(self, opt, var, mode=None):
+        return self.nerf_forward(opt, var, mode=mode)
+
+    def nerf_forward(self, opt, var, mode=None):
+        """model/nerf_adapt_st_gan.py:464-514 (the discriminator call of train mode stays with the engine)."""
+        pose = self.get_pose(opt, var, mode=mode)
+        depth_range = (var.z_near[:, :, None], var.z_far[:, :, None])
+        if opt.nerf.rand_rays and mode == "train":
+            ret = self.render(opt, pose, intr=var.intr, ray_idx=var.ray_idx, depth_range=depth_range,
+                              sample_idx=var.idx, mode=mode)
+        elif mode == "val":
+            ret = self.render_by_slices(opt, pose, intr=var.intr, depth_range=depth_range, object_mask=var.obj_mask,
+                                        sample_idx=None, mode=mode)
+        else:
+            R_dist = rotation_distance(var.pose[..., :3, :3], var.pose_anchor[..., :3, :3]).unsqueeze(-1)
+            k = int(opt.render.N_candidate)
+            cand = torch.topk(R_dist, k=k, dim=0, largest=False, sorted=True)[1]
+            latent_light_idx = cand[torch.randperm(len(cand))[0]][0]
+            ret = self.render_by_slices(opt, pose, intr=var.intr, depth_range=depth_range, object_mask=var.obj_mask,
+                                        sample_idx=latent_light_idx, mode=mode)
+        var.update(ret)
+        return var
+
+    def render(self, opt, pose, intr=None, ray_idx=None, depth_range=None, sample_idx=None, mode=None):
+        """model/nerf_adapt_st_gan.py:547-631 -> dict of 11 tensors."""
+        depth_min, depth_max = depth_range
+        if mode == "train":
+            B, h, w, _ = ray_idx.shape
+            center, ray = self.ray_sampler.get_rays(opt, intrinsics=intr, coords=ray_idx, pose=pose)
+            zn, zf = self.ray_sampler.get_bounds(opt, coords=ray_idx, z_near=depth_min, z_far=depth_max)
+            center, ray = center.view(B, h * w, 3), ray.view(B, h * w, 3)
+            zn, zf = zn.reshape(B, h * w), zf.reshape(B, h * w)
+        else:
+            B = len(pose)
+            center, ray = camera.get_center_and_ray(opt, pose, intr=intr, ray_idx=ray_idx)
+            zn = self.ray_batch_sample(depth_min, ray_idx).squeeze(-1)
+            zf = self.ray_batch_sample(depth_max, ray_idx).squeeze(-1)
+        if self._b200(opt, "nan_guard", False) and bool(ray.isnan().any()):
+            raise FloatingPointError("NaN in generated rays")
+        if opt.camera.ndc:
+            raise NotImplementedError("camera.ndc is false in every reference yaml; not implemented")
+
+        depth_samples = self.sample_depth(opt, B, (zn, zf), num_rays=ray.shape[1])       # [B,R,N,1]
+
+        if mode == "train":
+            lat_trans = self.latent_vars_trans.weight[sample_idx]
+            lat_light = self.latent_vars_light.weight[sample_idx]
+        elif mode == "val":
+            lat_trans = self.latent_vars_trans.weight[0][None]
+            lat_light = self.latent_vars_light.weight[0][None]
+        else:
+            if opt.render.transient == "zero":
+                lat_trans = torch.zeros(B, opt.nerf.N_latent_trans, device=ray.device)
+            elif opt.render.transient == "sample":
+                lat_trans = self.latent_vars_trans.weight[sample_idx][None]
+            else:
+                raise NotImplementedError
+            lat_light = self.latent_vars_light.weight[sample_idx][None]
+
+        rgb_samples, density_samples, uncert_samples = self.nerf.forward_samples(
+            opt, center=center, ray=ray, depth_samples=depth_samples, latent_variable_trans=lat_trans,
+            latent_variable_light=lat_light, mode=mode)
+        (rgb, rgb_static, rgb_transient, depth, opacity, opacity_static, opacity_transient, prob, uncert,
+         alpha_static, alpha_transient) = self.nerf.composite(opt, ray, rgb_samples, density_samples, depth_samples,
+                                                              uncert_samples)
+        return AttrDict(rgb=rgb, rgb_static=rgb_static, rgb_transient=rgb_transient, opacity=opacity,
+                        opacity_static=opacity_static, opacity_transient=opacity_transient, uncert=uncert, depth=depth,
+                        alpha_static=alpha_static, alpha_transient=alpha_transient, density=density_samples)
+
+    def _slice_rays(self, opt):
+        """Rays per launch.  The fused bf16 kernel keeps activations on chip, so a whole 480x640 frame is one
+        launch; the fp32 layer-by-layer path is bounded by its [S,256] activation buffers."""
+        user = self._b200(opt, "slice_rays")
+        if user:
+            return int(user)
+        n = opt.nerf.sample_intvs
+        budget = (1 << 26) if _common.mlp_precision(opt) == "bf16" else (1 << 21)
+        return max(int(opt.nerf.rand_rays or 2048), budget // n)
+
+    def render_by_slices(self, opt, pose, intr=None, depth_range=None, object_mask=None, sample_idx=None, mode=None):
+        """model/nerf_adapt_st_gan.py:633-680."""
+        HW = opt.H * opt.W
+        dev = pose.device
+        step = self._slice_rays(opt)
+        keys = ["rgb", "rgb_static", "rgb_transient", "opacity", "opacity_static", "opacity_transient", "depth",
+                "uncert", "alpha_static", "alpha_transient", "density"]
+        if mode == "val":
+            parts = {k: [] for k in keys}
+            B = len(pose)
+            for c in range(0, HW, step):
+                ray_idx = torch.arange(c, min(c + step, HW), device=dev)[None].expand(B, -1)
+                ret = self.render(opt, pose, intr=intr, ray_idx=ray_idx, depth_range=depth_range,
+                                  sample_idx=sample_idx, mode=mode)
+                for k in keys:
+                    parts[k].append(ret[k])
+            return AttrDict({k: (v[0] if len(v) == 1 else torch.cat(v, dim=1)) for k, v in parts.items()})
+
+        # mask prior: only object pixels are rendered, the rest keeps the defaults of :657-667 (B must be 1)
+        assert len(pose) == 1, "render_by_slices eval branch renders one view (reference :657-679)"
+        N = opt.nerf.sample_intvs
+        ray_idx_obj = (object_mask.view(HW) > 0).nonzero(as_tuple=True)[0]
+        ret_all = AttrDict()
+        for k in keys:
+            if k == "uncert":
+                ret_all[k] = torch.full((1, HW, 1), float(opt.nerf.min_uncert), device=dev)
+            elif k == "density":
+                ret_all[k] = torch.ones(1, HW, N, 2, device=dev)
+            elif "rgb" in k:
+                ret_all[k] = torch.zeros(1, HW, 3, device=dev)
+            elif "alpha" in k:
+                ret_all[k] = torch.ones(1, HW, N, device=dev)
+            else:
+                ret_all[k] = torch.zeros(1, HW, 1, device=dev)
+        for c in range(0, len(ray_idx_obj), step):
+            ray_idx = ray_idx_obj[c:c + step][None]
+            ret = self.render(opt, pose, intr=intr, ray_idx=ray_idx, depth_range=depth_range, sample_idx=sample_idx,
+                              mode=mode)
+            for k in keys:
+                ret_all[k][:, ray_idx[0]] = ret[k]
+        return ret_all
+
+    def sample_depth(self, opt, batch_size, depth_range, num_rays=None):
+        """model/nerf_adapt_st_gan.py:682-700.  The jitter is the same torch.rand draw as the reference (parity);
+        opt.b200.rng = 'philox' switches to the in-kernel stream."""
+        zn, zf = depth_range
+        num_rays = num_rays or opt.H * opt.W
+        zn, zf = zn.reshape(batch_size, num_rays), zf.reshape(batch_size, num_rays)
+        if opt.nerf.depth.param != "metric":
+            raise NotImplementedError("nerf.depth.param is 'metric' in every reference yaml")
+        N = opt.nerf.sample_intvs
+        if not opt.nerf.sample_stratified:
+            return ops.sample_depth(zn, zf, N, stratified=False)
+        if self._b200(opt, "rng", "torch") == "philox":
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+            return ops.sample_depth(zn, zf, N, seed=seed)
+        rand = torch.rand(batch_size, num_rays, N, 1, device=zn.device)
+        return ops.sample_depth(zn, zf, N, rand=rand)
+
+    @staticmethod
+    def ray_batch_sample(ray_identity, ray_idx):
+        """model/nerf_adapt_st_gan.py:702-710."""
+        assert ray_identity.shape[0] == ray_idx.shape[0]
+        return ops.gather_rows(ray_identity, ray_idx)
