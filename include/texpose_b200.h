@@ -156,6 +156,36 @@ int tp_plain_output_grad(const float* rgb, const float* density, const float* g_
 int tp_trunk_last_grad(const float* dz_sigma, const float* d_feat, int64_t ldd, const float* feat, int64_t ldf,
                        int64_t S, int F, float* dz, int64_t ldz, void* stream);
 
+/* ---- MLP, bf16 tensor-core path (K2): fused encode + trunk + both heads on tcgen05/TMEM ---------------------- */
+
+/* Number / size of the packed weight chunks the fused kernel streams (fixed by the canonical architecture:
+ * 8x256 trunk with skip at 4, 3x256 heads; options/nerf_lm_adapt_gan.yaml:9-18). */
+int tp_tc_num_chunks(void);
+int64_t tp_tc_chunk_bytes(void);
+/* Bytes of L2-resident scratch the forward needs (parked trunk features: SMs x 2 tiles x 64 KB). */
+int64_t tp_tc_scratch_bytes(void);
+
+/* Packs fp32 nn.Linear weights into the bf16 SMEM images of the chunks.  chunk_desc: DEVICE int64 [n_chunks,8] rows
+ * {W device pointer, ld, row0, rows_valid, col0, cols_valid, n_layout (256|16), 0}; packed: n_chunks*chunk_bytes. */
+int tp_tc_pack_weights(const int64_t* chunk_desc, int n_chunks, void* packed, void* stream);
+
+/* out[b,:] = bias + W[:, col0:col0+ncols] latent[b]   (per-image constants folded into a bias; fp32) */
+int tp_tc_image_bias(const float* W, int64_t ldw, int col0, int ncols, const float* bias, const float* latent, int B,
+                     int nout, float* out, void* stream);
+/* out[r,:] = imgbias[r / rays_per_image] + W[:, col0:col0+3+6L] [u, enc(u)], u = ray[r]/|ray[r]|  (256 outputs; fp32):
+ * the view-direction part of mlp_rgb[0] (layers/nerf_static_transient_light.py:104-117), once per ray. */
+int tp_tc_ray_bias(const float* ray, int64_t R, int64_t rays_per_image, int L_view, const float* W, int64_t ldw,
+                   int col0, const float* imgbias, float* out, void* stream);
+
+/* NeRF.forward_samples of the static/transient/light model (layers/nerf_static_transient_light.py:76-166), bf16
+ * operands / fp32 accumulate.  center, ray [rays,3]; depth [S] (S = rays*N); per_image = samples per image.
+ * biasbuf: 12x256 static biases (trunk 0-6, trunk 7 rows 1.., rgb 1-2, trans 1-2) + {trunk7 b[0], rgb3 b[0:3], trans3 b[0:5]}.
+ * Outputs rgb [S,3,2], density [S,2], uncert [S].  dbg_layer/dbg_out/flags: debugging aids (pass -1, NULL, 0). */
+int tp_tc_nerf_stl_forward(const float* center, const float* ray, const float* depth, int64_t S, int N,
+                           int64_t per_image, const void* packed, const float* biasbuf, const float* raybias,
+                           const float* imgbias, float* rgb, float* density, float* uncert, void* scratch,
+                           int64_t scratch_bytes, int dbg_layer, float* dbg_out, int flags, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

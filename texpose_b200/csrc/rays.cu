@@ -182,13 +182,14 @@ __global__ void aabb_kernel(const float* __restrict__ amin, const float* __restr
   }
 }
 
-// d_i = (u_i + i) * (1/N) * (far - near) + near, one rounding per reference op
-// (model/nerf_adapt_st_gan.py:690-697; torch divides by a Python scalar as a multiply by 1/N).
+// d_i = (u_i + i) / N * (far - near) + near, one rounding per reference op (model/nerf_adapt_st_gan.py:690-697).
+// IEEE division as torch's CPU kernel does (the pinned oracle); torch's CUDA kernel multiplies by fl(1/N) instead,
+// identical for the power-of-two N the yamls use (64, 128) and 1 ulp apart otherwise.
 __global__ void sample_depth_kernel(const float* __restrict__ z_near, const float* __restrict__ z_far,
                                     const float* __restrict__ rand, long long n_rays, int N, int mode,
                                     unsigned long long seed, float* __restrict__ out) {
   const long long total = n_rays * N;
-  const float inv_n = 1.0f / (float)N;
+  const float fn = (float)N;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / N;
@@ -202,7 +203,7 @@ __global__ void sample_depth_kernel(const float* __restrict__ z_near, const floa
       u = tp_u01(w);
     }
     const float lo = z_near[r], hi = z_far[r];
-    const float t = __fmul_rn(__fadd_rn(u, (float)k), inv_n);
+    const float t = __fdiv_rn(__fadd_rn(u, (float)k), fn);
     out[i] = __fadd_rn(__fmul_rn(t, __fsub_rn(hi, lo)), lo);
   }
 }

@@ -1,0 +1,151 @@
+"""Host side of the fused tcgen05 forward (csrc/mlp_tc.cu): weight packing, bias folding, launch.
+
+The packed bf16 weight image is an opaque caller-owned blob cached on the NeRF module and rebuilt when any
+parameter's `_version` changes ("re-packed when param._version changes").
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _C, ops
+
+_F = 256
+
+
+def supported(cfg, feat_p, rgb_p, trans_p) -> bool:
+    """The fused kernel is specialised for the architecture of options/nerf_lm_adapt_gan.yaml:9-18."""
+    if not (cfg.stl and cfg.view_dep and cfg.L_3D == 10 and tuple(cfg.skip) == (4,)):
+        return False
+    if len(feat_p) != 8 or len(rgb_p) != 4 or len(trans_p) != 4:
+        return False
+    want_f = [(256, 63)] + [(256, 256)] * 3 + [(256, 319)] + [(256, 256)] * 2 + [(257, 256)]
+    if [tuple(w.shape) for w, _ in feat_p] != want_f:
+        return False
+    k_rgb0 = 256 + cfg.view_cols + 3 + cfg.n_latent_light
+    if [tuple(w.shape) for w, _ in rgb_p] != [(256, k_rgb0), (256, 256), (256, 256), (3, 256)]:
+        return False
+    if [tuple(w.shape) for w, _ in trans_p] != [(256, 256 + cfg.n_latent_trans), (256, 256), (256, 256), (5, 256)]:
+        return False
+    return True
+
+
+def _chunk_table(cfg, feat_p, rgb_p, trans_p):
+    """Rows {ptr, ld, row0, rows_valid, col0, cols_valid, n_layout, 0} in the exact order the kernel consumes."""
+    rows = []
+
+    def big(W, col0, ncols, row0=0):      # N=256 x K=32 chunks over source columns [col0, col0+ncols)
+        for c in range(0, ncols, 32):
+            rows.append([W.data_ptr(), W.stride(0), row0, 256, col0 + c, min(32, ncols - c), 256, 0])
+
+    def small(W, nrows, row0=0):           # N=16 x K=256 chunk
+        rows.append([W.data_ptr(), W.stride(0), row0, nrows, 0, 256, 16, 0])
+
+    f = [w for w, _ in feat_p]
+    r = [w for w, _ in rgb_p]
+    t = [w for w, _ in trans_p]
+    big(f[0], 0, 63)
+    for li in (1, 2, 3):
+        big(f[li], 0, 256)
+    big(f[4], 0, 256)
+    big(f[4], 256, 63)
+    big(f[5], 0, 256)
+    big(f[6], 0, 256)
+    small(f[7], 1, row0=0)                 # density row
+    big(f[7], 0, 256, row0=1)              # feature rows 1..256
+    big(r[0], 0, 256)
+    big(r[0], 256 + cfg.view_cols, 3)      # raw xyz columns ride on the first K-chunk of the encoding tile
+    big(r[1], 0, 256)
+    big(r[2], 0, 256)
+    small(r[3], 3)
+    big(t[0], 0, 256)
+    big(t[1], 0, 256)
+    big(t[2], 0, 256)
+    small(t[3], 5)
+    return rows
+
+
+class Packed:
+    __slots__ = ("key", "weights", "biasbuf", "keep")
+
+
+def _version_key(params):
+    return tuple((p.data_ptr(), p._version) for p in params)
+
+
+def pack(cfg, holder, feat_p, rgb_p, trans_p, params_for_key) -> Packed:
+    key = _version_key(params_for_key)
+    cached = getattr(holder, "_packed", None)
+    if cached is not None and cached.key == key:
+        return cached
+    lib = _C.load()
+    n_chunks, chunk_bytes = lib.tp_tc_num_chunks(), lib.tp_tc_chunk_bytes()
+    table = _chunk_table(cfg, feat_p, rgb_p, trans_p)
+    assert len(table) == n_chunks, (len(table), n_chunks)
+    dev = feat_p[0][0].device
+    desc = torch.tensor(table, dtype=torch.int64, device=dev)
+    weights = torch.empty(n_chunks * chunk_bytes, dtype=torch.uint8, device=dev)
+    _C.call("tp_tc_pack_weights", ops._p(desc), n_chunks, ops._p(weights), ops._stream())
+    fb = [b for _, b in feat_p]
+    rb = [b for _, b in rgb_p]
+    tb = [b for _, b in trans_p]
+    small = torch.zeros(16, device=dev)
+    small[0] = fb[7][0]
+    small[1:4] = rb[3]
+    small[4:9] = tb[3]
+    biasbuf = torch.cat([fb[0], fb[1], fb[2], fb[3], fb[4], fb[5], fb[6], fb[7][1:], rb[1], rb[2], tb[1], tb[2],
+                         small]).contiguous()
+    out = Packed()
+    out.key, out.weights, out.biasbuf = key, weights, biasbuf
+    out.keep = desc
+    if holder is not None:
+        holder._packed = out
+    return out
+
+
+_scratch = {}
+
+
+def _scratch_for(dev):
+    k = (dev.type, dev.index)
+    if k not in _scratch:
+        n = _C.load().tp_tc_scratch_bytes()
+        _scratch[k] = torch.empty(n, dtype=torch.uint8, device=dev)
+    return _scratch[k]
+
+
+def forward(cfg, geom, lat_trans, lat_light, feat_p, rgb_p, trans_p, dbg_layer=-1, flags=0):
+    if geom.get("mode") != "rays":
+        raise NotImplementedError("the fused bf16 kernel is ray-parameterised (forward_samples)")
+    if not supported(cfg, feat_p, rgb_p, trans_p):
+        raise NotImplementedError("bf16 tensor-core path implements the nerf_lm_adapt_gan.yaml architecture only; "
+                                  "use opt.b200.mlp='fp32' for other layer shapes")
+    center, ray, depth = geom["center"], geom["ray"], geom["depth"]
+    B, R, N = geom["shape"]
+    S, per_image = geom["S"], geom["per_image"]
+    dev = depth.device
+    flat = [t for pair in (feat_p + rgb_p + trans_p) for t in pair]
+    pk = pack(cfg, cfg.packed, feat_p, rgb_p, trans_p, flat)
+    W_r0, b_r0 = rgb_p[0]
+    W_t0, b_t0 = trans_p[0]
+    img_r = torch.empty(B, _F, device=dev)
+    img_t = torch.empty(B, _F, device=dev)
+    _C.call("tp_tc_image_bias", ops._p(W_r0), W_r0.stride(0), 256 + cfg.view_cols + 3, cfg.n_latent_light, ops._p(b_r0),
+            ops._p(lat_light), B, _F, ops._p(img_r), ops._stream())
+    _C.call("tp_tc_image_bias", ops._p(W_t0), W_t0.stride(0), 256, cfg.n_latent_trans, ops._p(b_t0), ops._p(lat_trans),
+            B, _F, ops._p(img_t), ops._stream())
+    raybias = torch.empty(B * R, _F, device=dev)
+    _C.call("tp_tc_ray_bias", ops._p(ray), B * R, R, cfg.L_view, ops._p(W_r0), W_r0.stride(0), 256, ops._p(img_r),
+            ops._p(raybias), ops._stream())
+    rgb = torch.empty(S, 3, 2, device=dev)
+    density = torch.empty(S, 2, device=dev)
+    uncert = torch.empty(S, device=dev)
+    scratch = _scratch_for(dev)
+    dbg = torch.zeros(S, _F, device=dev) if dbg_layer >= 0 else None
+    _C.call("tp_tc_nerf_stl_forward", ops._p(center), ops._p(ray), ops._p(depth), S, N, per_image, ops._p(pk.weights),
+            ops._p(pk.biasbuf), ops._p(raybias), ops._p(img_t), ops._p(rgb), ops._p(density), ops._p(uncert),
+            ops._p(scratch), scratch.numel(), dbg_layer, ops._p(dbg), flags, ops._stream())
+    if dbg_layer >= 0:
+        return rgb, density, uncert, dbg
+    return rgb, density, uncert
