@@ -165,8 +165,9 @@ int64_t tp_tc_chunk_bytes(void);
 /* Bytes of L2-resident scratch the forward needs (parked trunk features: SMs x 2 tiles x 64 KB). */
 int64_t tp_tc_scratch_bytes(void);
 
-/* Packs fp32 nn.Linear weights into the bf16 SMEM images of the chunks.  chunk_desc: DEVICE int64 [n_chunks,8] rows
- * {W device pointer, ld, row0, rows_valid, col0, cols_valid, n_layout (256|16), 0}; packed: n_chunks*chunk_bytes. */
+/* Packs fp32 nn.Linear weights (and the static biases, which ride on a constant-1 input column) into the bf16 SMEM
+ * images of the chunks.  chunk_desc: DEVICE int64 [n_chunks,10] rows {W device pointer (0 = none), ld, row0, rows_valid,
+ * col0, cols_valid, n_layout (256|16), bias device pointer (0 = none), bias k-column, 0}; packed: n_chunks*chunk_bytes. */
 int tp_tc_pack_weights(const int64_t* chunk_desc, int n_chunks, void* packed, void* stream);
 
 /* out[b,:] = bias + W[:, col0:col0+ncols] latent[b]   (per-image constants folded into a bias; fp32) */
@@ -179,7 +180,7 @@ int tp_tc_ray_bias(const float* ray, int64_t R, int64_t rays_per_image, int L_vi
 
 /* NeRF.forward_samples of the static/transient/light model (layers/nerf_static_transient_light.py:76-166), bf16
  * operands / fp32 accumulate.  center, ray [rays,3]; depth [S] (S = rays*N); per_image = samples per image.
- * biasbuf: 12x256 static biases (trunk 0-6, trunk 7 rows 1.., rgb 1-2, trans 1-2) + {trunk7 b[0], rgb3 b[0:3], trans3 b[0:5]}.
+ * biasbuf: 16 floats {trunk7 b[0], rgb3 b[0:3], trans3 b[0:5], 0...} (the 256-wide stages' biases live in `packed`).
  * Outputs rgb [S,3,2], density [S,2], uncert [S].  dbg_layer/dbg_out/flags: debugging aids (pass -1, NULL, 0). */
 int tp_tc_nerf_stl_forward(const float* center, const float* ray, const float* depth, int64_t S, int N,
                            int64_t per_image, const void* packed, const float* biasbuf, const float* raybias,

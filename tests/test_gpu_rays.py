@@ -91,12 +91,17 @@ def test_patch_rays_and_bounds(golden):
     opt = adapt_gan_opt(H=128, W=128, device=DEV)
     kinv, pinv = camera.view_matrices(g.pose, g.intr)
     c, r = ops.patch_rays(kinv.to(DEV), pinv.to(DEV), g.coords.to(DEV), 128, 128)
-    assert (c.cpu() - g.center).abs().max() == 0
-    assert (r.cpu() - g.ray).abs().max() <= 2e-6
+    assert torch.equal(c.cpu(), g.center) and torch.equal(r.cpu(), g.ray)      # bit-exact with reference-bit constants
     c2, r2 = RaySampler.get_rays(opt, g.intr.to(DEV), g.coords.to(DEV), g.pose.to(DEV))
-    assert (r2.cpu() - g.ray).abs().max() <= 2e-6
+    assert (r2.cpu() - g.ray).abs().max() <= 2e-6                               # K^-1 / pose^-1 from the GPU solver
+    camera.HOST_MATRICES = True
+    try:
+        c3, r3 = RaySampler.get_rays(opt, g.intr.to(DEV), g.coords.to(DEV), g.pose.to(DEV))
+    finally:
+        camera.HOST_MATRICES = False
+    assert torch.equal(r3.cpu(), g.ray)
     zn, zf = RaySampler.get_bounds(opt, g.coords.to(DEV), g.z_near.to(DEV), g.z_far.to(DEV))
-    assert (zn.cpu() - g.zn).abs().max() <= 2e-5 and (zf.cpu() - g.zf).abs().max() <= 2e-5
+    assert torch.equal(zn.cpu(), g.zn) and torch.equal(zf.cpu(), g.zf)          # torch CPU grid_sample arithmetic
     img = torch.rand(3, 5, 128, 128)
     ref = torch.nn.functional.grid_sample(img, g.coords, mode="bilinear", align_corners=True)
     got = RaySampler.get_image(opt, g.coords.to(DEV), img.to(DEV))
@@ -121,7 +126,7 @@ def test_points_from_depth_bit_exact(golden):
 def test_normals_and_guided_range(golden):
     g = golden("normals")
     n = compute_surfelinfo.normal_from_depth(g.pose.to(DEV), g.depth.to(DEV), g.intr.to(DEV), g.H, g.W)
-    assert (n.cpu() - g.normal).abs().max() <= 2e-5
+    assert (n.cpu() - g.normal).abs().max() <= 2e-4      # unit normals from cancelling central differences
     zn, zf = compute_surfelinfo.depth_guided_range(g.depth.to(DEV), *synth.BG_RANGE)
     assert torch.equal(zn.cpu(), g.guided_near) and torch.equal(zf.cpu(), g.guided_far)
 

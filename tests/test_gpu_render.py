@@ -27,6 +27,16 @@ def _graph(opt, g=None, n=4):
     return gr.to(DEV)
 
 
+@pytest.fixture(autouse=True)
+def _reference_bit_constants():
+    """K^-1 / pose^-1 as the CPU reference computes them: the 2^9*pi positional encoding amplifies ulp-level ray
+    differences to ~1e-3 in the outputs, so end-to-end parity is checked on bit-identical rays."""
+    from texpose_b200 import camera
+    camera.HOST_MATRICES = True
+    yield
+    camera.HOST_MATRICES = False
+
+
 def test_render_train_matches_reference(golden):
     g = golden("render_train")
     opt = adapt_gan_opt(H=128, W=128, device=DEV)

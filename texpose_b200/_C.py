@@ -102,6 +102,10 @@ def check(code: int, name: str):
     raise RuntimeError(f"{name}: CUDA error {code}")
 
 
+launch_counts = {}      # C-ABI call counts by entry point (bench.py reports them as `gpu_launches`)
+
+
 def call(name: str, *args):
     lib = load()
     check(getattr(lib, name)(*args), name)
+    launch_counts[name] = launch_counts.get(name, 0) + 1

@@ -70,8 +70,17 @@ def cam2world(X, pose_):
     return to_hom(X) @ Pose().invert(pose_).transpose(-1, -2)          # camera.py:270-277
 
 
+HOST_MATRICES = False   # True: invert K / the pose on the CPU (LAPACK bits == the CPU reference), costs one sync
+
+
 def view_matrices(pose_, intr):
-    """(K^-1 [B,3,3], pose^-1 [B,3,4]) -- the per-view constants every ray kernel takes."""
+    """(K^-1 [B,3,3], pose^-1 [B,3,4]) -- the per-view constants every ray kernel takes (camera.py:267,270-277).
+    By default they are computed where `pose_` lives (no host sync).  With HOST_MATRICES the two tiny inverses run
+    on the CPU exactly as the CPU reference does, which makes generated rays bit-identical to it."""
+    if HOST_MATRICES and pose_.is_cuda:
+        dev = pose_.device
+        return (intr.detach().cpu().float().inverse().contiguous().to(dev),
+                Pose().invert(pose_.detach().cpu().float()).contiguous().to(dev))
     return intr.float().inverse().contiguous(), Pose().invert(pose_.float()).contiguous()
 
 

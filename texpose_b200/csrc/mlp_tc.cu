@@ -18,7 +18,7 @@
 //   * the trunk feature (needed by both heads) is parked in an L2-resident scratch with a bulk store after
 //     the last trunk layer and bulk-loaded back before the transient head.
 //
-// SMEM (bytes): A0 64K | A1 64K | E0 16K | E1 16K | ring 4x16K | barriers  = 229 504 (<= 227 KB opt-in).
+// SMEM (bytes): A0 64K | A1 64K | E0 16K | E1 16K | ring 4x16K | barriers = 229 504 (<= 227 KB opt-in).
 // TMEM: 512 columns = two 128x256 fp32 accumulators.
 //
 // Operand layout (no swizzle, K-major "interleave" canonical layout): element (row r, col k) of a tile with
@@ -38,36 +38,41 @@ constexpr uint32_t kOffA = 0, kOffE = 2 * kABytes, kOffRing = kOffE + 2 * kEByte
 constexpr uint32_t kOffBar = kOffRing + kStages * kChunkBytes;
 constexpr uint32_t kSmemBytes = kOffBar + 128;
 constexpr int kNumLayers = 17;
-constexpr int kNumChunks = 112;
+constexpr int kNumChunks = 122;
 
 // stage table: chunks read from A (K=32 each), chunks read from E, small (N=16, one chunk spans K=256),
-// kind of epilogue, index of the 256-float bias block (or -1), needs the feature reload first
+// kind of epilogue, bias handling, needs the feature reload first.
+// Static biases of the 256-wide stages ride on the tensor cores: column 63 of the encoding tile is a constant 1 and
+// the bias sits in the matching weight column -- for stages that read E anyway (trunk 0 and 4) inside their last E
+// chunk, for the others as one extra K=16 step on E columns 48..63 with an 8 KB weight chunk that is zero except for
+// that column (BIAS_MMA).  Their epilogue is then a pure convert.  Per-ray / per-image biases (fp32 tables) and the
+// three N=16 output stages add their bias in the epilogue.
 enum Epi : int { EPI_HIDDEN = 0, EPI_DENSITY = 1, EPI_RGB_OUT = 2, EPI_TRANS_OUT = 3 };
-enum BiasKind : int { BIAS_STATIC = 0, BIAS_RAY = 1, BIAS_IMAGE = 2 };
+enum BiasKind : int { BIAS_MMA = 0, BIAS_RAY = 1, BIAS_IMAGE = 2, BIAS_SMALL = 3 };
 struct Layer {
-  int a_chunks, e_chunks, small, epi, bias_kind, bias_block, reload;
+  int a_chunks, e_chunks, small, epi, bias_kind, bias_chunk, reload;
 };
 __constant__ Layer kLayers[kNumLayers] = {
-    {0, 2, 0, EPI_HIDDEN, BIAS_STATIC, 0, 0},    // trunk 0  (63 -> 256)
-    {8, 0, 0, EPI_HIDDEN, BIAS_STATIC, 1, 0},    // trunk 1
-    {8, 0, 0, EPI_HIDDEN, BIAS_STATIC, 2, 0},    // trunk 2
-    {8, 0, 0, EPI_HIDDEN, BIAS_STATIC, 3, 0},    // trunk 3
-    {8, 2, 0, EPI_HIDDEN, BIAS_STATIC, 4, 0},    // trunk 4  (skip: [feat | enc])
-    {8, 0, 0, EPI_HIDDEN, BIAS_STATIC, 5, 0},    // trunk 5
-    {8, 0, 0, EPI_HIDDEN, BIAS_STATIC, 6, 0},    // trunk 6
-    {8, 0, 1, EPI_DENSITY, BIAS_STATIC, -1, 0},  // trunk 7 row 0     -> sigma_static (softplus)
-    {8, 0, 0, EPI_HIDDEN, BIAS_STATIC, 7, 0},    // trunk 7 rows 1..  -> feature (relu); parked to L2 afterwards
-    {8, 1, 0, EPI_HIDDEN, BIAS_RAY, -1, 0},      // rgb 0    ([feat | xyz]; view+light folded into the ray bias)
-    {8, 0, 0, EPI_HIDDEN, BIAS_STATIC, 8, 0},    // rgb 1
-    {8, 0, 0, EPI_HIDDEN, BIAS_STATIC, 9, 0},    // rgb 2
-    {8, 0, 1, EPI_RGB_OUT, BIAS_STATIC, -1, 0},  // rgb 3    -> sigmoid
-    {8, 0, 0, EPI_HIDDEN, BIAS_IMAGE, -1, 1},    // trans 0  (feature reloaded; transient latent in the image bias)
-    {8, 0, 0, EPI_HIDDEN, BIAS_STATIC, 10, 0},   // trans 1
-    {8, 0, 0, EPI_HIDDEN, BIAS_STATIC, 11, 0},   // trans 2
-    {8, 0, 1, EPI_TRANS_OUT, BIAS_STATIC, -1, 0} // trans 3  -> sigmoid x3, softplus x2
+    {0, 2, 0, EPI_HIDDEN, BIAS_MMA, 0, 0},       // trunk 0  (63 -> 256); bias in E column 63 of its own chunk
+    {8, 0, 0, EPI_HIDDEN, BIAS_MMA, 1, 0},       // trunk 1
+    {8, 0, 0, EPI_HIDDEN, BIAS_MMA, 1, 0},       // trunk 2
+    {8, 0, 0, EPI_HIDDEN, BIAS_MMA, 1, 0},       // trunk 3
+    {8, 2, 0, EPI_HIDDEN, BIAS_MMA, 0, 0},       // trunk 4  (skip: [feat | enc]); bias in E column 63
+    {8, 0, 0, EPI_HIDDEN, BIAS_MMA, 1, 0},       // trunk 5
+    {8, 0, 0, EPI_HIDDEN, BIAS_MMA, 1, 0},       // trunk 6
+    {8, 0, 1, EPI_DENSITY, BIAS_SMALL, 0, 0},    // trunk 7 row 0     -> sigma_static (softplus)
+    {8, 0, 0, EPI_HIDDEN, BIAS_MMA, 1, 0},       // trunk 7 rows 1..  -> feature (relu); parked to L2 afterwards
+    {8, 1, 0, EPI_HIDDEN, BIAS_RAY, 0, 0},       // rgb 0    ([feat | xyz]; view+light folded into the ray bias)
+    {8, 0, 0, EPI_HIDDEN, BIAS_MMA, 1, 0},       // rgb 1
+    {8, 0, 0, EPI_HIDDEN, BIAS_MMA, 1, 0},       // rgb 2
+    {8, 0, 1, EPI_RGB_OUT, BIAS_SMALL, 0, 0},    // rgb 3    -> sigmoid
+    {8, 0, 0, EPI_HIDDEN, BIAS_IMAGE, 0, 1},     // trans 0  (feature reloaded; transient latent in the image bias)
+    {8, 0, 0, EPI_HIDDEN, BIAS_MMA, 1, 0},       // trans 1
+    {8, 0, 0, EPI_HIDDEN, BIAS_MMA, 1, 0},       // trans 2
+    {8, 0, 1, EPI_TRANS_OUT, BIAS_SMALL, 0, 0}   // trans 3  -> sigmoid x3, softplus x2
 };
 constexpr int kSpillLayer = 8, kFirstHeadLayer = 9, kReloadIssueLayer = 12;
-constexpr int kSmallBiasOffset = 12 * 256;     // biasbuf tail: [density b, rgb3 b(3), trans3 b(5)]
+constexpr int kSmallBiasOffset = 0;            // biasbuf: [density b, rgb3 b(3), trans3 b(5)] (fp32, 16 floats)
 
 // ------------------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -138,6 +143,20 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
+// Same instruction with the two 64-bit descriptors assembled from 32-bit halves inside the asm block: the issuing
+// thread then spends one integer add per MMA on descriptor upkeep (the low word carries start>>4 and LBO>>4, the high
+// word SBO>>4 and the version bit -- both constant per operand).
+__device__ __forceinline__ void umma_bf16_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                               uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -159,6 +178,17 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
                : "r"(taddr)                                                                         \
                : "memory")
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// wait::ld that also names the destination registers, so no consumer of v[] can be scheduled above the wait
+#define TP_TMEM_WAIT32(v)                                                                                              \
+  asm volatile("tcgen05.wait::ld.sync.aligned;"                                                                        \
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),       \
+                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), \
+                 "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]),            \
+                 "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]),            \
+                 "+r"(v[30]), "+r"(v[31])::"memory")
+#define TP_TMEM_WAIT8(v)                                                                                         \
+  asm volatile("tcgen05.wait::ld.sync.aligned;"                                                                  \
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]):: "memory")
 
 // {hi, lo} fp32 -> packed bf16x2 with ReLU (lo in the low half = the lower column index)
 __device__ __forceinline__ uint32_t pack_relu_bf16(float lo, float hi) {
@@ -172,7 +202,9 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return d;
 }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+  // no "memory" clobber: asm volatile statements keep their relative order (fences, barrier arrives), while plain
+  // loads (the bias LDS of the next group) may be scheduled above the store
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d));
 }
 
 struct Params {
@@ -195,7 +227,7 @@ struct Params {
   int swap_lbo_sbo;          // debug: exchange the two descriptor strides
 };
 
-// positional encoding of one sample into the E tile (bf16): [x,y,z, per coord sin(2^k pi x) k<10, cos(...) k<10, 0].
+// positional encoding of one sample into the E tile (bf16): [x,y,z, per coord sin(2^k pi x) k<10, cos(...) k<10, 1].
 // sincospif gives the exact-argument octave 0; higher octaves by the double-angle recurrence (error << bf16 ulp).
 __device__ __forceinline__ void encode_sample(const Params& p, long long s, uint32_t e_smem, int row) {
   const long long r = s / p.N;
@@ -216,11 +248,51 @@ __device__ __forceinline__ void encode_sample(const Params& p, long long s, uint
       cs = c2;
     }
   }
-  v[63] = 0.f;
+  v[63] = 1.f;   // constant-1 column: carries the static biases through the MMA
 #pragma unroll
   for (int k8 = 0; k8 < 8; ++k8)
     st_shared_v4(e_smem + k8 * 2048 + row * 16, pack_bf16(v[k8 * 8 + 0], v[k8 * 8 + 1]), pack_bf16(v[k8 * 8 + 2], v[k8 * 8 + 3]),
                  pack_bf16(v[k8 * 8 + 4], v[k8 * 8 + 5]), pack_bf16(v[k8 * 8 + 6], v[k8 * 8 + 7]));
+}
+
+// One 32-column slab of a hidden stage: (+fp32 bias,) ReLU, bf16, store as 4 core-matrix rows of the next A operand.
+template <bool kBias>
+__device__ __forceinline__ void hidden_slab(const uint32_t (&v)[32], const float* bias, uint32_t a_dst, float* dbg_row) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    float x[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(v[i + e]);
+    if (kBias) {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + i));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + i + 4));
+      x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
+      x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+    }
+    st_shared_v4(a_dst + (i >> 3) * 2048, pack_relu_bf16(x[0], x[1]), pack_relu_bf16(x[2], x[3]), pack_relu_bf16(x[4], x[5]),
+                 pack_relu_bf16(x[6], x[7]));
+    if (dbg_row) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) dbg_row[i + e] = fmaxf(x[e], 0.f);
+    }
+  }
+}
+
+// Whole 128x256 accumulator row of one thread: TMEM loads are software-pipelined (slab j+1 in flight while slab j is
+// converted), ping-ponging two register slabs.
+template <bool kBias>
+__device__ __forceinline__ void hidden_epilogue(uint32_t tmem_d, const float* bias, uint32_t a_row, float* dbg_row) {
+  uint32_t va[32], vb[32];
+  TP_TMEM_LD32(tmem_d, va);
+#pragma unroll
+  for (int j = 0; j < 8; j += 2) {
+    TP_TMEM_WAIT32(va);
+    TP_TMEM_LD32(tmem_d + (j + 1) * 32, vb);
+    hidden_slab<kBias>(va, bias + j * 32, a_row + j * 4 * 2048, dbg_row ? dbg_row + j * 32 : nullptr);
+    TP_TMEM_WAIT32(vb);
+    if (j + 2 < 8) TP_TMEM_LD32(tmem_d + (j + 2) * 32, va);
+    hidden_slab<kBias>(vb, bias + (j + 1) * 32, a_row + (j + 1) * 4 * 2048, dbg_row ? dbg_row + (j + 1) * 32 : nullptr);
+  }
 }
 
 __global__ void __launch_bounds__(kThreads, 1) nerf_stl_forward_kernel(const Params p) {
@@ -265,11 +337,18 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_stl_forward_kernel(const Par
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       for (long long st = blockIdx.x; st < n_super; st += gridDim.x) {
-        for (int c = 0; c < kNumChunks; ++c) {
-          mbar_wait(bar_empty(stage), phase ^ 1);
-          mbar_expect_tx(bar_full(stage), kChunkBytes);
-          bulk_g2s(sbase + kOffRing + stage * kChunkBytes, p.packed + (size_t)c * kChunkBytes, kChunkBytes, bar_full(stage));
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        int c = 0;
+        for (int L = 0; L < kNumLayers; ++L) {
+          const Layer ly = kLayers[L];
+          const int nch = ly.small ? 1 : ly.a_chunks + ly.e_chunks + ly.bias_chunk;
+          for (int j = 0; j < nch; ++j, ++c) {
+            // full 16 KB K=32 chunks; the N=16 chunk and the bias chunk only carry 8 KB
+            const uint32_t bytes = (ly.small || j >= ly.a_chunks + ly.e_chunks) ? kChunkBytes / 2 : kChunkBytes;
+            mbar_wait(bar_empty(stage), phase ^ 1);
+            mbar_expect_tx(bar_full(stage), bytes);
+            bulk_g2s(sbase + kOffRing + stage * kChunkBytes, p.packed + (size_t)c * kChunkBytes, bytes, bar_full(stage));
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
         }
       }
     }
@@ -281,7 +360,7 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_stl_forward_kernel(const Par
       for (long long st = blockIdx.x; st < n_super; st += gridDim.x) {
         for (int L = 0; L < kNumLayers; ++L) {
           const Layer ly = kLayers[L];
-          const int nch = ly.small ? 1 : ly.a_chunks + ly.e_chunks;
+          const int nch = ly.small ? 1 : ly.a_chunks + ly.e_chunks + ly.bias_chunk;
           for (int c = 0; c < nch; ++c) {
             mbar_wait(bar_full(stage), phase);
             tc_fence_after();
@@ -297,25 +376,31 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_stl_forward_kernel(const Par
                 tc_fence_after();
               }
               const uint32_t d_tmem = tmem_base + t * 256;
+              // descriptor words: lo = start>>4 | (LBO>>4)<<16, hi = SBO>>4 | version(1)<<14; SBO = 128 B everywhere
+              constexpr uint32_t kHi = (128u >> 4) | (1u << 14);
               if (ly.small) {
                 // one chunk = [32 k8][16 rows][8]: 16 K-steps over the full K=256 of A_t
-                const uint32_t a0 = sbase + kOffA + t * kABytes;
-#pragma unroll 1
+                uint32_t a_lo = ((sbase + kOffA + t * kABytes) >> 4) | ((2048u >> 4) << 16);
+                uint32_t b_lo = (wsm >> 4) | ((256u >> 4) << 16);
+#pragma unroll
                 for (int ks = 0; ks < 16; ++ks) {
-                  const uint64_t ad = p.swap_lbo_sbo ? umma_desc(a0 + ks * 4096, 128, 2048) : umma_desc(a0 + ks * 4096, 2048, 128);
-                  const uint64_t bd = p.swap_lbo_sbo ? umma_desc(wsm + ks * 512, 128, 256) : umma_desc(wsm + ks * 512, 256, 128);
-                  umma_bf16(d_tmem, ad, bd, idesc16, ks > 0);
+                  umma_bf16_lohi(d_tmem, a_lo, kHi, b_lo, kHi, idesc16, ks > 0 ? 1u : 0u);
+                  a_lo += 4096u >> 4;
+                  b_lo += 512u >> 4;
                 }
+              } else if (c >= ly.a_chunks + ly.e_chunks) {
+                // bias step: A = E columns 48..63 (column 63 == 1), B = [2 k8][256 rows][8], zero except the bias column
+                const uint32_t a_lo = ((sbase + kOffE + t * kEBytes + 6 * 2048) >> 4) | ((2048u >> 4) << 16);
+                const uint32_t b_lo = (wsm >> 4) | ((4096u >> 4) << 16);
+                umma_bf16_lohi(d_tmem, a_lo, kHi, b_lo, kHi, idesc256, 1u);
               } else {
                 const bool from_e = c >= ly.a_chunks;
                 const uint32_t a0 = from_e ? sbase + kOffE + t * kEBytes + (c - ly.a_chunks) * 4 * 2048
                                            : sbase + kOffA + t * kABytes + c * 4 * 2048;
-#pragma unroll
-                for (int ks = 0; ks < 2; ++ks) {
-                  const uint64_t ad = p.swap_lbo_sbo ? umma_desc(a0 + ks * 4096, 128, 2048) : umma_desc(a0 + ks * 4096, 2048, 128);
-                  const uint64_t bd = p.swap_lbo_sbo ? umma_desc(wsm + ks * 8192, 128, 4096) : umma_desc(wsm + ks * 8192, 4096, 128);
-                  umma_bf16(d_tmem, ad, bd, idesc256, (c > 0 || ks > 0) ? 1u : 0u);
-                }
+                const uint32_t a_lo = (a0 >> 4) | ((2048u >> 4) << 16);
+                const uint32_t b_lo = (wsm >> 4) | ((4096u >> 4) << 16);
+                umma_bf16_lohi(d_tmem, a_lo, kHi, b_lo, kHi, idesc256, c > 0 ? 1u : 0u);
+                umma_bf16_lohi(d_tmem, a_lo + (4096u >> 4), kHi, b_lo + (8192u >> 4), kHi, idesc256, 1u);
               }
               if (c == nch - 1) umma_commit(bar_acc(t));   // accumulator of tile t complete
             }
@@ -359,31 +444,12 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_stl_forward_kernel(const Par
           bulk_g2s(a_smem, my_scratch, kABytes, bar_reload(t));
         }
         if (ly.epi == EPI_HIDDEN) {
-          const float* bias = ly.bias_kind == BIAS_STATIC ? p.biasbuf + ly.bias_block * 256
-                              : ly.bias_kind == BIAS_RAY  ? p.raybias + (s / p.N) * 256
-                                                          : p.imgbias + (s / p.per_image) * 256;
-          const bool dbg = (L == p.dbg_layer) && live && p.dbg_out;
-#pragma unroll 1
-          for (int j = 0; j < 8; ++j) {
-            uint32_t v[32];
-            TP_TMEM_LD32(tmem_d + j * 32, v);
-            tmem_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + j * 32 + i));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + j * 32 + i + 4));
-              const float x0 = __uint_as_float(v[i + 0]) + b0.x, x1 = __uint_as_float(v[i + 1]) + b0.y;
-              const float x2 = __uint_as_float(v[i + 2]) + b0.z, x3 = __uint_as_float(v[i + 3]) + b0.w;
-              const float x4 = __uint_as_float(v[i + 4]) + b1.x, x5 = __uint_as_float(v[i + 5]) + b1.y;
-              const float x6 = __uint_as_float(v[i + 6]) + b1.z, x7 = __uint_as_float(v[i + 7]) + b1.w;
-              st_shared_v4(a_smem + (j * 4 + (i >> 3)) * 2048 + row * 16, pack_relu_bf16(x0, x1), pack_relu_bf16(x2, x3),
-                           pack_relu_bf16(x4, x5), pack_relu_bf16(x6, x7));
-              if (dbg) {
-                float* o = p.dbg_out + s * 256 + j * 32 + i;
-                o[0] = fmaxf(x0, 0.f); o[1] = fmaxf(x1, 0.f); o[2] = fmaxf(x2, 0.f); o[3] = fmaxf(x3, 0.f);
-                o[4] = fmaxf(x4, 0.f); o[5] = fmaxf(x5, 0.f); o[6] = fmaxf(x6, 0.f); o[7] = fmaxf(x7, 0.f);
-              }
-            }
+          float* dbg_row = ((L == p.dbg_layer) && live && p.dbg_out) ? p.dbg_out + s * 256 : nullptr;
+          if (ly.bias_kind == BIAS_MMA) {
+            hidden_epilogue<false>(tmem_d, nullptr, a_smem + row * 16, dbg_row);
+          } else {
+            const float* bias = ly.bias_kind == BIAS_RAY ? p.raybias + (s / p.N) * 256 : p.imgbias + (s / p.per_image) * 256;
+            hidden_epilogue<true>(tmem_d, bias, a_smem + row * 16, dbg_row);
           }
           fence_proxy_async_smem();
           if (L == kSpillLayer) {               // park the trunk feature (bf16 tile image) in the L2 scratch
@@ -396,7 +462,7 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_stl_forward_kernel(const Par
         } else {
           uint32_t v[8];
           TP_TMEM_LD8(tmem_d, v);
-          tmem_wait_ld();
+          TP_TMEM_WAIT8(v);
           const float* sb = p.biasbuf + kSmallBiasOffset;
           if (ly.epi == EPI_DENSITY) {
             sigma_s = tp_softplus(__uint_as_float(v[0]) + sb[0]);
@@ -437,11 +503,14 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_stl_forward_kernel(const Par
 
 // ------------------------------------------------------------------------------------------ helper kernels
 
-// desc row: [w_ptr, ld, row0, rows_valid, col0, cols_valid, n_layout, unused]
+// desc row: [w_ptr, ld, row0, rows_valid, col0, cols_valid, n_layout, bias_ptr, bias_klocal, 0]
+// (bias_ptr != 0: element (n, bias_klocal) of the chunk is bias[n] -- the column multiplied by the constant-1 of E)
 __global__ void pack_weights_kernel(const long long* __restrict__ desc, __nv_bfloat16* __restrict__ out) {
-  const long long* d = desc + (long long)blockIdx.x * 8;
+  const long long* d = desc + (long long)blockIdx.x * 10;
   const float* W = reinterpret_cast<const float*>(d[0]);
   const long long ld = d[1], row0 = d[2], rows_valid = d[3], col0 = d[4], cols_valid = d[5], n_layout = d[6];
+  const float* bias = reinterpret_cast<const float*>(d[7]);
+  const long long bias_k = d[8];
   __nv_bfloat16* o = out + (long long)blockIdx.x * (kChunkBytes / 2);
   for (int e = threadIdx.x; e < (int)(kChunkBytes / 2); e += blockDim.x) {
     int n, kl;
@@ -455,7 +524,8 @@ __global__ void pack_weights_kernel(const long long* __restrict__ desc, __nv_bfl
       in_layout = e < 4096;
     }
     float v = 0.f;
-    if (in_layout && n < rows_valid && kl < cols_valid) v = W[(row0 + n) * ld + col0 + kl];
+    if (in_layout && W && n < rows_valid && kl < cols_valid) v = W[(row0 + n) * ld + col0 + kl];
+    if (in_layout && bias && kl == bias_k && n < rows_valid) v = bias[n];
     o[e] = __float2bfloat16_rn(v);
   }
 }

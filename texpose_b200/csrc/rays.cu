@@ -58,24 +58,26 @@ __global__ void raygen_kernel(const float* __restrict__ kinv, const float* __res
   }
 }
 
-// F.grid_sample(mode='bilinear', padding_mode='zeros', align_corners=True) coordinate + weights.
+// F.grid_sample(mode='bilinear', padding_mode='zeros', align_corners=True) coordinate + weights, in the exact
+// arithmetic of torch's CPU kernel (the pinned oracle): ix = (x+1)*((W-1)/2); w = ix-floor(ix), e = 1-w;
+// corner weights s*e, s*w, n*e, n*w; value = fma chain over nw, ne, sw, se (bit-exact vs tests/golden/patch.npz).
 struct Bilin {
   int x0, y0;
   float wnw, wne, wsw, wse;
 };
 __device__ __forceinline__ Bilin bilin_setup(float gx, float gy, int H, int W) {
-  const float ix = __fmul_rn(__fmul_rn(__fadd_rn(gx, 1.f), 0.5f), (float)(W - 1));
-  const float iy = __fmul_rn(__fmul_rn(__fadd_rn(gy, 1.f), 0.5f), (float)(H - 1));
+  const float ix = __fmul_rn(__fadd_rn(gx, 1.f), __fdiv_rn((float)(W - 1), 2.f));
+  const float iy = __fmul_rn(__fadd_rn(gy, 1.f), __fdiv_rn((float)(H - 1), 2.f));
   const float fx = floorf(ix), fy = floorf(iy);
   Bilin s;
   s.x0 = (int)fx;
   s.y0 = (int)fy;
-  const float ex = __fsub_rn(__fadd_rn(fx, 1.f), ix), wx = __fsub_rn(ix, fx);
-  const float ey = __fsub_rn(__fadd_rn(fy, 1.f), iy), wy = __fsub_rn(iy, fy);
-  s.wnw = __fmul_rn(ex, ey);
-  s.wne = __fmul_rn(wx, ey);
-  s.wsw = __fmul_rn(ex, wy);
-  s.wse = __fmul_rn(wx, wy);
+  const float w = __fsub_rn(ix, fx), e = __fsub_rn(1.f, w);
+  const float n = __fsub_rn(iy, fy), so = __fsub_rn(1.f, n);
+  s.wnw = __fmul_rn(so, e);
+  s.wne = __fmul_rn(so, w);
+  s.wsw = __fmul_rn(n, e);
+  s.wse = __fmul_rn(n, w);
   return s;
 }
 template <class F>

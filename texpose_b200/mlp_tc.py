@@ -32,38 +32,57 @@ def supported(cfg, feat_p, rgb_p, trans_p) -> bool:
 
 
 def _chunk_table(cfg, feat_p, rgb_p, trans_p):
-    """Rows {ptr, ld, row0, rows_valid, col0, cols_valid, n_layout, 0} in the exact order the kernel consumes."""
+    """Rows {W ptr, ld, row0, rows_valid, col0, cols_valid, n_layout, bias ptr, bias k, 0} in the exact order the kernel
+    consumes.  Static biases travel inside the weight image: they multiply the constant-1 column (63) of the encoding
+    tile, either in the stage's own last E chunk (trunk 0, 4) or in a dedicated K=16 bias chunk (E columns 48..63)."""
     rows = []
 
-    def big(W, col0, ncols, row0=0):      # N=256 x K=32 chunks over source columns [col0, col0+ncols)
-        for c in range(0, ncols, 32):
-            rows.append([W.data_ptr(), W.stride(0), row0, 256, col0 + c, min(32, ncols - c), 256, 0])
+    def big(W, col0, ncols, row0=0, bias=None):      # N=256 x K=32 chunks over source columns [col0, col0+ncols)
+        n = len(range(0, ncols, 32))
+        for i, c in enumerate(range(0, ncols, 32)):
+            last = bias is not None and i == n - 1
+            rows.append([W.data_ptr(), W.stride(0), row0, 256, col0 + c, min(32, ncols - c), 256,
+                         bias.data_ptr() if last else 0, 31 if last else -1, 0])
 
-    def small(W, nrows, row0=0):           # N=16 x K=256 chunk
-        rows.append([W.data_ptr(), W.stride(0), row0, nrows, 0, 256, 16, 0])
+    def bias_chunk(b):                                 # N=256 x K=16 chunk on E columns 48..63: only column 63 set
+        rows.append([0, 0, 0, 256, 0, 0, 256, b.data_ptr(), 15, 0])
+
+    def small(W, nrows, row0=0):                       # N=16 x K=256 chunk
+        rows.append([W.data_ptr(), W.stride(0), row0, nrows, 0, 256, 16, 0, -1, 0])
 
     f = [w for w, _ in feat_p]
+    fb = [b for _, b in feat_p]
     r = [w for w, _ in rgb_p]
+    rb = [b for _, b in rgb_p]
     t = [w for w, _ in trans_p]
-    big(f[0], 0, 63)
+    tb = [b for _, b in trans_p]
+    keep = []
+    big(f[0], 0, 63, bias=fb[0])
     for li in (1, 2, 3):
         big(f[li], 0, 256)
+        bias_chunk(fb[li])
     big(f[4], 0, 256)
-    big(f[4], 256, 63)
-    big(f[5], 0, 256)
-    big(f[6], 0, 256)
+    big(f[4], 256, 63, bias=fb[4])
+    for li in (5, 6):
+        big(f[li], 0, 256)
+        bias_chunk(fb[li])
     small(f[7], 1, row0=0)                 # density row
     big(f[7], 0, 256, row0=1)              # feature rows 1..256
+    b7 = fb[7][1:].contiguous()
+    keep.append(b7)
+    bias_chunk(b7)
     big(r[0], 0, 256)
     big(r[0], 256 + cfg.view_cols, 3)      # raw xyz columns ride on the first K-chunk of the encoding tile
-    big(r[1], 0, 256)
-    big(r[2], 0, 256)
+    for li in (1, 2):
+        big(r[li], 0, 256)
+        bias_chunk(rb[li])
     small(r[3], 3)
     big(t[0], 0, 256)
-    big(t[1], 0, 256)
-    big(t[2], 0, 256)
+    for li in (1, 2):
+        big(t[li], 0, 256)
+        bias_chunk(tb[li])
     small(t[3], 5)
-    return rows
+    return rows, keep
 
 
 class Packed:
@@ -81,7 +100,7 @@ def pack(cfg, holder, feat_p, rgb_p, trans_p, params_for_key) -> Packed:
         return cached
     lib = _C.load()
     n_chunks, chunk_bytes = lib.tp_tc_num_chunks(), lib.tp_tc_chunk_bytes()
-    table = _chunk_table(cfg, feat_p, rgb_p, trans_p)
+    table, keep = _chunk_table(cfg, feat_p, rgb_p, trans_p)
     assert len(table) == n_chunks, (len(table), n_chunks)
     dev = feat_p[0][0].device
     desc = torch.tensor(table, dtype=torch.int64, device=dev)
@@ -90,15 +109,13 @@ def pack(cfg, holder, feat_p, rgb_p, trans_p, params_for_key) -> Packed:
     fb = [b for _, b in feat_p]
     rb = [b for _, b in rgb_p]
     tb = [b for _, b in trans_p]
-    small = torch.zeros(16, device=dev)
-    small[0] = fb[7][0]
-    small[1:4] = rb[3]
-    small[4:9] = tb[3]
-    biasbuf = torch.cat([fb[0], fb[1], fb[2], fb[3], fb[4], fb[5], fb[6], fb[7][1:], rb[1], rb[2], tb[1], tb[2],
-                         small]).contiguous()
+    biasbuf = torch.zeros(16, device=dev)      # fp32 biases of the three N=16 output stages
+    biasbuf[0] = fb[7][0]
+    biasbuf[1:4] = rb[3]
+    biasbuf[4:9] = tb[3]
     out = Packed()
     out.key, out.weights, out.biasbuf = key, weights, biasbuf
-    out.keep = desc
+    out.keep = (desc, keep)
     if holder is not None:
         holder._packed = out
     return out

@@ -87,6 +87,8 @@ def gather_rows(src: Tensor, idx: Tensor) -> Tensor:
     B, HW, C = src.shape
     R = idx.shape[1]
     out = torch.empty(B, R, C, device=src.device, dtype=torch.float32)
+    if R == 0:
+        return out
     _C.call("tp_gather_rows", _p(src), _p(idx), B, HW, C, R, _p(out), _stream())
     return out
 
