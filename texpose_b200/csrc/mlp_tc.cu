@@ -120,6 +120,18 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
+// One lane of a converged warp (elect.sync): the surrounding control flow stays warp-uniform, so descriptor and barrier
+// operands live in uniform registers and UTCHMMA / UBLKCP / UTCBAR need no per-instruction R2UR waterfall loop.
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
@@ -298,7 +310,8 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t tmem_d, const float* bi
 __global__ void __launch_bounds__(kThreads, 1) nerf_stl_forward_kernel(const Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform role index
+  const int lane = threadIdx.x & 31;
   // barriers
   const uint32_t bar0 = sbase + kOffBar;
   auto bar_full = [&](int s) { return bar0 + 8 * s; };
@@ -333,8 +346,8 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_stl_forward_kernel(const Par
   const long long n_super = (p.S + 255) / 256;
 
   if (warp == 8) {
-    // ================================================================ weight producer (one lane)
-    if (lane == 0) {
+    // ================================================================ weight producer (converged warp, one lane issues)
+    {
       uint32_t stage = 0, phase = 0;
       for (long long st = blockIdx.x; st < n_super; st += gridDim.x) {
         int c = 0;
@@ -345,16 +358,19 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_stl_forward_kernel(const Par
             // full 16 KB K=32 chunks; the N=16 chunk and the bias chunk only carry 8 KB
             const uint32_t bytes = (ly.small || j >= ly.a_chunks + ly.e_chunks) ? kChunkBytes / 2 : kChunkBytes;
             mbar_wait(bar_empty(stage), phase ^ 1);
-            mbar_expect_tx(bar_full(stage), bytes);
-            bulk_g2s(sbase + kOffRing + stage * kChunkBytes, p.packed + (size_t)c * kChunkBytes, bytes, bar_full(stage));
+            if (elect_one_sync()) {
+              mbar_expect_tx(bar_full(stage), bytes);
+              bulk_g2s(sbase + kOffRing + stage * kChunkBytes, p.packed + (size_t)c * kChunkBytes, bytes, bar_full(stage));
+            }
+            __syncwarp();
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
   } else if (warp == 9) {
-    // ================================================================ MMA issuer (one lane)
-    if (lane == 0) {
+    // ================================================================ MMA issuer (converged warp, one lane issues)
+    {
       uint32_t stage = 0, phase = 0, ready_ph[2] = {0, 0}, reload_ph[2] = {0, 0};
       const uint32_t idesc256 = umma_idesc(128, 256), idesc16 = umma_idesc(128, 16);
       for (long long st = blockIdx.x; st < n_super; st += gridDim.x) {
@@ -376,6 +392,7 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_stl_forward_kernel(const Par
                 tc_fence_after();
               }
               const uint32_t d_tmem = tmem_base + t * 256;
+              if (elect_one_sync()) {
               // descriptor words: lo = start>>4 | (LBO>>4)<<16, hi = SBO>>4 | version(1)<<14; SBO = 128 B everywhere
               constexpr uint32_t kHi = (128u >> 4) | (1u << 14);
               if (ly.small) {
@@ -403,8 +420,11 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_stl_forward_kernel(const Par
                 umma_bf16_lohi(d_tmem, a_lo + (4096u >> 4), kHi, b_lo + (8192u >> 4), kHi, idesc256, 1u);
               }
               if (c == nch - 1) umma_commit(bar_acc(t));   // accumulator of tile t complete
+              }
+              __syncwarp();
             }
-            umma_commit(bar_empty(stage));                 // ring slot reusable once these MMAs retire
+            if (elect_one_sync()) umma_commit(bar_empty(stage));   // ring slot reusable once these MMAs retire
+            __syncwarp();
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
