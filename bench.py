@@ -358,7 +358,7 @@ def bench_train(args, g, opt, dev, world, timed):
     ms, _ = timed(step, max(3, args.steps // 2), 2)
     g.eval()
     samples = B * P * P * NS
-    return dict(workload="C3 train step fwd+bwd, 4096 rays x 128 samples per GPU, bf16 fwd / fp32 bwd, grad allreduce",
+    return dict(workload="C3 train step fwd+bwd, 4096 rays x 128 samples per GPU, bf16 tcgen05 fwd + bwd (dX chain, dW GEMMs), grad allreduce",
                 value=world * samples / (ms * 1e-3), unit="samples/s", ms_per_step=ms, grad_allreduce_bytes=bucket.flat.numel() * 4)
 
 

@@ -181,11 +181,44 @@ int tp_tc_ray_bias(const float* ray, int64_t R, int64_t rays_per_image, int L_vi
 /* NeRF.forward_samples of the static/transient/light model (layers/nerf_static_transient_light.py:76-166), bf16
  * operands / fp32 accumulate.  center, ray [rays,3]; depth [S] (S = rays*N); per_image = samples per image.
  * biasbuf: 16 floats {trunk7 b[0], rgb3 b[0:3], trans3 b[0:5], 0...} (the 256-wide stages' biases live in `packed`).
- * Outputs rgb [S,3,2], density [S,2], uncert [S].  dbg_layer/dbg_out/flags: debugging aids (pass -1, NULL, 0). */
+ * Outputs rgb [S,3,2], density [S,2], uncert [S].  save: NULL, or tp_tc_save_bytes(S) bytes receiving, per 128-sample
+ * tile, the bf16 tile images [7][32 k8][128 rows][8] of {trunk feature, rgb hidden 1-3, transient hidden 1-3} that the
+ * backward consumes (training).  dbg_layer/dbg_out/flags: debugging aids (pass -1, NULL, 0). */
 int tp_tc_nerf_stl_forward(const float* center, const float* ray, const float* depth, int64_t S, int N,
                            int64_t per_image, const void* packed, const float* biasbuf, const float* raybias,
                            const float* imgbias, float* rgb, float* density, float* uncert, void* scratch,
-                           int64_t scratch_bytes, int dbg_layer, float* dbg_out, int flags, void* stream);
+                           int64_t scratch_bytes, void* save, int dbg_layer, float* dbg_out, int flags, void* stream);
+int64_t tp_tc_save_bytes(int64_t S);
+/* One slot of the saved tile images -> row-major fp32 [S,256]. */
+int tp_tc_unpack_images(const void* images, int slot, int n_slots, int64_t S, float* out, void* stream);
+
+/* ---- tensor-core backward of the two heads on the saved tile images (K2b, bf16 mode) ------------------------- */
+
+/* out[i] (=/+=) sum_z partial[z*count + i], fixed order (second stage of every split reduction). */
+int tp_reduce_partials(const float* partial, int splits, int64_t count, float* out, int accumulate, void* stream);
+
+int tp_tc_bwd_num_chunks(void);              /* chunks of the transposed weight image the chain kernel streams (34) */
+int64_t tp_tc_dz_bytes(int64_t S);           /* bytes of the dz tile images: ceil(S/128) x 6 x 64 KB */
+int tp_tc_dw_grid(int64_t S);                /* number of split partials tp_tc_dw_gemm writes */
+
+/* autograd of mlp_rgb[1..3] / mlp_trans[1..3] w.r.t. their inputs (layers/nerf_static_transient_light.py:118-134):
+ * dz_rgb [S,3], dz_trans [S,5] = grads of the output layers' pre-activations; packed_bwd = tp_tc_pack_weights image of
+ * {W3^T, W2^T, W1^T} of both heads (34 chunks, transpose flag); saved = activations of tp_tc_nerf_stl_forward.
+ * Writes the dz tile images [tiles][6] = {rgb dz2, dz1, dz0, trans dz2, dz1, dz0}. */
+int tp_tc_backward_chain(const float* dz_rgb, const float* dz_trans, int64_t S, const void* packed_bwd,
+                         const void* saved, void* dz_images, void* stream);
+
+/* partial[g] (256x256 fp32, g < tp_tc_dw_grid(S)) = sum over the tiles of split g of dz^T x, dz = slot a_slot of
+ * a_images, x = slot b_slot of b_images.  Reduce with tp_reduce_partials. */
+int tp_tc_dw_gemm(const void* a_images, int a_slot, int a_nslots, const void* b_images, int b_slot, int b_nslots,
+                  int64_t S, float* partial, int64_t partial_floats, int flags, void* stream);
+
+/* partial[blk][m][k] = sum_s thin[s][m] * x[s][k] for a thin fp32 operand [S,M], M in {1,3,5}; x = image slot. */
+int tp_tc_thin_dw(const float* thin, int M, const void* images, int slot, int n_slots, int64_t S, float* partial,
+                  int64_t partial_floats, int* n_blocks_out, void* stream);
+
+/* row-major fp32 [S,256] -> bf16 tile image slot (interop / tests). */
+int tp_tc_pack_images(const float* in, int64_t S, void* images, int slot, int n_slots, void* stream);
 
 #ifdef __cplusplus
 }

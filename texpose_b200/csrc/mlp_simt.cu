@@ -375,6 +375,13 @@ TP_API int tp_linear_backward_weight(const float* dY, int64_t lddy, const float*
   return tp_launch_status();
 }
 
+TP_API int tp_reduce_partials(const float* partial, int splits, int64_t count, float* out, int accumulate, void* stream) {
+  if (!partial || !out) return TP_ERR_BAD_ARG;
+  if (splits < 1 || count < 1) return TP_ERR_BAD_SHAPE;
+  reduce_partials_kernel<<<tp_grid_for(count, 256, 4), 256, 0, (cudaStream_t)stream>>>(partial, splits, count, out, accumulate);
+  return tp_launch_status();
+}
+
 TP_API int tp_group_colsum(const float* dY, int64_t lddy, int64_t S, int64_t group, int Nout, float* out,
                            float* workspace, int64_t workspace_floats, void* stream) {
   if (!dY || !out || !workspace) return TP_ERR_BAD_ARG;

@@ -24,15 +24,13 @@
 // Operand layout (no swizzle, K-major "interleave" canonical layout): element (row r, col k) of a tile with
 // `rows` rows lives at  (k/8)*rows*16 + r*16 + (k%8)*2  bytes -> 8x8 core matrices of 128 contiguous bytes,
 // LBO (K-direction core-matrix stride) = rows*16, SBO (8-row-group stride) = 128.
-#include "common.cuh"
+#include "tc_common.cuh"
 #include "../../include/texpose_b200.h"
 
 namespace tc {
 
 constexpr int kThreads = 320;          // warps 0-7 epilogue/encode, warp 8 TMA producer, warp 9 MMA issuer
 constexpr int kStages = 4;
-constexpr uint32_t kChunkBytes = 16384;
-constexpr uint32_t kABytes = 65536;    // 128 x 256 bf16
 constexpr uint32_t kEBytes = 16384;    // 128 x 64 bf16
 constexpr uint32_t kOffA = 0, kOffE = 2 * kABytes, kOffRing = kOffE + 2 * kEBytes;
 constexpr uint32_t kOffBar = kOffRing + kStages * kChunkBytes;
@@ -71,153 +69,11 @@ __constant__ Layer kLayers[kNumLayers] = {
     {8, 0, 0, EPI_HIDDEN, BIAS_MMA, 1, 0},       // trans 2
     {8, 0, 1, EPI_TRANS_OUT, BIAS_SMALL, 0, 0}   // trans 3  -> sigmoid x3, softplus x2
 };
-constexpr int kSpillLayer = 8, kFirstHeadLayer = 9, kReloadIssueLayer = 12;
+constexpr int kSpillLayer = 8, kReloadIssueLayer = 12;
+constexpr int kSaveSlots = 7;
+// activation-save slot of each stage (training): feat, rgb h1..h3, trans h1..h3; -1 = not saved
+__constant__ int kSaveSlot[kNumLayers] = {-1, -1, -1, -1, -1, -1, -1, -1, 0, 1, 2, 3, -1, 4, 5, 6, -1};
 constexpr int kSmallBiasOffset = 0;            // biasbuf: [density b, rgb3 b(3), trans3 b(5)] (fp32, 16 floats)
-
-// ------------------------------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) {
-  }
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src_smem, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-
-// One lane of a converged warp (elect.sync): the surrounding control flow stays warp-uniform, so descriptor and barrier
-// operands live in uniform registers and UTCHMMA / UBLKCP / UTCBAR need no per-instruction R2UR waterfall loop.
-__device__ __forceinline__ bool elect_one_sync() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t.reg .pred P;\n\t"
-      "elect.sync _|P, 0xffffffff;\n\t"
-      "selp.b32 %0, 1, 0, P;\n\t}"
-      : "=r"(pred));
-  return pred != 0;
-}
-
-__device__ __forceinline__ void named_bar_sync(int id, int threads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
-
-// UMMA shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
-// SBO>>4 [32,46), version=1 [46,48), layout_type [61,64) = 0 (SWIZZLE_NONE / interleave).
-__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
-  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
-         ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
-}
-// Instruction descriptor (cute::UMMA::InstrDescriptor), kind::f16: D=F32 (bits 4-5 = 1), A=B=BF16 (bits 7-9, 10-12 = 1),
-// both K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29).
-__host__ __device__ constexpr uint32_t umma_idesc(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-// Same instruction with the two 64-bit descriptors assembled from 32-bit halves inside the asm block: the issuing
-// thread then spends one integer add per MMA on descriptor upkeep (the low word carries start>>4 and LBO>>4, the high
-// word SBO>>4 and the version bit -- both constant per operand).
-__device__ __forceinline__ void umma_bf16_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
-                                               uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-      "mov.b64 da, {%1, %2};\n\t"
-      "mov.b64 db, {%3, %4};\n\t"
-      "setp.ne.b32 p, %6, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
-      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-#define TP_TMEM_LD32(taddr, v)                                                                                        \
-  asm volatile(                                                                                                       \
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                       \
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, "    \
-      "%23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"                                                          \
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),   \
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),        \
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),       \
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                     \
-      : "r"(taddr)                                                                                                    \
-      : "memory")
-#define TP_TMEM_LD8(taddr, v)                                                                       \
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"      \
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) \
-               : "r"(taddr)                                                                         \
-               : "memory")
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-// wait::ld that also names the destination registers, so no consumer of v[] can be scheduled above the wait
-#define TP_TMEM_WAIT32(v)                                                                                              \
-  asm volatile("tcgen05.wait::ld.sync.aligned;"                                                                        \
-               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),       \
-                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), \
-                 "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]),            \
-                 "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]),            \
-                 "+r"(v[30]), "+r"(v[31])::"memory")
-#define TP_TMEM_WAIT8(v)                                                                                         \
-  asm volatile("tcgen05.wait::ld.sync.aligned;"                                                                  \
-               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]):: "memory")
-
-// {hi, lo} fp32 -> packed bf16x2 with ReLU (lo in the low half = the lower column index)
-__device__ __forceinline__ uint32_t pack_relu_bf16(float lo, float hi) {
-  uint32_t d;
-  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
-  return d;
-}
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-  uint32_t d;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
-  return d;
-}
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  // no "memory" clobber: asm volatile statements keep their relative order (fences, barrier arrives), while plain
-  // loads (the bias LDS of the next group) may be scheduled above the store
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d));
-}
 
 struct Params {
   const float* center;       // [rays,3]
@@ -234,6 +90,7 @@ struct Params {
   float* density;            // [S,2]
   float* uncert;             // [S]
   uint8_t* scratch;          // gridDim.x x 2 x 64 KB (parked features)
+  uint8_t* save;             // optional [tiles][7][64 KB]: feat, rgb h1..h3, trans h1..h3 tile images for the backward
   int dbg_layer;
   float* dbg_out;            // [S,256] post-activation of stage dbg_layer (debug only)
   int swap_lbo_sbo;          // debug: exchange the two descriptor strides
@@ -371,7 +228,7 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_stl_forward_kernel(const Par
   } else if (warp == 9) {
     // ================================================================ MMA issuer (converged warp, one lane issues)
     {
-      uint32_t stage = 0, phase = 0, ready_ph[2] = {0, 0}, reload_ph[2] = {0, 0};
+      uint32_t stage = 0, phase = 0, ready_ph = 0, reload_ph = 0;   // per-tile phase bits (bit t)
       const uint32_t idesc256 = umma_idesc(128, 256), idesc16 = umma_idesc(128, 16);
       for (long long st = blockIdx.x; st < n_super; st += gridDim.x) {
         for (int L = 0; L < kNumLayers; ++L) {
@@ -383,11 +240,11 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_stl_forward_kernel(const Par
             const uint32_t wsm = sbase + kOffRing + stage * kChunkBytes;
             for (int t = 0; t < 2; ++t) {
               if (c == 0) {
-                mbar_wait(bar_ready(t), ready_ph[t]);
-                ready_ph[t] ^= 1;
+                mbar_wait(bar_ready(t), (ready_ph >> t) & 1u);
+                ready_ph ^= 1u << t;
                 if (ly.reload) {
-                  mbar_wait(bar_reload(t), reload_ph[t]);
-                  reload_ph[t] ^= 1;
+                  mbar_wait(bar_reload(t), (reload_ph >> t) & 1u);
+                  reload_ph ^= 1u << t;
                 }
                 tc_fence_after();
               }
@@ -437,6 +294,7 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_stl_forward_kernel(const Par
     const uint32_t tmem_d = tmem_base + ((uint32_t)(q * 32) << 16) + t * 256;
     uint8_t* my_scratch = p.scratch + ((size_t)blockIdx.x * 2 + t) * kABytes;
     uint32_t acc_ph = 0;
+    bool store_pending = false;      // a bulk store of A_t (feature park / activation save) may still be reading it
     for (long long st = blockIdx.x; st < n_super; st += gridDim.x) {
       const long long s_raw = (st * 2 + t) * 128 + row;
       const bool live = s_raw < p.S;
@@ -452,16 +310,17 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_stl_forward_kernel(const Par
         mbar_wait(bar_acc(t), acc_ph);
         acc_ph ^= 1;
         tc_fence_after();
-        if (L == kFirstHeadLayer) {            // the parked-feature store must have finished reading A_t
+        if (ly.epi == EPI_HIDDEN && store_pending) {   // the previous bulk store must have finished reading A_t
           if (row == 0) bulk_wait_read();
           named_bar_sync(1 + t, 128);
+          store_pending = false;
         }
         if (L == kReloadIssueLayer && row == 0) {
           // every MMA that reads A_t has retired (acc barrier) -> bring the trunk feature back for the transient head
           bulk_wait_all();
           fence_proxy_async_all();
           mbar_expect_tx(bar_reload(t), kABytes);
-          bulk_g2s(a_smem, my_scratch, kABytes, bar_reload(t));
+          bulk_g2s(a_smem, p.save ? p.save + ((size_t)(st * 2 + t) * kSaveSlots) * kABytes : my_scratch, kABytes, bar_reload(t));
         }
         if (ly.epi == EPI_HIDDEN) {
           float* dbg_row = ((L == p.dbg_layer) && live && p.dbg_out) ? p.dbg_out + s * 256 : nullptr;
@@ -472,12 +331,16 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_stl_forward_kernel(const Par
             hidden_epilogue<true>(tmem_d, bias, a_smem + row * 16, dbg_row);
           }
           fence_proxy_async_smem();
-          if (L == kSpillLayer) {               // park the trunk feature (bf16 tile image) in the L2 scratch
+          if (L == kSpillLayer || (p.save && kSaveSlot[L] >= 0)) {
+            // park the trunk feature (bf16 tile image) in the L2 scratch; in training mode every head activation is
+            // saved the same way -- the store overlaps the next stage's MMAs
             named_bar_sync(1 + t, 128);
             if (row == 0) {
-              bulk_s2g(my_scratch, a_smem, kABytes);
+              uint8_t* dst = p.save ? p.save + ((size_t)(st * 2 + t) * kSaveSlots + kSaveSlot[L]) * kABytes : my_scratch;
+              bulk_s2g(dst, a_smem, kABytes);
               bulk_commit();
             }
+            store_pending = true;
           }
         } else {
           uint32_t v[8];
@@ -523,14 +386,15 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_stl_forward_kernel(const Par
 
 // ------------------------------------------------------------------------------------------ helper kernels
 
-// desc row: [w_ptr, ld, row0, rows_valid, col0, cols_valid, n_layout, bias_ptr, bias_klocal, 0]
+// desc row: [w_ptr, ld, row0, rows_valid, col0, cols_valid, n_layout, bias_ptr, bias_klocal, transpose]
+// transpose != 0: chunk element (n, kl) = W[col0 + kl][row0 + n]  (B operand of the input-gradient GEMMs, dX = dZ W)
 // (bias_ptr != 0: element (n, bias_klocal) of the chunk is bias[n] -- the column multiplied by the constant-1 of E)
 __global__ void pack_weights_kernel(const long long* __restrict__ desc, __nv_bfloat16* __restrict__ out) {
   const long long* d = desc + (long long)blockIdx.x * 10;
   const float* W = reinterpret_cast<const float*>(d[0]);
   const long long ld = d[1], row0 = d[2], rows_valid = d[3], col0 = d[4], cols_valid = d[5], n_layout = d[6];
   const float* bias = reinterpret_cast<const float*>(d[7]);
-  const long long bias_k = d[8];
+  const long long bias_k = d[8], transpose = d[9];
   __nv_bfloat16* o = out + (long long)blockIdx.x * (kChunkBytes / 2);
   for (int e = threadIdx.x; e < (int)(kChunkBytes / 2); e += blockDim.x) {
     int n, kl;
@@ -544,7 +408,8 @@ __global__ void pack_weights_kernel(const long long* __restrict__ desc, __nv_bfl
       in_layout = e < 4096;
     }
     float v = 0.f;
-    if (in_layout && W && n < rows_valid && kl < cols_valid) v = W[(row0 + n) * ld + col0 + kl];
+    if (in_layout && W && n < rows_valid && kl < cols_valid)
+      v = transpose ? W[(col0 + kl) * ld + row0 + n] : W[(row0 + n) * ld + col0 + kl];
     if (in_layout && bias && kl == bias_k && n < rows_valid) v = bias[n];
     o[e] = __float2bfloat16_rn(v);
   }
@@ -562,43 +427,69 @@ __global__ void image_bias_kernel(const float* __restrict__ W, long long ldw, in
   }
 }
 
-// out[r, n] = imgbias[r / rays_per_image, n] + sum_j W[n, col0 + j] * viewenc(r)[j];  viewenc = [u, enc(u)], u = ray/|ray|
+// out[r, n] = imgbias[r / rays_per_image, n] + sum_j W[n, col0 + j] * viewenc(r)[j];  viewenc = [u, enc(u)], u = ray/|ray|.
+// One CTA = kRaysPerBlock rays: all encodings first (one barrier), then thread n keeps its weight column in registers
+// and streams the rays; stores are 1 KB-coalesced rows.
+constexpr int kRaysPerBlock = 64;
 __global__ void __launch_bounds__(256) ray_bias_kernel(const float* __restrict__ ray, long long R, long long rays_per_image,
                                                        int L, const float* __restrict__ W, long long ldw, int col0,
-                                                       const float* __restrict__ imgbias, float* __restrict__ out,
-                                                       int rays_per_block) {
-  extern __shared__ float sm[];      // Wv[vc][256] then enc[vc]
-  const int vc = 3 + 6 * L;
-  float* Wv = sm;
-  float* enc = sm + vc * 256;
-  for (int i = threadIdx.x; i < vc * 256; i += blockDim.x) {
-    const int j = i / 256, n = i % 256;
-    Wv[i] = W[n * ldw + col0 + j];
-  }
-  __syncthreads();
-  const long long r0 = (long long)blockIdx.x * rays_per_block;
-  for (long long r = r0; r < r0 + rays_per_block && r < R; ++r) {
-    if (threadIdx.x < 3 * (1 + 2 * L)) {
-      // thread -> one output column of the encoding
+                                                       const float* __restrict__ imgbias, float* __restrict__ out) {
+  __shared__ float enc[kRaysPerBlock][28];
+  const int vc = 3 + 6 * L;     // <= 27 (L_view <= 4)
+  const long long r0 = (long long)blockIdx.x * kRaysPerBlock;
+  for (int i = threadIdx.x; i < kRaysPerBlock * vc; i += blockDim.x) {
+    const int rr = i / vc, c = i - rr * vc;
+    const long long r = r0 + rr;
+    float val = 0.f;
+    if (r < R) {
       const float x = ray[r * 3], y = ray[r * 3 + 1], z = ray[r * 3 + 2];
       const float len = fmaxf(sqrtf(x * x + y * y + z * z), 1e-12f);
       const float u[3] = {x / len, y / len, z / len};
-      const int i = threadIdx.x;
-      float val;
-      if (i < 3) val = u[i];
+      if (c < 3) val = u[c];
       else {
-        const int e = i - 3, c = e / (2 * L), k = e % (2 * L);
-        const float arg = __fmul_rn(u[c], ldexpf(3.14159265358979323846f, k < L ? k : k - L));
+        const int e = c - 3, cc = e / (2 * L), k = e % (2 * L);
+        const float arg = __fmul_rn(u[cc], ldexpf(3.14159265358979323846f, k < L ? k : k - L));
         val = k < L ? sinf(arg) : cosf(arg);
       }
-      enc[i] = val;
     }
-    __syncthreads();
-    const int n = threadIdx.x;
+    enc[rr][c] = val;
+  }
+  float w[27];
+  const int n = threadIdx.x;
+#pragma unroll
+  for (int j = 0; j < 27; ++j) w[j] = j < vc ? W[n * ldw + col0 + j] : 0.f;
+  __syncthreads();
+  for (int rr = 0; rr < kRaysPerBlock; ++rr) {
+    const long long r = r0 + rr;
+    if (r >= R) break;
     float acc = imgbias[(r / rays_per_image) * 256 + n];
-    for (int j = 0; j < vc; ++j) acc = fmaf(Wv[j * 256 + n], enc[j], acc);
+#pragma unroll
+    for (int j = 0; j < 27; ++j) acc = fmaf(w[j], enc[rr][j], acc);
     out[r * 256 + n] = acc;
-    __syncthreads();
+  }
+}
+
+
+// tile image [tiles][n_slots][k8=32][128 rows][8] bf16 -> row-major fp32 [S,256] (consumers: the fp32 SIMT kernels)
+__global__ void unpack_images_kernel(const uint8_t* __restrict__ images, int slot, int n_slots, long long S,
+                                     float* __restrict__ out) {
+  const long long total = ((S + 127) / 128) * 4096;     // 16-byte vectors
+  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < total; v += (long long)gridDim.x * blockDim.x) {
+    const long long tile = v >> 12;
+    const int k8 = (int)((v >> 7) & 31), r = (int)(v & 127);
+    const long long s = tile * 128 + r;
+    if (s >= S) continue;
+    const uint4 q = *reinterpret_cast<const uint4*>(images + ((size_t)tile * n_slots + slot) * kABytes + k8 * 2048 + r * 16);
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      f[2 * e] = __uint_as_float(w[e] << 16);
+      f[2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u);
+    }
+    float4* o = reinterpret_cast<float4*>(out + s * 256 + k8 * 8);
+    o[0] = make_float4(f[0], f[1], f[2], f[3]);
+    o[1] = make_float4(f[4], f[5], f[6], f[7]);
   }
 }
 
@@ -608,9 +499,20 @@ TP_API int tp_tc_num_chunks(void) { return tc::kNumChunks; }
 TP_API int64_t tp_tc_chunk_bytes(void) { return tc::kChunkBytes; }
 TP_API int64_t tp_tc_scratch_bytes(void) { return (int64_t)tp_num_sms() * 2 * tc::kABytes; }
 
+TP_API int64_t tp_tc_save_bytes(int64_t S) { return ((S + 255) / 256) * 2 * tc::kSaveSlots * (int64_t)tc::kABytes; }
+
+TP_API int tp_tc_unpack_images(const void* images, int slot, int n_slots, int64_t S, float* out, void* stream) {
+  if (!images || !out) return TP_ERR_BAD_ARG;
+  if (slot < 0 || slot >= n_slots || S < 0) return TP_ERR_BAD_SHAPE;
+  if (S == 0) return TP_OK;
+  tc::unpack_images_kernel<<<tp_grid_for(((S + 127) / 128) * 4096, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint8_t*>(images), slot, n_slots, S, out);
+  return tp_launch_status();
+}
+
 TP_API int tp_tc_pack_weights(const int64_t* chunk_desc, int n_chunks, void* packed, void* stream) {
   if (!chunk_desc || !packed) return TP_ERR_BAD_ARG;
-  if (n_chunks != tc::kNumChunks) return TP_ERR_BAD_SHAPE;
+  if (n_chunks < 1) return TP_ERR_BAD_SHAPE;
   tc::pack_weights_kernel<<<n_chunks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const long long*>(chunk_desc),
                                                                     reinterpret_cast<__nv_bfloat16*>(packed));
   return tp_launch_status();
@@ -627,21 +529,17 @@ TP_API int tp_tc_image_bias(const float* W, int64_t ldw, int col0, int ncols, co
 TP_API int tp_tc_ray_bias(const float* ray, int64_t R, int64_t rays_per_image, int L_view, const float* W, int64_t ldw,
                           int col0, const float* imgbias, float* out, void* stream) {
   if (!ray || !W || !imgbias || !out) return TP_ERR_BAD_ARG;
-  if (R < 0 || rays_per_image < 1 || L_view < 0 || L_view > 16) return TP_ERR_BAD_SHAPE;
+  if (R < 0 || rays_per_image < 1 || L_view < 0 || L_view > 4) return TP_ERR_BAD_SHAPE;
   if (R == 0) return TP_OK;
-  const int vc = 3 + 6 * L_view;
-  const int rpb = 64;
-  const size_t smem = (size_t)(vc * 256 + vc) * sizeof(float);
-  cudaFuncSetAttribute(tc::ray_bias_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  tc::ray_bias_kernel<<<(unsigned)((R + rpb - 1) / rpb), 256, smem, (cudaStream_t)stream>>>(
-      ray, R, rays_per_image, L_view, W, ldw, col0, imgbias, out, rpb);
+  tc::ray_bias_kernel<<<(unsigned)((R + tc::kRaysPerBlock - 1) / tc::kRaysPerBlock), 256, 0, (cudaStream_t)stream>>>(
+      ray, R, rays_per_image, L_view, W, ldw, col0, imgbias, out);
   return tp_launch_status();
 }
 
 TP_API int tp_tc_nerf_stl_forward(const float* center, const float* ray, const float* depth, int64_t S, int N,
                                   int64_t per_image, const void* packed, const float* biasbuf, const float* raybias,
                                   const float* imgbias, float* rgb, float* density, float* uncert, void* scratch,
-                                  int64_t scratch_bytes, int dbg_layer, float* dbg_out, int flags, void* stream) {
+                                  int64_t scratch_bytes, void* save, int dbg_layer, float* dbg_out, int flags, void* stream) {
   if (!center || !ray || !depth || !packed || !biasbuf || !raybias || !imgbias || !rgb || !density || !uncert || !scratch)
     return TP_ERR_BAD_ARG;
   if (S < 0 || N < 1 || per_image < 1) return TP_ERR_BAD_SHAPE;
@@ -658,6 +556,8 @@ TP_API int tp_tc_nerf_stl_forward(const float* center, const float* ray, const f
   p.center = center; p.ray = ray; p.depth = depth; p.S = S; p.N = N; p.per_image = per_image;
   p.packed = reinterpret_cast<const uint8_t*>(packed); p.biasbuf = biasbuf; p.raybias = raybias; p.imgbias = imgbias;
   p.rgb = rgb; p.density = density; p.uncert = uncert; p.scratch = reinterpret_cast<uint8_t*>(scratch);
+  p.save = reinterpret_cast<uint8_t*>(save);
+  if (((uintptr_t)save & 15)) return TP_ERR_ALIGN;
   p.dbg_layer = dbg_layer; p.dbg_out = dbg_out; p.swap_lbo_sbo = flags & 1;
   cudaError_t e = cudaFuncSetAttribute(tc::nerf_stl_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)tc::kSmemBytes);

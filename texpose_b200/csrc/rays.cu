@@ -187,26 +187,44 @@ __global__ void aabb_kernel(const float* __restrict__ amin, const float* __restr
 // d_i = (u_i + i) / N * (far - near) + near, one rounding per reference op (model/nerf_adapt_st_gan.py:690-697).
 // IEEE division as torch's CPU kernel does (the pinned oracle); torch's CUDA kernel multiplies by fl(1/N) instead,
 // identical for the power-of-two N the yamls use (64, 128) and 1 ulp apart otherwise.
+__device__ __forceinline__ float stratified_depth(float u, int k, float fn, float lo, float hi) {
+  const float t = __fdiv_rn(__fadd_rn(u, (float)k), fn);
+  return __fadd_rn(__fmul_rn(t, __fsub_rn(hi, lo)), lo);
+}
+
 __global__ void sample_depth_kernel(const float* __restrict__ z_near, const float* __restrict__ z_far,
                                     const float* __restrict__ rand, long long n_rays, int N, int mode,
-                                    unsigned long long seed, float* __restrict__ out) {
+                                    float* __restrict__ out) {
   const long long total = n_rays * N;
   const float fn = (float)N;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / N;
     const int k = (int)(i - r * N);
-    float u;
-    if (mode == 0) u = rand[i];
-    else if (mode == 1) u = 0.5f;
-    else {
-      const uint4 x = tp_philox((uint32_t)(i >> 2), (uint32_t)((i >> 2) >> 32), (uint32_t)seed, (uint32_t)(seed >> 32));
-      const uint32_t w = (i & 3) == 0 ? x.x : (i & 3) == 1 ? x.y : (i & 3) == 2 ? x.z : x.w;
-      u = tp_u01(w);
+    out[i] = stratified_depth(mode == 0 ? rand[i] : 0.5f, k, fn, z_near[r], z_far[r]);
+  }
+}
+
+// In-kernel jitter: one Philox4x32-10 block per 4 consecutive samples (counter = sample index / 4), 16 B stores.
+__global__ void sample_depth_philox_kernel(const float* __restrict__ z_near, const float* __restrict__ z_far,
+                                           long long n_rays, int N, unsigned long long seed, float* __restrict__ out) {
+  const long long total = n_rays * N, quads = (total + 3) >> 2;
+  const float fn = (float)N;
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < quads; q += (long long)gridDim.x * blockDim.x) {
+    const uint4 x = tp_philox((uint32_t)q, (uint32_t)(q >> 32), (uint32_t)seed, (uint32_t)(seed >> 32));
+    const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+    float d[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const long long i = q * 4 + e;
+      if (i < total) {
+        const long long r = i / N;
+        d[e] = stratified_depth(tp_u01(w[e]), (int)(i - r * N), fn, z_near[r], z_far[r]);
+      } else d[e] = 0.f;
     }
-    const float lo = z_near[r], hi = z_far[r];
-    const float t = __fdiv_rn(__fadd_rn(u, (float)k), fn);
-    out[i] = __fadd_rn(__fmul_rn(t, __fsub_rn(hi, lo)), lo);
+    if (q * 4 + 3 < total) *reinterpret_cast<float4*>(out + q * 4) = make_float4(d[0], d[1], d[2], d[3]);
+    else
+      for (int e = 0; e < 4 && q * 4 + e < total; ++e) out[q * 4 + e] = d[e];
   }
 }
 
@@ -359,8 +377,12 @@ TP_API int tp_sample_depth(const float* z_near, const float* z_far, const float*
   TP_CHECK(n_rays >= 0 && N > 0, TP_ERR_BAD_SHAPE);
   TP_CHECK(mode >= 0 && mode <= 2 && (mode != 0 || rand), TP_ERR_BAD_ARG);
   if (n_rays == 0) return TP_OK;
-  sample_depth_kernel<<<tp_grid_for(n_rays * N, kThreads, 8), kThreads, 0, (cudaStream_t)stream>>>(
-      z_near, z_far, rand, n_rays, N, mode, seed, out);
+  if (mode == 2)
+    sample_depth_philox_kernel<<<tp_grid_for((n_rays * N + 3) / 4, kThreads, 8), kThreads, 0, (cudaStream_t)stream>>>(
+        z_near, z_far, n_rays, N, seed, out);
+  else
+    sample_depth_kernel<<<tp_grid_for(n_rays * N, kThreads, 8), kThreads, 0, (cudaStream_t)stream>>>(
+        z_near, z_far, rand, n_rays, N, mode, out);
   return tp_launch_status();
 }
 

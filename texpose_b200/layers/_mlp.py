@@ -6,8 +6,8 @@ reference are never materialised: each layer reads a *segmented* input (see tp_l
 
 Two arithmetic modes:
   fp32  -- SIMT FFMA kernels (mlp_simt.cu), the <=1e-4 parity mode, forward and backward;
-  bf16  -- fused tcgen05/TMEM forward (mlp_tc.cu) for the static/transient/light model; its backward
-           re-materialises the head activations with the fp32 kernels.
+  bf16  -- fused tcgen05/TMEM forward (mlp_tc.cu) for the static/transient/light model; in training it also saves
+           the head activations (bf16 tile images) that the backward consumes.
 """
 from __future__ import annotations
 
@@ -202,6 +202,21 @@ def mlp_backward(cfg: MLPConfig, sv: _Saved, S: int, per_image: int, feat_p, rgb
     return g_feat_layers, g_rgb_layers, g_trans_layers, d_lat_trans, d_lat_light
 
 
+def _inputs_from_images(cfg: MLPConfig, sv: _Saved, S: int, per_image: int):
+    """Layer inputs for the backward from the activations the fused bf16 forward saved (bf16 values, fp32 storage)."""
+    from .. import mlp_tc
+    geom = sv.geom
+    lt, ll = sv.lat
+    feat = mlp_tc.unpack_image(sv.images, mlp_tc.SLOT_FEAT, S)
+    xyz = ops.points_from_depth(geom["center"], geom["ray"], geom["depth"]).view(S, 3)
+    first = [(feat, 1, feat.shape[1]), geom["view_seg"](), (xyz, 1, 3), (ll, per_image, cfg.n_latent_light)]
+    sv.rgb_in = [first] + [[(mlp_tc.unpack_image(sv.images, mlp_tc.SLOT_RGB_H1 + i, S), 1, 256)] for i in range(3)]
+    first_t = [(feat, 1, feat.shape[1]), (lt, per_image, cfg.n_latent_trans)]
+    sv.trans_in = [first_t] + [[(mlp_tc.unpack_image(sv.images, mlp_tc.SLOT_TRANS_H1 + i, S), 1, 256)] for i in range(3)]
+    sv.feat, sv.trunk_in = feat, []
+    sv.images = None
+
+
 class NerfMLP(torch.autograd.Function):
     """(enc inputs, latents, *weights) -> (rgb, density[, uncert]) per sample, with the fused backward."""
 
@@ -216,12 +231,16 @@ class NerfMLP(torch.autograd.Function):
         ll = _c(lat_light) if lat_light is not None else None
         needs_grad = any(ctx.needs_input_grad)
         sv = _Saved() if (needs_grad and cfg.save_for_backward) else None
-        if cfg.precision == "bf16" and cfg.stl:
+        trunk_grad = any(ctx.needs_input_grad[4:4 + n_f])      # frozen in the reference (:34); fp32 path if unfrozen
+        if cfg.precision == "bf16" and cfg.stl and not trunk_grad:
             from .. import mlp_tc
-            rgb, density, uncert = mlp_tc.forward(cfg, geom, lt, ll, feat_p, rgb_p, trans_p)
-            if sv is not None:       # backward needs the head activations: re-materialise them in fp32
-                mlp_forward_fp32(cfg, geom["enc"](), geom["view_seg"](), lt, ll, S, per_image, feat_p, rgb_p,
-                                 trans_p, sv)
+            if sv is None:
+                rgb, density, uncert = mlp_tc.forward(cfg, geom, lt, ll, feat_p, rgb_p, trans_p)
+            else:
+                # training: the kernel also stores the head activations it computed (bf16 tile images); the backward
+                # consumes exactly those -- nothing is re-materialised
+                rgb, density, uncert, images = mlp_tc.forward(cfg, geom, lt, ll, feat_p, rgb_p, trans_p, save=True)
+                sv.images, sv.geom, sv.lat = images, geom, (lt, ll)
                 sv.rgb, sv.density, sv.uncert = rgb, density, uncert
         else:
             rgb, density, uncert = mlp_forward_fp32(cfg, geom["enc"](), geom["view_seg"](), lt, ll, S, per_image,
@@ -241,11 +260,24 @@ class NerfMLP(torch.autograd.Function):
         feat_p, rgb_p, trans_p = ctx.layers
         n_f, n_r, n_t = 2 * cfg.n_feat, 2 * cfg.n_rgb, 2 * cfg.n_trans
         need = ctx.needs_input_grad[4:]
+        g = lambda t: t.contiguous().float() if t is not None else None
+        if getattr(sv, "images", None) is not None:
+            # bf16 mode: tensor-core backward on the tile images the fused forward saved (csrc/mlp_tc_bwd.cu)
+            from .. import mlp_tc_bwd
+            gr, gt, d_lt, d_ll = mlp_tc_bwd.heads_backward(cfg, sv, S, ctx.per_image, rgb_p, trans_p, g(g_rgb), g(g_density),
+                                                           g(g_uncert), bool(ctx.needs_input_grad[2]),
+                                                           bool(ctx.needs_input_grad[3]))
+            out = [None] * n_f
+            for layers in (gr, gt):
+                for pair in layers:
+                    out += [pair[0], pair[1]]
+            out = [o if need[i] else None for i, o in enumerate(out)]
+            ctx.sv = None
+            return (None, None, d_lt, d_ll, *out)
 
         def layer_need(off, n):
             return [bool(need[off + 2 * i] or need[off + 2 * i + 1]) for i in range(n)]
 
-        g = lambda t: t.contiguous().float() if t is not None else None
         gf, gr, gt, d_lt, d_ll = mlp_backward(
             cfg, sv, S, ctx.per_image, feat_p, rgb_p, trans_p, g(g_rgb), g(g_density), g(g_uncert),
             layer_need(0, cfg.n_feat), layer_need(n_f, cfg.n_rgb), layer_need(n_f + n_r, cfg.n_trans),

@@ -16,7 +16,7 @@ _F = 256
 
 def supported(cfg, feat_p, rgb_p, trans_p) -> bool:
     """The fused kernel is specialised for the architecture of options/nerf_lm_adapt_gan.yaml:9-18."""
-    if not (cfg.stl and cfg.view_dep and cfg.L_3D == 10 and tuple(cfg.skip) == (4,)):
+    if not (cfg.stl and cfg.view_dep and cfg.L_3D == 10 and 0 <= cfg.L_view <= 4 and tuple(cfg.skip) == (4,)):
         return False
     if len(feat_p) != 8 or len(rgb_p) != 4 or len(trans_p) != 4:
         return False
@@ -132,7 +132,7 @@ def _scratch_for(dev):
     return _scratch[k]
 
 
-def forward(cfg, geom, lat_trans, lat_light, feat_p, rgb_p, trans_p, dbg_layer=-1, flags=0):
+def forward(cfg, geom, lat_trans, lat_light, feat_p, rgb_p, trans_p, dbg_layer=-1, flags=0, save=False):
     if geom.get("mode") != "rays":
         raise NotImplementedError("the fused bf16 kernel is ray-parameterised (forward_samples)")
     if not supported(cfg, feat_p, rgb_p, trans_p):
@@ -160,9 +160,22 @@ def forward(cfg, geom, lat_trans, lat_light, feat_p, rgb_p, trans_p, dbg_layer=-
     uncert = torch.empty(S, device=dev)
     scratch = _scratch_for(dev)
     dbg = torch.zeros(S, _F, device=dev) if dbg_layer >= 0 else None
+    images = torch.empty(_C.load().tp_tc_save_bytes(S), dtype=torch.uint8, device=dev) if save else None
     _C.call("tp_tc_nerf_stl_forward", ops._p(center), ops._p(ray), ops._p(depth), S, N, per_image, ops._p(pk.weights),
             ops._p(pk.biasbuf), ops._p(raybias), ops._p(img_t), ops._p(rgb), ops._p(density), ops._p(uncert),
-            ops._p(scratch), scratch.numel(), dbg_layer, ops._p(dbg), flags, ops._stream())
+            ops._p(scratch), scratch.numel(), ops._p(images), dbg_layer, ops._p(dbg), flags, ops._stream())
     if dbg_layer >= 0:
         return rgb, density, uncert, dbg
+    if save:
+        return rgb, density, uncert, images
     return rgb, density, uncert
+
+
+SLOT_FEAT, SLOT_RGB_H1, SLOT_TRANS_H1, N_SLOTS = 0, 1, 4, 7
+
+
+def unpack_image(images, slot: int, S: int) -> torch.Tensor:
+    """One saved activation (bf16 tile images) -> row-major fp32 [S,256]."""
+    out = torch.empty(S, _F, device=images.device)
+    _C.call("tp_tc_unpack_images", ops._p(images), slot, N_SLOTS, S, ops._p(out), ops._stream())
+    return out
