@@ -143,7 +143,7 @@ int tp_linear_backward_weight(const float* dY, int64_t lddy, const float* const*
                               float* dW, float* db, int accumulate, float* workspace, int64_t workspace_floats,
                               void* stream);
 
-/* out[g, :] = sum of dY rows of group g (rows g*group .. ); workspace >= 32 * ceil(S/group) * Nout floats. */
+/* out[g, :] = sum of dY rows of group g (rows g*group .. ); workspace >= min(256, ceil(group/512)) * ceil(S/group) * Nout floats. */
 int tp_group_colsum(const float* dY, int64_t lddy, int64_t S, int64_t group, int Nout, float* out, float* workspace,
                     int64_t workspace_floats, void* stream);
 
@@ -199,7 +199,7 @@ int tp_reduce_partials(const float* partial, int splits, int64_t count, float* o
 
 int tp_tc_bwd_num_chunks(void);              /* chunks of the transposed weight image the chain kernel streams (34) */
 int64_t tp_tc_dz_bytes(int64_t S);           /* bytes of the dz tile images: ceil(S/128) x 6 x 64 KB */
-int tp_tc_dw_grid(int64_t S);                /* number of split partials tp_tc_dw_gemm writes */
+int tp_tc_dw_splits(int64_t S, int n_jobs);  /* split partials per job that tp_tc_dw_gemm writes */
 
 /* autograd of mlp_rgb[1..3] / mlp_trans[1..3] w.r.t. their inputs (layers/nerf_static_transient_light.py:118-134):
  * dz_rgb [S,3], dz_trans [S,5] = grads of the output layers' pre-activations; packed_bwd = tp_tc_pack_weights image of
@@ -208,10 +208,18 @@ int tp_tc_dw_grid(int64_t S);                /* number of split partials tp_tc_d
 int tp_tc_backward_chain(const float* dz_rgb, const float* dz_trans, int64_t S, const void* packed_bwd,
                          const void* saved, void* dz_images, void* stream);
 
-/* partial[g] (256x256 fp32, g < tp_tc_dw_grid(S)) = sum over the tiles of split g of dz^T x, dz = slot a_slot of
- * a_images, x = slot b_slot of b_images.  Reduce with tp_reduce_partials. */
-int tp_tc_dw_gemm(const void* a_images, int a_slot, int a_nslots, const void* b_images, int b_slot, int b_nslots,
-                  int64_t S, float* partial, int64_t partial_floats, int flags, void* stream);
+/* n_jobs (<= 8) weight-gradient GEMMs in one launch: job j computes dz[a_slots[j]]^T x[b_slots[j]] (256x256 fp32) over all
+ * samples; partial is [splits][n_jobs][256][256] with splits = tp_tc_dw_splits(S, n_jobs).  a_slots/b_slots: HOST arrays.
+ * Reduce with tp_reduce_partials(partial, splits, n_jobs*65536, ...). */
+int tp_tc_dw_gemm(const void* a_images, int a_nslots, const void* b_images, int b_nslots, const int32_t* a_slots,
+                  const int32_t* b_slots, int n_jobs, int64_t S, float* partial, int64_t partial_floats, int flags,
+                  void* stream);
+
+/* out[r,:] = sum over the N samples of ray r of an image slot (per-ray column sums, fp32 [ceil(S/N),256]). */
+int tp_tc_image_ray_sums(const void* images, int slot, int n_slots, int64_t S, int N, float* out, void* stream);
+
+/* out[c] = sum_s x[s,c] for a thin fp32 matrix [S,C<=8]; workspace >= 2*SMs*C floats. */
+int tp_thin_colsum(const float* x, int64_t S, int C, float* out, float* workspace, int64_t workspace_floats, void* stream);
 
 /* partial[blk][m][k] = sum_s thin[s][m] * x[s][k] for a thin fp32 operand [S,M], M in {1,3,5}; x = image slot. */
 int tp_tc_thin_dw(const float* thin, int M, const void* images, int slot, int n_slots, int64_t S, float* partial,

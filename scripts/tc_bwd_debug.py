@@ -47,7 +47,7 @@ for head, layers, dz3, hs, base in (("rgb", rgb_p, dz_rgb, (H[3], H[2], H[1]), 0
 for flags in (0, 1):
     try:
         for name, a, b in (("rgb W2", 0, 2), ("trans W1", 4, 4), ("rgb W0 feat", 2, 0)):
-            got = bw.dw_gemm(dz, a, 6, images, b, 7, S, flags=flags)
+            got = bw.dw_gemm(dz, 6, images, 7, [(a, b), (a, b)], S, flags=flags)[1]
             torch.cuda.synchronize()
             ref = bw.unpack(dz, a, 6, S).t() @ H[b]
             print(f"flags={flags} dW {name}: max|ref| {ref.abs().max().item():.4f}  max err {(got - ref).abs().max().item():.3e}")
@@ -58,3 +58,6 @@ t = bw.thin_dw(dz_trans, images, 6, 7, S)
 print("thin dW trans3: err", (t - dz_trans.t() @ H[6]).abs().max().item(), "ref", (dz_trans.t() @ H[6]).abs().max().item())
 o = bw.thin_dw(torch.ones(S, 1, device=DEV), dz, 1, 6, S)
 print("colsum via thin: err", (o.view(-1) - bw.unpack(dz, 1, 6, S).sum(0)).abs().max().item())
+rs = bw.image_ray_sums(dz, 2, 6, S, N)
+print("ray sums: err", (rs - bw.unpack(dz, 2, 6, S).view(B * R, N, 256).sum(1)).abs().max().item())
+print("thin colsum: err", (bw.thin_colsum(dz_trans, S) - dz_trans.sum(0)).abs().max().item())

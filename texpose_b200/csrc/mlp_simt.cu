@@ -284,6 +284,14 @@ __global__ void trunk_last_grad_kernel(const float* __restrict__ dz_sigma, const
   }
 }
 
+// split-K factor of the weight-gradient GEMM: >= 256 rows per split, at most 64 splits
+inline int64_t dw_splits(int64_t S) {
+  int64_t splits = (S + 255) / 256;
+  if (splits < 1) splits = 1;
+  if (splits > 64) splits = 64;
+  return splits;
+}
+
 bool make_segs(Segs& sg, const float* const* ptr, const int64_t* ld, const int64_t* group, const int32_t* cols, int nseg) {
   if (nseg < 1 || nseg > 4 || !ptr || !ld || !group || !cols) return false;
   sg.n = nseg;
@@ -339,10 +347,7 @@ TP_API int tp_linear_backward_input(const float* dY, int64_t lddy, const float* 
 
 TP_API int64_t tp_linear_backward_weight_workspace(int64_t S, int Nout, int Ktot) {
   // floats: split-K partials of dW plus the column-sum partials of db
-  int64_t splits = (S + 4095) / 4096;
-  if (splits < 1) splits = 1;
-  if (splits > 64) splits = 64;
-  return splits * ((int64_t)Nout * Ktot + Nout);
+  return dw_splits(S) * ((int64_t)Nout * Ktot + Nout);
 }
 
 TP_API int tp_linear_backward_weight(const float* dY, int64_t lddy, const float* const* seg_ptr, const int64_t* seg_ld,
@@ -354,9 +359,7 @@ TP_API int tp_linear_backward_weight(const float* dY, int64_t lddy, const float*
   if (S < 1 || Nout < 1) return TP_ERR_BAD_SHAPE;
   const int K = sg.begin[nseg];
   if (workspace_floats < tp_linear_backward_weight_workspace(S, Nout, K)) return TP_ERR_WORKSPACE;
-  int64_t splits = (S + 4095) / 4096;
-  if (splits < 1) splits = 1;
-  if (splits > 64) splits = 64;
+  const int64_t splits = dw_splits(S);
   long long kps = (S + splits - 1) / splits;
   kps = (kps + BK - 1) / BK * BK;
   A_dYt fa{dY, lddy, Nout, S};
@@ -387,8 +390,8 @@ TP_API int tp_group_colsum(const float* dY, int64_t lddy, int64_t S, int64_t gro
   if (!dY || !out || !workspace) return TP_ERR_BAD_ARG;
   if (S < 1 || group < 1 || Nout < 1) return TP_ERR_BAD_SHAPE;
   const long long G = (S + group - 1) / group;
-  int slices = (int)((group + 4095) / 4096);
-  if (slices > 32) slices = 32;
+  int slices = (int)((group + 511) / 512);
+  if (slices > 256) slices = 256;
   if (workspace_floats < (long long)slices * G * Nout) return TP_ERR_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
   group_colsum_kernel<<<dim3((unsigned)G, (unsigned)slices), 256, 0, st>>>(dY, lddy, S, group, Nout, slices, workspace);

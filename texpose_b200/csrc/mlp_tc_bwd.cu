@@ -228,11 +228,14 @@ constexpr uint32_t kDwSlots = 3;                     // ring of 64 KB image slot
 constexpr uint32_t kDwOffBar = kDwSlots * kABytes;
 constexpr uint32_t kDwSmemBytes = kDwOffBar + 128;
 
+constexpr int kDwMaxJobs = 8;
 struct DwParams {
-  const uint8_t* a_images; int a_slot, a_nslots;     // dz  (M = n)
-  const uint8_t* b_images; int b_slot, b_nslots;     // x   (N = k)
+  const uint8_t* a_images; int a_nslots;             // dz  (M = n)
+  const uint8_t* b_images; int b_nslots;             // x   (N = k)
+  int a_slot[kDwMaxJobs], b_slot[kDwMaxJobs];        // job j: dW_j = dz[a_slot[j]]^T x[b_slot[j]]
+  int n_jobs, splits;                                // CTA -> (job = blockIdx % n_jobs, split = blockIdx / n_jobs)
   long long n_tiles;
-  float* partial;                                    // [gridDim.x][256][256]
+  float* partial;                                    // [splits][n_jobs][256][256]
   int swap_strides;                                  // debug
 };
 
@@ -266,17 +269,19 @@ __global__ void __launch_bounds__(kThreads, 1) dw_gemm_kernel(const DwParams p) 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // contiguous tile range of this CTA
-  const long long per = p.n_tiles / gridDim.x, rem = p.n_tiles % gridDim.x;
-  const long long t0 = blockIdx.x * per + (blockIdx.x < rem ? blockIdx.x : rem);
-  const long long t1 = t0 + per + (blockIdx.x < rem ? 1 : 0);
+  // job and contiguous tile range of this CTA
+  const int job = blockIdx.x % p.n_jobs, split = blockIdx.x / p.n_jobs;
+  const long long per = p.n_tiles / p.splits, rem = p.n_tiles % p.splits;
+  const long long t0 = split * per + (split < rem ? split : rem);
+  const long long t1 = t0 + per + (split < rem ? 1 : 0);
+  const int a_slot = p.a_slot[job], b_slot = p.b_slot[job];
 
   if (warp == 8) {
     uint32_t slot = 0, phase = 0;
     for (long long t = t0; t < t1; ++t) {
       for (int op = 0; op < 2; ++op) {
-        const uint8_t* src = op == 0 ? p.a_images + ((size_t)t * p.a_nslots + p.a_slot) * kABytes
-                                     : p.b_images + ((size_t)t * p.b_nslots + p.b_slot) * kABytes;
+        const uint8_t* src = op == 0 ? p.a_images + ((size_t)t * p.a_nslots + a_slot) * kABytes
+                                     : p.b_images + ((size_t)t * p.b_nslots + b_slot) * kABytes;
         mbar_wait(bar_empty(slot), phase ^ 1);
         if (elect_one_sync()) {
           mbar_expect_tx(bar_full(slot), kABytes);
@@ -321,7 +326,7 @@ __global__ void __launch_bounds__(kThreads, 1) dw_gemm_kernel(const DwParams p) 
   } else {
     // epilogue: accumulator rows n (TMEM lanes) x columns k -> partial[cta][n][k]
     const int q = warp & 3, h = warp >> 2, n = h * 128 + q * 32 + lane;
-    float* out = p.partial + ((size_t)blockIdx.x * 256 + n) * 256;
+    float* out = p.partial + (((size_t)split * p.n_jobs + job) * 256 + n) * 256;
     if (t1 > t0) {
       mbar_wait(bar_acc, 0);
       tc_fence_after();
@@ -401,6 +406,54 @@ __global__ void __launch_bounds__(256) thin_dw_kernel(const float* __restrict__ 
     }
 }
 
+// per-ray sums straight from a tile-image slot: out[r][k] = sum over the N samples of ray r of x[s][k].
+// One CTA per ray; thread = (k8, row group of 8); rows of one ray are contiguous 16 B vectors inside each tile.
+__global__ void __launch_bounds__(256) image_ray_sums_kernel(const uint8_t* __restrict__ images, int slot, int n_slots,
+                                                             long long S, int N, float* __restrict__ out) {
+  const long long ray = blockIdx.x;
+  const int k8 = threadIdx.x >> 3, g = threadIdx.x & 7;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int i = g; i < N; i += 8) {
+    const long long s = ray * N + i;
+    if (s >= S) break;
+    float x[8];
+    unpack8(*reinterpret_cast<const uint4*>(images + ((size_t)(s >> 7) * n_slots + slot) * kABytes + k8 * 2048 + (s & 127) * 16), x);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] += x[c];
+  }
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    float v = acc[c];
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    if (g == 0) out[ray * 256 + k8 * 8 + c] = v;
+  }
+}
+
+// column sums of a thin row-major fp32 matrix [S, C<=8]: partial[block][C]
+__global__ void __launch_bounds__(256) thin_colsum_kernel(const float* __restrict__ x, long long S, int C,
+                                                          float* __restrict__ partial) {
+  __shared__ float sm[8][8];
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x; s < S; s += (long long)gridDim.x * blockDim.x)
+    for (int c = 0; c < C; ++c) acc[c] += x[s * C + c];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    float v = acc[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) sm[w][c] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < C) {
+    float v = 0.f;
+    for (int i = 0; i < 8; ++i) v += sm[i][threadIdx.x];
+    partial[(size_t)blockIdx.x * C + threadIdx.x] = v;
+  }
+}
+
 // row-major fp32 [S,256] -> tile image slot (test / interop helper)
 __global__ void pack_images_kernel(const float* __restrict__ in, long long S, uint8_t* __restrict__ images, int slot,
                                    int n_slots) {
@@ -422,10 +475,12 @@ __global__ void pack_images_kernel(const float* __restrict__ in, long long S, ui
 
 TP_API int tp_tc_bwd_num_chunks(void) { return tcb::kBwdChunks; }
 TP_API int64_t tp_tc_dz_bytes(int64_t S) { return ((S + 127) / 128) * tcb::kDzSlots * (int64_t)tc::kABytes; }
-TP_API int tp_tc_dw_grid(int64_t S) {
+TP_API int tp_tc_dw_splits(int64_t S, int n_jobs) {
   const long long n_tiles = (S + 127) / 128;
-  const int sms = tp_num_sms();
-  return (int)(n_tiles < sms ? n_tiles : sms);
+  long long splits = tp_num_sms() / (n_jobs < 1 ? 1 : n_jobs);
+  if (splits < 1) splits = 1;
+  if (splits > n_tiles) splits = n_tiles;
+  return (int)splits;
 }
 
 TP_API int tp_tc_backward_chain(const float* dz_rgb, const float* dz_trans, int64_t S, const void* packed_bwd,
@@ -450,23 +505,49 @@ TP_API int tp_tc_backward_chain(const float* dz_rgb, const float* dz_trans, int6
   return tp_launch_status();
 }
 
-TP_API int tp_tc_dw_gemm(const void* a_images, int a_slot, int a_nslots, const void* b_images, int b_slot, int b_nslots,
-                         int64_t S, float* partial, int64_t partial_floats, int flags, void* stream) {
-  if (!a_images || !b_images || !partial) return TP_ERR_BAD_ARG;
-  if (S < 1 || a_slot < 0 || a_slot >= a_nslots || b_slot < 0 || b_slot >= b_nslots) return TP_ERR_BAD_SHAPE;
+TP_API int tp_tc_dw_gemm(const void* a_images, int a_nslots, const void* b_images, int b_nslots, const int32_t* a_slots,
+                         const int32_t* b_slots, int n_jobs, int64_t S, float* partial, int64_t partial_floats, int flags,
+                         void* stream) {
+  if (!a_images || !b_images || !partial || !a_slots || !b_slots) return TP_ERR_BAD_ARG;
+  if (S < 1 || n_jobs < 1 || n_jobs > tcb::kDwMaxJobs) return TP_ERR_BAD_SHAPE;
   if (((uintptr_t)a_images & 15) || ((uintptr_t)b_images & 15) || ((uintptr_t)partial & 15)) return TP_ERR_ALIGN;
   if (!tp_device_is_sm100()) return TP_ERR_ARCH;
-  const int grid = tp_tc_dw_grid(S);
-  if (partial_floats < (int64_t)grid * 65536) return TP_ERR_WORKSPACE;
   tcb::DwParams p;
-  p.a_images = reinterpret_cast<const uint8_t*>(a_images); p.a_slot = a_slot; p.a_nslots = a_nslots;
-  p.b_images = reinterpret_cast<const uint8_t*>(b_images); p.b_slot = b_slot; p.b_nslots = b_nslots;
+  p.a_images = reinterpret_cast<const uint8_t*>(a_images); p.a_nslots = a_nslots;
+  p.b_images = reinterpret_cast<const uint8_t*>(b_images); p.b_nslots = b_nslots;
+  for (int j = 0; j < n_jobs; ++j) {
+    if (a_slots[j] < 0 || a_slots[j] >= a_nslots || b_slots[j] < 0 || b_slots[j] >= b_nslots) return TP_ERR_BAD_SHAPE;
+    p.a_slot[j] = a_slots[j];
+    p.b_slot[j] = b_slots[j];
+  }
+  p.n_jobs = n_jobs; p.splits = tp_tc_dw_splits(S, n_jobs);
+  if (partial_floats < (int64_t)p.splits * n_jobs * 65536) return TP_ERR_WORKSPACE;
   p.n_tiles = (S + 127) / 128; p.partial = partial; p.swap_strides = flags & 1;
   cudaError_t e = cudaFuncSetAttribute(tcb::dw_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)tcb::kDwSmemBytes);
   if (e != cudaSuccess) return (int)e;
-  tcb::dw_gemm_kernel<<<grid, tcb::kThreads, tcb::kDwSmemBytes, (cudaStream_t)stream>>>(p);
+  tcb::dw_gemm_kernel<<<p.splits * n_jobs, tcb::kThreads, tcb::kDwSmemBytes, (cudaStream_t)stream>>>(p);
   return tp_launch_status();
+}
+
+TP_API int tp_tc_image_ray_sums(const void* images, int slot, int n_slots, int64_t S, int N, float* out, void* stream) {
+  if (!images || !out) return TP_ERR_BAD_ARG;
+  if (S < 1 || N < 1 || slot < 0 || slot >= n_slots) return TP_ERR_BAD_SHAPE;
+  const long long rays = (S + N - 1) / N;
+  tcb::image_ray_sums_kernel<<<(unsigned)rays, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint8_t*>(images), slot,
+                                                                              n_slots, S, N, out);
+  return tp_launch_status();
+}
+
+TP_API int tp_thin_colsum(const float* x, int64_t S, int C, float* out, float* workspace, int64_t workspace_floats,
+                          void* stream) {
+  if (!x || !out || !workspace) return TP_ERR_BAD_ARG;
+  if (S < 1 || C < 1 || C > 8) return TP_ERR_BAD_SHAPE;
+  int blocks = tp_grid_for(S, 256, 2);
+  if (workspace_floats < (int64_t)blocks * C) return TP_ERR_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  tcb::thin_colsum_kernel<<<blocks, 256, 0, st>>>(x, S, C, workspace);
+  return tp_reduce_partials(workspace, blocks, C, out, 0, stream);
 }
 
 TP_API int tp_tc_thin_dw(const float* thin, int M, const void* images, int slot, int n_slots, int64_t S, float* partial,

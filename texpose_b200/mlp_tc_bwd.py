@@ -58,13 +58,30 @@ def reduce_partials(partial, splits, count, out=None):
     return out
 
 
-def dw_gemm(a_images, a_slot, a_nslots, b_images, b_slot, b_nslots, S, flags=0):
-    """[256,256] fp32 = dz^T x over all samples (split over tiles, fixed-order reduce)."""
-    grid = _C.load().tp_tc_dw_grid(S)
-    partial = torch.empty(grid * 65536, device=a_images.device)
-    _C.call("tp_tc_dw_gemm", ops._p(a_images), a_slot, a_nslots, ops._p(b_images), b_slot, b_nslots, S, ops._p(partial),
+def dw_gemm(a_images, a_nslots, b_images, b_nslots, pairs, S, flags=0):
+    """[len(pairs),256,256] fp32: job j = dz[a]^T x[b] over all samples -- one launch, split over tiles, fixed-order reduce."""
+    n = len(pairs)
+    splits = _C.load().tp_tc_dw_splits(S, n)
+    partial = torch.empty(splits * n * 65536, device=a_images.device)
+    a_s = (ctypes.c_int32 * n)(*[a for a, _ in pairs])
+    b_s = (ctypes.c_int32 * n)(*[b for _, b in pairs])
+    _C.call("tp_tc_dw_gemm", ops._p(a_images), a_nslots, ops._p(b_images), b_nslots, a_s, b_s, n, S, ops._p(partial),
             partial.numel(), flags, ops._stream())
-    return reduce_partials(partial, grid, 65536).view(256, 256)
+    return reduce_partials(partial, splits, n * 65536).view(n, 256, 256)
+
+
+def image_ray_sums(images, slot, n_slots, S, N):
+    out = torch.empty((S + N - 1) // N, 256, device=images.device)
+    _C.call("tp_tc_image_ray_sums", ops._p(images), slot, n_slots, S, N, ops._p(out), ops._stream())
+    return out
+
+
+def thin_colsum(x, S):
+    C = x.shape[1]
+    ws = torch.empty(2 * 148 * 8 + 64, device=x.device)
+    out = torch.empty(C, device=x.device)
+    _C.call("tp_thin_colsum", ops._p(x), S, C, ops._p(out), ops._p(ws), ws.numel(), ops._stream())
+    return out
 
 
 def thin_dw(thin, images, slot, n_slots, S):
@@ -96,33 +113,28 @@ def heads_backward(cfg, sv, S, per_image, rgb_p, trans_p, g_rgb, g_density, g_un
             ops._p(g_uncert), S, ops._p(dz_rgb), ops._p(dz_trans), None, ops._stream())
     packed = pack_bwd(cfg.packed, rgb_p, trans_p)
     dz = backward_chain(dz_rgb, dz_trans, S, packed, sv.images)
-    ones = torch.ones(S, 1, device=dev)
-    out = {}
-    for head, layers, dz3, h3_slot in (("rgb", rgb_p, dz_rgb, 3), ("trans", trans_p, dz_trans, 6)):
-        grads = [None] * 4
-        # output layer: thin weight gradient + bias
-        grads[3] = (thin_dw(dz3, sv.images, h3_slot, FWD_SLOTS, S), ops.group_colsum(dz3, S, S).view(-1))
-        big = [dw_gemm(dz, a, DZ_SLOTS, sv.images, b, FWD_SLOTS, S) for a, b in _BIG_PAIRS[head]]
-        for li, (a, _) in zip((2, 1), _BIG_PAIRS[head][:2]):
-            grads[li] = (big[2 - li], thin_dw(ones, dz, a, DZ_SLOTS, S).view(-1))
-        out[head] = (grads, big[2])
+    # ---- all six 256x256 weight gradients in one launch: layers 2,1,0 of the rgb head, then of the transient head
+    big = dw_gemm(dz, DZ_SLOTS, sv.images, FWD_SLOTS, _BIG_PAIRS["rgb"] + _BIG_PAIRS["trans"], S)
+    # per-ray column sums of every dz image: bias gradients (summed over rays) and the per-ray / per-image columns of layer 0
+    ray_sums = [image_ray_sums(dz, k, DZ_SLOTS, S, N) for k in range(DZ_SLOTS)]           # each [B*R,256]
+    img_sums = [ops.group_colsum(r, B * R, R) for r in ray_sums]                          # each [B,256]
+    tot = [g.sum(dim=0) if B > 1 else g.view(-1).clone() for g in img_sums]
+    grads_r, grads_t = [None] * 4, [None] * 4
+    grads_r[3] = (thin_dw(dz_rgb, sv.images, 3, FWD_SLOTS, S), thin_colsum(dz_rgb, S))
+    grads_t[3] = (thin_dw(dz_trans, sv.images, 6, FWD_SLOTS, S), thin_colsum(dz_trans, S))
+    grads_r[2], grads_r[1] = (big[0], tot[0]), (big[1], tot[1])
+    grads_t[2], grads_t[1] = (big[3], tot[3]), (big[4], tot[4])
     # ---- layer 0 of each head: feature columns from the GEMM, per-sample xyz / per-ray view / per-image latent columns
     W_r0, W_t0 = rgb_p[0][0], trans_p[0][0]
-    dz0_r = unpack(dz, 2, DZ_SLOTS, S)
-    g_ray = ops.group_colsum(dz0_r, S, N)                         # [B*R,256] per-ray sums
-    g_img = ops.group_colsum(g_ray, B * R, R)                     # [B,256]
+    g_ray, g_img, g_timg = ray_sums[2], img_sums[2], img_sums[5]
     view_t, _, vc = geom["view_seg"]()
     dW_view, _ = ops.linear_backward_weight(g_ray, [(view_t, 1, vc)], B * R, want_bias=False)           # [256,27]
     xyz = ops.points_from_depth(geom["center"], geom["ray"], geom["depth"]).view(S, 3)
     dW_xyz = thin_dw(xyz, dz, 2, DZ_SLOTS, S).t().contiguous()                                          # [256,3]
     dW_light, _ = ops.linear_backward_weight(g_img, [(ll, 1, cfg.n_latent_light)], B, want_bias=False)  # [256,48]
-    grads_r, big_r0 = out["rgb"]
-    grads_r[0] = (torch.cat([big_r0, dW_view, dW_xyz, dW_light], dim=1), g_img.sum(dim=0) if B > 1 else g_img.view(-1).clone())
+    grads_r[0] = (torch.cat([big[2], dW_view, dW_xyz, dW_light], dim=1), tot[2])
     d_ll = ops.linear_backward_input(g_img, W_r0, B, cfg.n_latent_light, None, w_col0=256 + vc + 3) if need_lat_light else None
-    dz0_t = unpack(dz, 5, DZ_SLOTS, S)
-    g_timg = ops.group_colsum(dz0_t, S, per_image)                # [B,256]
     dW_lt, _ = ops.linear_backward_weight(g_timg, [(lt, 1, cfg.n_latent_trans)], B, want_bias=False)    # [256,16]
-    grads_t, big_t0 = out["trans"]
-    grads_t[0] = (torch.cat([big_t0, dW_lt], dim=1), g_timg.sum(dim=0) if B > 1 else g_timg.view(-1).clone())
+    grads_t[0] = (torch.cat([big[5], dW_lt], dim=1), tot[5])
     d_lt = ops.linear_backward_input(g_timg, W_t0, B, cfg.n_latent_trans, None, w_col0=256) if need_lat_trans else None
     return grads_r, grads_t, d_lt, d_ll

@@ -284,7 +284,8 @@ def linear_backward_weight(dY: Tensor, segs: Sequence[Seg], S: int, want_bias: b
 def group_colsum(dY: Tensor, S: int, group: int) -> Tensor:
     Nout = dY.shape[1]
     G = (S + group - 1) // group
-    ws = torch.empty(32 * G * Nout, device=dY.device, dtype=torch.float32)
+    slices = min(256, (group + 511) // 512)
+    ws = torch.empty(slices * G * Nout, device=dY.device, dtype=torch.float32)
     out = torch.empty(G, Nout, device=dY.device, dtype=torch.float32)
     _C.call("tp_group_colsum", _p(dY), dY.stride(0), S, group, Nout, _p(out), _p(ws), ws.numel(), _stream())
     return out
