@@ -29,7 +29,9 @@
 
 namespace tc {
 
-constexpr int kThreads = 320;          // warps 0-7 epilogue/encode, warp 8 TMA producer, warp 9 MMA issuer
+// kHalves epilogue warps per (tile, TMEM lane quarter): kHalves = 1 -> 8 epilogue warps (256 columns per thread),
+// kHalves = 2 -> 16 epilogue warps (128 columns per thread).  Then one TMA producer warp and one MMA issuer warp.
+template <int kHalves> constexpr int num_threads() { return (8 * kHalves + 2) * 32; }
 constexpr int kStages = 4;
 constexpr uint32_t kEBytes = 16384;    // 128 x 64 bf16
 constexpr uint32_t kOffA = 0, kOffE = 2 * kABytes, kOffRing = kOffE + 2 * kEBytes;
@@ -149,22 +151,25 @@ __device__ __forceinline__ void hidden_slab(const uint32_t (&v)[32], const float
 
 // Whole 128x256 accumulator row of one thread: TMEM loads are software-pipelined (slab j+1 in flight while slab j is
 // converted), ping-ponging two register slabs.
-template <bool kBias>
+template <bool kBias, int kSlabs>
 __device__ __forceinline__ void hidden_epilogue(uint32_t tmem_d, const float* bias, uint32_t a_row, float* dbg_row) {
   uint32_t va[32], vb[32];
   TP_TMEM_LD32(tmem_d, va);
 #pragma unroll
-  for (int j = 0; j < 8; j += 2) {
+  for (int j = 0; j < kSlabs; j += 2) {
     TP_TMEM_WAIT32(va);
     TP_TMEM_LD32(tmem_d + (j + 1) * 32, vb);
     hidden_slab<kBias>(va, bias + j * 32, a_row + j * 4 * 2048, dbg_row ? dbg_row + j * 32 : nullptr);
     TP_TMEM_WAIT32(vb);
-    if (j + 2 < 8) TP_TMEM_LD32(tmem_d + (j + 2) * 32, va);
+    if (j + 2 < kSlabs) TP_TMEM_LD32(tmem_d + (j + 2) * 32, va);
     hidden_slab<kBias>(vb, bias + (j + 1) * 32, a_row + (j + 1) * 4 * 2048, dbg_row ? dbg_row + (j + 1) * 32 : nullptr);
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 1) nerf_stl_forward_kernel(const Params p) {
+template <int kHalves>
+__global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_kernel(const Params p) {
+  constexpr int kEpiWarps = 8 * kHalves, kProducerWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
+  constexpr int kTileThreads = 128 * kHalves;     // epilogue threads working on one tile
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform role index
@@ -185,12 +190,12 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_stl_forward_kernel(const Par
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(bar_acc(t), 1);
-      mbar_init(bar_ready(t), 128);
+      mbar_init(bar_ready(t), kTileThreads);
       mbar_init(bar_reload(t), 1);
     }
     fence_barrier_init();
   }
-  if (warp == 9) {   // TMEM: all 512 columns (one CTA per SM)
+  if (warp == kMmaWarp) {   // TMEM: all 512 columns (one CTA per SM)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -202,7 +207,7 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_stl_forward_kernel(const Par
 
   const long long n_super = (p.S + 255) / 256;
 
-  if (warp == 8) {
+  if (warp == kProducerWarp) {
     // ================================================================ weight producer (converged warp, one lane issues)
     {
       uint32_t stage = 0, phase = 0;
@@ -225,7 +230,7 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_stl_forward_kernel(const Par
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == kMmaWarp) {
     // ================================================================ MMA issuer (converged warp, one lane issues)
     {
       uint32_t stage = 0, phase = 0, ready_ph = 0, reload_ph = 0;   // per-tile phase bits (bit t)
@@ -288,10 +293,13 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_stl_forward_kernel(const Par
       }
     }
   } else {
-    // ================================================================ encode + epilogue warps (0..7)
-    const int t = warp >> 2, q = warp & 3, row = q * 32 + lane;
+    // ================================================================ encode + epilogue warps
+    // warp -> (TMEM lane quarter q = warp % 4, tile t, column half); half 0 also encodes and owns the per-sample outputs
+    const int q = warp & 3, t = (warp >> 2) & 1, half = warp >> 3, row = q * 32 + lane;
+    constexpr int kCols = 256 / kHalves;            // accumulator columns converted per thread
     const uint32_t a_smem = sbase + kOffA + t * kABytes, e_smem = sbase + kOffE + t * kEBytes;
-    const uint32_t tmem_d = tmem_base + ((uint32_t)(q * 32) << 16) + t * 256;
+    const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16) + t * 256;
+    const uint32_t tmem_d = tmem_row + half * kCols;
     uint8_t* my_scratch = p.scratch + ((size_t)blockIdx.x * 2 + t) * kABytes;
     uint32_t acc_ph = 0;
     bool store_pending = false;      // a bulk store of A_t (feature park / activation save) may still be reading it
@@ -299,7 +307,7 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_stl_forward_kernel(const Par
       const long long s_raw = (st * 2 + t) * 128 + row;
       const bool live = s_raw < p.S;
       const long long s = live ? s_raw : p.S - 1;
-      encode_sample(p, s, e_smem, row);
+      if (half == 0) encode_sample(p, s, e_smem, row);
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(bar_ready(t));
@@ -311,11 +319,11 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_stl_forward_kernel(const Par
         acc_ph ^= 1;
         tc_fence_after();
         if (ly.epi == EPI_HIDDEN && store_pending) {   // the previous bulk store must have finished reading A_t
-          if (row == 0) bulk_wait_read();
-          named_bar_sync(1 + t, 128);
+          if (row == 0 && half == 0) bulk_wait_read();
+          named_bar_sync(1 + t, kTileThreads);
           store_pending = false;
         }
-        if (L == kReloadIssueLayer && row == 0) {
+        if (L == kReloadIssueLayer && row == 0 && half == 0) {
           // every MMA that reads A_t has retired (acc barrier) -> bring the trunk feature back for the transient head
           bulk_wait_all();
           fence_proxy_async_all();
@@ -323,28 +331,30 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_stl_forward_kernel(const Par
           bulk_g2s(a_smem, p.save ? p.save + ((size_t)(st * 2 + t) * kSaveSlots) * kABytes : my_scratch, kABytes, bar_reload(t));
         }
         if (ly.epi == EPI_HIDDEN) {
-          float* dbg_row = ((L == p.dbg_layer) && live && p.dbg_out) ? p.dbg_out + s * 256 : nullptr;
+          float* dbg_row = ((L == p.dbg_layer) && live && p.dbg_out) ? p.dbg_out + s * 256 + half * kCols : nullptr;
+          const uint32_t a_row = a_smem + half * (kCols / 8) * 2048 + row * 16;
           if (ly.bias_kind == BIAS_MMA) {
-            hidden_epilogue<false>(tmem_d, nullptr, a_smem + row * 16, dbg_row);
+            hidden_epilogue<false, kCols / 32>(tmem_d, nullptr, a_row, dbg_row);
           } else {
-            const float* bias = ly.bias_kind == BIAS_RAY ? p.raybias + (s / p.N) * 256 : p.imgbias + (s / p.per_image) * 256;
-            hidden_epilogue<true>(tmem_d, bias, a_smem + row * 16, dbg_row);
+            const float* bias = (ly.bias_kind == BIAS_RAY ? p.raybias + (s / p.N) * 256 : p.imgbias + (s / p.per_image) * 256) +
+                                half * kCols;
+            hidden_epilogue<true, kCols / 32>(tmem_d, bias, a_row, dbg_row);
           }
           fence_proxy_async_smem();
           if (L == kSpillLayer || (p.save && kSaveSlot[L] >= 0)) {
             // park the trunk feature (bf16 tile image) in the L2 scratch; in training mode every head activation is
             // saved the same way -- the store overlaps the next stage's MMAs
-            named_bar_sync(1 + t, 128);
-            if (row == 0) {
+            named_bar_sync(1 + t, kTileThreads);
+            if (row == 0 && half == 0) {
               uint8_t* dst = p.save ? p.save + ((size_t)(st * 2 + t) * kSaveSlots + kSaveSlot[L]) * kABytes : my_scratch;
               bulk_s2g(dst, a_smem, kABytes);
               bulk_commit();
             }
             store_pending = true;
           }
-        } else {
+        } else if (half == 0) {
           uint32_t v[8];
-          TP_TMEM_LD8(tmem_d, v);
+          TP_TMEM_LD8(tmem_row, v);
           TP_TMEM_WAIT8(v);
           const float* sb = p.biasbuf + kSmallBiasOffset;
           if (ly.epi == EPI_DENSITY) {
@@ -373,12 +383,12 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_stl_forward_kernel(const Par
         }
       }
     }
-    if (row == 0) bulk_wait_all();
+    if (row == 0 && half == 0) bulk_wait_all();
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
@@ -559,9 +569,13 @@ TP_API int tp_tc_nerf_stl_forward(const float* center, const float* ray, const f
   p.save = reinterpret_cast<uint8_t*>(save);
   if (((uintptr_t)save & 15)) return TP_ERR_ALIGN;
   p.dbg_layer = dbg_layer; p.dbg_out = dbg_out; p.swap_lbo_sbo = flags & 1;
-  cudaError_t e = cudaFuncSetAttribute(tc::nerf_stl_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)tc::kSmemBytes);
+  const bool wide = (flags & 2) == 0;       // default: 16 epilogue warps; flags bit 1 selects the 8-warp variant
+  cudaError_t e = wide ? cudaFuncSetAttribute(tc::nerf_stl_forward_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)tc::kSmemBytes)
+                       : cudaFuncSetAttribute(tc::nerf_stl_forward_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)tc::kSmemBytes);
   if (e != cudaSuccess) return (int)e;
-  tc::nerf_stl_forward_kernel<<<grid, tc::kThreads, tc::kSmemBytes, (cudaStream_t)stream>>>(p);
+  if (wide) tc::nerf_stl_forward_kernel<2><<<grid, tc::num_threads<2>(), tc::kSmemBytes, (cudaStream_t)stream>>>(p);
+  else tc::nerf_stl_forward_kernel<1><<<grid, tc::num_threads<1>(), tc::kSmemBytes, (cudaStream_t)stream>>>(p);
   return tp_launch_status();
 }

@@ -6,6 +6,7 @@ parameter's `_version` changes ("re-packed when param._version cha
 from __future__ import annotations
 
 import ctypes
+import os
 
 import torch
 
@@ -133,6 +134,7 @@ def _scratch_for(dev):
 
 
 def forward(cfg, geom, lat_trans, lat_light, feat_p, rgb_p, trans_p, dbg_layer=-1, flags=0, save=False):
+    flags = flags or int(os.environ.get("TEXPOSE_TC_FLAGS", "0"))     # bit 1: 8-epilogue-warp kernel variant (A/B)
     if geom.get("mode") != "rays":
         raise NotImplementedError("the fused bf16 kernel is ray-parameterised (forward_samples)")
     if not supported(cfg, feat_p, rgb_p, trans_p):
