@@ -81,6 +81,46 @@ def cpu_render_sample(n_rays, threads):
     return step, n_rays * NS
 
 
+def eager_gpu_sample(dev, n_chunks=8, chunk=2048):
+    """The reference's eager aten-op path (oracle port) run ON THE GPU in its own 2048-ray chunks (opt.nerf.rand_rays,
+    model/nerf_adapt_st_gan.py:669-679), cuBLAS fp32 -- the meaningful "before" on the same B200.  Reported as context only."""
+    import torch
+    from oracle import texpose_oracle as O
+    from texpose_b200 import synth
+    from texpose_b200.config import adapt_gan_opt
+    from texpose_b200.layers.nerf_static_transient_light import NeRF
+    torch.manual_seed(0)
+    m = NeRF(adapt_gan_opt()).to(dev)
+    L = lambda ml: [(l.weight.detach(), l.bias.detach()) for l in ml]
+    feat, rgb, trans = L(m.mlp_feat), L(m.mlp_rgb), L(m.mlp_trans)
+    pose, intr = synth.poses([0]).to(dev), synth.intrinsics(1).to(dev)
+    lo, hi = [t.to(dev) for t in synth.padded_aabb()]
+    lt, ll = [t.to(dev) for t in synth.latents(1)]
+
+    def run():
+        with torch.no_grad():
+            for c in range(n_chunks):
+                cen, ray = O.get_center_and_ray(pose, intr, H, W)          # whole frame per chunk, as the reference does
+                tn, tf, v = O.aabb_ray_intersection(lo, hi, cen, ray)
+                zn, zf = O.box_bounds_to_range(tn, tf, v, *synth.BG_RANGE)
+                idx = torch.arange(c * chunk, (c + 1) * chunk, device=dev)[None]
+                rand = torch.rand(1, chunk, NS, 1, device=dev)
+                O.render_stl(O.gather_rays(cen, idx), O.gather_rays(ray, idx), zn[:, idx[0]], zf[:, idx[0]], rand, NS, lt, ll,
+                             feat, rgb, trans)
+    run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    return dict(value=n_chunks * chunk * NS / (ms * 1e-3), unit=UNIT, kind="port",
+                sample=f"{n_chunks} chunks x {chunk} rays x {NS} samples, eager torch ops (oracle port of the reference path) on "
+                       f"this GPU, fp32 cuBLAS, full-frame ray generation per chunk as in the reference",
+                ms_per_frame_extrapolated=ms * (H * W / (n_chunks * chunk)))
+
+
 def run_reference(args, rank):
     import torch
     if rank != 0:
@@ -307,6 +347,10 @@ def run_ours(args, rank, world, local_rank):
     if train:
         line["train_step"] = train
     if not args.no_cpu_baseline:
+        try:
+            line["eager_gpu_baseline"] = eager_gpu_sample(dev)
+        except Exception as e:  # noqa: BLE001  (context only; never fails the bench)
+            line["eager_gpu_baseline"] = dict(error=str(e)[:200])
         threads = os.cpu_count() or 1
         cstep, csamples = cpu_render_sample(args.cpu_rays, threads)
         cstep()

@@ -16,7 +16,9 @@ summation order depends on the BLAS build).  The reference itself ships no tests
 no golden vectors, so these generated fixtures are the pin.
 
 All `file:line` citations are relative to /root/reference.
-Every function is stateless; network weights travel as plain lists of (W[out,in], b[out]).
+Every function is stateless and device-agnostic (plain torch ops): on CPU tensors it is the oracle / CPU baseline;
+`bench.py` also runs it on CUDA tensors to time the reference's eager aten-op path on the same B200 (context only).
+Network weights travel as plain lists of (W[out,in], b[out]).
 """
 from __future__ import annotations
 
@@ -69,8 +71,8 @@ def unproject_pixels(uv: Tensor, pose: Tensor, intr: Tensor) -> Tuple[Tensor, Te
 
 def get_center_and_ray(pose: Tensor, intr: Tensor, H: int, W: int) -> Tuple[Tensor, Tensor]:
     """Full-frame rays at pixel centres (x+0.5, y+0.5)  (camera.py:292-314)."""
-    ys = torch.arange(H, dtype=torch.float32).add_(0.5)
-    xs = torch.arange(W, dtype=torch.float32).add_(0.5)
+    ys = torch.arange(H, dtype=torch.float32, device=pose.device).add_(0.5)
+    xs = torch.arange(W, dtype=torch.float32, device=pose.device).add_(0.5)
     Y, X = torch.meshgrid(ys, xs, indexing="ij")
     uv = torch.stack([X, Y], dim=-1).view(-1, 2).repeat(len(pose), 1, 1)
     return unproject_pixels(uv, pose, intr)
@@ -152,7 +154,7 @@ def patch_bounds(coords: Tensor, z_near: Tensor, z_far: Tensor, H: int, W: int):
 def gather_rays(x: Tensor, ray_idx: Tensor) -> Tensor:
     """Graph.ray_batch_sample (model/nerf_adapt_st_gan.py:702-710) without the hard-coded .cuda()."""
     B, HW, C = x.shape
-    flat = ray_idx + HW * torch.arange(B).unsqueeze(1)
+    flat = ray_idx + HW * torch.arange(B, device=x.device).unsqueeze(1)
     return x.reshape(B * HW, C)[flat].view(B, ray_idx.shape[1], C)
 
 
@@ -163,7 +165,7 @@ def sample_depth(z_near: Tensor, z_far: Tensor, n: int, rand: Optional[Tensor]) 
     lo = z_near[:, :, None, None]
     hi = z_far[:, :, None, None]
     u = rand.clone() if rand is not None else 0.5
-    u = u + torch.arange(n)[None, None, :, None].float()
+    u = u + torch.arange(n, device=z_near.device)[None, None, :, None].float()
     return u / n * (hi - lo) + lo
 
 
@@ -180,7 +182,7 @@ def points_from_depth(center: Tensor, ray: Tensor, depth: Tensor) -> Tensor:
 def positional_encoding(x: Tensor, L: int) -> Tensor:
     """[...,C] -> [...,2*C*L]; per coordinate [sin f0..f_{L-1}, cos f0..f_{L-1}], f_k = 2^k*pi in fp32
     (layers/nerf_static_transient_light.py:217-223; c2f window off, yaml c2f.range null)."""
-    freq = 2 ** torch.arange(L, dtype=torch.float32) * math.pi
+    freq = 2 ** torch.arange(L, dtype=torch.float32, device=x.device) * math.pi
     s = x[..., None] * freq
     return torch.stack([s.sin(), s.cos()], dim=-2).flatten(-3)
 

@@ -95,7 +95,8 @@ struct Params {
   uint8_t* save;             // optional [tiles][7][64 KB]: feat, rgb h1..h3, trans h1..h3 tile images for the backward
   int dbg_layer;
   float* dbg_out;            // [S,256] post-activation of stage dbg_layer (debug only)
-  int swap_lbo_sbo;          // debug: exchange the two descriptor strides
+  int skew;                  // weight chunks tile 0 runs ahead of tile 1 inside a stage (0..2)
+  int dbg_drain;             // timing experiments only (wrong results): 1 = convert/store every other slab, 2 = also skip its TMEM load
 };
 
 // positional encoding of one sample into the E tile (bf16): [x,y,z, per coord sin(2^k pi x) k<10, cos(...) k<10, 1].
@@ -149,8 +150,64 @@ __device__ __forceinline__ void hidden_slab(const uint32_t (&v)[32], const float
   }
 }
 
+// Same with the bias row held distributed across the warp (lane l owns columns 4l..4l+3 of the thread's column range, in
+// `mine[0]`, and 128+4l.. in `mine[1]` when a thread converts 256 columns): valid when all 32 rows of the warp share one
+// bias row (N % 32 == 0).  8 shuffles per 8 columns replace 2 dependent L2 round trips.
+__device__ __forceinline__ void hidden_slab_wbias(const uint32_t (&v)[32], const float4 (&mine)[2], int col0, uint32_t a_dst,
+                                                  float* dbg_row) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const int c = col0 + i;                       // first column of this group within the thread's range
+    const float4 src = mine[(c >> 7) & 1];
+    const int l0 = (c & 127) >> 2;
+    float x[8];
+    x[0] = __uint_as_float(v[i + 0]) + __shfl_sync(0xffffffffu, src.x, l0);
+    x[1] = __uint_as_float(v[i + 1]) + __shfl_sync(0xffffffffu, src.y, l0);
+    x[2] = __uint_as_float(v[i + 2]) + __shfl_sync(0xffffffffu, src.z, l0);
+    x[3] = __uint_as_float(v[i + 3]) + __shfl_sync(0xffffffffu, src.w, l0);
+    x[4] = __uint_as_float(v[i + 4]) + __shfl_sync(0xffffffffu, src.x, l0 + 1);
+    x[5] = __uint_as_float(v[i + 5]) + __shfl_sync(0xffffffffu, src.y, l0 + 1);
+    x[6] = __uint_as_float(v[i + 6]) + __shfl_sync(0xffffffffu, src.z, l0 + 1);
+    x[7] = __uint_as_float(v[i + 7]) + __shfl_sync(0xffffffffu, src.w, l0 + 1);
+    st_shared_v4(a_dst + (i >> 3) * 2048, pack_relu_bf16(x[0], x[1]), pack_relu_bf16(x[2], x[3]), pack_relu_bf16(x[4], x[5]),
+                 pack_relu_bf16(x[6], x[7]));
+    if (dbg_row) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) dbg_row[i + e] = fmaxf(x[e], 0.f);
+    }
+  }
+}
+
+template <int kSlabs>
+__device__ __forceinline__ void hidden_epilogue_wbias(uint32_t tmem_d, const float4 (&mine)[2], uint32_t a_row, float* dbg_row) {
+  uint32_t va[32], vb[32];
+  TP_TMEM_LD32(tmem_d, va);
+#pragma unroll
+  for (int j = 0; j < kSlabs; j += 2) {
+    TP_TMEM_WAIT32(va);
+    TP_TMEM_LD32(tmem_d + (j + 1) * 32, vb);
+    hidden_slab_wbias(va, mine, j * 32, a_row + j * 4 * 2048, dbg_row ? dbg_row + j * 32 : nullptr);
+    TP_TMEM_WAIT32(vb);
+    if (j + 2 < kSlabs) TP_TMEM_LD32(tmem_d + (j + 2) * 32, va);
+    hidden_slab_wbias(vb, mine, (j + 1) * 32, a_row + (j + 1) * 4 * 2048, dbg_row ? dbg_row + (j + 1) * 32 : nullptr);
+  }
+}
+
 // Whole 128x256 accumulator row of one thread: TMEM loads are software-pipelined (slab j+1 in flight while slab j is
 // converted), ping-ponging two register slabs.
+// timing experiment (results are wrong on purpose): what bounds the drain -- the TMEM read or the convert/store?
+template <int kSlabs>
+__device__ __noinline__ void hidden_epilogue_experiment(uint32_t tmem_d, uint32_t a_row, int mode) {
+  uint32_t v[32];
+  for (int j = 0; j < kSlabs; ++j) {
+    if (mode == 2 && (j & 1)) continue;
+    TP_TMEM_LD32(tmem_d + j * 32, v);
+    TP_TMEM_WAIT32(v);
+    if (j & 1) continue;
+    hidden_slab<false>(v, nullptr, a_row + j * 4 * 2048, nullptr);
+  }
+}
+
 template <bool kBias, int kSlabs>
 __device__ __forceinline__ void hidden_epilogue(uint32_t tmem_d, const float* bias, uint32_t a_row, float* dbg_row) {
   uint32_t va[32], vb[32];
@@ -232,18 +289,26 @@ __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_ke
     }
   } else if (warp == kMmaWarp) {
     // ================================================================ MMA issuer (converged warp, one lane issues)
+    // Inside a stage tile 0 runs `skew` weight chunks ahead of tile 1 (both still consume every chunk from the same ring
+    // slot): T0's accumulator completes 256*(skew+1) cycles before T1's, so T0's epilogue -- and T0's first MMAs of the next
+    // stage -- overlap T1's MMAs / epilogue instead of leaving the tensor pipe idle.
     {
-      uint32_t stage = 0, phase = 0, ready_ph = 0, reload_ph = 0;   // per-tile phase bits (bit t)
+      uint32_t chunk_base = 0, ready_ph = 0, reload_ph = 0;   // per-tile phase bits (bit t)
       const uint32_t idesc256 = umma_idesc(128, 256), idesc16 = umma_idesc(128, 16);
+      constexpr uint32_t kHi = (128u >> 4) | (1u << 14);   // SBO = 128 B, descriptor version 1
       for (long long st = blockIdx.x; st < n_super; st += gridDim.x) {
         for (int L = 0; L < kNumLayers; ++L) {
           const Layer ly = kLayers[L];
           const int nch = ly.small ? 1 : ly.a_chunks + ly.e_chunks + ly.bias_chunk;
-          for (int c = 0; c < nch; ++c) {
-            mbar_wait(bar_full(stage), phase);
-            tc_fence_after();
-            const uint32_t wsm = sbase + kOffRing + stage * kChunkBytes;
+          const int skew = p.skew < nch ? p.skew : nch;
+          for (int step = 0; step < nch + skew; ++step) {
+#pragma unroll
             for (int t = 0; t < 2; ++t) {
+              const int c = t == 0 ? step : step - skew;
+              if (c < 0 || c >= nch) continue;
+              const uint32_t abs_chunk = chunk_base + c;
+              const uint32_t stage = abs_chunk % kStages, phase = (abs_chunk / kStages) & 1u;
+              if (t == 0) mbar_wait(bar_full(stage), phase);          // first touch of this ring slot
               if (c == 0) {
                 mbar_wait(bar_ready(t), (ready_ph >> t) & 1u);
                 ready_ph ^= 1u << t;
@@ -251,44 +316,43 @@ __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_ke
                   mbar_wait(bar_reload(t), (reload_ph >> t) & 1u);
                   reload_ph ^= 1u << t;
                 }
-                tc_fence_after();
               }
+              tc_fence_after();
+              const uint32_t wsm = sbase + kOffRing + stage * kChunkBytes;
               const uint32_t d_tmem = tmem_base + t * 256;
               if (elect_one_sync()) {
-              // descriptor words: lo = start>>4 | (LBO>>4)<<16, hi = SBO>>4 | version(1)<<14; SBO = 128 B everywhere
-              constexpr uint32_t kHi = (128u >> 4) | (1u << 14);
-              if (ly.small) {
-                // one chunk = [32 k8][16 rows][8]: 16 K-steps over the full K=256 of A_t
-                uint32_t a_lo = ((sbase + kOffA + t * kABytes) >> 4) | ((2048u >> 4) << 16);
-                uint32_t b_lo = (wsm >> 4) | ((256u >> 4) << 16);
+                // descriptor words: lo = start>>4 | (LBO>>4)<<16, hi = SBO>>4 | version(1)<<14
+                if (ly.small) {
+                  // one chunk = [32 k8][16 rows][8]: 16 K-steps over the full K=256 of A_t
+                  uint32_t a_lo = ((sbase + kOffA + t * kABytes) >> 4) | ((2048u >> 4) << 16);
+                  uint32_t b_lo = (wsm >> 4) | ((256u >> 4) << 16);
 #pragma unroll
-                for (int ks = 0; ks < 16; ++ks) {
-                  umma_bf16_lohi(d_tmem, a_lo, kHi, b_lo, kHi, idesc16, ks > 0 ? 1u : 0u);
-                  a_lo += 4096u >> 4;
-                  b_lo += 512u >> 4;
+                  for (int ks = 0; ks < 16; ++ks) {
+                    umma_bf16_lohi(d_tmem, a_lo, kHi, b_lo, kHi, idesc16, ks > 0 ? 1u : 0u);
+                    a_lo += 4096u >> 4;
+                    b_lo += 512u >> 4;
+                  }
+                } else if (c >= ly.a_chunks + ly.e_chunks) {
+                  // bias step: A = E columns 48..63 (column 63 == 1), B = [2 k8][256 rows][8], zero except the bias column
+                  const uint32_t a_lo = ((sbase + kOffE + t * kEBytes + 6 * 2048) >> 4) | ((2048u >> 4) << 16);
+                  const uint32_t b_lo = (wsm >> 4) | ((4096u >> 4) << 16);
+                  umma_bf16_lohi(d_tmem, a_lo, kHi, b_lo, kHi, idesc256, 1u);
+                } else {
+                  const bool from_e = c >= ly.a_chunks;
+                  const uint32_t a0 = from_e ? sbase + kOffE + t * kEBytes + (c - ly.a_chunks) * 4 * 2048
+                                             : sbase + kOffA + t * kABytes + c * 4 * 2048;
+                  const uint32_t a_lo = (a0 >> 4) | ((2048u >> 4) << 16);
+                  const uint32_t b_lo = (wsm >> 4) | ((4096u >> 4) << 16);
+                  umma_bf16_lohi(d_tmem, a_lo, kHi, b_lo, kHi, idesc256, c > 0 ? 1u : 0u);
+                  umma_bf16_lohi(d_tmem, a_lo + (4096u >> 4), kHi, b_lo + (8192u >> 4), kHi, idesc256, 1u);
                 }
-              } else if (c >= ly.a_chunks + ly.e_chunks) {
-                // bias step: A = E columns 48..63 (column 63 == 1), B = [2 k8][256 rows][8], zero except the bias column
-                const uint32_t a_lo = ((sbase + kOffE + t * kEBytes + 6 * 2048) >> 4) | ((2048u >> 4) << 16);
-                const uint32_t b_lo = (wsm >> 4) | ((4096u >> 4) << 16);
-                umma_bf16_lohi(d_tmem, a_lo, kHi, b_lo, kHi, idesc256, 1u);
-              } else {
-                const bool from_e = c >= ly.a_chunks;
-                const uint32_t a0 = from_e ? sbase + kOffE + t * kEBytes + (c - ly.a_chunks) * 4 * 2048
-                                           : sbase + kOffA + t * kABytes + c * 4 * 2048;
-                const uint32_t a_lo = (a0 >> 4) | ((2048u >> 4) << 16);
-                const uint32_t b_lo = (wsm >> 4) | ((4096u >> 4) << 16);
-                umma_bf16_lohi(d_tmem, a_lo, kHi, b_lo, kHi, idesc256, c > 0 ? 1u : 0u);
-                umma_bf16_lohi(d_tmem, a_lo + (4096u >> 4), kHi, b_lo + (8192u >> 4), kHi, idesc256, 1u);
-              }
-              if (c == nch - 1) umma_commit(bar_acc(t));   // accumulator of tile t complete
+                if (c == nch - 1) umma_commit(bar_acc(t));       // accumulator of tile t complete
+                if (t == 1) umma_commit(bar_empty(stage));       // ring slot reusable once both tiles' MMAs retire
               }
               __syncwarp();
             }
-            if (elect_one_sync()) umma_commit(bar_empty(stage));   // ring slot reusable once these MMAs retire
-            __syncwarp();
-            if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
+          chunk_base += nch;
         }
       }
     }
@@ -302,6 +366,9 @@ __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_ke
     const uint32_t tmem_d = tmem_row + half * kCols;
     uint8_t* my_scratch = p.scratch + ((size_t)blockIdx.x * 2 + t) * kABytes;
     uint32_t acc_ph = 0;
+    // all 32 rows of a warp share the ray (and image) when N is a multiple of 32; tail rows are clamped to the last
+    // sample, which then belongs to the same ray as the warp's live rows
+    const bool warp_bias = (p.N % 32 == 0) && !(p.dbg_drain & 4);
     bool store_pending = false;      // a bulk store of A_t (feature park / activation save) may still be reading it
     for (long long st = blockIdx.x; st < n_super; st += gridDim.x) {
       const long long s_raw = (st * 2 + t) * 128 + row;
@@ -315,6 +382,16 @@ __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_ke
       float sigma_s = 0.f, rgb_s[3] = {0.f, 0.f, 0.f};
       for (int L = 0; L < kNumLayers; ++L) {
         const Layer ly = kLayers[L];
+        // table biases (per ray / per image): when every row of this warp shares the bias row, each lane fetches its
+        // float4 slice(s) now -- the L2 latency hides behind the MMAs of this stage
+        float4 wb[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+        const bool table_bias = ly.epi == EPI_HIDDEN && ly.bias_kind != BIAS_MMA;
+        if (table_bias && warp_bias) {
+          const float* brow = (ly.bias_kind == BIAS_RAY ? p.raybias + (s / p.N) * 256 : p.imgbias + (s / p.per_image) * 256) +
+                              half * kCols;
+          wb[0] = __ldg(reinterpret_cast<const float4*>(brow) + lane);
+          if (kCols == 256) wb[1] = __ldg(reinterpret_cast<const float4*>(brow + 128) + lane);
+        }
         mbar_wait(bar_acc(t), acc_ph);
         acc_ph ^= 1;
         tc_fence_after();
@@ -333,8 +410,12 @@ __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_ke
         if (ly.epi == EPI_HIDDEN) {
           float* dbg_row = ((L == p.dbg_layer) && live && p.dbg_out) ? p.dbg_out + s * 256 + half * kCols : nullptr;
           const uint32_t a_row = a_smem + half * (kCols / 8) * 2048 + row * 16;
-          if (ly.bias_kind == BIAS_MMA) {
+          if (p.dbg_drain == 1 || p.dbg_drain == 2) {
+            hidden_epilogue_experiment<kCols / 32>(tmem_d, a_row, p.dbg_drain);
+          } else if (ly.bias_kind == BIAS_MMA || p.dbg_drain == 3) {   // 3: timing experiment, bias tables ignored
             hidden_epilogue<false, kCols / 32>(tmem_d, nullptr, a_row, dbg_row);
+          } else if (warp_bias) {
+            hidden_epilogue_wbias<kCols / 32>(tmem_d, wb, a_row, dbg_row);
           } else {
             const float* bias = (ly.bias_kind == BIAS_RAY ? p.raybias + (s / p.N) * 256 : p.imgbias + (s / p.per_image) * 256) +
                                 half * kCols;
@@ -568,7 +649,8 @@ TP_API int tp_tc_nerf_stl_forward(const float* center, const float* ray, const f
   p.rgb = rgb; p.density = density; p.uncert = uncert; p.scratch = reinterpret_cast<uint8_t*>(scratch);
   p.save = reinterpret_cast<uint8_t*>(save);
   if (((uintptr_t)save & 15)) return TP_ERR_ALIGN;
-  p.dbg_layer = dbg_layer; p.dbg_out = dbg_out; p.swap_lbo_sbo = flags & 1;
+  p.dbg_layer = dbg_layer; p.dbg_out = dbg_out; p.dbg_drain = (flags >> 2) & 7;
+  p.skew = ((flags >> 5) & 3) ? ((flags >> 5) & 3) - 1 : 1;      // default skew 1; flags bits 5-6 = skew+1 override (A/B)
   const bool wide = (flags & 2) == 0;       // default: 16 epilogue warps; flags bit 1 selects the 8-warp variant
   cudaError_t e = wide ? cudaFuncSetAttribute(tc::nerf_stl_forward_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               (int)tc::kSmemBytes)
