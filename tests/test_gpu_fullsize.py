@@ -39,7 +39,11 @@ def test_c2_full_frame_properties_and_shard_equality():
         assert torch.equal(full[k], again[k]), k                         # deterministic
         assert torch.isfinite(full[k]).all(), k
     assert (full.opacity - 1).abs().max() < 1e-4 and (full.opacity_static - 1).abs().max() < 1e-4
-    assert (full.rgb >= 0).all() and (full.rgb <= 1 + 1e-4).all()
+    # own-chain composites are convex combinations; `rgb` is not (both terms use the joint transmittance and
+    # alpha_s + alpha_t >= alpha: layers/nerf_static_transient_light.py:193-205), so it is only bounded by 2
+    assert (full.rgb_static >= 0).all() and (full.rgb_static <= 1 + 1e-4).all()
+    assert (full.rgb_transient >= 0).all() and (full.rgb_transient <= 1 + 1e-4).all()
+    assert (full.rgb >= 0).all() and (full.rgb <= 2 + 1e-4).all()
     assert (full.depth >= zn[:, :, None] - 1e-3).all() and (full.depth <= zf[:, :, None] + 1e-3).all()
     # 8-way row-block ray shards (what 8 GPUs would each render) == the whole frame, bit for bit
     world = 8
