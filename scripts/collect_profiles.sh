@@ -20,3 +20,8 @@ python bench.py --steps 10 --warmup 3 > gpurun_out/r01_bench.json 2> gpurun_out/
 kill $SMI
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r01_bench_reference.json 2>> gpurun_out/r01_bench.err
 tail -c 3000 gpurun_out/r01_bench.json
+# (5) training step: launch list + DRAM traffic of the tensor-core backward kernels
+ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file gpurun_out/r01_train_launches.csv python scripts/train_profile.py 3 > /dev/null 2>&1
+ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed \
+    --clock-control none -k regex:"backward_chain|dw_gemm|nerf_stl_forward|image_ray_sums|thin_dw" -s 10 -c 12 --csv --log-file gpurun_out/r01_train_kernels.csv \
+    python scripts/train_profile.py 2 > /dev/null 2>&1
