@@ -1,0 +1,100 @@
+// Stage table, kernel parameters and the per-sample encoder shared by the fused forward kernels (mlp_tc.cu: two lock-stepped
+// tiles per CTA; mlp_tc_v2.cu: one tile per CTA, cluster-multicast weights).  Both consume the same packed weight image.
+#pragma once
+#include "tc_common.cuh"
+
+namespace tc {
+
+constexpr uint32_t kEBytes = 16384;    // 128 x 64 bf16 encoding tile
+constexpr int kNumLayers = 17;
+constexpr int kNumChunks = 122;
+
+// stage table: chunks read from A (K=32 each), chunks read from E, small (N=16, one chunk spans K=256),
+// kind of epilogue, bias handling, needs the feature reload first.
+// Static biases of the 256-wide stages ride on the tensor cores: column 63 of the encoding tile is a constant 1 and
+// the bias sits in the matching weight column -- for stages that read E anyway (trunk 0 and 4) inside their last E
+// chunk, for the others as one extra K=16 step on E columns 48..63 with an 8 KB weight chunk that is zero except for
+// that column (BIAS_MMA).  Their epilogue is then a pure convert.  Per-ray / per-image biases (fp32 tables) and the
+// three N=16 output stages add their bias in the epilogue.
+enum Epi : int { EPI_HIDDEN = 0, EPI_DENSITY = 1, EPI_RGB_OUT = 2, EPI_TRANS_OUT = 3 };
+enum BiasKind : int { BIAS_MMA = 0, BIAS_RAY = 1, BIAS_IMAGE = 2, BIAS_SMALL = 3 };
+struct Layer {
+  int a_chunks, e_chunks, small, epi, bias_kind, bias_chunk, reload;
+};
+static __constant__ Layer kLayers[kNumLayers] = {
+    {0, 2, 0, EPI_HIDDEN, BIAS_MMA, 0, 0},       // trunk 0  (63 -> 256); bias in E column 63 of its own chunk
+    {8, 0, 0, EPI_HIDDEN, BIAS_MMA, 1, 0},       // trunk 1
+    {8, 0, 0, EPI_HIDDEN, BIAS_MMA, 1, 0},       // trunk 2
+    {8, 0, 0, EPI_HIDDEN, BIAS_MMA, 1, 0},       // trunk 3
+    {8, 2, 0, EPI_HIDDEN, BIAS_MMA, 0, 0},       // trunk 4  (skip: [feat | enc]); bias in E column 63
+    {8, 0, 0, EPI_HIDDEN, BIAS_MMA, 1, 0},       // trunk 5
+    {8, 0, 0, EPI_HIDDEN, BIAS_MMA, 1, 0},       // trunk 6
+    {8, 0, 1, EPI_DENSITY, BIAS_SMALL, 0, 0},    // trunk 7 row 0     -> sigma_static (softplus)
+    {8, 0, 0, EPI_HIDDEN, BIAS_MMA, 1, 0},       // trunk 7 rows 1..  -> feature (relu); parked to L2 afterwards
+    {8, 1, 0, EPI_HIDDEN, BIAS_RAY, 0, 0},       // rgb 0    ([feat | xyz]; view+light folded into the ray bias)
+    {8, 0, 0, EPI_HIDDEN, BIAS_MMA, 1, 0},       // rgb 1
+    {8, 0, 0, EPI_HIDDEN, BIAS_MMA, 1, 0},       // rgb 2
+    {8, 0, 1, EPI_RGB_OUT, BIAS_SMALL, 0, 0},    // rgb 3    -> sigmoid
+    {8, 0, 0, EPI_HIDDEN, BIAS_IMAGE, 0, 1},     // trans 0  (feature reloaded; transient latent in the image bias)
+    {8, 0, 0, EPI_HIDDEN, BIAS_MMA, 1, 0},       // trans 1
+    {8, 0, 0, EPI_HIDDEN, BIAS_MMA, 1, 0},       // trans 2
+    {8, 0, 1, EPI_TRANS_OUT, BIAS_SMALL, 0, 0}   // trans 3  -> sigmoid x3, softplus x2
+};
+constexpr int kSpillLayer = 8, kReloadIssueLayer = 12;
+constexpr int kSaveSlots = 7;
+// activation-save slot of each stage (training): feat, rgb h1..h3, trans h1..h3; -1 = not saved
+static __constant__ int kSaveSlot[kNumLayers] = {-1, -1, -1, -1, -1, -1, -1, -1, 0, 1, 2, 3, -1, 4, 5, 6, -1};
+constexpr int kSmallBiasOffset = 0;            // biasbuf: [density b, rgb3 b(3), trans3 b(5)] (fp32, 16 floats)
+
+struct Params {
+  const float* center;       // [rays,3]
+  const float* ray;          // [rays,3]
+  const float* depth;        // [S]
+  long long S;
+  int N;                     // samples per ray
+  long long per_image;       // samples per image
+  const uint8_t* packed;     // kNumChunks x 16 KB weight image
+  const float* biasbuf;      // 12 x 256 static biases + 16 small
+  const float* raybias;      // [rays,256]  rgb-0 bias incl. view encoding + light latent
+  const float* imgbias;      // [images,256] trans-0 bias incl. transient latent
+  float* rgb;                // [S,3,2]
+  float* density;            // [S,2]
+  float* uncert;             // [S]
+  uint8_t* scratch;          // gridDim.x x 2 x 64 KB (parked features)
+  uint8_t* save;             // optional [tiles][7][64 KB]: feat, rgb h1..h3, trans h1..h3 tile images for the backward
+  int dbg_layer;
+  float* dbg_out;            // [S,256] post-activation of stage dbg_layer (debug only)
+  int skew;                  // weight chunks tile 0 runs ahead of tile 1 inside a stage (0..2)
+  int dbg_drain;             // timing experiments only (wrong results): 1 = convert/store every other slab, 2 = also skip its TMEM load
+};
+
+// positional encoding of one sample into the E tile (bf16): [x,y,z, per coord sin(2^k pi x) k<10, cos(...) k<10, 1].
+// sincospif gives the exact-argument octave 0; higher octaves by the double-angle recurrence (error << bf16 ulp).
+__device__ __forceinline__ void encode_sample(const Params& p, long long s, uint32_t e_smem, int row) {
+  const long long r = s / p.N;
+  const float d = p.depth[s];
+  float v[64];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const float x = __fadd_rn(p.center[r * 3 + j], __fmul_rn(p.ray[r * 3 + j], d));
+    v[j] = x;
+    float sn, cs;
+    sincospif(x, &sn, &cs);
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {
+      v[3 + j * 20 + k] = sn;
+      v[3 + j * 20 + 10 + k] = cs;
+      const float s2 = 2.f * sn * cs, c2 = (cs - sn) * (cs + sn);
+      sn = s2;
+      cs = c2;
+    }
+  }
+  v[63] = 1.f;   // constant-1 column: carries the static biases through the MMA
+#pragma unroll
+  for (int k8 = 0; k8 < 8; ++k8)
+    st_shared_v4(e_smem + k8 * 2048 + row * 16, pack_bf16(v[k8 * 8 + 0], v[k8 * 8 + 1]), pack_bf16(v[k8 * 8 + 2], v[k8 * 8 + 3]),
+                 pack_bf16(v[k8 * 8 + 4], v[k8 * 8 + 5]), pack_bf16(v[k8 * 8 + 6], v[k8 * 8 + 7]));
+}
+
+
+}  // namespace tc
