@@ -215,6 +215,24 @@ int tp_tc_dw_gemm(const void* a_images, int a_nslots, const void* b_images, int 
                   const int32_t* b_slots, int n_jobs, int64_t S, float* partial, int64_t partial_floats, int flags,
                   void* stream);
 
+/* Fused backward of both heads in five launches (replaces tp_tc_backward_chain + tp_tc_dw_gemm + the thin helpers): the dX chain
+ * kernel also accumulates, on the tensor pipe, every thin gradient -- bias gradients, output-layer weight gradients, the xyz /
+ * view-direction columns of mlp_rgb[0], per-image sums for the latent terms -- then two finish kernels and the six 256x256
+ * weight-gradient GEMMs write the reference's parameter gradients (autograd of layers/nerf_static_transient_light.py:104-137
+ * under the losses of model/nerf_adapt_st_gan.py:747-763) straight into caller tensors.
+ * grads: HOST array of 16 DEVICE pointers {rgb dW0 [256,ld_r0], db0, dW1 [256,256], db1, dW2, db2, dW3 [3,256], db3 [3],
+ * transient dW0 [256,ld_t0], db0, dW1, db1, dW2, db2, dW3 [5,256], db3 [5]}.  d_lat_* [B,n] or NULL.  B = images,
+ * per_image = samples per image (B*per_image >= S).  Requires tp_tc_heads_backward_supported(S, per_image) (a CTA's contiguous
+ * tile range may touch at most 4 images); workspace >= tp_tc_heads_backward_workspace(S, B) floats. */
+int tp_tc_heads_backward_supported(int64_t S, int64_t per_image);
+int64_t tp_tc_heads_backward_workspace(int64_t S, int B);
+int tp_tc_heads_backward(const float* dz_rgb, const float* dz_trans, int64_t S, int N, int64_t per_image, int B,
+                         const float* center, const float* ray, const float* depth, int L_view,
+                         const void* packed_bwd, const void* saved, void* dz_images, const float* W_r0,
+                         int64_t ld_r0, const float* W_t0, int64_t ld_t0, const float* lat_light, int n_light,
+                         const float* lat_trans, int n_trans, float* const* grads, float* d_lat_light,
+                         float* d_lat_trans, float* workspace, int64_t workspace_floats, void* stream);
+
 /* out[r,:] = sum over the N samples of ray r of an image slot (per-ray column sums, fp32 [ceil(S/N),256]). */
 int tp_tc_image_ray_sums(const void* images, int slot, int n_slots, int64_t S, int N, float* out, void* stream);
 

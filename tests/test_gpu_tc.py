@@ -135,3 +135,43 @@ def test_c3_shape_gradients_bf16():
     for n, a, b in pairs:
         err, mag = (a - b).abs().max().item(), b.abs().max().item()
         assert err <= max(TOL, 0.015 * mag), (n, err, mag)
+
+
+@pytest.mark.parametrize("B,R,N", [(3, 50, 48), (2, 1200, 32), (16, 256, 128)])
+def test_fused_backward_matches_multikernel(B, R, N, monkeypatch):
+    """tp_tc_heads_backward (thin gradients on the tensor pipe inside the dX chain kernel, 5 launches) against the
+    multi-kernel sequence it replaces, on multi-image / ragged batches: same bf16 dz operands, so the two agree to the
+    bf16 rounding of the thin operands (xyz, view encoding)."""
+    from texpose_b200 import mlp_tc_bwd
+    S = B * R * N
+    assert mlp_tc_bwd.fused_supported(S, R * N)
+    g = torch.Generator().manual_seed(11)
+    center = (torch.randn(B, R, 3, generator=g) * 0.02 + torch.tensor([0.3, 0.2, -0.8])).to(DEV)
+    ray = (torch.randn(B, R, 3, generator=g) * 0.1 + torch.tensor([0.0, 0.0, 1.0])).to(DEV)
+    depth = ((torch.rand(B, R, N, 1, generator=g) + torch.arange(N)[None, None, :, None]) / N * 1.2 + 0.2).to(DEV)
+    lt0, ll0 = synth.latents(B)
+    image = torch.rand(B, R, 3, generator=g).to(DEV)
+    opt, m = _module("bf16")
+
+    def grads(mode):
+        monkeypatch.setenv("TEXPOSE_BWD", mode)
+        for p in m.parameters():
+            p.grad = None
+        lt, ll = lt0.to(DEV).requires_grad_(True), ll0.to(DEV).requires_grad_(True)
+        out = m.forward_samples(opt, center, ray, depth, lt, ll, mode="train")
+        comp = m.composite(opt, ray, *out[:2], depth, out[2])
+        loss = ((image - comp[0]) ** 2 / comp[8] ** 2).mean() + torch.log(comp[8] ** 2).mean() + 0.01 * out[1][..., -1].mean()
+        loss.backward()
+        named = list(m.mlp_rgb.named_parameters(prefix="mlp_rgb")) + list(m.mlp_trans.named_parameters(prefix="mlp_trans"))
+        return [("latent_trans", lt.grad.clone()), ("latent_light", ll.grad.clone())] + [(n, p.grad.clone()) for n, p in named]
+
+    a, b = grads("fused"), grads("unfused")
+    for (n, x), (_, y) in zip(a, b):
+        err, mag = (x - y).abs().max().item(), y.abs().max().item()
+        print(f"  {n:22s} |grad|max {mag:9.3e}  fused-vs-multikernel {err:9.3e}")
+        assert x.shape == y.shape and torch.isfinite(x).all()
+        assert err <= 5e-3 * mag + 1e-7, (n, err, mag)
+    # deterministic: fixed-order reductions everywhere
+    c = grads("fused")
+    for (n, x), (_, y) in zip(a, c):
+        assert torch.equal(x, y), n

@@ -222,6 +222,389 @@ __global__ void __launch_bounds__(kThreads, 1) backward_chain_kernel(const BwdPa
   }
 }
 
+// UMMA instruction descriptor with both operands MN-major (bits 15, 16)
+__host__ __device__ constexpr uint32_t umma_idesc_mn(int M, int N) { return umma_idesc(M, N) | (1u << 15) | (1u << 16); }
+
+// ------------------------------------------------------------------------------------------ fused chain + thin gradients
+//
+// Same dX chain, plus every "thin" gradient of the two heads, computed by the otherwise idle tensor pipe while the operands are
+// in SMEM anyway (the chain is HBM-bound).  All of them have the form  D[n, j] = sum_s X[s, n] * T[s, j]  with X a 128 x 256 tile
+// image already resident (a dz tile in A, or the saved h3 tile in M) used as an MN-major A operand (2 x M=128 feature halves),
+// and T a thin bf16 tile [128 samples x 16|48] built by the epilogue warps, used as an MN-major B operand:
+//
+//   block S  (N=16)  X = dz2 / dz1 of either head,   T = 1 in column {0,1,3,4}            -> bias gradients of layers 2, 1
+//   block R  (N=48)  X = dz0 of the rgb head,        T = [image indicators 4 | xyz 3 | view encoding 27]
+//                                                     -> per-image sums (bias, light-latent terms), dW columns of xyz / view
+//   block T  (N=16)  X = dz0 of the transient head,  T = the same tile's first 16 columns  -> per-image sums (cols 0..3)
+//   block O  (N=16)  X = h3 of a head (mask tile),   T = that head's dz3 tile              -> weight gradient of the output layer
+//
+// The accumulators (224 TMEM columns beside the chain's 256) run over ALL tiles of the CTA, which therefore processes a
+// contiguous tile range; "image indicators" are relative to the first image the range touches (<= 4 images per CTA, checked by
+// the host).  One flush per CTA at the end; bwd_finish_kernels reduce over CTAs in fixed order (deterministic).
+constexpr uint32_t kOffTS = kOffZ + 8192;             // [2 k8][128][8]: a single 1-column, rewritten per stage
+constexpr uint32_t kOffTI = kOffTS + 4096;            // 2 x [2 k8][128][8]: image-indicator tile (block T), by tile parity
+constexpr uint32_t kOffTR = kOffTI + 2 * 4096;        // [6 k8][128][8]: indicator | xyz | view tile (block R)
+constexpr uint32_t kTRBytes = 12288;
+constexpr uint32_t kOffRingF = kOffTR + kTRBytes;
+static_assert(kOffRingF + kStages * kChunkBytes + 128 <= 232448, "fused chain kernel exceeds 227 KB of shared memory");
+constexpr uint32_t kOffBarF = kOffRingF + kStages * kChunkBytes;
+constexpr uint32_t kSmemBytesF = kOffBarF + 128;
+// TMEM columns of the extra accumulators (feature half h at +N*h)
+constexpr uint32_t kColS = 256, kColT = 288, kColOr = 320, kColOt = 352, kColR = 384, kColRh = 64;
+constexpr int kMaxImagesPerCta = 4;
+// compact columns of the per-CTA partial [kXCols][256]
+constexpr int kXdb = 0;        // 4: rgb db2, rgb db1, trans db2, trans db1
+constexpr int kXimgR = 4;      // 4: per-image sums of rgb dz0 (local image index)
+constexpr int kXxyz = 8;       // 3
+constexpr int kXview = 11;     // 27
+constexpr int kXimgT = 38;     // 4: per-image sums of trans dz0
+constexpr int kXwr = 42;       // 3: rgb output-layer weight gradient rows
+constexpr int kXwt = 45;       // 5: transient output-layer weight gradient rows
+constexpr int kXCols = 50;
+
+struct FusedParams {
+  BwdParams b;
+  const float* center;        // [rays,3]
+  const float* ray;           // [rays,3]
+  const float* depth;         // [S]
+  int N;                      // samples per ray
+  long long per_image;        // samples per image
+  int L_view;
+  float* extras;              // [grid][kXCols][256]
+  float* thin_sums;           // [grid][4 warps][8]: column sums of dz_rgb (3) and dz_trans (5)
+};
+
+__device__ __forceinline__ void tile_range(long long n_tiles, int grid, int cta, long long& t0, long long& t1) {
+  const long long per = n_tiles / grid, rem = n_tiles % grid;
+  t0 = cta * per + (cta < rem ? cta : rem);
+  t1 = t0 + per + (cta < rem ? 1 : 0);
+}
+
+// T_R row of one sample: [ind(4) | xyz(3) | u(3), per coord sin(2^k pi u) k<L, cos(...) k<L | 0...] as 48 bf16
+__device__ __forceinline__ void write_tr_row(const FusedParams& p, long long s, long long img0, uint32_t dst_row,
+                                             uint32_t ti_row) {
+  float v[48];
+#pragma unroll
+  for (int i = 0; i < 48; ++i) v[i] = 0.f;
+  if (s < p.b.S) {
+    const long long r = s / p.N;
+    const long long li = s / p.per_image - img0;
+#pragma unroll
+    for (int j = 0; j < kMaxImagesPerCta; ++j) v[j] = (li == j) ? 1.f : 0.f;
+    const float d = p.depth[s];
+    float dir[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      dir[j] = p.ray[r * 3 + j];
+      v[4 + j] = __fadd_rn(p.center[r * 3 + j], __fmul_rn(dir[j], d));
+    }
+    const float len = fmaxf(sqrtf(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]), 1e-12f);
+    const int L = p.L_view;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const float u = dir[j] / len;
+      v[7 + j] = u;
+      float sn, cs;
+      sincospif(u, &sn, &cs);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (k < L) {
+          v[10 + j * 2 * L + k] = sn;
+          v[10 + j * 2 * L + L + k] = cs;
+        }
+        const float s2 = 2.f * sn * cs, c2 = (cs - sn) * (cs + sn);
+        sn = s2;
+        cs = c2;
+      }
+    }
+  }
+#pragma unroll
+  for (int k8 = 0; k8 < 6; ++k8)
+    st_shared_v4(dst_row + k8 * 2048, pack_bf16(v[k8 * 8], v[k8 * 8 + 1]), pack_bf16(v[k8 * 8 + 2], v[k8 * 8 + 3]),
+                 pack_bf16(v[k8 * 8 + 4], v[k8 * 8 + 5]), pack_bf16(v[k8 * 8 + 6], v[k8 * 8 + 7]));
+  st_shared_v4(ti_row, pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), 0u, 0u);
+  st_shared_v4(ti_row + 2048, 0u, 0u, 0u, 0u);
+}
+
+__global__ void __launch_bounds__(kThreads, 1) backward_chain_fused_kernel(const FusedParams fp) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const BwdParams& p = fp.b;
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t bar0 = sbase + kOffBarF;
+  auto bar_full = [&](int s) { return bar0 + 8 * s; };
+  auto bar_empty = [&](int s) { return bar0 + 8 * (kStages + s); };
+  const uint32_t bar_acc = bar0 + 8 * (2 * kStages), bar_ready = bar_acc + 8, bar_mask = bar_acc + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBarF + 8 * (2 * kStages + 3));
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(bar_full(s), 1);
+      mbar_init(bar_empty(s), 1);
+    }
+    mbar_init(bar_acc, 1);
+    mbar_init(bar_ready, 256);
+    mbar_init(bar_mask, 1);
+    fence_barrier_init();
+  }
+  if (warp == 9) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const long long n_tiles = (p.S + 127) / 128;
+  long long t0, t1;
+  tile_range(n_tiles, gridDim.x, blockIdx.x, t0, t1);
+
+  if (warp == 8) {
+    // ================================================================ weight producer
+    uint32_t stage = 0, phase = 0;
+    for (long long tile = t0; tile < t1; ++tile) {
+      int c = 0;
+      for (int s = 0; s < kNumStagesPerTile; ++s) {
+        const int nch = (s % 3 == 0) ? 1 : 8;
+        for (int j = 0; j < nch; ++j, ++c) {
+          const uint32_t bytes = (s % 3 == 0) ? kChunkBytes / 2 : kChunkBytes;
+          mbar_wait(bar_empty(stage), phase ^ 1);
+          if (elect_one_sync()) {
+            mbar_expect_tx(bar_full(stage), bytes);
+            bulk_g2s(sbase + kOffRingF + stage * kChunkBytes, p.packed + (size_t)c * kChunkBytes, bytes, bar_full(stage));
+          }
+          __syncwarp();
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ================================================================ MMA issuer: chain stages + thin-gradient MMAs
+    uint32_t stage = 0, phase = 0, ready_ph = 0, mask_cnt = 0;
+    const uint32_t idesc = umma_idesc(128, 256);
+    const uint32_t idesc_x16 = umma_idesc_mn(128, 16), idesc_x48 = umma_idesc_mn(128, 48);
+    constexpr uint32_t kHi = (128u >> 4) | (1u << 14);          // K-major operands: SBO 128
+    constexpr uint32_t kHiMn = (2048u >> 4) | (1u << 14);       // MN-major operands: SBO 2048 (next 8 features / columns)
+    const uint32_t a_tile = sbase + kOffA, m_tile = sbase + kOffM, ts_tile = sbase + kOffTS;
+    // D[128 x n] (+)= X^T T over the 128 samples of the tile, for both feature halves
+    auto thin_mma = [&](uint32_t col, uint32_t ncols, uint32_t x_tile, uint32_t t_tile, uint32_t id, bool first) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint32_t a_lo = ((x_tile + h * 32768 + ks * 256) >> 4) | ((128u >> 4) << 16);
+          const uint32_t b_lo = ((t_tile + ks * 256) >> 4) | ((128u >> 4) << 16);
+          umma_bf16_lohi(tmem_base + col + h * ncols, a_lo, kHiMn, b_lo, kHiMn, id, (first && ks == 0) ? 0u : 1u);
+        }
+      }
+    };
+    for (long long tile = t0; tile < t1; ++tile) {
+      const uint32_t tr_tile = sbase + kOffTR;
+      const uint32_t tr_prev = sbase + kOffTI + (uint32_t)((tile - t0 + 1) & 1) * 4096;
+      const bool first_tile = tile == t0;
+      for (int s = 0; s < kNumStagesPerTile; ++s) {
+        const int nch = (s % 3 == 0) ? 1 : 8;
+        for (int c = 0; c < nch; ++c) {
+          mbar_wait(bar_full(stage), phase);
+          if (c == 0) {
+            mbar_wait(bar_ready, ready_ph);
+            ready_ph ^= 1;
+            if (s % 3 == 0) mbar_wait(bar_mask, (mask_cnt + s) & 1u);     // h3 tile of this head is the X operand of block O
+          }
+          tc_fence_after();
+          const uint32_t wsm = sbase + kOffRingF + stage * kChunkBytes;
+          if (elect_one_sync()) {
+            if (c == 0) {
+              // thin-gradient MMAs on the operands that are complete at this point
+              if (s == 0) {
+                if (tile > t0) thin_mma(kColT, 16, a_tile, tr_prev, idesc_x16, tile == t0 + 1);     // trans dz0 of the previous tile
+                thin_mma(kColOr, 16, m_tile, sbase + kOffZ, idesc_x16, first_tile);
+              } else if (s == 3) {
+                thin_mma(kColR, kColRh, a_tile, tr_tile, idesc_x48, first_tile);                     // rgb dz0
+                thin_mma(kColOt, 16, m_tile, sbase + kOffZ + 4096, idesc_x16, first_tile);
+              } else {
+                thin_mma(kColS, 16, a_tile, ts_tile, idesc_x16, first_tile && s == 1);              // dz2 / dz1 column sums
+              }
+            }
+            const uint32_t b_lo = (wsm >> 4) | ((4096u >> 4) << 16);
+            if (s % 3 == 0) {   // K=16 step on the dz3 tile of this head
+              const uint32_t a_lo = ((sbase + kOffZ + (s / 3) * 4096) >> 4) | ((2048u >> 4) << 16);
+              umma_bf16_lohi(tmem_base, a_lo, kHi, b_lo, kHi, idesc, 0u);
+            } else {
+              const uint32_t a_lo = ((a_tile + c * 4 * 2048) >> 4) | ((2048u >> 4) << 16);
+              umma_bf16_lohi(tmem_base, a_lo, kHi, b_lo, kHi, idesc, c > 0 ? 1u : 0u);
+              umma_bf16_lohi(tmem_base, a_lo + (4096u >> 4), kHi, b_lo + (8192u >> 4), kHi, idesc, 1u);
+            }
+            if (c == nch - 1) umma_commit(bar_acc);
+            umma_commit(bar_empty(stage));
+          }
+          __syncwarp();
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+      mask_cnt += kNumStagesPerTile;
+    }
+    // trans dz0 of the last tile, then hand the accumulators to the flush
+    mbar_wait(bar_ready, ready_ph);
+    tc_fence_after();
+    if (elect_one_sync()) {
+      thin_mma(kColT, 16, a_tile, sbase + kOffTI + (uint32_t)((t1 - 1 - t0) & 1) * 4096, idesc_x16, t1 - t0 == 1);
+      umma_commit(bar_acc);
+    }
+    __syncwarp();
+  } else {
+    // ================================================================ epilogue warps: mask, convert, store dz images, thin tiles
+    const int q = warp & 3, half = warp >> 2, row = q * 32 + lane;
+    const uint32_t a_smem = sbase + kOffA, m_smem = sbase + kOffM;
+    const uint32_t tmem_d = tmem_base + ((uint32_t)(q * 32) << 16) + half * 128;
+    uint32_t acc_ph = 0, mask_ph = 0;
+    bool store_pending = false;
+    const long long img0 = (t0 * 128) / fp.per_image;
+    float zsum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (threadIdx.x == 32) {
+      mbar_expect_tx(bar_mask, kABytes);
+      bulk_g2s(m_smem, p.saved + ((size_t)t0 * kFwdSlots + kMaskSlot[0]) * kABytes, kABytes, bar_mask);
+    }
+    for (long long tile = t0; tile < t1; ++tile) {
+      const long long s_row = tile * 128 + row;
+      if (half == 0) {
+        // dz3 tiles of both heads: [2 k8][128 rows][8] bf16, columns >= 3 / 5 zero
+        float zr[3] = {0.f, 0.f, 0.f}, zt[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+        if (s_row < p.S) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) zr[c] = p.dz_rgb[s_row * 3 + c];
+#pragma unroll
+          for (int c = 0; c < 5; ++c) zt[c] = p.dz_trans[s_row * 5 + c];
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) zsum[c] += zr[c];
+#pragma unroll
+        for (int c = 0; c < 5; ++c) zsum[3 + c] += zt[c];
+        const uint32_t z0 = sbase + kOffZ + row * 16;
+        st_shared_v4(z0, pack_bf16(zr[0], zr[1]), pack_bf16(zr[2], 0.f), 0u, 0u);
+        st_shared_v4(z0 + 2048, 0u, 0u, 0u, 0u);
+        st_shared_v4(z0 + 4096, pack_bf16(zt[0], zt[1]), pack_bf16(zt[2], zt[3]), pack_bf16(zt[4], 0.f), 0u);
+        st_shared_v4(z0 + 4096 + 2048, 0u, 0u, 0u, 0u);
+      } else {
+        write_tr_row(fp, s_row, img0, sbase + kOffTR + row * 16, sbase + kOffTI + (uint32_t)((tile - t0) & 1) * 4096 + row * 16);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(bar_ready);
+
+      for (int s = 0; s < kNumStagesPerTile; ++s) {
+        mbar_wait(bar_acc, acc_ph);
+        acc_ph ^= 1;
+        mbar_wait(bar_mask, mask_ph);
+        mask_ph ^= 1;
+        tc_fence_after();
+        if (store_pending) {          // the previous dz image store must have finished reading A
+          if (threadIdx.x == 0) bulk_wait_read();
+          named_bar_sync(1, 256);
+          store_pending = false;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t v[32];
+          TP_TMEM_LD32(tmem_d + j * 32, v);
+          TP_TMEM_WAIT32(v);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint32_t off = (uint32_t)(half * 16 + j * 4 + i) * 2048 + row * 16;
+            uint32_t m0, m1, m2, m3;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(m0), "=r"(m1), "=r"(m2), "=r"(m3) : "r"(m_smem + off));
+            const uint32_t mw[4] = {m0, m1, m2, m3};
+            uint32_t o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float lo = (mw[e] & 0xffffu) ? __uint_as_float(v[i * 8 + 2 * e]) : 0.f;
+              const float hi = (mw[e] >> 16) ? __uint_as_float(v[i * 8 + 2 * e + 1]) : 0.f;
+              o[e] = pack_bf16(lo, hi);
+            }
+            st_shared_v4(a_smem + off, o[0], o[1], o[2], o[3]);
+          }
+        }
+        if (half == 1 && s % 3 != 2) {     // the 1-column of block S for the dz tile just written: column = dz slot
+          const uint32_t one = 0x3F80u << ((s & 1) * 16);
+          const int w = s >> 1;
+          st_shared_v4(sbase + kOffTS + row * 16, w == 0 ? one : 0u, w == 1 ? one : 0u, w == 2 ? one : 0u, 0u);
+          st_shared_v4(sbase + kOffTS + 2048 + row * 16, 0u, 0u, 0u, 0u);
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, 256);           // every thread finished reading M and writing A
+        if (threadIdx.x == 0) {
+          bulk_s2g(p.dz_out + ((size_t)tile * kDzSlots + s) * kABytes, a_smem, kABytes);
+          bulk_commit();
+        }
+        store_pending = true;
+        if (threadIdx.x == 32) {          // prefetch the next stage's mask tile (possibly of this CTA's next tile)
+          const bool last = s == kNumStagesPerTile - 1;
+          const long long nt = last ? tile + 1 : tile;
+          if (nt < t1) {
+            mbar_expect_tx(bar_mask, kABytes);
+            bulk_g2s(m_smem, p.saved + ((size_t)nt * kFwdSlots + kMaskSlot[last ? 0 : s + 1]) * kABytes, kABytes, bar_mask);
+          }
+        }
+        if (s != kNumStagesPerTile - 1) {
+          tc_fence_before();
+          mbar_arrive(bar_ready);
+        }
+      }
+    }
+    // last tile: release the trans-dz0 thin MMA, then flush the thin accumulators of this CTA
+    tc_fence_before();
+    mbar_arrive(bar_ready);
+    mbar_wait(bar_acc, acc_ph);
+    tc_fence_after();
+    {
+      const int n = half * 128 + row;
+      float* P = fp.extras + (size_t)blockIdx.x * kXCols * 256 + n;
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+      auto flush = [&](uint32_t col, int ncols, int x0, int src0) {   // TMEM columns [col, col+8) -> P[x0 + i] for i < ncols (from src0)
+        uint32_t v[8];
+        TP_TMEM_LD8(lane_addr + col, v);
+        TP_TMEM_WAIT8(v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (i >= src0 && i < src0 + ncols) P[(size_t)(x0 + i - src0) * 256] = __uint_as_float(v[i]);
+      };
+      const uint32_t cS = kColS + half * 16, cT = kColT + half * 16, cOr = kColOr + half * 16, cOt = kColOt + half * 16;
+      const uint32_t cR = kColR + half * kColRh;
+      flush(cS, 2, kXdb, 0);            // slots 0, 1
+      flush(cS, 2, kXdb + 2, 3);        // slots 3, 4
+      flush(cR, 4, kXimgR, 0);
+      flush(cR, 3, kXxyz, 4);
+      flush(cR, 1, kXview, 7);
+      flush(cR + 8, 8, kXview + 1, 0);
+      flush(cR + 16, 8, kXview + 9, 0);
+      flush(cR + 24, 8, kXview + 17, 0);
+      flush(cR + 32, 2, kXview + 25, 0);
+      flush(cT, 4, kXimgT, 0);
+      flush(cOr, 3, kXwr, 0);
+      flush(cOt, 5, kXwt, 0);
+    }
+    if (half == 0) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float v = zsum[c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) fp.thin_sums[((size_t)blockIdx.x * 4 + q) * 8 + c] = v;
+      }
+    }
+    if (threadIdx.x == 0) bulk_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------------------------------ dW = dz^T x on tile images
 
 constexpr uint32_t kDwSlots = 3;                     // ring of 64 KB image slots: A_i, B_i, A_{i+1}, ...
@@ -239,8 +622,6 @@ struct DwParams {
   int swap_strides;                                  // debug
 };
 
-// UMMA instruction descriptor with both operands MN-major (bits 15, 16)
-__host__ __device__ constexpr uint32_t umma_idesc_mn(int M, int N) { return umma_idesc(M, N) | (1u << 15) | (1u << 16); }
 
 __global__ void __launch_bounds__(kThreads, 1) dw_gemm_kernel(const DwParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -350,6 +731,115 @@ __global__ void __launch_bounds__(kThreads, 1) dw_gemm_kernel(const DwParams p) 
   if (warp == 9) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------ finish: per-CTA partials -> gradients
+
+struct FinishParams {
+  const float* extras;        // [grid][kXCols][256]
+  const float* thin_sums;     // [grid][4][8]
+  int grid;
+  long long n_tiles, per_image;
+  int B, vc, n_light, n_trans;
+  float* tot;                 // [kXCols][256] column totals over the CTAs (indicator columns unused)
+  float* img;                 // [2][B][256] per-image sums of rgb dz0 / transient dz0
+  const float* W_r0; long long ld_r0;      // mlp_rgb[0].weight  [256, 256 + vc + 3 + n_light]
+  const float* W_t0; long long ld_t0;      // mlp_trans[0].weight [256, 256 + n_trans]
+  const float* lat_light;     // [B, n_light]
+  const float* lat_trans;     // [B, n_trans]
+  float* g[16];               // rgb {dW0, db0, dW1, db1, dW2, db2, dW3, db3}, transient likewise (dW1, dW2 come from the GEMM)
+  float* d_lat_light;         // [B, n_light] or NULL
+  float* d_lat_trans;         // [B, n_trans] or NULL
+};
+
+// one block per compact column; fixed CTA order
+__global__ void __launch_bounds__(256) bwd_finish1_kernel(const FinishParams f) {
+  const int c = blockIdx.x, n = threadIdx.x;
+  const bool ind_r = c >= kXimgR && c < kXimgR + kMaxImagesPerCta, ind_t = c >= kXimgT && c < kXimgT + kMaxImagesPerCta;
+  if (!ind_r && !ind_t) {
+    float acc = 0.f;
+    for (int cta = 0; cta < f.grid; ++cta) acc += f.extras[((size_t)cta * kXCols + c) * 256 + n];
+    f.tot[c * 256 + n] = acc;
+    return;
+  }
+  if (c != kXimgR && c != kXimgT) return;
+  float* out = f.img + (size_t)(ind_t ? 1 : 0) * f.B * 256;
+  for (int b = 0; b < f.B; ++b) {
+    float acc = 0.f;
+    for (int cta = 0; cta < f.grid; ++cta) {
+      long long t0, t1;
+      tile_range(f.n_tiles, f.grid, cta, t0, t1);
+      const long long j = b - (t0 * 128) / f.per_image;
+      if (j >= 0 && j < kMaxImagesPerCta) acc += f.extras[((size_t)cta * kXCols + c + j) * 256 + n];
+    }
+    out[(size_t)b * 256 + n] = acc;
+  }
+}
+
+// blocks 0..B-1: latent gradients of image b; block B: rgb-head thin outputs; block B+1: transient-head thin outputs
+__global__ void __launch_bounds__(256) bwd_finish2_kernel(const FinishParams f) {
+  const int n = threadIdx.x;
+  const float* gimg = f.img;
+  const float* gtimg = f.img + (size_t)f.B * 256;
+  if ((int)blockIdx.x < f.B) {
+    const int b = blockIdx.x;
+    if (n < f.n_light && f.d_lat_light) {
+      float acc = 0.f;
+      for (int i = 0; i < 256; ++i) acc = fmaf(gimg[b * 256 + i], f.W_r0[i * f.ld_r0 + 256 + f.vc + 3 + n], acc);
+      f.d_lat_light[b * f.n_light + n] = acc;
+    } else if (n >= 64 && n - 64 < f.n_trans && f.d_lat_trans) {
+      const int k = n - 64;
+      float acc = 0.f;
+      for (int i = 0; i < 256; ++i) acc = fmaf(gtimg[b * 256 + i], f.W_t0[i * f.ld_t0 + 256 + k], acc);
+      f.d_lat_trans[b * f.n_trans + k] = acc;
+    }
+    return;
+  }
+  const bool trans = (int)blockIdx.x == f.B + 1;
+  float* const* g = f.g + (trans ? 8 : 0);
+  const float* gi = trans ? gtimg : gimg;
+  g[5][n] = f.tot[(kXdb + (trans ? 2 : 0)) * 256 + n];          // db2
+  g[3][n] = f.tot[(kXdb + (trans ? 3 : 1)) * 256 + n];          // db1
+  float b0 = 0.f;
+  for (int b = 0; b < f.B; ++b) b0 += gi[b * 256 + n];
+  g[1][n] = b0;                                                  // db0
+  if (!trans) {
+    float* row = g[0] + (size_t)n * f.ld_r0 + 256;
+    for (int i = 0; i < f.vc; ++i) row[i] = f.tot[(kXview + i) * 256 + n];
+    for (int j = 0; j < 3; ++j) row[f.vc + j] = f.tot[(kXxyz + j) * 256 + n];
+    for (int k = 0; k < f.n_light; ++k) {
+      float acc = 0.f;
+      for (int b = 0; b < f.B; ++b) acc = fmaf(gi[b * 256 + n], f.lat_light[b * f.n_light + k], acc);
+      row[f.vc + 3 + k] = acc;
+    }
+    for (int j = 0; j < 3; ++j) g[6][j * 256 + n] = f.tot[(kXwr + j) * 256 + n];
+  } else {
+    float* row = g[0] + (size_t)n * f.ld_t0 + 256;
+    for (int k = 0; k < f.n_trans; ++k) {
+      float acc = 0.f;
+      for (int b = 0; b < f.B; ++b) acc = fmaf(gi[b * 256 + n], f.lat_trans[b * f.n_trans + k], acc);
+      row[k] = acc;
+    }
+    for (int j = 0; j < 5; ++j) g[6][j * 256 + n] = f.tot[(kXwt + j) * 256 + n];
+  }
+  const int nb = trans ? 5 : 3, off = trans ? 3 : 0;
+  if (n < nb) {
+    float acc = 0.f;
+    for (int i = 0; i < f.grid * 4; ++i) acc += f.thin_sums[(size_t)i * 8 + off + n];
+    g[7][n] = acc;                                               // db3
+  }
+}
+
+// second stage of the weight-gradient GEMMs, writing each job with its own leading dimension (no torch.cat afterwards)
+struct DwOut { float* ptr[kDwMaxJobs]; long long ld[kDwMaxJobs]; };
+__global__ void dw_reduce_kernel(const float* __restrict__ partial, int splits, int n_jobs, const DwOut o) {
+  const long long total = (long long)n_jobs * 65536;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int job = (int)(i >> 16), rc = (int)(i & 65535);
+    float acc = 0.f;
+    for (int z = 0; z < splits; ++z) acc += partial[((size_t)z * n_jobs + job) * 65536 + rc];
+    o.ptr[job][(size_t)(rc >> 8) * o.ld[job] + (rc & 255)] = acc;
   }
 }
 
@@ -575,5 +1065,96 @@ TP_API int tp_tc_pack_images(const float* in, int64_t S, void* images, int slot,
   if (S == 0) return TP_OK;
   tcb::pack_images_kernel<<<tp_grid_for(((S + 127) / 128) * 4096, 256, 8), 256, 0, (cudaStream_t)stream>>>(
       in, S, reinterpret_cast<uint8_t*>(images), slot, n_slots);
+  return tp_launch_status();
+}
+
+static int fused_grid(long long n_tiles) {
+  int grid = tp_num_sms();
+  if (n_tiles < grid) grid = (int)n_tiles;
+  return grid < 1 ? 1 : grid;
+}
+
+TP_API int tp_tc_heads_backward_supported(int64_t S, int64_t per_image) {
+  if (S < 1 || per_image < 1) return 0;
+  const long long n_tiles = (S + 127) / 128;
+  const int grid = fused_grid(n_tiles);
+  const long long span = ((n_tiles + grid - 1) / grid) * 128;      // samples of the longest contiguous CTA range
+  return (span - 1 + per_image - 1) / per_image + 1 <= tcb::kMaxImagesPerCta ? 1 : 0;
+}
+
+TP_API int64_t tp_tc_heads_backward_workspace(int64_t S, int B) {
+  const long long n_tiles = (S + 127) / 128;
+  const int grid = fused_grid(n_tiles);
+  return (int64_t)grid * tcb::kXCols * 256 + (int64_t)grid * 32 + tcb::kXCols * 256 + 2LL * B * 256 +
+         (int64_t)tp_tc_dw_splits(S, 6) * 6 * 65536;
+}
+
+TP_API int tp_tc_heads_backward(const float* dz_rgb, const float* dz_trans, int64_t S, int N, int64_t per_image, int B,
+                                const float* center, const float* ray, const float* depth, int L_view,
+                                const void* packed_bwd, const void* saved, void* dz_images, const float* W_r0,
+                                int64_t ld_r0, const float* W_t0, int64_t ld_t0, const float* lat_light, int n_light,
+                                const float* lat_trans, int n_trans, float* const* grads, float* d_lat_light,
+                                float* d_lat_trans, float* workspace, int64_t workspace_floats, void* stream) {
+  if (!dz_rgb || !dz_trans || !center || !ray || !depth || !packed_bwd || !saved || !dz_images || !W_r0 || !W_t0 ||
+      !lat_light || !lat_trans || !grads || !workspace)
+    return TP_ERR_BAD_ARG;
+  for (int i = 0; i < 16; ++i)
+    if (!grads[i]) return TP_ERR_BAD_ARG;
+  if (S < 1 || N < 1 || per_image < 1 || B < 1 || L_view < 0 || L_view > 4 || n_light < 0 || n_light > 64 || n_trans < 0 ||
+      n_trans > 64 || (int64_t)B * per_image < S)
+    return TP_ERR_BAD_SHAPE;
+  const int vc = 3 + 6 * L_view;
+  if (ld_r0 < 256 + vc + 3 + n_light || ld_t0 < 256 + n_trans) return TP_ERR_BAD_SHAPE;
+  if (!tp_tc_heads_backward_supported(S, per_image)) return TP_ERR_BAD_SHAPE;
+  if (((uintptr_t)packed_bwd & 15) || ((uintptr_t)saved & 15) || ((uintptr_t)dz_images & 15) || ((uintptr_t)workspace & 15))
+    return TP_ERR_ALIGN;
+  if (!tp_device_is_sm100()) return TP_ERR_ARCH;
+  if (workspace_floats < tp_tc_heads_backward_workspace(S, B)) return TP_ERR_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long n_tiles = (S + 127) / 128;
+  const int grid = fused_grid(n_tiles);
+  float* extras = workspace;
+  float* thin_sums = extras + (size_t)grid * tcb::kXCols * 256;
+  float* tot = thin_sums + (size_t)grid * 32;
+  float* img = tot + tcb::kXCols * 256;
+  float* partial = img + 2 * (size_t)B * 256;
+
+  tcb::FusedParams fp;
+  fp.b.dz_rgb = dz_rgb; fp.b.dz_trans = dz_trans; fp.b.S = S;
+  fp.b.packed = reinterpret_cast<const uint8_t*>(packed_bwd);
+  fp.b.saved = reinterpret_cast<const uint8_t*>(saved);
+  fp.b.dz_out = reinterpret_cast<uint8_t*>(dz_images);
+  fp.center = center; fp.ray = ray; fp.depth = depth; fp.N = N; fp.per_image = per_image; fp.L_view = L_view;
+  fp.extras = extras; fp.thin_sums = thin_sums;
+  cudaError_t e = cudaFuncSetAttribute(tcb::backward_chain_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)tcb::kSmemBytesF);
+  if (e != cudaSuccess) return (int)e;
+  tcb::backward_chain_fused_kernel<<<grid, tcb::kThreads, tcb::kSmemBytesF, st>>>(fp);
+
+  tcb::FinishParams f;
+  f.extras = extras; f.thin_sums = thin_sums; f.grid = grid; f.n_tiles = n_tiles; f.per_image = per_image;
+  f.B = B; f.vc = vc; f.n_light = n_light; f.n_trans = n_trans; f.tot = tot; f.img = img;
+  f.W_r0 = W_r0; f.ld_r0 = ld_r0; f.W_t0 = W_t0; f.ld_t0 = ld_t0; f.lat_light = lat_light; f.lat_trans = lat_trans;
+  for (int i = 0; i < 16; ++i) f.g[i] = grads[i];
+  f.d_lat_light = d_lat_light; f.d_lat_trans = d_lat_trans;
+  tcb::bwd_finish1_kernel<<<tcb::kXCols, 256, 0, st>>>(f);
+  tcb::bwd_finish2_kernel<<<B + 2, 256, 0, st>>>(f);
+
+  // the six 256 x 256 weight gradients: layers 2, 1, 0 of the rgb head, then of the transient head
+  tcb::DwParams p;
+  p.a_images = reinterpret_cast<const uint8_t*>(dz_images); p.a_nslots = tcb::kDzSlots;
+  p.b_images = reinterpret_cast<const uint8_t*>(saved); p.b_nslots = tcb::kFwdSlots;
+  const int a_slot[6] = {0, 1, 2, 3, 4, 5}, b_slot[6] = {2, 1, 0, 5, 4, 0};
+  for (int j = 0; j < 6; ++j) { p.a_slot[j] = a_slot[j]; p.b_slot[j] = b_slot[j]; }
+  p.n_jobs = 6; p.splits = tp_tc_dw_splits(S, 6); p.n_tiles = n_tiles; p.partial = partial; p.swap_strides = 0;
+  e = cudaFuncSetAttribute(tcb::dw_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcb::kDwSmemBytes);
+  if (e != cudaSuccess) return (int)e;
+  tcb::dw_gemm_kernel<<<p.splits * 6, tcb::kThreads, tcb::kDwSmemBytes, st>>>(p);
+  tcb::DwOut o;
+  const int gidx[6] = {4, 2, 0, 12, 10, 8};          // grads[] index of dW2, dW1, dW0 per head
+  for (int j = 0; j < 6; ++j) { o.ptr[j] = grads[gidx[j]]; o.ld[j] = 256; }
+  o.ld[2] = ld_r0; o.ld[5] = ld_t0;
+  for (int j = 6; j < tcb::kDwMaxJobs; ++j) { o.ptr[j] = nullptr; o.ld[j] = 0; }
+  tcb::dw_reduce_kernel<<<tp_grid_for(6 * 65536, 256, 4), 256, 0, st>>>(partial, p.splits, 6, o);
   return tp_launch_status();
 }

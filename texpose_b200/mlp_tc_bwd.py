@@ -6,6 +6,7 @@ the trunk is frozen (layers/nerf_static_transient_light.py:34).
 from __future__ import annotations
 
 import ctypes
+import os
 
 import torch
 
@@ -101,8 +102,54 @@ def unpack(images, slot, n_slots, S):
     return out
 
 
+def fused_supported(S, per_image) -> bool:
+    return bool(_C.load().tp_tc_heads_backward_supported(S, per_image))
+
+
 def heads_backward(cfg, sv, S, per_image, rgb_p, trans_p, g_rgb, g_density, g_uncert, need_lat_trans, need_lat_light):
-    """Returns (rgb layer grads [(dW,db)]*4, trans layer grads, d_lat_trans, d_lat_light)."""
+    """Returns (rgb layer grads [(dW,db)]*4, trans layer grads, d_lat_trans, d_lat_light).
+
+    Default: five launches (tp_tc_heads_backward).  The multi-kernel sequence below it is kept for batches whose images are
+    so small that one CTA's tile range would touch more than four of them, and as the cross-check in the tests
+    (TEXPOSE_BWD=unfused)."""
+    if os.environ.get("TEXPOSE_BWD", "fused") != "unfused" and fused_supported(S, per_image):
+        return heads_backward_fused(cfg, sv, S, per_image, rgb_p, trans_p, g_rgb, g_density, g_uncert, need_lat_trans,
+                                    need_lat_light)
+    return heads_backward_unfused(cfg, sv, S, per_image, rgb_p, trans_p, g_rgb, g_density, g_uncert, need_lat_trans,
+                                  need_lat_light)
+
+
+def heads_backward_fused(cfg, sv, S, per_image, rgb_p, trans_p, g_rgb, g_density, g_uncert, need_lat_trans, need_lat_light):
+    dev = sv.rgb.device
+    geom = sv.geom
+    lt, ll = sv.lat
+    B, R, N = geom["shape"]
+    dz_rgb = torch.empty(S, 3, device=dev)
+    dz_trans = torch.empty(S, 5, device=dev)
+    _C.call("tp_stl_output_grad", ops._p(sv.rgb), ops._p(sv.density), ops._p(sv.uncert), ops._p(g_rgb), ops._p(g_density),
+            ops._p(g_uncert), S, ops._p(dz_rgb), ops._p(dz_trans), None, ops._stream())
+    packed = pack_bwd(cfg.packed, rgb_p, trans_p)
+    lib = _C.load()
+    dz = torch.empty(lib.tp_tc_dz_bytes(S), dtype=torch.uint8, device=dev)
+    ws = torch.empty(lib.tp_tc_heads_backward_workspace(S, B), device=dev)
+    grads = []
+    for layers in (rgb_p, trans_p):
+        for W, b in layers:
+            grads += [torch.empty_like(W), torch.empty_like(b)]
+    W_r0, W_t0 = rgb_p[0][0], trans_p[0][0]
+    d_ll = torch.empty(B, cfg.n_latent_light, device=dev) if need_lat_light else None
+    d_lt = torch.empty(B, cfg.n_latent_trans, device=dev) if need_lat_trans else None
+    center, ray, depth = geom["center"], geom["ray"], geom["depth"]
+    gp = (ctypes.c_void_p * 16)(*[t.data_ptr() for t in grads])
+    _C.call("tp_tc_heads_backward", ops._p(dz_rgb), ops._p(dz_trans), S, N, per_image, B, ops._p(center), ops._p(ray),
+            ops._p(depth), cfg.L_view, ops._p(packed), ops._p(sv.images), ops._p(dz), ops._p(W_r0), W_r0.stride(0),
+            ops._p(W_t0), W_t0.stride(0), ops._p(ll), cfg.n_latent_light, ops._p(lt), cfg.n_latent_trans, gp,
+            ops._p(d_ll), ops._p(d_lt), ops._p(ws), ws.numel(), ops._stream())
+    pairs = [(grads[2 * i], grads[2 * i + 1]) for i in range(8)]
+    return pairs[:4], pairs[4:], d_lt, d_ll
+
+
+def heads_backward_unfused(cfg, sv, S, per_image, rgb_p, trans_p, g_rgb, g_density, g_uncert, need_lat_trans, need_lat_light):
     dev = sv.rgb.device
     geom = sv.geom
     lt, ll = sv.lat
