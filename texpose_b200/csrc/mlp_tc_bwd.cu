@@ -743,7 +743,7 @@ struct FinishParams {
   long long n_tiles, per_image;
   int B, vc, n_light, n_trans;
   float* tot;                 // [kXCols][256] column totals over the CTAs (indicator columns unused)
-  float* img;                 // [2][B][256] per-image sums of rgb dz0 / transient dz0
+  float* img;                 // [2][4][B][256] per-image sums of rgb dz0 / transient dz0, one slab per indicator column
   const float* W_r0; long long ld_r0;      // mlp_rgb[0].weight  [256, 256 + vc + 3 + n_light]
   const float* W_t0; long long ld_t0;      // mlp_trans[0].weight [256, 256 + n_trans]
   const float* lat_light;     // [B, n_light]
@@ -753,74 +753,124 @@ struct FinishParams {
   float* d_lat_trans;         // [B, n_trans] or NULL
 };
 
-// one block per compact column; fixed CTA order
+// one block per compact column; fixed CTA order.  Indicator columns: column j of a CTA holds the sum over the samples of
+// image (first image of the CTA's range + j) -> segmented sum over the CTAs into imgj[head][j][b][:] (images a (CTA, j) pair
+// never touches stay zero; finish2 adds the four j slabs).
 __global__ void __launch_bounds__(256) bwd_finish1_kernel(const FinishParams f) {
+  __shared__ int img0_s[1024];
   const int c = blockIdx.x, n = threadIdx.x;
   const bool ind_r = c >= kXimgR && c < kXimgR + kMaxImagesPerCta, ind_t = c >= kXimgT && c < kXimgT + kMaxImagesPerCta;
+  const float* src = f.extras + (size_t)c * 256 + n;
+  const size_t stride = (size_t)kXCols * 256;
   if (!ind_r && !ind_t) {
     float acc = 0.f;
-    for (int cta = 0; cta < f.grid; ++cta) acc += f.extras[((size_t)cta * kXCols + c) * 256 + n];
+    int cta = 0;
+    for (; cta + 8 <= f.grid; cta += 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = src[(size_t)(cta + u) * stride];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc += v[u];
+    }
+    for (; cta < f.grid; ++cta) acc += src[(size_t)cta * stride];
     f.tot[c * 256 + n] = acc;
     return;
   }
-  if (c != kXimgR && c != kXimgT) return;
-  float* out = f.img + (size_t)(ind_t ? 1 : 0) * f.B * 256;
-  for (int b = 0; b < f.B; ++b) {
-    float acc = 0.f;
-    for (int cta = 0; cta < f.grid; ++cta) {
-      long long t0, t1;
-      tile_range(f.n_tiles, f.grid, cta, t0, t1);
-      const long long j = b - (t0 * 128) / f.per_image;
-      if (j >= 0 && j < kMaxImagesPerCta) acc += f.extras[((size_t)cta * kXCols + c + j) * 256 + n];
-    }
-    out[(size_t)b * 256 + n] = acc;
+  for (int cta = n; cta < f.grid; cta += 256) {
+    long long t0, t1;
+    tile_range(f.n_tiles, f.grid, cta, t0, t1);
+    img0_s[cta] = (int)((t0 * 128) / f.per_image);
   }
+  __syncthreads();
+  const int j = ind_r ? c - kXimgR : c - kXimgT;
+  float* out = f.img + ((size_t)(ind_t ? 1 : 0) * kMaxImagesPerCta + j) * f.B * 256 + n;
+  for (int b = 0; b < f.B; ++b) out[(size_t)b * 256] = 0.f;
+  int cur = -1;
+  float acc = 0.f;
+  for (int cta0 = 0; cta0 < f.grid; cta0 += 8) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = cta0 + u < f.grid ? src[(size_t)(cta0 + u) * stride] : 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (cta0 + u >= f.grid) break;
+      const int b = img0_s[cta0 + u] + j;
+      if (b != cur) {
+        if (cur >= 0 && cur < f.B) out[(size_t)cur * 256] = acc;
+        cur = b;
+        acc = 0.f;
+      }
+      acc += v[u];
+    }
+  }
+  if (cur >= 0 && cur < f.B) out[(size_t)cur * 256] = acc;
 }
 
 // blocks 0..B-1: latent gradients of image b; block B: rgb-head thin outputs; block B+1: transient-head thin outputs
 __global__ void __launch_bounds__(256) bwd_finish2_kernel(const FinishParams f) {
   const int n = threadIdx.x;
-  const float* gimg = f.img;
-  const float* gtimg = f.img + (size_t)f.B * 256;
+  extern __shared__ float gsm[];       // blocks < B: [2][256] sums of image b; blocks >= B: nothing
+  const size_t slab = (size_t)f.B * 256;
+  auto image_sum = [&](int head, int b, int i) {
+    const float* q = f.img + (size_t)head * kMaxImagesPerCta * slab + (size_t)b * 256 + i;
+    return ((q[0] + q[slab]) + q[2 * slab]) + q[3 * slab];
+  };
   if ((int)blockIdx.x < f.B) {
     const int b = blockIdx.x;
+    gsm[n] = image_sum(0, b, n);
+    gsm[256 + n] = image_sum(1, b, n);
+    __syncthreads();
     if (n < f.n_light && f.d_lat_light) {
       float acc = 0.f;
-      for (int i = 0; i < 256; ++i) acc = fmaf(gimg[b * 256 + i], f.W_r0[i * f.ld_r0 + 256 + f.vc + 3 + n], acc);
+      for (int i = 0; i < 256; ++i) acc = fmaf(gsm[i], f.W_r0[i * f.ld_r0 + 256 + f.vc + 3 + n], acc);
       f.d_lat_light[b * f.n_light + n] = acc;
     } else if (n >= 64 && n - 64 < f.n_trans && f.d_lat_trans) {
       const int k = n - 64;
       float acc = 0.f;
-      for (int i = 0; i < 256; ++i) acc = fmaf(gtimg[b * 256 + i], f.W_t0[i * f.ld_t0 + 256 + k], acc);
+      for (int i = 0; i < 256; ++i) acc = fmaf(gsm[256 + i], f.W_t0[i * f.ld_t0 + 256 + k], acc);
       f.d_lat_trans[b * f.n_trans + k] = acc;
     }
     return;
   }
   const bool trans = (int)blockIdx.x == f.B + 1;
+  const int head = trans ? 1 : 0;
   float* const* g = f.g + (trans ? 8 : 0);
-  const float* gi = trans ? gtimg : gimg;
   g[5][n] = f.tot[(kXdb + (trans ? 2 : 0)) * 256 + n];          // db2
   g[3][n] = f.tot[(kXdb + (trans ? 3 : 1)) * 256 + n];          // db1
   float b0 = 0.f;
-  for (int b = 0; b < f.B; ++b) b0 += gi[b * 256 + n];
+  for (int b = 0; b < f.B; ++b) b0 += image_sum(head, b, n);
   g[1][n] = b0;                                                  // db0
   if (!trans) {
     float* row = g[0] + (size_t)n * f.ld_r0 + 256;
     for (int i = 0; i < f.vc; ++i) row[i] = f.tot[(kXview + i) * 256 + n];
     for (int j = 0; j < 3; ++j) row[f.vc + j] = f.tot[(kXxyz + j) * 256 + n];
-    for (int k = 0; k < f.n_light; ++k) {
-      float acc = 0.f;
-      for (int b = 0; b < f.B; ++b) acc = fmaf(gi[b * 256 + n], f.lat_light[b * f.n_light + k], acc);
-      row[f.vc + 3 + k] = acc;
+    float acc[64];
+#pragma unroll
+    for (int k = 0; k < 64; ++k) acc[k] = 0.f;
+    for (int b = 0; b < f.B; ++b) {
+      const float gb = image_sum(0, b, n);
+#pragma unroll
+      for (int k = 0; k < 64; ++k)
+        if (k < f.n_light) acc[k] = fmaf(gb, f.lat_light[b * f.n_light + k], acc[k]);
     }
+#pragma unroll
+    for (int k = 0; k < 64; ++k)
+      if (k < f.n_light) row[f.vc + 3 + k] = acc[k];
     for (int j = 0; j < 3; ++j) g[6][j * 256 + n] = f.tot[(kXwr + j) * 256 + n];
   } else {
     float* row = g[0] + (size_t)n * f.ld_t0 + 256;
-    for (int k = 0; k < f.n_trans; ++k) {
-      float acc = 0.f;
-      for (int b = 0; b < f.B; ++b) acc = fmaf(gi[b * 256 + n], f.lat_trans[b * f.n_trans + k], acc);
-      row[k] = acc;
+    float acc[64];
+#pragma unroll
+    for (int k = 0; k < 64; ++k) acc[k] = 0.f;
+    for (int b = 0; b < f.B; ++b) {
+      const float gb = image_sum(1, b, n);
+#pragma unroll
+      for (int k = 0; k < 64; ++k)
+        if (k < f.n_trans) acc[k] = fmaf(gb, f.lat_trans[b * f.n_trans + k], acc[k]);
     }
+#pragma unroll
+    for (int k = 0; k < 64; ++k)
+      if (k < f.n_trans) row[k] = acc[k];
     for (int j = 0; j < 5; ++j) g[6][j * 256 + n] = f.tot[(kXwt + j) * 256 + n];
   }
   const int nb = trans ? 5 : 3, off = trans ? 3 : 0;
@@ -1085,7 +1135,7 @@ TP_API int tp_tc_heads_backward_supported(int64_t S, int64_t per_image) {
 TP_API int64_t tp_tc_heads_backward_workspace(int64_t S, int B) {
   const long long n_tiles = (S + 127) / 128;
   const int grid = fused_grid(n_tiles);
-  return (int64_t)grid * tcb::kXCols * 256 + (int64_t)grid * 32 + tcb::kXCols * 256 + 2LL * B * 256 +
+  return (int64_t)grid * tcb::kXCols * 256 + (int64_t)grid * 32 + tcb::kXCols * 256 + 8LL * B * 256 +
          (int64_t)tp_tc_dw_splits(S, 6) * 6 * 65536;
 }
 
@@ -1117,7 +1167,7 @@ TP_API int tp_tc_heads_backward(const float* dz_rgb, const float* dz_trans, int6
   float* thin_sums = extras + (size_t)grid * tcb::kXCols * 256;
   float* tot = thin_sums + (size_t)grid * 32;
   float* img = tot + tcb::kXCols * 256;
-  float* partial = img + 2 * (size_t)B * 256;
+  float* partial = img + 8 * (size_t)B * 256;
 
   tcb::FusedParams fp;
   fp.b.dz_rgb = dz_rgb; fp.b.dz_trans = dz_trans; fp.b.S = S;
@@ -1138,7 +1188,7 @@ TP_API int tp_tc_heads_backward(const float* dz_rgb, const float* dz_trans, int6
   for (int i = 0; i < 16; ++i) f.g[i] = grads[i];
   f.d_lat_light = d_lat_light; f.d_lat_trans = d_lat_trans;
   tcb::bwd_finish1_kernel<<<tcb::kXCols, 256, 0, st>>>(f);
-  tcb::bwd_finish2_kernel<<<B + 2, 256, 0, st>>>(f);
+  tcb::bwd_finish2_kernel<<<B + 2, 256, 2 * 256 * sizeof(float), st>>>(f);
 
   // the six 256 x 256 weight gradients: layers 2, 1, 0 of the rgb head, then of the transient head
   tcb::DwParams p;
