@@ -383,8 +383,8 @@ def bench_train(args, g, opt, dev, world, timed):
     coords, _ = synth.patch_coords(B, P, seed=2)
     coords = coords.to(dev)
     idx = torch.arange(B, device=dev) % 8
-    image = torch.rand(B, P * P, 3, device=dev)
-    mask = (torch.rand(B, P * P, 1, device=dev) > 0.3).float()
+    image = torch.rand(B, 3, 128, 128, device=dev)
+    mask = (torch.rand(B, 128, 128, device=dev) > 0.3).float()
     params = [p for p in g.parameters() if p.requires_grad]
     bucket = parallel.GradBucket(params)
     g.train()
@@ -394,15 +394,16 @@ def bench_train(args, g, opt, dev, world, timed):
             p.grad = None
         ret = g.render(opt_t, pose, intr=intr, ray_idx=coords, depth_range=(zn[:, :, None], zf[:, :, None]),
                        sample_idx=idx, mode="train")
-        loss = (mask * ((image - ret.rgb) ** 2 / ret.uncert ** 2)).sum() / (mask.sum() + 1e-5) \
-            + (5 + torch.log(ret.uncert ** 2).mean() / 2) + 0.01 * ret.density[..., -1].mean()
-        loss.backward()
+        var = AttrDict(idx=idx, image=image, obj_mask=mask, ray_idx=coords)
+        var.update(ret)
+        loss = g.compute_loss(opt_t, var, mode="train")      # patch gather + render / uncert / trans_reg terms + seeds, fused
+        loss["all"].backward()
         bucket.allreduce_mean()
 
     ms, _ = timed(step, max(3, args.steps // 2), 2)
     g.eval()
     samples = B * P * P * NS
-    return dict(workload="C3 train step fwd+bwd, 4096 rays x 128 samples per GPU, bf16 tcgen05 fwd + bwd (dX chain, dW GEMMs), grad allreduce",
+    return dict(workload="C3 train step fwd+bwd, 4096 rays x 128 samples per GPU, fused patch loss, bf16 tcgen05 fwd + bwd (dX chain with thin gradients, dW GEMMs), grad allreduce",
                 value=world * samples / (ms * 1e-3), unit="samples/s", ms_per_step=ms, grad_allreduce_bytes=bucket.flat.numel() * 4)
 
 

@@ -246,6 +246,21 @@ int tp_tc_thin_dw(const float* thin, int M, const void* images, int slot, int n_
 /* row-major fp32 [S,256] -> bf16 tile image slot (interop / tests). */
 int tp_tc_pack_images(const float* in, int64_t S, void* images, int slot, int n_slots, void* stream);
 
+/* ---- fused patch gather + ray-wise losses + backward seeds ---------------------------------------- */
+
+/* Graph.compute_loss(train_step='nerf') ray-wise terms and Model.summarize_loss (model/nerf_adapt_st_gan.py:712-763,
+ * model/base.py:145-157) in two launches.  image [B,3,H,W]; obj_mask [B,H,W] raw (>0 = object); coords [B,R,2] in [-1,1]
+ * (R = h*w patch rays); rgb [B,R,3], uncert [B,R], density [B*R*N,2] = outputs of the render.  terms: bit 0 render
+ * (uncertainty-weighted masked MSE), bit 1 uncert (5 + mean log u^2 / 2), bit 2 trans_reg (mean transient density); w_* =
+ * 10^loss_weight.  Writes image_sample [B,3,R] (bilinear, align_corners=True), mask_sample [B,R] (nearest,
+ * align_corners=False), losses[4] = {render, uncert, trans_reg, all}, and d(all)/d{rgb, uncert, density} (g_density [B*R*N,2]
+ * may be NULL).  Deterministic (fixed-order reductions).  workspace >= tp_patch_loss_workspace() floats. */
+int64_t tp_patch_loss_workspace(void);
+int tp_patch_loss(const float* image, const float* obj_mask, const float* coords, int B, int R, int H, int W,
+                  const float* rgb, const float* uncert, const float* density, int N, float w_render, float w_uncert,
+                  float w_trans_reg, int terms, float* image_sample, float* mask_sample, float* losses, float* g_rgb,
+                  float* g_uncert, float* g_density, float* workspace, int64_t workspace_floats, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -179,6 +179,43 @@ def case_render_train(ns, opt128):
     return out
 
 
+def case_loss(ns, opt128):
+    """Graph.compute_loss(train_step='nerf') + Model.summarize_loss of the reference (model/nerf_adapt_st_gan.py:712-763,
+    model/base.py:145-157) with the yaml's ray-wise terms (render, uncert, trans_reg); the VGG / GAN / Lab terms are switched
+    off (loss_weight None) -- they need pretrained nets and are outside the path.  Also FlexPatchSampler (seeded)."""
+    import copy
+    from easydict import EasyDict as edict
+    opt = copy.deepcopy(opt128)
+    opt.loss_weight.feat = None
+    opt.loss_weight.gan_nerf = None
+    opt.loss_weight.lab = None
+    opt.gan = None
+    B, P, N = 3, 8, 16
+    g = ref_import.build_graph(ns, opt, n_images=4, seed=0)
+    gen = torch.Generator().manual_seed(31)
+    image = torch.rand(B, 3, 128, 128, generator=gen)
+    obj_mask = (torch.rand(B, 128, 128, generator=gen) > 0.4).float() * 255.0      # masks arrive as 0 / 255 maps
+    coords, _ = synth.patch_coords(B, P, seed=5)
+    coords[1] = coords[1] * 1.02                                                     # a few samples land outside [-1, 1]
+    rgb = torch.rand(B, P * P, 3, generator=gen).requires_grad_(True)
+    uncert = (torch.rand(B, P * P, 1, generator=gen) * 0.8 + 0.05).requires_grad_(True)
+    density = (torch.rand(B, P * P, N, 2, generator=gen) * 3).requires_grad_(True)
+    var = edict(idx=torch.arange(B), rgb=rgb, uncert=uncert, density=density, image=image, obj_mask=obj_mask,
+                ray_idx=coords, opacity=torch.rand(B, P * P, 1, generator=gen))
+    loss = g.compute_loss(opt, var, mode="train", train_step="nerf")
+    base = __import__("importlib").import_module("model.base")
+    loss = base.Model.summarize_loss(None, opt, var, loss)
+    loss.all.backward()
+    torch.manual_seed(77)
+    sampler = ns.patch_sampler.FlexPatchSampler(random_shift=True, random_scale=True, min_scale=0.25, max_scale=1.0)
+    fc, fs = sampler(nbatch=5, patch_size=6, device="cpu")
+    return dict(image=image, obj_mask=obj_mask, coords=coords, rgb=rgb, uncert=uncert, density=density, H=128, W=128,
+                image_sample=var.image_sample, mask_sample=var.mask_sample, l_render=loss.render, l_uncert=loss.uncert,
+                l_trans_reg=loss.trans_reg, l_all=loss["all"], g_rgb=rgb.grad, g_uncert=uncert.grad, g_density=density.grad,
+                w_render=opt.loss_weight.render, w_uncert=opt.loss_weight.uncert, w_trans_reg=opt.loss_weight.trans_reg,
+                flex_coords=fc, flex_scales=fs, flex_seed=77)
+
+
 def case_plain(ns):
     """layers/nerf.py NeRF (trunk trainable) with the nerf_lm_env.yaml dims: forward, composite, grads."""
     opt = ref_import.load_yaml_opt("nerf_lm_env", H=480, W=640)
@@ -233,6 +270,7 @@ def main():
         render_train=lambda: case_render_train(ns, opt128),
         plain=lambda: case_plain(ns),
         normals=case_normals,
+        loss=lambda: case_loss(ns, opt128),
     )
     for name, fn in cases.items():
         d = _np(fn())

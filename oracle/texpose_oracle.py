@@ -317,6 +317,61 @@ def nerf_losses(rgb: Tensor, uncert: Tensor, density: Tensor, image: Tensor, mas
     return render, unc, trans_reg
 
 
+def sample_patch_targets(image: Tensor, obj_mask: Tensor, coords: Tensor):
+    """Patch gather of Graph.compute_loss (model/nerf_adapt_st_gan.py:716-731): image [B,3,H,W] bilinear with
+    align_corners=True; mask binarised (>0), sampled with mode='nearest' and the DEFAULT align_corners=False, i.e. pixel
+    x = ((c+1)*W-1)/2 rounded half-to-even, zero outside the image.  Returns [B,3,h,w], [B,1,h,w]."""
+    B, _, H, W = image.shape
+    m = (obj_mask > 0).float().contiguous().view(B, 1, H, W)
+    img_s = F.grid_sample(image.contiguous(), coords, mode="bilinear", align_corners=True)
+    x = ((coords[..., 0] + 1) * W - 1) / 2
+    y = ((coords[..., 1] + 1) * H - 1) / 2
+    xi, yi = torch.round(x).long(), torch.round(y).long()          # torch.round = nearbyint (half to even)
+    inside = (xi >= 0) & (xi < W) & (yi >= 0) & (yi < H)
+    flat = (yi.clamp(0, H - 1) * W + xi.clamp(0, W - 1)).view(B, -1)
+    vals = torch.gather(m.view(B, H * W), 1, flat).view_as(x)
+    mask_s = torch.where(inside, vals, torch.zeros_like(vals))[:, None]
+    return img_s, mask_s
+
+
+def patch_losses(image: Tensor, obj_mask: Tensor, coords: Tensor, rgb: Tensor, uncert: Tensor, density: Tensor,
+                 w_render: Optional[float] = 0.0, w_uncert: Optional[float] = 0.0, w_trans_reg: Optional[float] = -2.0):
+    """Graph.compute_loss(train_step='nerf') ray-wise terms + Model.summarize_loss (model/nerf_adapt_st_gan.py:712-763,
+    model/base.py:145-157): rgb [B,h*w,3], uncert [B,h*w,1], density [B,h*w,N,2]; weights in log10 scale, None = term off."""
+    B, h, w, _ = coords.shape
+    img_s, mask_s = sample_patch_targets(image, obj_mask, coords)
+    rgb_i = rgb.view(B, h, w, 3).permute(0, 3, 1, 2)
+    unc_i = uncert.view(B, h, w, 1).permute(0, 3, 1, 2)
+    out = dict(image_sample=img_s, mask_sample=mask_s)
+    total = 0.0
+    if w_render is not None:
+        out["render"] = (mask_s * ((img_s - rgb_i) ** 2 / unc_i ** 2)).sum() / (mask_s.sum() + 1e-5)
+        total = total + 10 ** float(w_render) * out["render"]
+    if w_uncert is not None:
+        out["uncert"] = 5 + torch.log(uncert ** 2).mean() / 2
+        total = total + 10 ** float(w_uncert) * out["uncert"]
+    if w_trans_reg is not None:
+        out["trans_reg"] = density[..., -1].mean()
+        total = total + 10 ** float(w_trans_reg) * out["trans_reg"]
+    out["all"] = total
+    return out
+
+
+def flex_patch_coords(nbatch: int, patch_size: int, min_scale: float = 0.25, max_scale: float = 1.0):
+    """FlexPatchSampler.__call__ (tools/patch_sampler.py:80-114) with random_scale = random_shift = True and no annealing:
+    three draws from the global torch RNG in the reference's order (scales, h offset, w offset)."""
+    lin = torch.linspace(-1, 1, patch_size)
+    w, h = torch.meshgrid([lin, lin], indexing="ij")
+    h, w = h[None, ..., None], w[None, ..., None]
+    scales = torch.rand((nbatch, 1, 1, 1)) * (max_scale - min_scale) + min_scale
+    h, w = h * scales, w * scales
+    max_offset = 1 - scales
+    h_offset = (torch.rand((nbatch, 1, 1, 1)) * 2.0 - 1.0) * max_offset
+    w_offset = (torch.rand((nbatch, 1, 1, 1)) * 2.0 - 1.0) * max_offset
+    h, w = h + h_offset, w + w_offset
+    return torch.cat([h, w], dim=-1).contiguous(), scales.contiguous()
+
+
 # --------------------------------------------------------------------------------------
 # surfel info  (compute_surfelinfo.py)
 # --------------------------------------------------------------------------------------

@@ -22,14 +22,15 @@ lo, hi = [t.to(dev) for t in synth.padded_aabb()]
 zn, zf = compute_box.box_range(pose, intr, lo, hi, 128, 128, *synth.BG_RANGE)
 coords = synth.patch_coords(B, P, seed=2)[0].to(dev)
 idx = torch.arange(B, device=dev) % 8
-image = torch.rand(B, P * P, 3, device=dev)
-mask = (torch.rand(B, P * P, 1, device=dev) > 0.3).float()
+image = torch.rand(B, 3, 128, 128, device=dev)
+mask = (torch.rand(B, 128, 128, device=dev) > 0.3).float()
 for it in range(int(sys.argv[1]) if len(sys.argv) > 1 else 3):
     for p in g.parameters():
         p.grad = None
     ret = g.render(opt, pose, intr=intr, ray_idx=coords, depth_range=(zn[:, :, None], zf[:, :, None]), sample_idx=idx, mode="train")
-    loss = (mask * ((image - ret.rgb) ** 2 / ret.uncert ** 2)).sum() / (mask.sum() + 1e-5) \
-        + (5 + torch.log(ret.uncert ** 2).mean() / 2) + 0.01 * ret.density[..., -1].mean()
+    var = AttrDict(idx=idx, image=image, obj_mask=mask, ray_idx=coords)
+    var.update(ret)
+    loss = g.compute_loss(opt, var, mode="train")["all"]
     loss.backward()
 torch.cuda.synchronize()
 print("ok", float(loss))

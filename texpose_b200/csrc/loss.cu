@@ -1,0 +1,170 @@
+// Fused patch gather + ray-wise loss terms + backward seeds.
+//
+// Reference: Graph.compute_loss(train_step='nerf') (model/nerf_adapt_st_gan.py:712-763) and Model.summarize_loss
+// (model/base.py:145-157).  There it is ~30 aten kernels (4 grid_samples, permutes, elementwise chains, 4 reductions) plus
+// their autograd replay; here two launches produce the sampled targets, the loss terms and d(loss.all)/d{rgb, uncert,
+// density} directly:
+//
+//   patch_loss_partial_kernel   per ray: bilinear image sample (align_corners=True, bit-exact with torch's CPU kernel),
+//                               nearest mask sample (align_corners=False: x = ((c+1)W-1)/2, round half to even, zero outside),
+//                               block partials of  sum m (I-rgb)^2/u^2,  sum m,  sum log u^2;  grid-stride partials of
+//                               sum density[...,1].
+//   patch_loss_grad_kernel      fixed-order reduction of the partials (deterministic), the loss scalars, and the seeds
+//                               g_rgb = w_r * -2 m (I-rgb) / u^2 / (M + 1e-5)
+//                               g_unc = w_r * -2 m sum_c (I-rgb)^2 / u^3 / (M + 1e-5) + w_u / (u * rays)
+//                               g_density[..., 1] = w_t / samples.
+// HBM-bound; algorithmic bytes: 40 B/ray in + 32 B/ray out, 8 B/sample in + 8 B/sample out (the density terms).
+#include "bilinear.cuh"
+#include "../../include/texpose_b200.h"
+
+namespace {
+
+constexpr int kLossThreads = 256;
+
+struct LossParams {
+  const float* image;      // [B,3,H,W]
+  const float* obj_mask;   // [B,H,W] raw map (> 0 = object)
+  const float* coords;     // [B,R,2] in [-1,1]
+  int B, R, H, W;
+  const float* rgb;        // [B,R,3]
+  const float* uncert;     // [B,R]
+  const float* density;    // [B*R*N,2]
+  long long S;             // B*R*N
+  float w_render, w_uncert, w_trans;   // linear weights (10^w); 0 with the term bit cleared = off
+  int terms;               // bit 0 render, bit 1 uncert, bit 2 trans_reg
+  float* image_sample;     // [B,3,R]
+  float* mask_sample;      // [B,R]
+  float* losses;           // [4] render, uncert, trans_reg, all
+  float* g_rgb;            // [B,R,3]
+  float* g_uncert;         // [B,R]
+  float* g_density;        // [S,2] or NULL
+  float* partial;          // [blocks][4]
+  int blocks;
+};
+
+__device__ __forceinline__ float block_sum(float v, float* sm) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+  if (threadIdx.x == 0)
+    for (int i = 0; i < kLossThreads / 32; ++i) t += sm[i];
+  return t;     // valid in thread 0
+}
+
+__global__ void __launch_bounds__(kLossThreads) patch_loss_partial_kernel(const LossParams p) {
+  __shared__ float sm[kLossThreads / 32];
+  const long long rays = (long long)p.B * p.R;
+  float a = 0.f, m_sum = 0.f, lg = 0.f, tr = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < rays; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / p.R);
+    const long long r = i - (long long)b * p.R;
+    const float gx = p.coords[i * 2], gy = p.coords[i * 2 + 1];
+    const Bilin s = bilin_setup(gx, gy, p.H, p.W);
+    // nearest, align_corners=False (the default the reference's mask lookups fall into, :729-730)
+    const float fx = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(gx, 1.f), (float)p.W), 1.f), 2.f);
+    const float fy = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(gy, 1.f), (float)p.H), 1.f), 2.f);
+    const float rx = nearbyintf(fx), ry = nearbyintf(fy);
+    float m = 0.f;
+    if (rx >= 0.f && rx < (float)p.W && ry >= 0.f && ry < (float)p.H)
+      m = p.obj_mask[((long long)b * p.H + (int)ry) * p.W + (int)rx] > 0.f ? 1.f : 0.f;
+    p.mask_sample[i] = m;
+    const float u = p.uncert[i];
+    float e2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float* img = p.image + ((long long)b * 3 + c) * p.H * p.W;
+      const float I = bilin_apply(s, p.H, p.W, [&](int y, int x) { return img[(long long)y * p.W + x]; });
+      p.image_sample[((long long)b * 3 + c) * p.R + r] = I;
+      const float d = I - p.rgb[i * 3 + c];
+      e2 += d * d / (u * u);
+    }
+    a += m * e2;
+    m_sum += m;
+    lg += logf(u * u);
+  }
+  if (p.terms & 4)
+    for (long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x; s < p.S; s += (long long)gridDim.x * blockDim.x)
+      tr += p.density[s * 2 + 1];
+  const float A = block_sum(a, sm), M = block_sum(m_sum, sm), L = block_sum(lg, sm), T = block_sum(tr, sm);
+  if (threadIdx.x == 0) {
+    float* o = p.partial + (size_t)blockIdx.x * 4;
+    o[0] = A; o[1] = M; o[2] = L; o[3] = T;
+  }
+}
+
+__global__ void __launch_bounds__(kLossThreads) patch_loss_grad_kernel(const LossParams p) {
+  __shared__ float tot[4];
+  if (threadIdx.x < 4) {                 // every block re-reduces the (few hundred) partials in the same fixed order
+    float t = 0.f;
+    for (int i = 0; i < p.blocks; ++i) t += p.partial[(size_t)i * 4 + threadIdx.x];
+    tot[threadIdx.x] = t;
+  }
+  __syncthreads();
+  const long long rays = (long long)p.B * p.R;
+  const float denom = tot[1] + 1e-5f;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const float l_r = tot[0] / denom, l_u = 5.f + tot[2] / (float)rays / 2.f, l_t = p.S > 0 ? tot[3] / (float)p.S : 0.f;
+    float all = 0.f;
+    if (p.terms & 1) all += p.w_render * l_r;
+    if (p.terms & 2) all += p.w_uncert * l_u;
+    if (p.terms & 4) all += p.w_trans * l_t;
+    p.losses[0] = (p.terms & 1) ? l_r : 0.f;
+    p.losses[1] = (p.terms & 2) ? l_u : 0.f;
+    p.losses[2] = (p.terms & 4) ? l_t : 0.f;
+    p.losses[3] = all;
+  }
+  const float kr = (p.terms & 1) ? p.w_render / denom : 0.f;
+  const float ku = (p.terms & 2) ? p.w_uncert / (float)rays : 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < rays; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / p.R);
+    const long long r = i - (long long)b * p.R;
+    const float m = p.mask_sample[i], u = p.uncert[i];
+    const float iu2 = 1.f / (u * u);
+    float e2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float d = p.image_sample[((long long)b * 3 + c) * p.R + r] - p.rgb[i * 3 + c];
+      p.g_rgb[i * 3 + c] = -2.f * kr * m * d * iu2;
+      e2 += d * d;
+    }
+    p.g_uncert[i] = -2.f * kr * m * e2 * iu2 / u + ku / u;
+  }
+  if (p.g_density) {
+    const float gt = (p.terms & 4) && p.S > 0 ? p.w_trans / (float)p.S : 0.f;
+    float2* g = reinterpret_cast<float2*>(p.g_density);
+    for (long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x; s < p.S; s += (long long)gridDim.x * blockDim.x)
+      g[s] = make_float2(0.f, gt);
+  }
+}
+
+}  // namespace
+
+TP_API int64_t tp_patch_loss_workspace(void) { return (int64_t)tp_num_sms() * 2 * 4; }
+
+TP_API int tp_patch_loss(const float* image, const float* obj_mask, const float* coords, int B, int R, int H, int W,
+                         const float* rgb, const float* uncert, const float* density, int N, float w_render, float w_uncert,
+                         float w_trans_reg, int terms, float* image_sample, float* mask_sample, float* losses, float* g_rgb,
+                         float* g_uncert, float* g_density, float* workspace, int64_t workspace_floats, void* stream) {
+  if (!image || !obj_mask || !coords || !rgb || !uncert || !image_sample || !mask_sample || !losses || !g_rgb || !g_uncert ||
+      !workspace)
+    return TP_ERR_BAD_ARG;
+  if ((terms & 4) && !density) return TP_ERR_BAD_ARG;
+  if (B < 1 || R < 1 || H < 2 || W < 2 || N < 0 || (terms & ~7)) return TP_ERR_BAD_SHAPE;
+  if (((uintptr_t)g_density & 7)) return TP_ERR_ALIGN;
+  LossParams p;
+  p.image = image; p.obj_mask = obj_mask; p.coords = coords; p.B = B; p.R = R; p.H = H; p.W = W;
+  p.rgb = rgb; p.uncert = uncert; p.density = density; p.S = (long long)B * R * N;
+  p.w_render = w_render; p.w_uncert = w_uncert; p.w_trans = w_trans_reg; p.terms = terms;
+  p.image_sample = image_sample; p.mask_sample = mask_sample; p.losses = losses;
+  p.g_rgb = g_rgb; p.g_uncert = g_uncert; p.g_density = g_density; p.partial = workspace;
+  const long long work = (terms & 4) ? p.S : (long long)B * R;
+  p.blocks = tp_grid_for(work > (long long)B * R ? work : (long long)B * R, kLossThreads, 2);
+  if (workspace_floats < (int64_t)p.blocks * 4) return TP_ERR_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  patch_loss_partial_kernel<<<p.blocks, kLossThreads, 0, st>>>(p);
+  patch_loss_grad_kernel<<<p.blocks, kLossThreads, 0, st>>>(p);
+  return tp_launch_status();
+}

@@ -19,6 +19,7 @@ from ..config import AttrDict
 from ..layers.nerf_static_transient_light import NeRF
 from ..layers import _common
 from ..tools.ray_sampler import RaySampler
+from ..tools.patch_sampler import FlexPatchSampler
 
 
 def rotation_distance(R1, R2, eps=1e-7):
@@ -34,6 +35,7 @@ class Graph(torch.nn.Module):
         super().__init__()
         self.nerf = NeRF(opt)
         self.ray_sampler = RaySampler(opt)
+        self.patch_sampler = FlexPatchSampler(random_shift=True, random_scale=True, min_scale=0.25, max_scale=1.0)   # :424
         if n_train_images is not None:      # the reference attaches these in Model.build_networks (:56-59)
             self.latent_vars_trans = torch.nn.Embedding(n_train_images, opt.nerf.N_latent_trans)
             torch.nn.init.normal_(self.latent_vars_trans.weight)
@@ -50,6 +52,48 @@ class Graph(torch.nn.Module):
     def _b200(opt, key, default=None):
         b = opt.get("b200") if hasattr(opt, "get") else None
         return b.get(key, default) if b else default
+
+    def get_ray_idx(self, opt, var):
+        """model/nerf_adapt_st_gan.py:430-434."""
+        coords, scales = self.patch_sampler(nbatch=opt.batch_size, patch_size=opt.patch_size, device=opt.device)
+        var.ray_idx = coords
+        var.ray_scales = scales
+        return var
+
+    def compute_loss(self, opt, var, mode=None, train_step="nerf"):
+        """Ray-wise terms of model/nerf_adapt_st_gan.py:712-763 (render / uncert / trans_reg) fused with the patch gather and
+        their backward seeds (csrc/loss.cu).  `loss.all` (Model.summarize_loss, model/base.py:145-157) is computed in the same
+        pass; backpropagate it.  The VGG / Lab / GAN terms need the engine's pretrained nets and stay with it (they read
+        var.image_sample / var.mask_sample, which are filled here as in the reference)."""
+        if train_step != "nerf":
+            raise NotImplementedError("discriminator losses stay with the engine (out of the hot path, SURVEY.md 8)")
+        lw = opt.loss_weight
+        for k in ("mask", "feat", "lab", "gan_nerf", "depth"):
+            if lw.get(k) is not None:
+                raise NotImplementedError(f"loss_weight.{k}: term is outside the hot path (SURVEY.md 8, out of scope)")
+        if not opt.nerf.mask_obj:
+            raise NotImplementedError("nerf.mask_obj=False (plain MSE) is not enabled in any yaml of the path")
+        if not (opt.nerf.rand_rays and mode in ("train", "test-optim")):
+            raise NotImplementedError("full-frame loss (no patch gather) is not on the training path")
+        B = len(var.idx)
+        image = var.image.contiguous()
+        obj_mask = var.obj_mask.contiguous().view(B, opt.H, opt.W)
+        weights = (lw.get("render"), lw.get("uncert"), lw.get("trans_reg"))
+        losses, img_s, mask_s = ops.PatchLoss.apply(var.rgb, var.uncert, var.density, image, obj_mask, var.ray_idx, weights)
+        var.image_sample, var.mask_sample = img_s, mask_s
+        if "image_syn" in var and "mask_syn" in var:     # consumed only by the engine's VGG / Lab terms (:719-731)
+            F = torch.nn.functional
+            var.image_syn_sample = F.grid_sample(var.image_syn.contiguous(), var.ray_idx, mode="bilinear", align_corners=True)
+            var.mask_syn_sample = F.grid_sample((var.mask_syn > 0).float().view(B, 1, opt.H, opt.W), var.ray_idx, mode="nearest",
+                                                align_corners=False)
+        else:
+            var.image_syn_sample, var.mask_syn_sample = img_s, mask_s
+        loss = AttrDict()
+        for i, k in enumerate(("render", "uncert", "trans_reg")):
+            if weights[i] is not None:
+                loss[k] = losses[i]
+        loss["all"] = losses[3]
+        return loss
 
     # ---------------------------------------------------------------- reference interface
     def forward(self, opt, var, mode=None):

@@ -234,6 +234,53 @@ class CompositePlain(torch.autograd.Function):
         return None, d_rgb, d_den, None, None
 
 
+# ------------------------------------------------------------------------------------------------- fused losses
+
+
+class PatchLoss(torch.autograd.Function):
+    """Ray-wise terms of Graph.compute_loss(train_step='nerf') + Model.summarize_loss (model/nerf_adapt_st_gan.py:712-763,
+    model/base.py:145-157): patch gather of image / mask, the three loss terms, `all`, and the backward seeds, in two
+    launches (csrc/loss.cu).  weights: log10 loss weights (render, uncert, trans_reg); None switches a term off.
+    Returns (losses[4] = render, uncert, trans_reg, all; image_sample [B,3,h,w]; mask_sample [B,1,h,w])."""
+
+    @staticmethod
+    def forward(ctx, rgb, uncert, density, image, obj_mask, coords, weights):
+        _need_cuda(rgb, uncert, image, obj_mask, coords)
+        B, h, w, _ = coords.shape
+        R = h * w
+        H, W = image.shape[-2:]
+        rgb_c, unc_c = _f32(rgb.detach()), _f32(uncert.detach())
+        den_c = _f32(density.detach()) if density is not None else None
+        N = den_c.shape[2] if den_c is not None else 0
+        dev = rgb_c.device
+        terms, lin = 0, []
+        for i, wgt in enumerate(weights):
+            terms |= (1 << i) if wgt is not None else 0
+            lin.append(10 ** float(wgt) if wgt is not None else 0.0)
+        if den_c is None:
+            terms &= ~4
+        img_s = torch.empty(B, 3, h, w, device=dev)
+        mask_s = torch.empty(B, 1, h, w, device=dev)
+        losses = torch.empty(4, device=dev)
+        g_rgb, g_unc = torch.empty_like(rgb_c), torch.empty_like(unc_c)
+        g_den = torch.empty_like(den_c) if (den_c is not None and density.requires_grad) else None
+        ws = torch.empty(_C.load().tp_patch_loss_workspace(), device=dev)
+        _C.call("tp_patch_loss", _p(_f32(image)), _p(_f32(obj_mask)), _p(_f32(coords)), B, R, H, W, _p(rgb_c), _p(unc_c),
+                _p(den_c), N, lin[0], lin[1], lin[2], terms, _p(img_s), _p(mask_s), _p(losses), _p(g_rgb), _p(g_unc),
+                _p(g_den), _p(ws), ws.numel(), _stream())
+        ctx.seeds = (g_rgb, g_unc, g_den)
+        ctx.mark_non_differentiable(img_s, mask_s)
+        return losses, img_s, mask_s
+
+    @staticmethod
+    def backward(ctx, g_losses, _gi, _gm):
+        g_rgb, g_unc, g_den = ctx.seeds
+        ctx.seeds = None
+        # the seeds are d(all)/d(.): exact when the caller backpropagates losses[3] (Model.summarize_loss' `all`)
+        s = g_losses[3]
+        return g_rgb * s, g_unc * s, (g_den * s if g_den is not None else None), None, None, None, None
+
+
 # ------------------------------------------------------------------------------------------------- fp32 MLP layers
 
 Seg = Tuple[Tensor, int, int]   # (tensor [rows, ld], group, cols)
