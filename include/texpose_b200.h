@@ -261,6 +261,17 @@ int tp_patch_loss(const float* image, const float* obj_mask, const float* coords
                   float w_trans_reg, int terms, float* image_sample, float* mask_sample, float* losses, float* g_rgb,
                   float* g_uncert, float* g_density, float* workspace, int64_t workspace_floats, void* stream);
 
+/* ---- eval-frame epilogue --------------------------------------------------------------------------- */
+
+/* Model.evaluate_full per frame (model/nerf_adapt_st_gan.py:341-362) for B views at once, no host sync: rgb [B,HW,3]
+ * (rgb_static of the render) -> rgb_map [B,3,HW]; depth [B,HW] -> depth_map = depth / depth_scale; image [B,3,HW] * mask
+ * [B,HW] -> image_masked; mse[b] = mean((rgb_map - image_masked)^2), psnr[b] = -10 log10(mse[b]) stay on the device.
+ * workspace >= tp_eval_epilogue_workspace(B) floats. */
+int64_t tp_eval_epilogue_workspace(int B);
+int tp_eval_epilogue(const float* rgb, const float* depth, const float* image, const float* mask, int B, int64_t HW,
+                     float depth_scale, float* rgb_map, float* depth_map, float* image_masked, float* mse, float* psnr,
+                     float* workspace, int64_t workspace_floats, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -372,6 +372,18 @@ def flex_patch_coords(nbatch: int, patch_size: int, min_scale: float = 0.25, max
     return torch.cat([h, w], dim=-1).contiguous(), scales.contiguous()
 
 
+def eval_frame(rgb_static: Tensor, depth: Tensor, image: Tensor, obj_mask: Tensor, H: int, W: int, depth_scale: float):
+    """Per-frame part of Model.evaluate_full (model/nerf_adapt_st_gan.py:341-362) for native-resolution frames (the
+    interpolate calls at :347-351 are identities then): maps, image * mask, and PSNR = -10 log10 MSE -- per view."""
+    B = rgb_static.shape[0]
+    rgb_map = rgb_static.view(B, H, W, 3).permute(0, 3, 1, 2)
+    depth_map = depth.view(B, H, W, 1).permute(0, 3, 1, 2) / depth_scale
+    mask_map = obj_mask.view(B, H, W, 1).permute(0, 3, 1, 2)
+    image_masked = image.view(B, 3, H, W) * mask_map
+    mse = ((rgb_map - image_masked) ** 2).flatten(1).mean(dim=1)
+    return dict(rgb_map=rgb_map, depth_map=depth_map, image_masked=image_masked, mse=mse, psnr=-10 * mse.log10())
+
+
 # --------------------------------------------------------------------------------------
 # surfel info  (compute_surfelinfo.py)
 # --------------------------------------------------------------------------------------

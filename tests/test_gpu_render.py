@@ -116,3 +116,41 @@ def test_render_by_slices_val_and_eval_vs_oracle():
     assert (out["rgb"][:, bg.to(DEV)] == 0).all() and (out["uncert"][:, bg.to(DEV)] == 0.05).all()
     assert (out["density"][:, bg.to(DEV)] == 1).all() and (out["alpha_static"][:, bg.to(DEV)] == 1).all()
     assert (out["depth"][:, bg.to(DEV)] == 0).all()
+
+
+def test_batched_eval_views_and_frame_epilogue():
+    """the eval branch for B > 1 views equals B single-view calls (the reference is B = 1 only), the latent
+    pick runs per view on the device, and the per-frame epilogue (maps + PSNR, no host sync) matches the oracle."""
+    H, W, N = 24, 32, 32
+    opt = adapt_gan_opt(H=H, W=W, sample_intvs=N, device=DEV)
+    opt.nerf.sample_stratified = False
+    gr = _graph(opt)
+    seeds = [0, 2, 5]
+    pose = synth.poses(seeds)
+    intr = synth.intrinsics(len(seeds)).clone()
+    intr[:, :2] *= 0.05
+    lo, hi = synth.padded_aabb()
+    zn, zf = compute_box.box_range(pose.to(DEV), intr.to(DEV), lo.to(DEV), hi.to(DEV), H, W, *synth.BG_RANGE)
+    c, r = O.get_center_and_ray(pose, intr, H, W)
+    _, _, v = O.aabb_ray_intersection(lo, hi, c, r)
+    mask = v.view(len(seeds), H, W).float().to(DEV)
+    anchors = synth.poses([5, 1, 0, 3]).to(DEV)
+    opt.render.N_candidate = 1                       # nearest anchor: view 0 -> row 2, view 1 -> some row, view 2 -> row 0
+    var = AttrDict(pose=pose.to(DEV), intr=intr.to(DEV), z_near=zn, z_far=zf, obj_mask=mask, pose_anchor=anchors,
+                   idx=torch.arange(len(seeds), device=DEV))
+    with torch.no_grad():
+        out = gr.nerf_forward(opt, AttrDict(var), mode="eval_noalign")
+        for b in range(len(seeds)):
+            one = AttrDict(pose=var.pose[b:b + 1], intr=var.intr[b:b + 1], z_near=zn[b:b + 1], z_far=zf[b:b + 1],
+                           obj_mask=mask[b:b + 1], pose_anchor=anchors, idx=var.idx[b:b + 1])
+            ref = gr.nerf_forward(opt, one, mode="eval_noalign")
+            for k in ("rgb", "rgb_static", "depth", "opacity", "uncert", "density", "alpha_static"):
+                assert torch.equal(out[k][b:b + 1], ref[k]), (b, k)
+        gen = torch.Generator().manual_seed(8)
+        out.image = torch.rand(len(seeds), 3, H, W, generator=gen).to(DEV)
+        ev = gr.evaluate_frame(opt, out)
+    want = O.eval_frame(out.rgb_static.cpu(), out.depth.cpu(), out.image.cpu(), mask.cpu(), H, W, float(opt.nerf.depth.scale))
+    for k in ("rgb_map", "depth_map", "image_masked"):
+        assert torch.equal(ev[k].cpu(), want[k].contiguous()), k
+    assert (ev.mse.cpu() - want["mse"]).abs().max() <= 1e-6 * want["mse"].max()
+    assert (ev.psnr.cpu() - want["psnr"]).abs().max() <= 1e-4

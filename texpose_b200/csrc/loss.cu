@@ -168,3 +168,68 @@ TP_API int tp_patch_loss(const float* image, const float* obj_mask, const float*
   patch_loss_grad_kernel<<<p.blocks, kLossThreads, 0, st>>>(p);
   return tp_launch_status();
 }
+
+// ------------------------------------------------------------------------------------------ eval-frame epilogue
+//
+// Model.evaluate_full per frame (model/nerf_adapt_st_gan.py:341-362): rgb_static [B,HW,3] -> rgb_map [B,3,H,W]; depth ->
+// depth_map / depth.scale; image * mask; PSNR = -10 log10(mean((rgb_map - image*mask)^2)) -- the reference does this with six
+// permute/mul/mse kernels and a .item() sync per frame (B = 1); here one pass over the pixels for any B, per-view MSE / PSNR
+// left on the device (fixed-order two-stage reduction).  HBM-bound: 32 B in + 28 B out per pixel.
+namespace {
+
+constexpr int kEvalBlocksPerView = 64;
+
+__global__ void __launch_bounds__(256) eval_epilogue_kernel(const float* __restrict__ rgb, const float* __restrict__ depth,
+                                                            const float* __restrict__ image, const float* __restrict__ mask,
+                                                            long long HW, float depth_scale, float* __restrict__ rgb_map,
+                                                            float* __restrict__ depth_map, float* __restrict__ image_masked,
+                                                            float* __restrict__ partial) {
+  __shared__ float sm[8];
+  const int b = blockIdx.y;
+  float acc = 0.f;
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < HW; p += (long long)gridDim.x * blockDim.x) {
+    const long long i = (long long)b * HW + p;
+    const float mv = mask[i];                          // evaluate_full multiplies by the 0/1 obj_mask map as it is (:343,358)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float r = rgb[i * 3 + c];
+      const float im = image[((long long)b * 3 + c) * HW + p] * mv;
+      rgb_map[((long long)b * 3 + c) * HW + p] = r;
+      image_masked[((long long)b * 3 + c) * HW + p] = im;
+      const float d = r - im;
+      acc += d * d;
+    }
+    depth_map[i] = depth[i] / depth_scale;
+  }
+  const float t = block_sum(acc, sm);
+  if (threadIdx.x == 0) partial[(size_t)b * gridDim.x + blockIdx.x] = t;
+}
+
+__global__ void eval_psnr_kernel(const float* __restrict__ partial, int blocks, long long HW, int B, float* __restrict__ mse,
+                                 float* __restrict__ psnr) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float t = 0.f;
+  for (int i = 0; i < blocks; ++i) t += partial[(size_t)b * blocks + i];
+  const float m = t / (float)(3 * HW);
+  mse[b] = m;
+  psnr[b] = -10.f * log10f(m);
+}
+
+}  // namespace
+
+TP_API int64_t tp_eval_epilogue_workspace(int B) { return (int64_t)B * kEvalBlocksPerView; }
+
+TP_API int tp_eval_epilogue(const float* rgb, const float* depth, const float* image, const float* mask, int B, int64_t HW,
+                            float depth_scale, float* rgb_map, float* depth_map, float* image_masked, float* mse, float* psnr,
+                            float* workspace, int64_t workspace_floats, void* stream) {
+  if (!rgb || !depth || !image || !mask || !rgb_map || !depth_map || !image_masked || !mse || !psnr || !workspace)
+    return TP_ERR_BAD_ARG;
+  if (B < 1 || HW < 1 || !(depth_scale > 0.f)) return TP_ERR_BAD_SHAPE;
+  if (workspace_floats < tp_eval_epilogue_workspace(B)) return TP_ERR_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  eval_epilogue_kernel<<<dim3(kEvalBlocksPerView, B), 256, 0, st>>>(rgb, depth, image, mask, HW, depth_scale, rgb_map,
+                                                                    depth_map, image_masked, workspace);
+  eval_psnr_kernel<<<(B + 63) / 64, 64, 0, st>>>(workspace, kEvalBlocksPerView, HW, B, mse, psnr);
+  return tp_launch_status();
+}

@@ -110,10 +110,14 @@ class Graph(torch.nn.Module):
             ret = self.render_by_slices(opt, pose, intr=var.intr, depth_range=depth_range, object_mask=var.obj_mask,
                                         sample_idx=None, mode=mode)
         else:
-            R_dist = rotation_distance(var.pose[..., :3, :3], var.pose_anchor[..., :3, :3]).unsqueeze(-1)
+            # latent pick (:489-494): the light latent of one of the N_candidate nearest training poses, chosen by ONE
+            # randperm draw as in the reference; evaluated per view so a batch of B > 1 frames works, and left on the device
+            R_dist = rotation_distance(var.pose[:, None, :3, :3], var.pose_anchor[None, :, :3, :3])        # [B, N_train]
             k = int(opt.render.N_candidate)
-            cand = torch.topk(R_dist, k=k, dim=0, largest=False, sorted=True)[1]
-            latent_light_idx = cand[torch.randperm(len(cand))[0]][0]
+            cand = torch.topk(R_dist, k=k, dim=1, largest=False, sorted=True)[1]                           # [B, k]
+            latent_light_idx = cand[:, int(torch.randperm(k)[0])]                                          # [B]
+            if len(var.pose) == 1:
+                latent_light_idx = latent_light_idx[0]
             ret = self.render_by_slices(opt, pose, intr=var.intr, depth_range=depth_range, object_mask=var.obj_mask,
                                         sample_idx=latent_light_idx, mode=mode)
         var.update(ret)
@@ -193,29 +197,52 @@ class Graph(torch.nn.Module):
                     parts[k].append(ret[k])
             return AttrDict({k: (v[0] if len(v) == 1 else torch.cat(v, dim=1)) for k, v in parts.items()})
 
-        # mask prior: only object pixels are rendered, the rest keeps the defaults of :657-667 (B must be 1)
-        assert len(pose) == 1, "render_by_slices eval branch renders one view (reference :657-679)"
+        # mask prior: only object pixels are rendered, the rest keeps the defaults of :657-667.  The reference is B = 1 only
+        # (its defaults are [1,HW,.] tensors); here every view of the batch gets its own ray list.
+        B = len(pose)
         N = opt.nerf.sample_intvs
-        ray_idx_obj = (object_mask.view(HW) > 0).nonzero(as_tuple=True)[0]
         ret_all = AttrDict()
         for k in keys:
             if k == "uncert":
-                ret_all[k] = torch.full((1, HW, 1), float(opt.nerf.min_uncert), device=dev)
+                ret_all[k] = torch.full((B, HW, 1), float(opt.nerf.min_uncert), device=dev)
             elif k == "density":
-                ret_all[k] = torch.ones(1, HW, N, 2, device=dev)
+                ret_all[k] = torch.ones(B, HW, N, 2, device=dev)
             elif "rgb" in k:
-                ret_all[k] = torch.zeros(1, HW, 3, device=dev)
+                ret_all[k] = torch.zeros(B, HW, 3, device=dev)
             elif "alpha" in k:
-                ret_all[k] = torch.ones(1, HW, N, device=dev)
+                ret_all[k] = torch.ones(B, HW, N, device=dev)
             else:
-                ret_all[k] = torch.zeros(1, HW, 1, device=dev)
-        for c in range(0, len(ray_idx_obj), step):
-            ray_idx = ray_idx_obj[c:c + step][None]
-            ret = self.render(opt, pose, intr=intr, ray_idx=ray_idx, depth_range=depth_range, sample_idx=sample_idx,
-                              mode=mode)
-            for k in keys:
-                ret_all[k][:, ray_idx[0]] = ret[k]
+                ret_all[k] = torch.zeros(B, HW, 1, device=dev)
+        masks = object_mask.reshape(B, HW)
+        for b in range(B):
+            ray_idx_obj = (masks[b] > 0).nonzero(as_tuple=True)[0]
+            sl = slice(b, b + 1)
+            idx_b = sample_idx if (sample_idx is None or torch.as_tensor(sample_idx).dim() == 0) else sample_idx[b]
+            for c in range(0, len(ray_idx_obj), step):
+                ray_idx = ray_idx_obj[c:c + step][None]
+                ret = self.render(opt, pose[sl], intr=intr[sl] if intr is not None else None,
+                                  depth_range=tuple(d[sl] for d in depth_range), ray_idx=ray_idx, sample_idx=idx_b, mode=mode)
+                for k in keys:
+                    ret_all[k][b, ray_idx[0]] = ret[k][0]
         return ret_all
+
+    def evaluate_frame(self, opt, var):
+        """Per-frame numbers of Model.evaluate_full (model/nerf_adapt_st_gan.py:341-362) for every view of the batch, without a
+        host sync: rgb_map [B,3,H,W] (from rgb_static), depth_map [B,1,H,W] in metres, image * mask, per-view MSE / PSNR on
+        the device (csrc/loss.cu, tp_eval_epilogue).  SSIM / LPIPS need third-party nets and stay with the engine."""
+        B, H, W = len(var.pose), opt.H, opt.W
+        dev = var.rgb_static.device
+        rgb_map = torch.empty(B, 3, H, W, device=dev)
+        depth_map = torch.empty(B, 1, H, W, device=dev)
+        image_masked = torch.empty(B, 3, H, W, device=dev)
+        mse, psnr = torch.empty(B, device=dev), torch.empty(B, device=dev)
+        lib = ops._C.load()
+        ws = torch.empty(lib.tp_eval_epilogue_workspace(B), device=dev)
+        f = ops._f32
+        ops._C.call("tp_eval_epilogue", ops._p(f(var.rgb_static)), ops._p(f(var.depth)), ops._p(f(var.image)),
+                    ops._p(f(var.obj_mask)), B, H * W, float(opt.nerf.depth.scale), ops._p(rgb_map), ops._p(depth_map),
+                    ops._p(image_masked), ops._p(mse), ops._p(psnr), ops._p(ws), ws.numel(), ops._stream())
+        return AttrDict(rgb_map=rgb_map, depth_map=depth_map, image_masked=image_masked, mse=mse, psnr=psnr)
 
     def sample_depth(self, opt, batch_size, depth_range, num_rays=None):
         """model/nerf_adapt_st_gan.py:682-700.  The jitter is the same torch.rand draw as the reference (parity);

@@ -178,6 +178,7 @@ class CompositeSTL(torch.autograd.Function):
     @staticmethod
     def forward(ctx, ray, rgb, density, depth, uncert, min_uncert):
         _need_cuda(ray, rgb, density, depth, uncert)
+        ctx.set_materialize_grads(False)      # unused outputs reach the kernel as NULL instead of zero-filled tensors
         ray_c, rgb_c, den_c, dep_c, unc_c = _f32(ray), _f32(rgb), _f32(density), _f32(depth), _f32(uncert)
         B, R, N = den_c.shape[:3]
         dev = ray_c.device
@@ -210,6 +211,7 @@ class CompositePlain(torch.autograd.Function):
     @staticmethod
     def forward(ctx, ray, rgb, density, depth, bgcolor):
         _need_cuda(ray, rgb, density, depth)
+        ctx.set_materialize_grads(False)
         ray_c, rgb_c, den_c, dep_c = _f32(ray), _f32(rgb), _f32(density), _f32(depth)
         B, R, N = den_c.shape[:3]
         dev = ray_c.device
