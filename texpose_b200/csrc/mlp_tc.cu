@@ -37,8 +37,11 @@ constexpr uint32_t kOffA = 0, kOffE = 2 * kABytes, kOffRing = kOffE + 2 * kEByte
 constexpr uint32_t kOffBar = kOffRing + kStages * kChunkBytes;
 constexpr uint32_t kSmemBytes = kOffBar + 128;
 // One 32-column slab of a hidden stage: (+fp32 bias,) ReLU, bf16, store as 4 core-matrix rows of the next A operand.
-template <bool kBias>
-__device__ __forceinline__ void hidden_slab(const uint32_t (&v)[32], const float* bias, uint32_t a_dst, float* dbg_row) {
+// kBits (training): also returns the ReLU mask of the 32 columns (bit e = column e is positive) -- one funnel shift per
+// element collects the sign bits; the backward reads these 4 KB bitmasks instead of the 64 KB activation tiles.
+template <bool kBias, bool kBits = false>
+__device__ __forceinline__ uint32_t hidden_slab(const uint32_t (&v)[32], const float* bias, uint32_t a_dst, float* dbg_row) {
+  uint32_t signs = 0u;
 #pragma unroll
   for (int i = 0; i < 32; i += 8) {
     float x[8];
@@ -50,6 +53,10 @@ __device__ __forceinline__ void hidden_slab(const uint32_t (&v)[32], const float
       x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
       x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
     }
+    if (kBits) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) signs = __funnelshift_l(__float_as_uint(x[e]), signs, 1);
+    }
     st_shared_v4(a_dst + (i >> 3) * 2048, pack_relu_bf16(x[0], x[1]), pack_relu_bf16(x[2], x[3]), pack_relu_bf16(x[4], x[5]),
                  pack_relu_bf16(x[6], x[7]));
     if (dbg_row) {
@@ -57,13 +64,16 @@ __device__ __forceinline__ void hidden_slab(const uint32_t (&v)[32], const float
       for (int e = 0; e < 8; ++e) dbg_row[i + e] = fmaxf(x[e], 0.f);
     }
   }
+  return __brev(~signs);      // element 0 was shifted in first: reverse; positive = sign bit clear
 }
 
 // Same with the bias row held distributed across the warp (lane l owns columns 4l..4l+3 of the thread's column range, in
 // `mine[0]`, and 128+4l.. in `mine[1]` when a thread converts 256 columns): valid when all 32 rows of the warp share one
 // bias row (N % 32 == 0).  8 shuffles per 8 columns replace 2 dependent L2 round trips.
-__device__ __forceinline__ void hidden_slab_wbias(const uint32_t (&v)[32], const float4 (&mine)[2], int col0, uint32_t a_dst,
-                                                  float* dbg_row) {
+template <bool kBits = false>
+__device__ __forceinline__ uint32_t hidden_slab_wbias(const uint32_t (&v)[32], const float4 (&mine)[2], int col0, uint32_t a_dst,
+                                                      float* dbg_row) {
+  uint32_t signs = 0u;
 #pragma unroll
   for (int i = 0; i < 32; i += 8) {
     const int c = col0 + i;                       // first column of this group within the thread's range
@@ -78,6 +88,10 @@ __device__ __forceinline__ void hidden_slab_wbias(const uint32_t (&v)[32], const
     x[5] = __uint_as_float(v[i + 5]) + __shfl_sync(0xffffffffu, src.y, l0 + 1);
     x[6] = __uint_as_float(v[i + 6]) + __shfl_sync(0xffffffffu, src.z, l0 + 1);
     x[7] = __uint_as_float(v[i + 7]) + __shfl_sync(0xffffffffu, src.w, l0 + 1);
+    if (kBits) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) signs = __funnelshift_l(__float_as_uint(x[e]), signs, 1);
+    }
     st_shared_v4(a_dst + (i >> 3) * 2048, pack_relu_bf16(x[0], x[1]), pack_relu_bf16(x[2], x[3]), pack_relu_bf16(x[4], x[5]),
                  pack_relu_bf16(x[6], x[7]));
     if (dbg_row) {
@@ -85,20 +99,24 @@ __device__ __forceinline__ void hidden_slab_wbias(const uint32_t (&v)[32], const
       for (int e = 0; e < 8; ++e) dbg_row[i + e] = fmaxf(x[e], 0.f);
     }
   }
+  return __brev(~signs);
 }
 
-template <int kSlabs>
-__device__ __forceinline__ void hidden_epilogue_wbias(uint32_t tmem_d, const float4 (&mine)[2], uint32_t a_row, float* dbg_row) {
+template <int kSlabs, bool kBits = false>
+__device__ __forceinline__ void hidden_epilogue_wbias(uint32_t tmem_d, const float4 (&mine)[2], uint32_t a_row, float* dbg_row,
+                                                      uint32_t* words = nullptr) {      // words: plane j at words[j * 128]
   uint32_t va[32], vb[32];
   TP_TMEM_LD32(tmem_d, va);
 #pragma unroll
   for (int j = 0; j < kSlabs; j += 2) {
     TP_TMEM_WAIT32(va);
     TP_TMEM_LD32(tmem_d + (j + 1) * 32, vb);
-    hidden_slab_wbias(va, mine, j * 32, a_row + j * 4 * 2048, dbg_row ? dbg_row + j * 32 : nullptr);
+    const uint32_t w0 = hidden_slab_wbias<kBits>(va, mine, j * 32, a_row + j * 4 * 2048, dbg_row ? dbg_row + j * 32 : nullptr);
     TP_TMEM_WAIT32(vb);
     if (j + 2 < kSlabs) TP_TMEM_LD32(tmem_d + (j + 2) * 32, va);
-    hidden_slab_wbias(vb, mine, (j + 1) * 32, a_row + (j + 1) * 4 * 2048, dbg_row ? dbg_row + (j + 1) * 32 : nullptr);
+    const uint32_t w1 = hidden_slab_wbias<kBits>(vb, mine, (j + 1) * 32, a_row + (j + 1) * 4 * 2048,
+                                                 dbg_row ? dbg_row + (j + 1) * 32 : nullptr);
+    if (kBits) { words[j * 128] = w0; words[(j + 1) * 128] = w1; }
   }
 }
 
@@ -117,18 +135,21 @@ __device__ __noinline__ void hidden_epilogue_experiment(uint32_t tmem_d, uint32_
   }
 }
 
-template <bool kBias, int kSlabs>
-__device__ __forceinline__ void hidden_epilogue(uint32_t tmem_d, const float* bias, uint32_t a_row, float* dbg_row) {
+template <bool kBias, int kSlabs, bool kBits = false>
+__device__ __forceinline__ void hidden_epilogue(uint32_t tmem_d, const float* bias, uint32_t a_row, float* dbg_row,
+                                                uint32_t* words = nullptr) {
   uint32_t va[32], vb[32];
   TP_TMEM_LD32(tmem_d, va);
 #pragma unroll
   for (int j = 0; j < kSlabs; j += 2) {
     TP_TMEM_WAIT32(va);
     TP_TMEM_LD32(tmem_d + (j + 1) * 32, vb);
-    hidden_slab<kBias>(va, bias + j * 32, a_row + j * 4 * 2048, dbg_row ? dbg_row + j * 32 : nullptr);
+    const uint32_t w0 = hidden_slab<kBias, kBits>(va, bias + j * 32, a_row + j * 4 * 2048, dbg_row ? dbg_row + j * 32 : nullptr);
     TP_TMEM_WAIT32(vb);
     if (j + 2 < kSlabs) TP_TMEM_LD32(tmem_d + (j + 2) * 32, va);
-    hidden_slab<kBias>(vb, bias + (j + 1) * 32, a_row + (j + 1) * 4 * 2048, dbg_row ? dbg_row + (j + 1) * 32 : nullptr);
+    const uint32_t w1 = hidden_slab<kBias, kBits>(vb, bias + (j + 1) * 32, a_row + (j + 1) * 4 * 2048,
+                                                  dbg_row ? dbg_row + (j + 1) * 32 : nullptr);
+    if (kBits) { words[j * 128] = w0; words[(j + 1) * 128] = w1; }
   }
 }
 
@@ -319,7 +340,22 @@ __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_ke
         if (ly.epi == EPI_HIDDEN) {
           float* dbg_row = ((L == p.dbg_layer) && live && p.dbg_out) ? p.dbg_out + s * 256 + half * kCols : nullptr;
           const uint32_t a_row = a_smem + half * (kCols / 8) * 2048 + row * 16;
-          if (p.dbg_drain == 1 || p.dbg_drain == 2) {
+          const int mslot = p.bits ? kMaskBitSlot[L] : -1;
+          if (mslot >= 0) {
+            // training: h1 / h2 of either head also leave a ReLU bitmask [128 rows][256 bits] for the backward chain
+            // word planes [8][128 rows]: plane = 32-column slab, so a warp's store of one slab is 128 contiguous bytes
+            uint32_t* words = reinterpret_cast<uint32_t*>(p.bits + ((size_t)(st * 2 + t) * 4 + mslot) * kMaskBitBytes) +
+                              half * (kCols / 32) * 128 + row;
+            if (ly.bias_kind == BIAS_MMA) {
+              hidden_epilogue<false, kCols / 32, true>(tmem_d, nullptr, a_row, dbg_row, words);
+            } else if (warp_bias) {
+              hidden_epilogue_wbias<kCols / 32, true>(tmem_d, wb, a_row, dbg_row, words);
+            } else {
+              const float* bias = (ly.bias_kind == BIAS_RAY ? p.raybias + (s / p.N) * 256 : p.imgbias + (s / p.per_image) * 256) +
+                                  half * kCols;
+              hidden_epilogue<true, kCols / 32, true>(tmem_d, bias, a_row, dbg_row, words);
+            }
+          } else if (p.dbg_drain == 1 || p.dbg_drain == 2) {
             hidden_epilogue_experiment<kCols / 32>(tmem_d, a_row, p.dbg_drain);
           } else if (ly.bias_kind == BIAS_MMA || p.dbg_drain == 3) {   // 3: timing experiment, bias tables ignored
             hidden_epilogue<false, kCols / 32>(tmem_d, nullptr, a_row, dbg_row);
@@ -501,7 +537,10 @@ TP_API int tp_tc_num_chunks(void) { return tc::kNumChunks; }
 TP_API int64_t tp_tc_chunk_bytes(void) { return tc::kChunkBytes; }
 TP_API int64_t tp_tc_scratch_bytes(void) { return (int64_t)tp_num_sms() * 2 * tc::kABytes; }
 
-TP_API int64_t tp_tc_save_bytes(int64_t S) { return ((S + 255) / 256) * 2 * tc::kSaveSlots * (int64_t)tc::kABytes; }
+// save buffer: [tiles][7][64 KB] tile images, then [tiles][4][4 KB] ReLU bitmasks (tiles rounded up to whole super-tiles)
+TP_API int64_t tp_tc_save_bytes(int64_t S) {
+  return ((S + 255) / 256) * 2 * (tc::kSaveSlots * (int64_t)tc::kABytes + tc::kMaskBitSlots * (int64_t)tc::kMaskBitBytes);
+}
 
 TP_API int tp_tc_unpack_images(const void* images, int slot, int n_slots, int64_t S, float* out, void* stream) {
   if (!images || !out) return TP_ERR_BAD_ARG;
@@ -560,6 +599,8 @@ TP_API int tp_tc_nerf_stl_forward(const float* center, const float* ray, const f
   p.rgb = rgb; p.density = density; p.uncert = uncert; p.scratch = reinterpret_cast<uint8_t*>(scratch);
   p.save = reinterpret_cast<uint8_t*>(save);
   if (((uintptr_t)save & 15)) return TP_ERR_ALIGN;
+  p.bits = save ? p.save + ((S + 255) / 256) * 2 * tc::kSaveSlots * (size_t)tc::kABytes : nullptr;
+  if (save && (flags & 128)) return TP_ERR_BAD_ARG;           // the experimental kernel does not write the ReLU bitmasks
   p.dbg_layer = dbg_layer; p.dbg_out = dbg_out; p.dbg_drain = (flags >> 2) & 7;
   p.skew = ((flags >> 5) & 3) ? ((flags >> 5) & 3) - 1 : 1;      // default skew 1; flags bits 5-6 = skew+1 override (A/B)
   if (flags & 128) return tp_tc_v2_launch(p, flags, (cudaStream_t)stream);   // experimental single-tile / cluster kernel

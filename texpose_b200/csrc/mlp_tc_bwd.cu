@@ -30,6 +30,8 @@ constexpr int kBwdChunks = 34;                       // (1 + 8 + 8) x 2
 constexpr int kFwdSlots = 7, kDzSlots = 6;
 // forward-save slot holding the mask of each stage: rgb h3,h2,h1 = 3,2,1; trans h3,h2,h1 = 6,5,4
 __constant__ int kMaskSlot[kNumStagesPerTile] = {3, 2, 1, 6, 5, 4};
+// ReLU-bitmask slot (rgb h1, h2, trans h1, h2 = 0..3) that masks each stage of the fused kernel; -1: the h3 tile in M
+__constant__ int kBitSlot[kNumStagesPerTile] = {-1, 1, 0, -1, 3, 2};
 
 struct BwdParams {
   const float* dz_rgb;        // [S,3]  grad w.r.t. rgb-head output pre-activations
@@ -382,7 +384,7 @@ __global__ void __launch_bounds__(kThreads, 1) backward_chain_fused_kernel(const
     }
   } else if (warp == 9) {
     // ================================================================ MMA issuer: chain stages + thin-gradient MMAs
-    uint32_t stage = 0, phase = 0, ready_ph = 0, mask_cnt = 0;
+    uint32_t stage = 0, phase = 0, ready_ph = 0;
     const uint32_t idesc = umma_idesc(128, 256);
     const uint32_t idesc_x16 = umma_idesc_mn(128, 16), idesc_x48 = umma_idesc_mn(128, 48);
     constexpr uint32_t kHi = (128u >> 4) | (1u << 14);          // K-major operands: SBO 128
@@ -411,7 +413,7 @@ __global__ void __launch_bounds__(kThreads, 1) backward_chain_fused_kernel(const
           if (c == 0) {
             mbar_wait(bar_ready, ready_ph);
             ready_ph ^= 1;
-            if (s % 3 == 0) mbar_wait(bar_mask, (mask_cnt + s) & 1u);     // h3 tile of this head is the X operand of block O
+            if (s % 3 == 0) mbar_wait(bar_mask, s == 3 ? 1u : 0u);        // h3 tile of this head (2 loads per tile): X operand of block O
           }
           tc_fence_after();
           const uint32_t wsm = sbase + kOffRingF + stage * kChunkBytes;
@@ -444,7 +446,6 @@ __global__ void __launch_bounds__(kThreads, 1) backward_chain_fused_kernel(const
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
-      mask_cnt += kNumStagesPerTile;
     }
     // trans dz0 of the last tile, then hand the accumulators to the flush
     mbar_wait(bar_ready, ready_ph);
@@ -462,6 +463,8 @@ __global__ void __launch_bounds__(kThreads, 1) backward_chain_fused_kernel(const
     uint32_t acc_ph = 0, mask_ph = 0;
     bool store_pending = false;
     const long long img0 = (t0 * 128) / fp.per_image;
+    // ReLU bitmasks of h1 / h2 (written by the forward behind the tile images): word planes [8][128 rows] per tile and slot
+    const uint8_t* bits = p.saved + ((p.S + 255) / 256) * 2 * (size_t)kFwdSlots * kABytes;
     float zsum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (threadIdx.x == 32) {
       mbar_expect_tx(bar_mask, kABytes);
@@ -495,10 +498,19 @@ __global__ void __launch_bounds__(kThreads, 1) backward_chain_fused_kernel(const
       mbar_arrive(bar_ready);
 
       for (int s = 0; s < kNumStagesPerTile; ++s) {
+        const bool tile_mask = s % 3 == 0;       // stages 0 / 3 mask with the h3 tile in M (it is also block O's operand)
+        uint32_t mbw[4] = {0u, 0u, 0u, 0u};
+        if (!tile_mask) {                        // others: h2 / h1 bitmask words of this thread's row half, fetched before the wait
+          const uint32_t* w = reinterpret_cast<const uint32_t*>(bits + ((size_t)tile * 4 + kBitSlot[s]) * 4096) + half * 4 * 128 + row;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) mbw[j] = __ldg(w + j * 128);
+        }
         mbar_wait(bar_acc, acc_ph);
         acc_ph ^= 1;
-        mbar_wait(bar_mask, mask_ph);
-        mask_ph ^= 1;
+        if (tile_mask) {
+          mbar_wait(bar_mask, mask_ph);
+          mask_ph ^= 1;
+        }
         tc_fence_after();
         if (store_pending) {          // the previous dz image store must have finished reading A
           if (threadIdx.x == 0) bulk_wait_read();
@@ -513,15 +525,25 @@ __global__ void __launch_bounds__(kThreads, 1) backward_chain_fused_kernel(const
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const uint32_t off = (uint32_t)(half * 16 + j * 4 + i) * 2048 + row * 16;
-            uint32_t m0, m1, m2, m3;
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(m0), "=r"(m1), "=r"(m2), "=r"(m3) : "r"(m_smem + off));
-            const uint32_t mw[4] = {m0, m1, m2, m3};
             uint32_t o[4];
+            if (tile_mask) {
+              uint32_t m0, m1, m2, m3;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(m0), "=r"(m1), "=r"(m2), "=r"(m3) : "r"(m_smem + off));
+              const uint32_t mw[4] = {m0, m1, m2, m3};
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float lo = (mw[e] & 0xffffu) ? __uint_as_float(v[i * 8 + 2 * e]) : 0.f;
-              const float hi = (mw[e] >> 16) ? __uint_as_float(v[i * 8 + 2 * e + 1]) : 0.f;
-              o[e] = pack_bf16(lo, hi);
+              for (int e = 0; e < 4; ++e) {
+                const float lo = (mw[e] & 0xffffu) ? __uint_as_float(v[i * 8 + 2 * e]) : 0.f;
+                const float hi = (mw[e] >> 16) ? __uint_as_float(v[i * 8 + 2 * e + 1]) : 0.f;
+                o[e] = pack_bf16(lo, hi);
+              }
+            } else {
+              const uint32_t byte = (mbw[j] >> (i * 8)) & 0xffu;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float lo = (byte & (1u << (2 * e))) ? __uint_as_float(v[i * 8 + 2 * e]) : 0.f;
+                const float hi = (byte & (2u << (2 * e))) ? __uint_as_float(v[i * 8 + 2 * e + 1]) : 0.f;
+                o[e] = pack_bf16(lo, hi);
+              }
             }
             st_shared_v4(a_smem + off, o[0], o[1], o[2], o[3]);
           }
@@ -539,12 +561,11 @@ __global__ void __launch_bounds__(kThreads, 1) backward_chain_fused_kernel(const
           bulk_commit();
         }
         store_pending = true;
-        if (threadIdx.x == 32) {          // prefetch the next stage's mask tile (possibly of this CTA's next tile)
-          const bool last = s == kNumStagesPerTile - 1;
-          const long long nt = last ? tile + 1 : tile;
+        if (threadIdx.x == 32 && tile_mask) {    // M is free again: fetch the next h3 tile (trans h3 of this tile / rgb h3 of the next)
+          const long long nt = s == 3 ? tile + 1 : tile;
           if (nt < t1) {
             mbar_expect_tx(bar_mask, kABytes);
-            bulk_g2s(m_smem, p.saved + ((size_t)nt * kFwdSlots + kMaskSlot[last ? 0 : s + 1]) * kABytes, kABytes, bar_mask);
+            bulk_g2s(m_smem, p.saved + ((size_t)nt * kFwdSlots + kMaskSlot[s == 3 ? 0 : 3]) * kABytes, kABytes, bar_mask);
           }
         }
         if (s != kNumStagesPerTile - 1) {

@@ -44,6 +44,11 @@ constexpr int kSpillLayer = 8, kReloadIssueLayer = 12;
 constexpr int kSaveSlots = 7;
 // activation-save slot of each stage (training): feat, rgb h1..h3, trans h1..h3; -1 = not saved
 static __constant__ int kSaveSlot[kNumLayers] = {-1, -1, -1, -1, -1, -1, -1, -1, 0, 1, 2, 3, -1, 4, 5, 6, -1};
+// ReLU-bitmask slot of each stage (training): rgb h1, h2, trans h1, h2 -> 0..3 ([8 word planes][128 rows] = 4 KB per tile and slot,
+// stored behind the tile images of the save buffer); the backward chain reads these instead of the 64 KB activation tiles
+static __constant__ int kMaskBitSlot[kNumLayers] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, 0, 1, -1, -1, 2, 3, -1, -1};
+constexpr int kMaskBitSlots = 4;
+constexpr uint32_t kMaskBitBytes = 4096;
 constexpr int kSmallBiasOffset = 0;            // biasbuf: [density b, rgb3 b(3), trans3 b(5)] (fp32, 16 floats)
 
 struct Params {
@@ -61,6 +66,7 @@ struct Params {
   float* density;            // [S,2]
   float* uncert;             // [S]
   uint8_t* scratch;          // gridDim.x x 2 x 64 KB (parked features)
+  uint8_t* bits;             // optional [tiles][4][8 planes][128 rows] ReLU bitmask words (training; lives behind `save`)
   uint8_t* save;             // optional [tiles][7][64 KB]: feat, rgb h1..h3, trans h1..h3 tile images for the backward
   int dbg_layer;
   float* dbg_out;            // [S,256] post-activation of stage dbg_layer (debug only)
