@@ -44,7 +44,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + sources() + ["-o", LIB_PATH]
+    extra = os.environ.get("TEXPOSE_NVCC_EXTRA", "").split()      # e.g. -DTP_CHAIN_PROF for scripts/chain_prof.py
+    cmd = [nvcc] + NVCC_FLAGS + extra + sources() + ["-o", LIB_PATH]
     if verbose:
         print(" ".join(cmd), file=sys.stderr)
     subprocess.run(cmd, check=True, cwd=CSRC)

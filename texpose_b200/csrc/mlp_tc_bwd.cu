@@ -14,6 +14,13 @@
 #include "tc_common.cuh"
 #include "../../include/texpose_b200.h"
 
+// cycle-counter instrumentation of the fused chain kernel (scripts/chain_prof.py): compiled in only with -DTP_CHAIN_PROF
+#ifdef TP_CHAIN_PROF
+#define TP_PF(...) __VA_ARGS__
+#else
+#define TP_PF(...)
+#endif
+
 namespace tcb {
 using namespace tc;
 
@@ -274,6 +281,7 @@ struct FusedParams {
   int L_view;
   float* extras;              // [grid][kXCols][256]
   float* thin_sums;           // [grid][4 warps][8]: column sums of dz_rgb (3) and dz_trans (5)
+  long long* prof;            // optional [grid][16] cycle counters of the MMA warp and of epilogue warp 0 (debugging aid: workspace tail, see the API)
 };
 
 __device__ __forceinline__ void tile_range(long long n_tiles, int grid, int cta, long long& t0, long long& t1) {
@@ -328,7 +336,9 @@ __device__ __forceinline__ void write_tr_row(const FusedParams& p, long long s, 
   st_shared_v4(ti_row + 2048, 0u, 0u, 0u, 0u);
 }
 
-__global__ void __launch_bounds__(kThreads, 1) backward_chain_fused_kernel(const FusedParams fp) {
+constexpr int kFEpiWarps = 16, kFEpiThreads = kFEpiWarps * 32, kFThreads = kFEpiThreads + 64;   // + producer warp + MMA warp
+
+__global__ void __launch_bounds__(kFThreads, 1) backward_chain_fused_kernel(const FusedParams fp) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const BwdParams& p = fp.b;
   const uint32_t sbase = smem_u32(smem);
@@ -346,11 +356,11 @@ __global__ void __launch_bounds__(kThreads, 1) backward_chain_fused_kernel(const
       mbar_init(bar_empty(s), 1);
     }
     mbar_init(bar_acc, 1);
-    mbar_init(bar_ready, 256);
+    mbar_init(bar_ready, kFEpiThreads);
     mbar_init(bar_mask, 1);
     fence_barrier_init();
   }
-  if (warp == 9) {
+  if (warp == kFEpiWarps + 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -363,7 +373,7 @@ __global__ void __launch_bounds__(kThreads, 1) backward_chain_fused_kernel(const
   long long t0, t1;
   tile_range(n_tiles, gridDim.x, blockIdx.x, t0, t1);
 
-  if (warp == 8) {
+  if (warp == kFEpiWarps) {
     // ================================================================ weight producer
     uint32_t stage = 0, phase = 0;
     for (long long tile = t0; tile < t1; ++tile) {
@@ -382,7 +392,7 @@ __global__ void __launch_bounds__(kThreads, 1) backward_chain_fused_kernel(const
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == kFEpiWarps + 1) {
     // ================================================================ MMA issuer: chain stages + thin-gradient MMAs
     uint32_t stage = 0, phase = 0, ready_ph = 0;
     const uint32_t idesc = umma_idesc(128, 256);
@@ -402,6 +412,8 @@ __global__ void __launch_bounds__(kThreads, 1) backward_chain_fused_kernel(const
         }
       }
     };
+    TP_PF(long long pf_full = 0, pf_ready = 0, pf_mask = 0, pf_issue = 0;)
+    TP_PF(const long long pf_t0 = clock64();)
     for (long long tile = t0; tile < t1; ++tile) {
       const uint32_t tr_tile = sbase + kOffTR;
       const uint32_t tr_prev = sbase + kOffTI + (uint32_t)((tile - t0 + 1) & 1) * 4096;
@@ -409,17 +421,35 @@ __global__ void __launch_bounds__(kThreads, 1) backward_chain_fused_kernel(const
       for (int s = 0; s < kNumStagesPerTile; ++s) {
         const int nch = (s % 3 == 0) ? 1 : 8;
         for (int c = 0; c < nch; ++c) {
+          TP_PF(long long pf_a = clock64();)
           mbar_wait(bar_full(stage), phase);
+          TP_PF(long long pf_b = clock64();)
+          TP_PF(pf_full += pf_b - pf_a;)
           if (c == 0) {
             mbar_wait(bar_ready, ready_ph);
             ready_ph ^= 1;
+            TP_PF(pf_a = clock64();)
+            TP_PF(pf_ready += pf_a - pf_b;)
             if (s % 3 == 0) mbar_wait(bar_mask, s == 3 ? 1u : 0u);        // h3 tile of this head (2 loads per tile): X operand of block O
+            TP_PF(pf_b = clock64();)
+            TP_PF(pf_mask += pf_b - pf_a;)
           }
           tc_fence_after();
           const uint32_t wsm = sbase + kOffRingF + stage * kChunkBytes;
           if (elect_one_sync()) {
-            if (c == 0) {
-              // thin-gradient MMAs on the operands that are complete at this point
+            const uint32_t b_lo = (wsm >> 4) | ((4096u >> 4) << 16);
+            if (s % 3 == 0) {   // K=16 step on the dz3 tile of this head
+              const uint32_t a_lo = ((sbase + kOffZ + (s / 3) * 4096) >> 4) | ((2048u >> 4) << 16);
+              umma_bf16_lohi(tmem_base, a_lo, kHi, b_lo, kHi, idesc, 0u);
+            } else {
+              const uint32_t a_lo = ((a_tile + c * 4 * 2048) >> 4) | ((2048u >> 4) << 16);
+              umma_bf16_lohi(tmem_base, a_lo, kHi, b_lo, kHi, idesc, c > 0 ? 1u : 0u);
+              umma_bf16_lohi(tmem_base, a_lo + (4096u >> 4), kHi, b_lo + (8192u >> 4), kHi, idesc, 1u);
+            }
+            if (c == (nch == 1 ? 0 : 1)) {
+              // thin-gradient MMAs on the operands that are complete at this point; issued behind the first main MMAs so
+              // their issue cost overlaps tensor-pipe work instead of delaying the stage (they only have to precede the
+              // accumulator commit: the epilogue it releases overwrites A)
               if (s == 0) {
                 if (tile > t0) thin_mma(kColT, 16, a_tile, tr_prev, idesc_x16, tile == t0 + 1);     // trans dz0 of the previous tile
                 thin_mma(kColOr, 16, m_tile, sbase + kOffZ, idesc_x16, first_tile);
@@ -430,23 +460,19 @@ __global__ void __launch_bounds__(kThreads, 1) backward_chain_fused_kernel(const
                 thin_mma(kColS, 16, a_tile, ts_tile, idesc_x16, first_tile && s == 1);              // dz2 / dz1 column sums
               }
             }
-            const uint32_t b_lo = (wsm >> 4) | ((4096u >> 4) << 16);
-            if (s % 3 == 0) {   // K=16 step on the dz3 tile of this head
-              const uint32_t a_lo = ((sbase + kOffZ + (s / 3) * 4096) >> 4) | ((2048u >> 4) << 16);
-              umma_bf16_lohi(tmem_base, a_lo, kHi, b_lo, kHi, idesc, 0u);
-            } else {
-              const uint32_t a_lo = ((a_tile + c * 4 * 2048) >> 4) | ((2048u >> 4) << 16);
-              umma_bf16_lohi(tmem_base, a_lo, kHi, b_lo, kHi, idesc, c > 0 ? 1u : 0u);
-              umma_bf16_lohi(tmem_base, a_lo + (4096u >> 4), kHi, b_lo + (8192u >> 4), kHi, idesc, 1u);
-            }
             if (c == nch - 1) umma_commit(bar_acc);
             umma_commit(bar_empty(stage));
           }
           __syncwarp();
+          TP_PF(pf_issue += clock64() - pf_b;)
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
+    TP_PF(if (fp.prof && lane == 0) {
+      long long* o = fp.prof + (size_t)blockIdx.x * 16;
+      o[0] = clock64() - pf_t0; o[1] = pf_full; o[2] = pf_ready; o[3] = pf_mask; o[4] = pf_issue; o[5] = t1 - t0;
+    })
     // trans dz0 of the last tile, then hand the accumulators to the flush
     mbar_wait(bar_ready, ready_ph);
     tc_fence_after();
@@ -457,22 +483,52 @@ __global__ void __launch_bounds__(kThreads, 1) backward_chain_fused_kernel(const
     __syncwarp();
   } else {
     // ================================================================ epilogue warps: mask, convert, store dz images, thin tiles
-    const int q = warp & 3, half = warp >> 2, row = q * 32 + lane;
+    // warp -> (TMEM lane quarter q, column quarter cq): each thread converts 64 accumulator columns (two 32-column slabs)
+    const int q = warp & 3, cq = warp >> 2, row = q * 32 + lane;
     const uint32_t a_smem = sbase + kOffA, m_smem = sbase + kOffM;
-    const uint32_t tmem_d = tmem_base + ((uint32_t)(q * 32) << 16) + half * 128;
+    const uint32_t tmem_d = tmem_base + ((uint32_t)(q * 32) << 16) + cq * 64;
     uint32_t acc_ph = 0, mask_ph = 0;
     bool store_pending = false;
     const long long img0 = (t0 * 128) / fp.per_image;
     // ReLU bitmasks of h1 / h2 (written by the forward behind the tile images): word planes [8][128 rows] per tile and slot
     const uint8_t* bits = p.saved + ((p.S + 255) / 256) * 2 * (size_t)kFwdSlots * kABytes;
     float zsum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    TP_PF(long long pe_acc = 0, pe_mask = 0, pe_store = 0, pe_conv = 0, pe_bar = 0;)
     if (threadIdx.x == 32) {
       mbar_expect_tx(bar_mask, kABytes);
       bulk_g2s(m_smem, p.saved + ((size_t)t0 * kFwdSlots + kMaskSlot[0]) * kABytes, kABytes, bar_mask);
     }
+    // one 32-column slab: mask, bf16, store as 4 core-matrix rows of the dz tile (= next A operand / dz image)
+    auto convert_slab = [&](const uint32_t (&v)[32], int k8_0, bool tile_mask, uint32_t word) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t off = (uint32_t)(k8_0 + i) * 2048 + row * 16;
+        uint32_t o[4];
+        if (tile_mask) {
+          uint32_t m0, m1, m2, m3;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(m0), "=r"(m1), "=r"(m2), "=r"(m3) : "r"(m_smem + off));
+          const uint32_t mw[4] = {m0, m1, m2, m3};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float lo = (mw[e] & 0xffffu) ? __uint_as_float(v[i * 8 + 2 * e]) : 0.f;
+            const float hi = (mw[e] >> 16) ? __uint_as_float(v[i * 8 + 2 * e + 1]) : 0.f;
+            o[e] = pack_bf16(lo, hi);
+          }
+        } else {
+          const uint32_t byte = (word >> (i * 8)) & 0xffu;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float lo = (byte & (1u << (2 * e))) ? __uint_as_float(v[i * 8 + 2 * e]) : 0.f;
+            const float hi = (byte & (2u << (2 * e))) ? __uint_as_float(v[i * 8 + 2 * e + 1]) : 0.f;
+            o[e] = pack_bf16(lo, hi);
+          }
+        }
+        st_shared_v4(a_smem + off, o[0], o[1], o[2], o[3]);
+      }
+    };
     for (long long tile = t0; tile < t1; ++tile) {
       const long long s_row = tile * 128 + row;
-      if (half == 0) {
+      if (cq == 0) {
         // dz3 tiles of both heads: [2 k8][128 rows][8] bf16, columns >= 3 / 5 zero
         float zr[3] = {0.f, 0.f, 0.f}, zt[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
         if (s_row < p.S) {
@@ -490,7 +546,7 @@ __global__ void __launch_bounds__(kThreads, 1) backward_chain_fused_kernel(const
         st_shared_v4(z0 + 2048, 0u, 0u, 0u, 0u);
         st_shared_v4(z0 + 4096, pack_bf16(zt[0], zt[1]), pack_bf16(zt[2], zt[3]), pack_bf16(zt[4], 0.f), 0u);
         st_shared_v4(z0 + 4096 + 2048, 0u, 0u, 0u, 0u);
-      } else {
+      } else if (cq == 1) {
         write_tr_row(fp, s_row, img0, sbase + kOffTR + row * 16, sbase + kOffTI + (uint32_t)((tile - t0) & 1) * 4096 + row * 16);
       }
       fence_proxy_async_smem();
@@ -499,63 +555,50 @@ __global__ void __launch_bounds__(kThreads, 1) backward_chain_fused_kernel(const
 
       for (int s = 0; s < kNumStagesPerTile; ++s) {
         const bool tile_mask = s % 3 == 0;       // stages 0 / 3 mask with the h3 tile in M (it is also block O's operand)
-        uint32_t mbw[4] = {0u, 0u, 0u, 0u};
-        if (!tile_mask) {                        // others: h2 / h1 bitmask words of this thread's row half, fetched before the wait
-          const uint32_t* w = reinterpret_cast<const uint32_t*>(bits + ((size_t)tile * 4 + kBitSlot[s]) * 4096) + half * 4 * 128 + row;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) mbw[j] = __ldg(w + j * 128);
+        uint32_t w0 = 0u, w1 = 0u;
+        if (!tile_mask) {                        // others: h2 / h1 bitmask words of this thread's 64 columns, fetched before the wait
+          const uint32_t* w = reinterpret_cast<const uint32_t*>(bits + ((size_t)tile * 4 + kBitSlot[s]) * 4096) + cq * 2 * 128 + row;
+          w0 = __ldg(w);
+          w1 = __ldg(w + 128);
         }
+        TP_PF(long long pe_a = clock64();)
         mbar_wait(bar_acc, acc_ph);
         acc_ph ^= 1;
+        TP_PF(long long pe_b = clock64();)
+        TP_PF(pe_acc += pe_b - pe_a;)
         if (tile_mask) {
           mbar_wait(bar_mask, mask_ph);
           mask_ph ^= 1;
         }
         tc_fence_after();
+        TP_PF(pe_a = clock64();)
+        TP_PF(pe_mask += pe_a - pe_b;)
+        // (18 warps leave 96 registers per thread: one slab in flight per thread, four warps per scheduler hide the latency)
+        uint32_t va[32];
+        TP_TMEM_LD32(tmem_d, va);
         if (store_pending) {          // the previous dz image store must have finished reading A
           if (threadIdx.x == 0) bulk_wait_read();
-          named_bar_sync(1, 256);
+          named_bar_sync(1, kFEpiThreads);
           store_pending = false;
         }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint32_t v[32];
-          TP_TMEM_LD32(tmem_d + j * 32, v);
-          TP_TMEM_WAIT32(v);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const uint32_t off = (uint32_t)(half * 16 + j * 4 + i) * 2048 + row * 16;
-            uint32_t o[4];
-            if (tile_mask) {
-              uint32_t m0, m1, m2, m3;
-              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(m0), "=r"(m1), "=r"(m2), "=r"(m3) : "r"(m_smem + off));
-              const uint32_t mw[4] = {m0, m1, m2, m3};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float lo = (mw[e] & 0xffffu) ? __uint_as_float(v[i * 8 + 2 * e]) : 0.f;
-                const float hi = (mw[e] >> 16) ? __uint_as_float(v[i * 8 + 2 * e + 1]) : 0.f;
-                o[e] = pack_bf16(lo, hi);
-              }
-            } else {
-              const uint32_t byte = (mbw[j] >> (i * 8)) & 0xffu;
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float lo = (byte & (1u << (2 * e))) ? __uint_as_float(v[i * 8 + 2 * e]) : 0.f;
-                const float hi = (byte & (2u << (2 * e))) ? __uint_as_float(v[i * 8 + 2 * e + 1]) : 0.f;
-                o[e] = pack_bf16(lo, hi);
-              }
-            }
-            st_shared_v4(a_smem + off, o[0], o[1], o[2], o[3]);
-          }
-        }
-        if (half == 1 && s % 3 != 2) {     // the 1-column of block S for the dz tile just written: column = dz slot
+        TP_PF(pe_b = clock64();)
+        TP_PF(pe_store += pe_b - pe_a;)
+        TP_TMEM_WAIT32(va);
+        convert_slab(va, cq * 8, tile_mask, w0);
+        TP_TMEM_LD32(tmem_d + 32, va);
+        TP_TMEM_WAIT32(va);
+        convert_slab(va, cq * 8 + 4, tile_mask, w1);
+        if (cq == 1 && s % 3 != 2) {       // the 1-column of block S for the dz tile just written: column = dz slot
           const uint32_t one = 0x3F80u << ((s & 1) * 16);
           const int w = s >> 1;
           st_shared_v4(sbase + kOffTS + row * 16, w == 0 ? one : 0u, w == 1 ? one : 0u, w == 2 ? one : 0u, 0u);
           st_shared_v4(sbase + kOffTS + 2048 + row * 16, 0u, 0u, 0u, 0u);
         }
         fence_proxy_async_smem();
-        named_bar_sync(1, 256);           // every thread finished reading M and writing A
+        TP_PF(pe_a = clock64();)
+        TP_PF(pe_conv += pe_a - pe_b;)
+        named_bar_sync(1, kFEpiThreads);  // every thread finished reading M and writing A
+        TP_PF(pe_bar += clock64() - pe_a;)
         if (threadIdx.x == 0) {
           bulk_s2g(p.dz_out + ((size_t)tile * kDzSlots + s) * kABytes, a_smem, kABytes);
           bulk_commit();
@@ -579,8 +622,8 @@ __global__ void __launch_bounds__(kThreads, 1) backward_chain_fused_kernel(const
     mbar_arrive(bar_ready);
     mbar_wait(bar_acc, acc_ph);
     tc_fence_after();
-    {
-      const int n = half * 128 + row;
+    if (cq < 2) {                                 // column quarters 0 / 1 flush the accumulators of feature half 0 / 1
+      const int half = cq, n = half * 128 + row;
       float* P = fp.extras + (size_t)blockIdx.x * kXCols * 256 + n;
       const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
       auto flush = [&](uint32_t col, int ncols, int x0, int src0) {   // TMEM columns [col, col+8) -> P[x0 + i] for i < ncols (from src0)
@@ -606,7 +649,7 @@ __global__ void __launch_bounds__(kThreads, 1) backward_chain_fused_kernel(const
       flush(cOr, 3, kXwr, 0);
       flush(cOt, 5, kXwt, 0);
     }
-    if (half == 0) {
+    if (cq == 0) {
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         float v = zsum[c];
@@ -616,11 +659,15 @@ __global__ void __launch_bounds__(kThreads, 1) backward_chain_fused_kernel(const
       }
     }
     if (threadIdx.x == 0) bulk_wait_all();
+    TP_PF(if (fp.prof && threadIdx.x == 0) {
+      long long* o = fp.prof + (size_t)blockIdx.x * 16 + 8;
+      o[0] = pe_acc; o[1] = pe_mask; o[2] = pe_store; o[3] = pe_conv; o[4] = pe_bar;
+    })
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == kFEpiWarps + 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
@@ -1197,10 +1244,14 @@ TP_API int tp_tc_heads_backward(const float* dz_rgb, const float* dz_trans, int6
   fp.b.dz_out = reinterpret_cast<uint8_t*>(dz_images);
   fp.center = center; fp.ray = ray; fp.depth = depth; fp.N = N; fp.per_image = per_image; fp.L_view = L_view;
   fp.extras = extras; fp.thin_sums = thin_sums;
+  // debugging aid: a workspace with 2*16*grid extra floats receives the MMA warp's cycle counters in its tail
+  const int64_t need = tp_tc_heads_backward_workspace(S, B);
+  fp.prof = workspace_floats >= need + 32 * (int64_t)grid ? reinterpret_cast<long long*>(workspace + ((need + 1) & ~(int64_t)1)) : nullptr;
   cudaError_t e = cudaFuncSetAttribute(tcb::backward_chain_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)tcb::kSmemBytesF);
   if (e != cudaSuccess) return (int)e;
-  tcb::backward_chain_fused_kernel<<<grid, tcb::kThreads, tcb::kSmemBytesF, st>>>(fp);
+  tcb::backward_chain_fused_kernel<<<grid, tcb::kFThreads, tcb::kSmemBytesF, st>>>(fp);
+  if (int rc = tp_launch_status()) return rc;
 
   tcb::FinishParams f;
   f.extras = extras; f.thin_sums = thin_sums; f.grid = grid; f.n_tiles = n_tiles; f.per_image = per_image;
