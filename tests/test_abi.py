@@ -32,3 +32,30 @@ def test_no_torch_types_in_abi():
 def test_sources_are_sm100a_only():
     assert "arch=compute_100a,code=sm_100a" in " ".join(_C.NVCC_FLAGS)
     assert os.path.exists(_C.LIB_PATH)
+
+
+def test_host_side_helpers_without_gpu():
+    """Pure host arithmetic of the C-ABI (no kernel launch): workspace sizes and the fused-backward applicability rule."""
+    lib = _C.load()
+    assert lib.tp_patch_loss_workspace() >= 8 and lib.tp_eval_epilogue_workspace(3) == 3 * 64
+    assert lib.tp_tc_dz_bytes(129) == 2 * 6 * 65536
+    assert lib.tp_tc_save_bytes(129) == 2 * (7 * 65536 + 4 * 4096)        # tile images + ReLU bitmasks, whole super-tiles
+    # one tile per CTA (few tiles): a 128-sample range may touch at most 4 images -> images of >= 64 samples
+    assert lib.tp_tc_heads_backward_supported(16 * 256 * 128, 256 * 128) == 1
+    assert lib.tp_tc_heads_backward_supported(64 * 4 * 8, 32) == 0
+    assert lib.tp_tc_heads_backward_supported(0, 128) == 0
+
+
+def test_flex_patch_sampler_matches_oracle_on_cpu():
+    """FlexPatchSampler is host logic (three torch.rand draws): identical to the oracle restatement for the same RNG state,
+    and the coordinates stay inside [-1, 1] (tools/patch_sampler.py:100-110)."""
+    import torch
+    from oracle import texpose_oracle as O
+    from texpose_b200.tools.patch_sampler import FlexPatchSampler
+    for seed, (B, P) in enumerate([(1, 2), (7, 16), (3, 5)]):
+        torch.manual_seed(seed)
+        want = O.flex_patch_coords(B, P)
+        torch.manual_seed(seed)
+        got = FlexPatchSampler()(nbatch=B, patch_size=P, device="cpu")
+        assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
+        assert got[0].shape == (B, P, P, 2) and got[0].abs().max() <= 1.0

@@ -175,3 +175,25 @@ def test_fused_backward_matches_multikernel(B, R, N, monkeypatch):
     c = grads("fused")
     for (n, x), (_, y) in zip(a, c):
         assert torch.equal(x, y), n
+
+
+def test_backward_falls_back_when_images_are_tiny():
+    """Images of 32 samples: a CTA's tile range would touch more than four of them -> tp_tc_heads_backward is not applicable
+    and the host takes the multi-kernel sequence; gradients still match the fp32 kernels within the bf16 tolerance."""
+    from texpose_b200 import mlp_tc_bwd
+    B, R, N = 64, 4, 8
+    assert not mlp_tc_bwd.fused_supported(B * R * N, R * N)
+    g = torch.Generator().manual_seed(2)
+    center = (torch.randn(B, R, 3, generator=g) * 0.02 + torch.tensor([0.3, 0.2, -0.8])).to(DEV)
+    ray = (torch.randn(B, R, 3, generator=g) * 0.1 + torch.tensor([0.0, 0.0, 1.0])).to(DEV)
+    depth = ((torch.rand(B, R, N, 1, generator=g) + torch.arange(N)[None, None, :, None]) / N * 1.2 + 0.2).to(DEV)
+    lt0, ll0 = synth.latents(B)
+    res = {}
+    for prec in ("bf16", "fp32"):
+        opt, m = _module(prec)
+        lt, ll = lt0.to(DEV).requires_grad_(True), ll0.to(DEV).requires_grad_(True)
+        out = m.forward_samples(opt, center, ray, depth, lt, ll, mode="train")
+        (out[0].mean() + out[1][..., 1].mean() + out[2].mean()).backward()
+        res[prec] = [lt.grad, ll.grad] + [p.grad for p in list(m.mlp_rgb.parameters()) + list(m.mlp_trans.parameters())]
+    for a, b in zip(res["bf16"], res["fp32"]):
+        assert (a - b).abs().max() <= max(1e-3, 0.02 * b.abs().max().item())

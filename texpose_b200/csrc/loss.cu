@@ -165,6 +165,7 @@ TP_API int tp_patch_loss(const float* image, const float* obj_mask, const float*
   if (workspace_floats < (int64_t)p.blocks * 4) return TP_ERR_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
   patch_loss_partial_kernel<<<p.blocks, kLossThreads, 0, st>>>(p);
+  if (int rc = tp_launch_status()) return rc;
   patch_loss_grad_kernel<<<p.blocks, kLossThreads, 0, st>>>(p);
   return tp_launch_status();
 }
@@ -230,6 +231,7 @@ TP_API int tp_eval_epilogue(const float* rgb, const float* depth, const float* i
   cudaStream_t st = (cudaStream_t)stream;
   eval_epilogue_kernel<<<dim3(kEvalBlocksPerView, B), 256, 0, st>>>(rgb, depth, image, mask, HW, depth_scale, rgb_map,
                                                                     depth_map, image_masked, workspace);
+  if (int rc = tp_launch_status()) return rc;
   eval_psnr_kernel<<<(B + 63) / 64, 64, 0, st>>>(workspace, kEvalBlocksPerView, HW, B, mse, psnr);
   return tp_launch_status();
 }

@@ -1155,6 +1155,7 @@ TP_API int tp_thin_colsum(const float* x, int64_t S, int C, float* out, float* w
   if (workspace_floats < (int64_t)blocks * C) return TP_ERR_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
   tcb::thin_colsum_kernel<<<blocks, 256, 0, st>>>(x, S, C, workspace);
+  if (int rc = tp_launch_status()) return rc;
   return tp_reduce_partials(workspace, blocks, C, out, 0, stream);
 }
 
@@ -1260,7 +1261,9 @@ TP_API int tp_tc_heads_backward(const float* dz_rgb, const float* dz_trans, int6
   for (int i = 0; i < 16; ++i) f.g[i] = grads[i];
   f.d_lat_light = d_lat_light; f.d_lat_trans = d_lat_trans;
   tcb::bwd_finish1_kernel<<<tcb::kXCols, 256, 0, st>>>(f);
+  if (int rc = tp_launch_status()) return rc;
   tcb::bwd_finish2_kernel<<<B + 2, 256, 2 * 256 * sizeof(float), st>>>(f);
+  if (int rc = tp_launch_status()) return rc;
 
   // the six 256 x 256 weight gradients: layers 2, 1, 0 of the rgb head, then of the transient head
   tcb::DwParams p;
@@ -1272,6 +1275,7 @@ TP_API int tp_tc_heads_backward(const float* dz_rgb, const float* dz_trans, int6
   e = cudaFuncSetAttribute(tcb::dw_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcb::kDwSmemBytes);
   if (e != cudaSuccess) return (int)e;
   tcb::dw_gemm_kernel<<<p.splits * 6, tcb::kThreads, tcb::kDwSmemBytes, st>>>(p);
+  if (int rc = tp_launch_status()) return rc;
   tcb::DwOut o;
   const int gidx[6] = {4, 2, 0, 12, 10, 8};          // grads[] index of dW2, dW1, dW0 per head
   for (int j = 0; j < 6; ++j) { o.ptr[j] = grads[gidx[j]]; o.ld[j] = 256; }

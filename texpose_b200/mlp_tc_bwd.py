@@ -13,6 +13,7 @@ import torch
 from . import _C, ops
 
 FWD_SLOTS, DZ_SLOTS = 7, 6
+last_profile_workspace = None       # (workspace tensor, float offset of the counters) of the last instrumented call
 # forward-save slots: 0 feat, 1-3 rgb h1..h3, 4-6 trans h1..h3; dz slots: rgb dz2,dz1,dz0, trans dz2,dz1,dz0
 _BIG_PAIRS = {"rgb": [(0, 2), (1, 1), (2, 0)], "trans": [(3, 5), (4, 4), (5, 0)]}      # (dz slot, x slot) for layers 2,1,0
 
@@ -131,7 +132,12 @@ def heads_backward_fused(cfg, sv, S, per_image, rgb_p, trans_p, g_rgb, g_density
     packed = pack_bwd(cfg.packed, rgb_p, trans_p)
     lib = _C.load()
     dz = torch.empty(lib.tp_tc_dz_bytes(S), dtype=torch.uint8, device=dev)
-    ws = torch.empty(lib.tp_tc_heads_backward_workspace(S, B), device=dev)
+    need = lib.tp_tc_heads_backward_workspace(S, B)
+    prof = bool(os.environ.get("TEXPOSE_CHAIN_PROF"))       # scripts/chain_prof.py: cycle counters land in the workspace tail
+    ws = torch.empty(need + (32 * 160 + 2 if prof else 0), device=dev)
+    if prof:
+        global last_profile_workspace
+        last_profile_workspace = (ws, (need + 1) & ~1)
     grads = []
     for layers in (rgb_p, trans_p):
         for W, b in layers:
