@@ -45,35 +45,38 @@ class GradBucket:
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
 
     def pack(self):
-        off = 0
-        for p, n in zip(self.params, self.sizes):
-            if p.grad is None:
-                self.flat[off:off + n].zero_()
-            else:
-                self.flat[off:off + n].copy_(p.grad.reshape(-1))
-            off += n
+        """One launch: concatenate the gradients into the flat buffer (missing gradients count as zero)."""
+        base = self.flat.untyped_storage().data_ptr()
+        parts = []
+        for p in self.params:
+            g = p.grad if p.grad is not None else torch.zeros_like(p)
+            if g.untyped_storage().data_ptr() == base:      # a view left by the previous unpack, accumulated into: no aliasing
+                g = g.clone()
+            parts.append(g.reshape(-1))
+        if parts:
+            torch.cat(parts, out=self.flat)
         return self.flat
 
     def unpack(self):
+        """No copy back: every .grad becomes a view into the reduced flat buffer."""
         off = 0
         for p, n in zip(self.params, self.sizes):
-            g = self.flat[off:off + n].view_as(p)
-            if p.grad is None:
-                p.grad = g.clone()
-            else:
-                p.grad.copy_(g)
+            p.grad = self.flat[off:off + n].view_as(p)
             off += n
 
     def allreduce_mean(self, group=None):
-        """sum-allreduce then divide by the world size (per-shard losses are means)."""
+        """Mean over the ranks of every gradient (per-shard losses are means): one concatenation, one allreduce."""
         if not (dist.is_available() and dist.is_initialized()):
             return
         world = dist.get_world_size(group)
         if world == 1:
             return
         self.pack()
-        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
-        self.flat.div_(world)
+        if dist.get_backend(group) == "nccl":
+            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=group)
+        else:                                       # gloo (CPU tests) has no AVG
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+            self.flat.div_(world)
         self.unpack()
 
 
