@@ -170,6 +170,10 @@ int64_t tp_tc_scratch_bytes(void);
  * col0, cols_valid, n_layout (256|16), bias device pointer (0 = none), bias k-column, 0}; packed: n_chunks*chunk_bytes. */
 int tp_tc_pack_weights(const int64_t* chunk_desc, int n_chunks, void* packed, void* stream);
 
+/* Re-orders a tp_tc_pack_weights image for the CTA-pair kernel (tp_tc_nerf_stl_forward flags bit 10: tcgen05 cta_group::2 over
+ * clusters of two CTAs, each SM holding half of every weight chunk): rank r's half of chunk c at c*16 KB + r*8 KB. */
+int tp_tc_pair_weights(const void* packed, void* pair_packed, void* stream);
+
 /* out[b,:] = bias + W[:, col0:col0+ncols] latent[b]   (per-image constants folded into a bias; fp32) */
 int tp_tc_image_bias(const float* W, int64_t ldw, int col0, int ncols, const float* bias, const float* latent, int B,
                      int nout, float* out, void* stream);

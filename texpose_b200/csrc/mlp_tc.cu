@@ -25,6 +25,7 @@
 // `rows` rows lives at  (k/8)*rows*16 + r*16 + (k%8)*2  bytes -> 8x8 core matrices of 128 contiguous bytes,
 // LBO (K-direction core-matrix stride) = rows*16, SBO (8-row-group stride) = 128.
 #include "mlp_tc_shared.cuh"
+#include "mlp_tc_epilogue.cuh"
 #include "../../include/texpose_b200.h"
 
 namespace tc {
@@ -36,123 +37,6 @@ constexpr int kStages = 4;
 constexpr uint32_t kOffA = 0, kOffE = 2 * kABytes, kOffRing = kOffE + 2 * kEBytes;
 constexpr uint32_t kOffBar = kOffRing + kStages * kChunkBytes;
 constexpr uint32_t kSmemBytes = kOffBar + 128;
-// One 32-column slab of a hidden stage: (+fp32 bias,) ReLU, bf16, store as 4 core-matrix rows of the next A operand.
-// kBits (training): also returns the ReLU mask of the 32 columns (bit e = column e is positive) -- one funnel shift per
-// element collects the sign bits; the backward reads these 4 KB bitmasks instead of the 64 KB activation tiles.
-template <bool kBias, bool kBits = false>
-__device__ __forceinline__ uint32_t hidden_slab(const uint32_t (&v)[32], const float* bias, uint32_t a_dst, float* dbg_row) {
-  uint32_t signs = 0u;
-#pragma unroll
-  for (int i = 0; i < 32; i += 8) {
-    float x[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(v[i + e]);
-    if (kBias) {
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + i));
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + i + 4));
-      x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
-      x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
-    }
-    if (kBits) {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) signs = __funnelshift_l(__float_as_uint(x[e]), signs, 1);
-    }
-    st_shared_v4(a_dst + (i >> 3) * 2048, pack_relu_bf16(x[0], x[1]), pack_relu_bf16(x[2], x[3]), pack_relu_bf16(x[4], x[5]),
-                 pack_relu_bf16(x[6], x[7]));
-    if (dbg_row) {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) dbg_row[i + e] = fmaxf(x[e], 0.f);
-    }
-  }
-  return __brev(~signs);      // element 0 was shifted in first: reverse; positive = sign bit clear
-}
-
-// Same with the bias row held distributed across the warp (lane l owns columns 4l..4l+3 of the thread's column range, in
-// `mine[0]`, and 128+4l.. in `mine[1]` when a thread converts 256 columns): valid when all 32 rows of the warp share one
-// bias row (N % 32 == 0).  8 shuffles per 8 columns replace 2 dependent L2 round trips.
-template <bool kBits = false>
-__device__ __forceinline__ uint32_t hidden_slab_wbias(const uint32_t (&v)[32], const float4 (&mine)[2], int col0, uint32_t a_dst,
-                                                      float* dbg_row) {
-  uint32_t signs = 0u;
-#pragma unroll
-  for (int i = 0; i < 32; i += 8) {
-    const int c = col0 + i;                       // first column of this group within the thread's range
-    const float4 src = mine[(c >> 7) & 1];
-    const int l0 = (c & 127) >> 2;
-    float x[8];
-    x[0] = __uint_as_float(v[i + 0]) + __shfl_sync(0xffffffffu, src.x, l0);
-    x[1] = __uint_as_float(v[i + 1]) + __shfl_sync(0xffffffffu, src.y, l0);
-    x[2] = __uint_as_float(v[i + 2]) + __shfl_sync(0xffffffffu, src.z, l0);
-    x[3] = __uint_as_float(v[i + 3]) + __shfl_sync(0xffffffffu, src.w, l0);
-    x[4] = __uint_as_float(v[i + 4]) + __shfl_sync(0xffffffffu, src.x, l0 + 1);
-    x[5] = __uint_as_float(v[i + 5]) + __shfl_sync(0xffffffffu, src.y, l0 + 1);
-    x[6] = __uint_as_float(v[i + 6]) + __shfl_sync(0xffffffffu, src.z, l0 + 1);
-    x[7] = __uint_as_float(v[i + 7]) + __shfl_sync(0xffffffffu, src.w, l0 + 1);
-    if (kBits) {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) signs = __funnelshift_l(__float_as_uint(x[e]), signs, 1);
-    }
-    st_shared_v4(a_dst + (i >> 3) * 2048, pack_relu_bf16(x[0], x[1]), pack_relu_bf16(x[2], x[3]), pack_relu_bf16(x[4], x[5]),
-                 pack_relu_bf16(x[6], x[7]));
-    if (dbg_row) {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) dbg_row[i + e] = fmaxf(x[e], 0.f);
-    }
-  }
-  return __brev(~signs);
-}
-
-template <int kSlabs, bool kBits = false>
-__device__ __forceinline__ void hidden_epilogue_wbias(uint32_t tmem_d, const float4 (&mine)[2], uint32_t a_row, float* dbg_row,
-                                                      uint32_t* words = nullptr) {      // words: plane j at words[j * 128]
-  uint32_t va[32], vb[32];
-  TP_TMEM_LD32(tmem_d, va);
-#pragma unroll
-  for (int j = 0; j < kSlabs; j += 2) {
-    TP_TMEM_WAIT32(va);
-    TP_TMEM_LD32(tmem_d + (j + 1) * 32, vb);
-    const uint32_t w0 = hidden_slab_wbias<kBits>(va, mine, j * 32, a_row + j * 4 * 2048, dbg_row ? dbg_row + j * 32 : nullptr);
-    TP_TMEM_WAIT32(vb);
-    if (j + 2 < kSlabs) TP_TMEM_LD32(tmem_d + (j + 2) * 32, va);
-    const uint32_t w1 = hidden_slab_wbias<kBits>(vb, mine, (j + 1) * 32, a_row + (j + 1) * 4 * 2048,
-                                                 dbg_row ? dbg_row + (j + 1) * 32 : nullptr);
-    if (kBits) { words[j * 128] = w0; words[(j + 1) * 128] = w1; }
-  }
-}
-
-// Whole 128x256 accumulator row of one thread: TMEM loads are software-pipelined (slab j+1 in flight while slab j is
-// converted), ping-ponging two register slabs.
-// timing experiment (results are wrong on purpose): what bounds the drain -- the TMEM read or the convert/store?
-template <int kSlabs>
-__device__ __noinline__ void hidden_epilogue_experiment(uint32_t tmem_d, uint32_t a_row, int mode) {
-  uint32_t v[32];
-  for (int j = 0; j < kSlabs; ++j) {
-    if (mode == 2 && (j & 1)) continue;
-    TP_TMEM_LD32(tmem_d + j * 32, v);
-    TP_TMEM_WAIT32(v);
-    if (j & 1) continue;
-    hidden_slab<false>(v, nullptr, a_row + j * 4 * 2048, nullptr);
-  }
-}
-
-template <bool kBias, int kSlabs, bool kBits = false>
-__device__ __forceinline__ void hidden_epilogue(uint32_t tmem_d, const float* bias, uint32_t a_row, float* dbg_row,
-                                                uint32_t* words = nullptr) {
-  uint32_t va[32], vb[32];
-  TP_TMEM_LD32(tmem_d, va);
-#pragma unroll
-  for (int j = 0; j < kSlabs; j += 2) {
-    TP_TMEM_WAIT32(va);
-    TP_TMEM_LD32(tmem_d + (j + 1) * 32, vb);
-    const uint32_t w0 = hidden_slab<kBias, kBits>(va, bias + j * 32, a_row + j * 4 * 2048, dbg_row ? dbg_row + j * 32 : nullptr);
-    TP_TMEM_WAIT32(vb);
-    if (j + 2 < kSlabs) TP_TMEM_LD32(tmem_d + (j + 2) * 32, va);
-    const uint32_t w1 = hidden_slab<kBias, kBits>(vb, bias + (j + 1) * 32, a_row + (j + 1) * 4 * 2048,
-                                                  dbg_row ? dbg_row + (j + 1) * 32 : nullptr);
-    if (kBits) { words[j * 128] = w0; words[(j + 1) * 128] = w1; }
-  }
-}
-
 template <int kHalves>
 __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_kernel(const Params p) {
   constexpr int kEpiWarps = 8 * kHalves, kProducerWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
@@ -177,7 +61,7 @@ __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_ke
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(bar_acc(t), 1);
-      mbar_init(bar_ready(t), kTileThreads);
+      mbar_init(bar_ready(t), kTileThreads / 32);     // one arrive per epilogue warp of the tile
       mbar_init(bar_reload(t), 1);
     }
     fence_barrier_init();
@@ -307,7 +191,8 @@ __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_ke
       if (half == 0) encode_sample(p, s, e_smem, row);
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(bar_ready(t));
+      __syncwarp();                    // every lane's st.shared + proxy fence precede the warp's single arrive
+      if (lane == 0) mbar_arrive(bar_ready(t));
 
       float sigma_s = 0.f, rgb_s[3] = {0.f, 0.f, 0.f};
       for (int L = 0; L < kNumLayers; ++L) {
@@ -405,7 +290,8 @@ __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_ke
         }
         if (L != kNumLayers - 1) {   // the next super-tile's encode arrival covers the last stage
           tc_fence_before();
-          mbar_arrive(bar_ready(t));
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_ready(t));
         }
       }
     }
@@ -532,6 +418,7 @@ __global__ void unpack_images_kernel(const uint8_t* __restrict__ images, int slo
 }  // namespace tc
 
 int tp_tc_v2_launch(const tc::Params& p, int flags, cudaStream_t stream);   // mlp_tc_v2.cu
+int tp_tc_pair_launch(const tc::Params& p, cudaStream_t stream);            // mlp_tc_pair.cu
 
 TP_API int tp_tc_num_chunks(void) { return tc::kNumChunks; }
 TP_API int64_t tp_tc_chunk_bytes(void) { return tc::kChunkBytes; }
@@ -604,6 +491,10 @@ TP_API int tp_tc_nerf_stl_forward(const float* center, const float* ray, const f
   p.dbg_layer = dbg_layer; p.dbg_out = dbg_out; p.dbg_drain = (flags >> 2) & 7;
   p.skew = ((flags >> 5) & 3) ? ((flags >> 5) & 3) - 1 : 1;      // default skew 1; flags bits 5-6 = skew+1 override (A/B)
   if (flags & 128) return tp_tc_v2_launch(p, flags, (cudaStream_t)stream);   // experimental single-tile / cluster kernel
+  if (flags & 1024) {     // CTA-pair kernel (cta_group::2); `packed` must be the pair image; flags bits 11-13 = skew + 1 (default 4)
+    p.skew = ((flags >> 11) & 7) ? ((flags >> 11) & 7) - 1 : 4;
+    return tp_tc_pair_launch(p, (cudaStream_t)stream);
+  }
   const bool wide = (flags & 2) == 0;       // default: 16 epilogue warps; flags bit 1 selects the 8-warp variant
   cudaError_t e = wide ? cudaFuncSetAttribute(tc::nerf_stl_forward_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               (int)tc::kSmemBytes)

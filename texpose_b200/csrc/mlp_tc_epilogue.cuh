@@ -1,0 +1,125 @@
+// Accumulator-drain helpers of the fused forward kernels (mlp_tc.cu: one CTA per SM; mlp_tc_pair.cu: CTA pairs, cta_group::2):
+// TMEM -> registers -> (+bias) ReLU -> bf16 -> SMEM A operand of the next stage, optionally emitting the ReLU bitmask.
+#pragma once
+#include "mlp_tc_shared.cuh"
+
+namespace tc {
+
+// One 32-column slab of a hidden stage: (+fp32 bias,) ReLU, bf16, store as 4 core-matrix rows of the next A operand.
+// kBits (training): also returns the ReLU mask of the 32 columns (bit e = column e is positive) -- one funnel shift per
+// element collects the sign bits; the backward reads these 4 KB bitmasks instead of the 64 KB activation tiles.
+template <bool kBias, bool kBits = false>
+__device__ __forceinline__ uint32_t hidden_slab(const uint32_t (&v)[32], const float* bias, uint32_t a_dst, float* dbg_row) {
+  uint32_t signs = 0u;
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    float x[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(v[i + e]);
+    if (kBias) {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + i));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + i + 4));
+      x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
+      x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+    }
+    if (kBits) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) signs = __funnelshift_l(__float_as_uint(x[e]), signs, 1);
+    }
+    st_shared_v4(a_dst + (i >> 3) * 2048, pack_relu_bf16(x[0], x[1]), pack_relu_bf16(x[2], x[3]), pack_relu_bf16(x[4], x[5]),
+                 pack_relu_bf16(x[6], x[7]));
+    if (dbg_row) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) dbg_row[i + e] = fmaxf(x[e], 0.f);
+    }
+  }
+  return __brev(~signs);      // element 0 was shifted in first: reverse; positive = sign bit clear
+}
+
+// Same with the bias row held distributed across the warp (lane l owns columns 4l..4l+3 of the thread's column range, in
+// `mine[0]`, and 128+4l.. in `mine[1]` when a thread converts 256 columns): valid when all 32 rows of the warp share one
+// bias row (N % 32 == 0).  8 shuffles per 8 columns replace 2 dependent L2 round trips.
+template <bool kBits = false>
+__device__ __forceinline__ uint32_t hidden_slab_wbias(const uint32_t (&v)[32], const float4 (&mine)[2], int col0, uint32_t a_dst,
+                                                      float* dbg_row) {
+  uint32_t signs = 0u;
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const int c = col0 + i;                       // first column of this group within the thread's range
+    const float4 src = mine[(c >> 7) & 1];
+    const int l0 = (c & 127) >> 2;
+    float x[8];
+    x[0] = __uint_as_float(v[i + 0]) + __shfl_sync(0xffffffffu, src.x, l0);
+    x[1] = __uint_as_float(v[i + 1]) + __shfl_sync(0xffffffffu, src.y, l0);
+    x[2] = __uint_as_float(v[i + 2]) + __shfl_sync(0xffffffffu, src.z, l0);
+    x[3] = __uint_as_float(v[i + 3]) + __shfl_sync(0xffffffffu, src.w, l0);
+    x[4] = __uint_as_float(v[i + 4]) + __shfl_sync(0xffffffffu, src.x, l0 + 1);
+    x[5] = __uint_as_float(v[i + 5]) + __shfl_sync(0xffffffffu, src.y, l0 + 1);
+    x[6] = __uint_as_float(v[i + 6]) + __shfl_sync(0xffffffffu, src.z, l0 + 1);
+    x[7] = __uint_as_float(v[i + 7]) + __shfl_sync(0xffffffffu, src.w, l0 + 1);
+    if (kBits) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) signs = __funnelshift_l(__float_as_uint(x[e]), signs, 1);
+    }
+    st_shared_v4(a_dst + (i >> 3) * 2048, pack_relu_bf16(x[0], x[1]), pack_relu_bf16(x[2], x[3]), pack_relu_bf16(x[4], x[5]),
+                 pack_relu_bf16(x[6], x[7]));
+    if (dbg_row) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) dbg_row[i + e] = fmaxf(x[e], 0.f);
+    }
+  }
+  return __brev(~signs);
+}
+
+template <int kSlabs, bool kBits = false>
+__device__ __forceinline__ void hidden_epilogue_wbias(uint32_t tmem_d, const float4 (&mine)[2], uint32_t a_row, float* dbg_row,
+                                                      uint32_t* words = nullptr) {      // words: plane j at words[j * 128]
+  uint32_t va[32], vb[32];
+  TP_TMEM_LD32(tmem_d, va);
+#pragma unroll
+  for (int j = 0; j < kSlabs; j += 2) {
+    TP_TMEM_WAIT32(va);
+    TP_TMEM_LD32(tmem_d + (j + 1) * 32, vb);
+    const uint32_t w0 = hidden_slab_wbias<kBits>(va, mine, j * 32, a_row + j * 4 * 2048, dbg_row ? dbg_row + j * 32 : nullptr);
+    TP_TMEM_WAIT32(vb);
+    if (j + 2 < kSlabs) TP_TMEM_LD32(tmem_d + (j + 2) * 32, va);
+    const uint32_t w1 = hidden_slab_wbias<kBits>(vb, mine, (j + 1) * 32, a_row + (j + 1) * 4 * 2048,
+                                                 dbg_row ? dbg_row + (j + 1) * 32 : nullptr);
+    if (kBits) { words[j * 128] = w0; words[(j + 1) * 128] = w1; }
+  }
+}
+
+// Whole 128x256 accumulator row of one thread: TMEM loads are software-pipelined (slab j+1 in flight while slab j is
+// converted), ping-ponging two register slabs.
+// timing experiment (results are wrong on purpose): what bounds the drain -- the TMEM read or the convert/store?
+template <int kSlabs>
+__device__ __noinline__ void hidden_epilogue_experiment(uint32_t tmem_d, uint32_t a_row, int mode) {
+  uint32_t v[32];
+  for (int j = 0; j < kSlabs; ++j) {
+    if (mode == 2 && (j & 1)) continue;
+    TP_TMEM_LD32(tmem_d + j * 32, v);
+    TP_TMEM_WAIT32(v);
+    if (j & 1) continue;
+    hidden_slab<false>(v, nullptr, a_row + j * 4 * 2048, nullptr);
+  }
+}
+
+template <bool kBias, int kSlabs, bool kBits = false>
+__device__ __forceinline__ void hidden_epilogue(uint32_t tmem_d, const float* bias, uint32_t a_row, float* dbg_row,
+                                                uint32_t* words = nullptr) {
+  uint32_t va[32], vb[32];
+  TP_TMEM_LD32(tmem_d, va);
+#pragma unroll
+  for (int j = 0; j < kSlabs; j += 2) {
+    TP_TMEM_WAIT32(va);
+    TP_TMEM_LD32(tmem_d + (j + 1) * 32, vb);
+    const uint32_t w0 = hidden_slab<kBias, kBits>(va, bias + j * 32, a_row + j * 4 * 2048, dbg_row ? dbg_row + j * 32 : nullptr);
+    TP_TMEM_WAIT32(vb);
+    if (j + 2 < kSlabs) TP_TMEM_LD32(tmem_d + (j + 2) * 32, va);
+    const uint32_t w1 = hidden_slab<kBias, kBits>(vb, bias + (j + 1) * 32, a_row + (j + 1) * 4 * 2048,
+                                                  dbg_row ? dbg_row + (j + 1) * 32 : nullptr);
+    if (kBits) { words[j * 128] = w0; words[(j + 1) * 128] = w1; }
+  }
+}
+
+}  // namespace tc

@@ -13,6 +13,7 @@ import torch
 from . import _C, ops
 
 _F = 256
+PAIR_KERNEL = 1024      # tp_tc_nerf_stl_forward flags bit 10: cta_group::2 kernel over CTA pairs (csrc/mlp_tc_pair.cu)
 
 
 def supported(cfg, feat_p, rgb_p, trans_p) -> bool:
@@ -87,7 +88,7 @@ def _chunk_table(cfg, feat_p, rgb_p, trans_p):
 
 
 class Packed:
-    __slots__ = ("key", "weights", "biasbuf", "keep")
+    __slots__ = ("key", "weights", "weights_pair", "biasbuf", "keep")
 
 
 def _version_key(params):
@@ -116,6 +117,7 @@ def pack(cfg, holder, feat_p, rgb_p, trans_p, params_for_key) -> Packed:
     biasbuf[4:9] = tb[3]
     out = Packed()
     out.key, out.weights, out.biasbuf = key, weights, biasbuf
+    out.weights_pair = None                    # built on first use of the CTA-pair kernel (flags bit 10)
     out.keep = (desc, keep)
     if holder is not None:
         holder._packed = out
@@ -163,7 +165,13 @@ def forward(cfg, geom, lat_trans, lat_light, feat_p, rgb_p, trans_p, dbg_layer=-
     scratch = _scratch_for(dev)
     dbg = torch.zeros(S, _F, device=dev) if dbg_layer >= 0 else None
     images = torch.empty(_C.load().tp_tc_save_bytes(S), dtype=torch.uint8, device=dev) if save else None
-    _C.call("tp_tc_nerf_stl_forward", ops._p(center), ops._p(ray), ops._p(depth), S, N, per_image, ops._p(pk.weights),
+    weights = pk.weights
+    if flags & PAIR_KERNEL:
+        if pk.weights_pair is None:
+            pk.weights_pair = torch.empty_like(pk.weights)
+            _C.call("tp_tc_pair_weights", ops._p(pk.weights), ops._p(pk.weights_pair), ops._stream())
+        weights = pk.weights_pair
+    _C.call("tp_tc_nerf_stl_forward", ops._p(center), ops._p(ray), ops._p(depth), S, N, per_image, ops._p(weights),
             ops._p(pk.biasbuf), ops._p(raybias), ops._p(img_t), ops._p(rgb), ops._p(density), ops._p(uncert),
             ops._p(scratch), scratch.numel(), ops._p(images), dbg_layer, ops._p(dbg), flags, ops._stream())
     if dbg_layer >= 0:
