@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(kFThreads, 1) backward_chain_fused_kernel(cons
       mbar_init(bar_empty(s), 1);
     }
     mbar_init(bar_acc, 1);
-    mbar_init(bar_ready, kFEpiThreads);
+    mbar_init(bar_ready, kFEpiWarps);      // one arrive per epilogue warp
     mbar_init(bar_mask, 1);
     fence_barrier_init();
   }
@@ -551,7 +551,8 @@ __global__ void __launch_bounds__(kFThreads, 1) backward_chain_fused_kernel(cons
       }
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(bar_ready);
+      __syncwarp();                 // every lane's st.shared + proxy fence precede the warp's single arrive
+      if (lane == 0) mbar_arrive(bar_ready);
 
       for (int s = 0; s < kNumStagesPerTile; ++s) {
         const bool tile_mask = s % 3 == 0;       // stages 0 / 3 mask with the h3 tile in M (it is also block O's operand)
@@ -613,13 +614,15 @@ __global__ void __launch_bounds__(kFThreads, 1) backward_chain_fused_kernel(cons
         }
         if (s != kNumStagesPerTile - 1) {
           tc_fence_before();
-          mbar_arrive(bar_ready);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_ready);
         }
       }
     }
     // last tile: release the trans-dz0 thin MMA, then flush the thin accumulators of this CTA
     tc_fence_before();
-    mbar_arrive(bar_ready);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_ready);
     mbar_wait(bar_acc, acc_ph);
     tc_fence_after();
     if (cq < 2) {                                 // column quarters 0 / 1 flush the accumulators of feature half 0 / 1
