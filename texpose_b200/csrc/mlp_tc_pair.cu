@@ -93,6 +93,13 @@ __device__ __forceinline__ void umma2_commit_both(uint32_t bar) {
                : "memory");
 }
 
+// chunk groups of a (stage, tile) pass: the first chunk alone (so the stage starts as soon as the A operand is ready), then
+// groups of four; the peer forwards "my weight halves landed" once per group, the leader's gate releases a group at a time
+__device__ __forceinline__ bool group_start(int c) { return c == 0 || ((c - 1) & 3) == 0; }
+__device__ __forceinline__ bool group_end(int c, int nch) { return c == 0 || ((c - 1) & 3) == 3 || c == nch - 1; }
+// a role can run at most kRing chunks = kRing groups ahead of its consumer: 2 * kRing barriers per kind rule out a phase overrun
+constexpr int kPeerBars = 16;
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nerf_stl_forward_pair_kernel(const Params p, int iters) {
   constexpr int kProducerWarp = 16, kCtrlWarp = 17, kGateWarp = 18;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -109,24 +116,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nerf_st
   auto bar_acc = [&](int t) { return bar0 + 8 * (2 * kRing + t); };
   auto bar_ready = [&](int t) { return bar0 + 8 * (2 * kRing + 2 + t); };
   auto bar_reload = [&](int t) { return bar0 + 8 * (2 * kRing + 4 + t); };
-  auto bar_peer = [&](int s) { return bar0 + 8 * (2 * kRing + 6 + s); };     // leader: peer's chunk half landed / tile 0 ready
-  const uint32_t bar_peer_t1 = bar0 + 8 * (3 * kRing + 6);                    // leader: peer's tile 1 ready for this stage
-  auto bar_go = [&](int s) { return bar0 + 8 * (3 * kRing + 7 + s); };       // leader: every operand of this ring slot is in place
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBar + 8 * (4 * kRing + 7));
+  auto bar_pready = [&](int t) { return bar0 + 8 * (2 * kRing + 6 + t); };    // leader: the peer's A operand of tile t is written
+  auto bar_peer = [&](int g) { return bar0 + 8 * (2 * kRing + 8 + g); };      // leader: the peer's weight halves of group g landed
+  auto bar_go = [&](int g) { return bar0 + 8 * (2 * kRing + 8 + kPeerBars + g); };   // leader: group g is in place in both CTAs
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBar + 8 * (2 * kRing + 8 + 2 * kPeerBars));
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kRing; ++s) {
       mbar_init(bar_full(s), 1);
       mbar_init(bar_empty(s), 1);
-      mbar_init(bar_peer(s), 1);
-      mbar_init(bar_go(s), 1);
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(bar_acc(t), 1);
       mbar_init(bar_ready(t), 16);         // one arrive per epilogue warp
       mbar_init(bar_reload(t), 1);
+      mbar_init(bar_pready(t), 16);        // the peer's 16 epilogue warps arrive remotely
     }
-    mbar_init(bar_peer_t1, 1);
+    for (int g = 0; g < kPeerBars; ++g) {
+      mbar_init(bar_peer(g), 1);
+      mbar_init(bar_go(g), 1);
+    }
     fence_barrier_init();
   }
   if (warp == kCtrlWarp) {   // TMEM: all 512 columns in both CTAs of the pair
@@ -175,7 +184,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nerf_st
     if (warp == kGateWarp && rank != 0) {
       // the peer has no gate work
     } else {
-      constexpr int kGroup = 3, kPeerBars = 4;
       uint32_t cnt = 0, gcnt = 0, ready_ph = 0, reload_ph = 0;
       const uint32_t peer_base = map_to_rank(bar_peer(0), 0);
       for (int it = 0; it < iters; ++it) {
@@ -186,25 +194,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nerf_st
           for (int t = 0; t < 2; ++t) {
             for (int c = 0; c < nch; ++c, ++cnt) {
               const uint32_t stage = cnt % kRing, phase = (cnt / kRing) & 1u;
-              const bool group_start = c % kGroup == 0, group_end = (c % kGroup == kGroup - 1) || c == nch - 1;
               mbar_wait(bar_full(stage), phase);
-              if (c == 0) {
-                mbar_wait(bar_ready(t), (ready_ph >> t) & 1u);
-                ready_ph ^= 1u << t;
-                if (ly.reload) {
-                  mbar_wait(bar_reload(t), (reload_ph >> t) & 1u);
-                  reload_ph ^= 1u << t;
-                }
+              if (c == 0 && ly.reload) {
+                mbar_wait(bar_reload(t), (reload_ph >> t) & 1u);
+                reload_ph ^= 1u << t;
               }
               if (rank != 0) {
-                if (group_end) {
+                // peer: weight halves of the group landed (its A-operand readiness goes to the leader directly from the
+                // epilogue warps, bar_pready)
+                if (group_end(c, nch)) {
                   if (elect_one_sync()) mbar_arrive_remote(peer_base + 8 * (gcnt % kPeerBars));
                   __syncwarp();
                   ++gcnt;
                 }
               } else {
-                if (group_start) mbar_wait_cluster(bar_peer(gcnt % kPeerBars), (gcnt / kPeerBars) & 1u);
-                if (group_end) {                 // every chunk of the group is in place in both CTAs: release it to the MMA warp
+                if (c == 0) {
+                  mbar_wait(bar_ready(t), (ready_ph >> t) & 1u);
+                  mbar_wait(bar_pready(t), (ready_ph >> t) & 1u);
+                  ready_ph ^= 1u << t;
+                }
+                if (group_start(c)) mbar_wait_cluster(bar_peer(gcnt % kPeerBars), (gcnt / kPeerBars) & 1u);
+                if (group_end(c, nch)) {         // every chunk of the group is in place in both CTAs: release it to the MMA warp
                   if (elect_one_sync()) mbar_arrive(bar_go(gcnt % kPeerBars));
                   __syncwarp();
                   ++gcnt;
@@ -217,7 +227,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nerf_st
     }
   } else if (warp == kCtrlWarp) {
     // ================================================================ MMA issuer (leader only): one wait per chunk
-    constexpr int kGroup = 3, kPeerBars = 4;           // must match the gate warp
     uint32_t cnt = 0, gcnt = 0;
     const uint32_t idesc256 = umma_idesc(256, 256), idesc16 = umma_idesc(256, 16);
     constexpr uint32_t kHi = (128u >> 4) | (1u << 14);   // SBO = 128 B, descriptor version 1
@@ -231,7 +240,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nerf_st
           for (int c = 0; c < nch; ++c, ++cnt) {
             const uint32_t stage = cnt % kRing;
             PP(long long pa = clock64();)
-            if (c % kGroup == 0) {
+            if (group_start(c)) {
               mbar_wait(bar_go(gcnt % kPeerBars), (gcnt / kPeerBars) & 1u);
               ++gcnt;
               tc_fence_after();
@@ -288,6 +297,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nerf_st
     const bool warp_bias = (p.N % 32 == 0);
     uint32_t acc_ph = 0;                       // bit t
     bool store_pending[2] = {false, false};
+    const uint32_t pready_remote = map_to_rank(bar_pready(0), 0);     // leader's barrier for the peer's A-operand readiness
     PP(long long pe_acc = 0, pe_work = 0;)
     for (int it = 0; it < iters; ++it) {
       const long long st = ((long long)it * n_pairs + pair) * 2 + rank;     // super-tile of this CTA (may lie beyond the end)
@@ -305,8 +315,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nerf_st
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(bar_ready(0));
-        mbar_arrive(bar_ready(1));
+        if (rank == 0) {
+          mbar_arrive(bar_ready(0));
+          mbar_arrive(bar_ready(1));
+        } else {
+          mbar_arrive_remote(pready_remote);
+          mbar_arrive_remote(pready_remote + 8);
+        }
       }
 
       float sigma_s[2] = {0.f, 0.f}, rgb_s[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
@@ -409,7 +424,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nerf_st
           if (L != kNumLayers - 1) {   // the next super-tile's encode arrival covers the last stage
             tc_fence_before();
             __syncwarp();                // every lane's st.shared + proxy fence precede the warp's single arrive
-            if (lane == 0) mbar_arrive(bar_ready(t));
+            if (lane == 0) {
+              if (rank == 0) mbar_arrive(bar_ready(t));
+              else mbar_arrive_remote(pready_remote + 8 * t);
+            }
           }
           PP(pe_work += clock64() - eb;)
         }
