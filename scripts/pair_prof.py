@@ -30,7 +30,17 @@ c = out[3].view(-1)[:148 * 16 * 2].view(torch.int64).view(148, 16).cpu()
 lead, peer = c[0::2].double(), c[1::2].double()
 stages = lead[:, 7] * 17
 f = lambda t, i: (t[:, i] / stages).mean().item()
-print("flags", flags, "per stage (both tiles), leader ctrl warp: total %.0f | wait weights %.0f | wait own A t0 %.0f t1 %.0f | wait peer t0 %.0f t1 %.0f | issue %.0f"
+print("flags", flags, "per stage (both tiles), leader ctrl warp: total %.0f | wait go %.0f | in elect: MMA issue %.0f commits %.0f | wait peer t0 %.0f t1 %.0f | issue %.0f"
       % tuple(f(lead, i) for i in range(7)))
 print("   peer ctrl warp: wait weights %.0f | wait own A t0 %.0f t1 %.0f" % (f(peer, 1), f(peer, 2), f(peer, 3)))
 print("   epilogue warp 0 (both tiles): leader wait acc %.0f work %.0f | peer wait acc %.0f work %.0f" % (f(lead, 8), f(lead, 9), f(peer, 8), f(peer, 9)))
+
+tr = out[3].view(-1).view(torch.int64)[148 * 16:148 * 16 + 2 * 17 * 2 * 8].view(2, 17, 2, 8).cpu()
+lead = tr[0]
+base = int(lead[1, 0, 0])
+print("leader CTA, iteration 3, cycles relative to stage 1 / tile 0 first MMA.  columns: first MMA | last issue | epilogue woke | drain done | gate saw own ready | gate saw peer ready | go raised")
+for L in range(1, 12):
+    for t in range(2):
+        e = lead[L, t] - base
+        print("L%2d t%d  mma0 %6d  last %6d (+%5d)  epi woke %6d (+%5d)  drained %6d (+%5d)  own ready seen %6d (+%5d)  peer ready %6d (+%5d)  go %6d (+%4d)" % (
+            L, t, e[0], e[1], e[1] - e[0], e[2], e[2] - e[1], e[3], e[3] - e[2], e[6], e[6] - e[3], e[4], e[4] - e[6], e[5], e[5] - e[4]))

@@ -22,16 +22,22 @@
 // cycle-counter instrumentation (scripts/pair_prof.py): compiled in only with -DTP_PAIR_PROF
 #ifdef TP_PAIR_PROF
 #define PP(...) __VA_ARGS__
+// event trace of one iteration of CTA pair 0: trace[cta][stage][tile][event] (clock64), behind the per-CTA counters
+#define PTRACE(L, t, ev)                                                                                             \
+  if (p.dbg_layer == 100 && p.dbg_out && it == 3 && blockIdx.x < 2)                                                  \
+  reinterpret_cast<long long*>(p.dbg_out)[148 * 16 + ((blockIdx.x * 17 + (L)) * 2 + (t)) * 8 + (ev)] = clock64()
 #else
 #define PP(...)
+#define PTRACE(L, t, ev)
 #endif
 
 namespace tc3 {
 using namespace tc;
 
 constexpr int kThreads = 19 * 32;              // 16 epilogue warps, producer warp, control warp, gate warp
-constexpr int kRing = 8;
-constexpr uint32_t kSlotBytes = 8192;          // one chunk half
+constexpr int kRing = 4;
+constexpr uint32_t kHalfBytes = 8192;          // one chunk half
+constexpr uint32_t kSlotBytes = 2 * kHalfBytes; // a ring slot holds the halves of two consecutive chunks of a pass
 constexpr uint32_t kOffA = 0, kOffE = 2 * kABytes, kOffRing = kOffE + 2 * kEBytes;
 constexpr uint32_t kOffBar = kOffRing + kRing * kSlotBytes;
 constexpr uint32_t kSmemBytes = kOffBar + 512;
@@ -95,8 +101,10 @@ __device__ __forceinline__ void umma2_commit_both(uint32_t bar) {
 
 // chunk groups of a (stage, tile) pass: the first chunk alone (so the stage starts as soon as the A operand is ready), then
 // groups of four; the peer forwards "my weight halves landed" once per group, the leader's gate releases a group at a time
-__device__ __forceinline__ bool group_start(int c) { return c == 0 || ((c - 1) & 3) == 0; }
-__device__ __forceinline__ bool group_end(int c, int nch) { return c == 0 || ((c - 1) & 3) == 3 || c == nch - 1; }
+// (in units of ring slots = chunk pairs: the first slot alone, then pairs of slots -- half the 4-slot ring, so the other
+// half keeps prefetching)
+__device__ __forceinline__ bool group_start(int sl) { return sl == 0 || (sl & 1) == 1; }
+__device__ __forceinline__ bool group_end(int sl, int nsl) { return sl == 0 || (sl & 1) == 0 || sl == nsl - 1; }
 // a role can run at most kRing chunks = kRing groups ahead of its consumer: 2 * kRing barriers per kind rule out a phase overrun
 constexpr int kPeerBars = 16;
 
@@ -159,15 +167,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nerf_st
       for (int L = 0; L < kNumLayers; ++L) {
         const Layer ly = kLayers[L];
         const int nch = ly.small ? 1 : ly.a_chunks + ly.e_chunks + ly.bias_chunk;
+        const int nsl = (nch + 1) / 2;
         for (int t = 0; t < 2; ++t) {
-          for (int j = 0; j < nch; ++j, ++cnt) {
-            const uint32_t bytes = (ly.small || j >= ly.a_chunks + ly.e_chunks) ? kSlotBytes / 2 : kSlotBytes;
+          for (int sl = 0; sl < nsl; ++sl, ++cnt) {
             const uint32_t stage = cnt % kRing, phase = (cnt / kRing) & 1u;
+            uint32_t bytes[2] = {0u, 0u};
+            for (int k = 0; k < 2; ++k) {
+              const int j = 2 * sl + k;
+              if (j < nch) bytes[k] = (ly.small || j >= ly.a_chunks + ly.e_chunks) ? kHalfBytes / 2 : kHalfBytes;
+            }
             mbar_wait(bar_empty(stage), phase ^ 1);
             if (elect_one_sync()) {
-              mbar_expect_tx(bar_full(stage), bytes);
-              bulk_g2s(sbase + kOffRing + stage * kSlotBytes, p.packed + (size_t)(c0 + j) * kChunkBytes + rank * kSlotBytes, bytes,
-                       bar_full(stage));
+              mbar_expect_tx(bar_full(stage), bytes[0] + bytes[1]);
+              for (int k = 0; k < 2; ++k)
+                if (bytes[k])
+                  bulk_g2s(sbase + kOffRing + stage * kSlotBytes + k * kHalfBytes,
+                           p.packed + (size_t)(c0 + 2 * sl + k) * kChunkBytes + rank * kHalfBytes, bytes[k], bar_full(stage));
             }
             __syncwarp();
           }
@@ -192,31 +207,35 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nerf_st
           const int nch = ly.small ? 1 : ly.a_chunks + ly.e_chunks + ly.bias_chunk;
 #pragma unroll 1
           for (int t = 0; t < 2; ++t) {
-            for (int c = 0; c < nch; ++c, ++cnt) {
+            const int nsl = (nch + 1) / 2;
+            for (int sl = 0; sl < nsl; ++sl, ++cnt) {
               const uint32_t stage = cnt % kRing, phase = (cnt / kRing) & 1u;
               mbar_wait(bar_full(stage), phase);
-              if (c == 0 && ly.reload) {
+              if (sl == 0 && ly.reload) {
                 mbar_wait(bar_reload(t), (reload_ph >> t) & 1u);
                 reload_ph ^= 1u << t;
               }
               if (rank != 0) {
                 // peer: weight halves of the group landed (its A-operand readiness goes to the leader directly from the
                 // epilogue warps, bar_pready)
-                if (group_end(c, nch)) {
+                if (group_end(sl, nsl)) {
                   if (elect_one_sync()) mbar_arrive_remote(peer_base + 8 * (gcnt % kPeerBars));
                   __syncwarp();
                   ++gcnt;
                 }
               } else {
-                if (c == 0) {
+                if (sl == 0) {
                   mbar_wait(bar_ready(t), (ready_ph >> t) & 1u);
+                  PP(if (lane == 0) { PTRACE(L, t, 6); })
                   mbar_wait(bar_pready(t), (ready_ph >> t) & 1u);
                   ready_ph ^= 1u << t;
+                  PP(if (lane == 0) { PTRACE(L, t, 4); })
                 }
-                if (group_start(c)) mbar_wait_cluster(bar_peer(gcnt % kPeerBars), (gcnt / kPeerBars) & 1u);
-                if (group_end(c, nch)) {         // every chunk of the group is in place in both CTAs: release it to the MMA warp
+                if (group_start(sl)) mbar_wait_cluster(bar_peer(gcnt % kPeerBars), (gcnt / kPeerBars) & 1u);
+                if (group_end(sl, nsl)) {        // every chunk of the group is in place in both CTAs: release it to the MMA warp
                   if (elect_one_sync()) mbar_arrive(bar_go(gcnt % kPeerBars));
                   __syncwarp();
+                  PP(if (lane == 0 && sl == 0) { PTRACE(L, t, 5); })
                   ++gcnt;
                 }
               }
@@ -226,7 +245,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nerf_st
       }
     }
   } else if (warp == kCtrlWarp) {
-    // ================================================================ MMA issuer (leader only): one wait per chunk
+    // ================================================================ MMA issuer (leader only): one wait per group of slots
     uint32_t cnt = 0, gcnt = 0;
     const uint32_t idesc256 = umma_idesc(256, 256), idesc16 = umma_idesc(256, 16);
     constexpr uint32_t kHi = (128u >> 4) | (1u << 14);   // SBO = 128 B, descriptor version 1
@@ -237,47 +256,57 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nerf_st
         const int nch = ly.small ? 1 : ly.a_chunks + ly.e_chunks + ly.bias_chunk;
 #pragma unroll 1
         for (int t = 0; t < 2; ++t) {
-          for (int c = 0; c < nch; ++c, ++cnt) {
+          const int nsl = (nch + 1) / 2;
+          for (int sl = 0; sl < nsl; ++sl, ++cnt) {
             const uint32_t stage = cnt % kRing;
             PP(long long pa = clock64();)
-            if (group_start(c)) {
+            if (group_start(sl)) {
               mbar_wait(bar_go(gcnt % kPeerBars), (gcnt / kPeerBars) & 1u);
               ++gcnt;
               tc_fence_after();
             }
             PP(long long pb = clock64(); pf_full += pb - pa;)
-            const uint32_t wsm = sbase + kOffRing + stage * kSlotBytes;
+            PP(if (lane == 0 && sl == 0) { PTRACE(L, t, 0); })
             const uint32_t d_tmem = tmem_base + t * 256;
             if (elect_one_sync()) {
-              if (ly.small) {
-                // half chunk = [32 k8][8 rows][8]: 16 K-steps over the full K=256 of A_t
-                uint32_t a_lo = dlo(sbase + kOffA + t * kABytes, 2048u);
-                uint32_t b_lo = dlo(wsm, 128u);
 #pragma unroll
-                for (int ks = 0; ks < 16; ++ks) {
-                  umma2_bf16_lohi(d_tmem, a_lo, kHi, b_lo, kHi, idesc16, ks > 0 ? 1u : 0u);
-                  a_lo += 4096u >> 4;
-                  b_lo += 256u >> 4;
+              for (int k = 0; k < 2; ++k) {
+                const int c = 2 * sl + k;
+                if (c >= nch) break;
+                const uint32_t wsm = sbase + kOffRing + stage * kSlotBytes + k * kHalfBytes;
+                if (ly.small) {
+                  // half chunk = [32 k8][8 rows][8]: 16 K-steps over the full K=256 of A_t
+                  uint32_t a_lo = dlo(sbase + kOffA + t * kABytes, 2048u);
+                  uint32_t b_lo = dlo(wsm, 128u);
+#pragma unroll
+                  for (int ks = 0; ks < 16; ++ks) {
+                    umma2_bf16_lohi(d_tmem, a_lo, kHi, b_lo, kHi, idesc16, ks > 0 ? 1u : 0u);
+                    a_lo += 4096u >> 4;
+                    b_lo += 256u >> 4;
+                  }
+                } else if (c >= ly.a_chunks + ly.e_chunks) {
+                  // bias step: A = E columns 48..63 (column 63 == 1), B half = [2 k8][128 rows][8]
+                  const uint32_t a_lo = dlo(sbase + kOffE + t * kEBytes + 6 * 2048, 2048u);
+                  const uint32_t b_lo = dlo(wsm, 2048u);
+                  umma2_bf16_lohi(d_tmem, a_lo, kHi, b_lo, kHi, idesc256, 1u);
+                } else {
+                  const bool from_e = c >= ly.a_chunks;
+                  const uint32_t a0 = from_e ? sbase + kOffE + t * kEBytes + (c - ly.a_chunks) * 4 * 2048
+                                             : sbase + kOffA + t * kABytes + c * 4 * 2048;
+                  const uint32_t a_lo = dlo(a0, 2048u);
+                  const uint32_t b_lo = dlo(wsm, 2048u);
+                  umma2_bf16_lohi(d_tmem, a_lo, kHi, b_lo, kHi, idesc256, c > 0 ? 1u : 0u);
+                  umma2_bf16_lohi(d_tmem, a_lo + (4096u >> 4), kHi, b_lo + (4096u >> 4), kHi, idesc256, 1u);
                 }
-              } else if (c >= ly.a_chunks + ly.e_chunks) {
-                // bias step: A = E columns 48..63 (column 63 == 1), B half = [2 k8][128 rows][8]
-                const uint32_t a_lo = dlo(sbase + kOffE + t * kEBytes + 6 * 2048, 2048u);
-                const uint32_t b_lo = dlo(wsm, 2048u);
-                umma2_bf16_lohi(d_tmem, a_lo, kHi, b_lo, kHi, idesc256, 1u);
-              } else {
-                const bool from_e = c >= ly.a_chunks;
-                const uint32_t a0 = from_e ? sbase + kOffE + t * kEBytes + (c - ly.a_chunks) * 4 * 2048
-                                           : sbase + kOffA + t * kABytes + c * 4 * 2048;
-                const uint32_t a_lo = dlo(a0, 2048u);
-                const uint32_t b_lo = dlo(wsm, 2048u);
-                umma2_bf16_lohi(d_tmem, a_lo, kHi, b_lo, kHi, idesc256, c > 0 ? 1u : 0u);
-                umma2_bf16_lohi(d_tmem, a_lo + (4096u >> 4), kHi, b_lo + (4096u >> 4), kHi, idesc256, 1u);
               }
-              if (c == nch - 1) umma2_commit_both(bar_acc(t));       // accumulators of tile t complete in both CTAs
+              PP(const long long pm = clock64(); pf_ready[0] += pm - pb;)
+              if (sl == nsl - 1) umma2_commit_both(bar_acc(t));      // accumulators of tile t complete in both CTAs
               umma2_commit_both(bar_empty(stage));                   // ring slot reusable in both CTAs
+              PP(pf_ready[1] += clock64() - pm;)
             }
             __syncwarp();
             PP(pf_issue += clock64() - pb;)
+            PP(if (lane == 0 && sl == nsl - 1) { PTRACE(L, t, 1); })
           }
         }
       }
@@ -347,6 +376,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nerf_st
           acc_ph ^= 1u << t;
           tc_fence_after();
           PP(const long long eb = clock64(); pe_acc += eb - ea;)
+          PP(if (threadIdx.x == 0) { PTRACE(L, t, 2); })
           if (ly.epi == EPI_HIDDEN && store_pending[t]) {   // the previous bulk store must have finished reading A_t
             if (threadIdx.x == 0) bulk_wait_read();
             named_bar_sync(1, 512);
@@ -421,6 +451,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nerf_st
               }
             }
           }
+          PP(if (threadIdx.x == 0) { PTRACE(L, t, 3); })
           if (L != kNumLayers - 1) {   // the next super-tile's encode arrival covers the last stage
             tc_fence_before();
             __syncwarp();                // every lane's st.shared + proxy fence precede the warp's single arrive
