@@ -877,7 +877,8 @@ __global__ void __launch_bounds__(256) bwd_finish1_kernel(const FinishParams f) 
   if (cur >= 0 && cur < f.B) out[(size_t)cur * 256] = acc;
 }
 
-// blocks 0..B-1: latent gradients of image b; block B: rgb-head thin outputs; block B+1: transient-head thin outputs
+constexpr int kFinishParts = 8;      // 8 latent columns each (n_latent <= 64)
+// blocks 0..B-1: latent gradients of image b; then kFinishParts blocks per head for the thin outputs of that head
 __global__ void __launch_bounds__(256) bwd_finish2_kernel(const FinishParams f) {
   const int n = threadIdx.x;
   extern __shared__ float gsm[];       // blocks < B: [2][256] sums of image b; blocks >= B: nothing
@@ -903,45 +904,39 @@ __global__ void __launch_bounds__(256) bwd_finish2_kernel(const FinishParams f) 
     }
     return;
   }
-  const bool trans = (int)blockIdx.x == f.B + 1;
-  const int head = trans ? 1 : 0;
+  // blocks B .. B + 2 * kFinishParts - 1: (head, part); a part owns 8 latent columns of layer 0, part 0 also the rest
+  const int hb = (int)blockIdx.x - f.B, head = hb / kFinishParts, part = hb % kFinishParts;
+  const bool trans = head == 1;
   float* const* g = f.g + (trans ? 8 : 0);
+  const int n_lat = trans ? f.n_trans : f.n_light;
+  const float* lat = trans ? f.lat_trans : f.lat_light;
+  const long long ld = trans ? f.ld_t0 : f.ld_r0;
+  float* row = g[0] + (size_t)n * ld + 256 + (trans ? 0 : f.vc + 3);
+  const int k0 = part * 8;
+  if (k0 < n_lat) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int b = 0; b < f.B; ++b) {
+      const float gb = image_sum(head, b, n);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (k0 + k < n_lat) acc[k] = fmaf(gb, lat[b * n_lat + k0 + k], acc[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (k0 + k < n_lat) row[k0 + k] = acc[k];
+  }
+  if (part != 0) return;
   g[5][n] = f.tot[(kXdb + (trans ? 2 : 0)) * 256 + n];          // db2
   g[3][n] = f.tot[(kXdb + (trans ? 3 : 1)) * 256 + n];          // db1
   float b0 = 0.f;
   for (int b = 0; b < f.B; ++b) b0 += image_sum(head, b, n);
   g[1][n] = b0;                                                  // db0
   if (!trans) {
-    float* row = g[0] + (size_t)n * f.ld_r0 + 256;
-    for (int i = 0; i < f.vc; ++i) row[i] = f.tot[(kXview + i) * 256 + n];
-    for (int j = 0; j < 3; ++j) row[f.vc + j] = f.tot[(kXxyz + j) * 256 + n];
-    float acc[64];
-#pragma unroll
-    for (int k = 0; k < 64; ++k) acc[k] = 0.f;
-    for (int b = 0; b < f.B; ++b) {
-      const float gb = image_sum(0, b, n);
-#pragma unroll
-      for (int k = 0; k < 64; ++k)
-        if (k < f.n_light) acc[k] = fmaf(gb, f.lat_light[b * f.n_light + k], acc[k]);
-    }
-#pragma unroll
-    for (int k = 0; k < 64; ++k)
-      if (k < f.n_light) row[f.vc + 3 + k] = acc[k];
+    float* vrow = g[0] + (size_t)n * f.ld_r0 + 256;
+    for (int i = 0; i < f.vc; ++i) vrow[i] = f.tot[(kXview + i) * 256 + n];
+    for (int j = 0; j < 3; ++j) vrow[f.vc + j] = f.tot[(kXxyz + j) * 256 + n];
     for (int j = 0; j < 3; ++j) g[6][j * 256 + n] = f.tot[(kXwr + j) * 256 + n];
   } else {
-    float* row = g[0] + (size_t)n * f.ld_t0 + 256;
-    float acc[64];
-#pragma unroll
-    for (int k = 0; k < 64; ++k) acc[k] = 0.f;
-    for (int b = 0; b < f.B; ++b) {
-      const float gb = image_sum(1, b, n);
-#pragma unroll
-      for (int k = 0; k < 64; ++k)
-        if (k < f.n_trans) acc[k] = fmaf(gb, f.lat_trans[b * f.n_trans + k], acc[k]);
-    }
-#pragma unroll
-    for (int k = 0; k < 64; ++k)
-      if (k < f.n_trans) row[k] = acc[k];
     for (int j = 0; j < 5; ++j) g[6][j * 256 + n] = f.tot[(kXwt + j) * 256 + n];
   }
   const int nb = trans ? 5 : 3, off = trans ? 3 : 0;
@@ -1265,7 +1260,7 @@ TP_API int tp_tc_heads_backward(const float* dz_rgb, const float* dz_trans, int6
   f.d_lat_light = d_lat_light; f.d_lat_trans = d_lat_trans;
   tcb::bwd_finish1_kernel<<<tcb::kXCols, 256, 0, st>>>(f);
   if (int rc = tp_launch_status()) return rc;
-  tcb::bwd_finish2_kernel<<<B + 2, 256, 2 * 256 * sizeof(float), st>>>(f);
+  tcb::bwd_finish2_kernel<<<B + 2 * tcb::kFinishParts, 256, 2 * 256 * sizeof(float), st>>>(f);
   if (int rc = tp_launch_status()) return rc;
 
   // the six 256 x 256 weight gradients: layers 2, 1, 0 of the rgb head, then of the transient head
