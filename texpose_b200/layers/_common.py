@@ -30,10 +30,12 @@ def tf_init_(linear: torch.nn.Linear, out=None):
 
 
 def mlp_precision(opt) -> str:
-    """'fp32' (SIMT, <=1e-4 parity) or 'bf16' (tcgen05 forward, <=1e-2).  opt.b200.mlp > $TEXPOSE_B200_MLP > fp32."""
+    """'fp32' (SIMT kernels, <=1e-4 parity with the reference), 'bf16' (tcgen05 forward + backward, <=1e-2) or 'auto' = bf16
+    whenever the fused kernel implements the architecture (options/nerf_lm_adapt_gan.yaml, frozen trunk, ray-parameterised
+    call) and fp32 otherwise.  opt.b200.mlp > $TEXPOSE_B200_MLP > auto."""
     b = opt.get("b200") if hasattr(opt, "get") else None
-    p = (b.get("mlp") if b else None) or os.environ.get("TEXPOSE_B200_MLP") or "fp32"
-    if p not in ("fp32", "bf16"):
+    p = (b.get("mlp") if b else None) or os.environ.get("TEXPOSE_B200_MLP") or "auto"
+    if p not in ("fp32", "bf16", "auto"):
         raise ValueError(f"unknown MLP precision {p!r}")
     return p
 

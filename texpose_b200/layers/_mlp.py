@@ -32,7 +32,7 @@ class MLPConfig:
     n_trans: int                # 0 for the plain model
     n_latent_light: int = 0
     n_latent_trans: int = 0
-    precision: str = "fp32"     # "fp32" | "bf16"
+    precision: str = "fp32"     # "fp32" | "bf16" | "auto" (bf16 when the fused kernel implements the architecture)
     save_for_backward: bool = True
     packed: object = None       # bf16 weight image for the tcgen05 kernel (mlp_tc.pack), or None
 
@@ -232,7 +232,11 @@ class NerfMLP(torch.autograd.Function):
         needs_grad = any(ctx.needs_input_grad)
         sv = _Saved() if (needs_grad and cfg.save_for_backward) else None
         trunk_grad = any(ctx.needs_input_grad[4:4 + n_f])      # frozen in the reference (:34); fp32 path if unfrozen
-        if cfg.precision == "bf16" and cfg.stl and not trunk_grad:
+        use_tc = cfg.precision == "bf16" and cfg.stl and not trunk_grad
+        if cfg.precision == "auto" and cfg.stl and not trunk_grad and geom.get("mode") == "rays":
+            from .. import mlp_tc
+            use_tc = mlp_tc.supported(cfg, feat_p, rgb_p, trans_p)
+        if use_tc:
             from .. import mlp_tc
             if sv is None:
                 rgb, density, uncert = mlp_tc.forward(cfg, geom, lt, ll, feat_p, rgb_p, trans_p)

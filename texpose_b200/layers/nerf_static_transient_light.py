@@ -75,6 +75,16 @@ class NeRF(torch.nn.Module):
                          n_latent_trans=opt.nerf.N_latent_trans, precision=_common.mlp_precision(opt),
                          save_for_backward=torch.is_grad_enabled(), packed=self)
 
+    def uses_tensor_cores(self, opt, mode="val") -> bool:
+        """True when forward_samples of this module will take the fused tcgen05 path under `opt` (opt.b200.mlp)."""
+        cfg = self._config(opt, mode)
+        if cfg.precision == "fp32":
+            return False
+        from .. import mlp_tc
+        pairs = lambda ml: [(l.weight, l.bias) for l in ml]
+        ok = mlp_tc.supported(cfg, pairs(self.mlp_feat), pairs(self.mlp_rgb), pairs(self.mlp_trans))
+        return ok and not any(p.requires_grad for p in self.mlp_feat.parameters())
+
     def _run(self, cfg, geom, latent_variable_trans, latent_variable_light):
         params = _common.flat_params(self.mlp_feat, self.mlp_rgb, self.mlp_trans)
         return NerfMLP.apply(cfg, geom, latent_variable_trans, latent_variable_light, *params)

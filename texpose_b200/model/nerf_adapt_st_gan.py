@@ -176,7 +176,7 @@ class Graph(torch.nn.Module):
         if user:
             return int(user)
         n = opt.nerf.sample_intvs
-        budget = (1 << 26) if _common.mlp_precision(opt) == "bf16" else (1 << 21)
+        budget = (1 << 26) if self.nerf.uses_tensor_cores(opt) else (1 << 21)
         return max(int(opt.nerf.rand_rays or 2048), budget // n)
 
     def render_by_slices(self, opt, pose, intr=None, depth_range=None, object_mask=None, sample_idx=None, mode=None):
