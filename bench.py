@@ -23,6 +23,7 @@ sys.path.insert(0, ROOT)
 
 H, W, NS = 480, 640, 128
 FLOP_PER_SAMPLE_FWD = 1_821_184          # SURVEY.md 8d (dense, unpadded)
+FLOP_PER_SAMPLE_FWD_BWD = 3_220_992      # forward + backward with the trunk frozen
 METRIC, UNIT = "ray-samples/sec", "samples/s"
 
 
@@ -404,7 +405,8 @@ def bench_train(args, g, opt, dev, world, timed):
     g.eval()
     samples = B * P * P * NS
     return dict(workload="C3 train step fwd+bwd, 4096 rays x 128 samples per GPU, fused patch loss, bf16 tcgen05 fwd + bwd (dX chain with thin gradients, dW GEMMs), grad allreduce",
-                value=world * samples / (ms * 1e-3), unit="samples/s", ms_per_step=ms, grad_allreduce_bytes=bucket.flat.numel() * 4)
+                value=world * samples / (ms * 1e-3), unit="samples/s", ms_per_step=ms, grad_allreduce_bytes=bucket.flat.numel() * 4,
+                tflops_per_gpu=FLOP_PER_SAMPLE_FWD_BWD * samples / (ms * 1e-3) / 1e12, flop_per_sample=FLOP_PER_SAMPLE_FWD_BWD)
 
 
 def main():
