@@ -30,7 +30,7 @@ c = out[3].view(-1)[:148 * 16 * 2].view(torch.int64).view(148, 16).cpu()
 lead, peer = c[0::2].double(), c[1::2].double()
 stages = lead[:, 7] * 17
 f = lambda t, i: (t[:, i] / stages).mean().item()
-print("flags", flags, "per stage (both tiles), leader ctrl warp: total %.0f | wait go %.0f | in elect: MMA issue %.0f commits %.0f | wait peer t0 %.0f t1 %.0f | issue %.0f"
+print("flags", flags, "per stage (both tiles), leader ctrl warp: total %.0f | wait go %.0f | in elect: MMA issue %.0f commits %.0f | wait weights %.0f, own A %.0f | issue window %.0f"
       % tuple(f(lead, i) for i in range(7)))
 print("   peer ctrl warp: wait weights %.0f | wait own A t0 %.0f t1 %.0f" % (f(peer, 1), f(peer, 2), f(peer, 3)))
 print("   epilogue warp 0 (both tiles): leader wait acc %.0f work %.0f | peer wait acc %.0f work %.0f" % (f(lead, 8), f(lead, 9), f(peer, 8), f(peer, 9)))

@@ -1,20 +1,27 @@
 // K2, CTA-pair variant (flags bit 10 of tp_tc_nerf_stl_forward): the fused forward of mlp_tc.cu issued as
-// tcgen05.mma.cta_group::2 over a cluster of two CTAs (the two SMs of a TPC).
+// tcgen05.mma.cta_group::2 over a cluster of two CTAs (the two SMs of a TPC).  Experimental: bit-identical to the default
+// kernel, measured 8-12 % slower (profiles/r01b_summary.md 5); kept as the measured alternative.
 //
-// Why: the single-CTA kernel is limited by energy and SMEM bytes per FLOP (profiles/r01b_summary.md 2).  With cta_group::2 one
-// MMA covers M = 256 rows -- the 128-sample tile of the leader CTA and the 128-sample tile of its peer -- against ONE
-// B operand of which each SM holds half (N/2 rows):
+// Why it was built: the single-CTA kernel is limited by energy and SMEM bytes per FLOP (profiles/r01b_summary.md 2).  With
+// cta_group::2 one MMA covers M = 256 rows -- the 128-sample tile of the leader CTA and the 128-sample tile of its peer --
+// against ONE B operand of which each SM holds half (N/2 rows):
 //   * SMEM operand reads per SM and MMA drop from 12 KB (A 4 + B 8) to 8 KB (A 4 + B/2 4);
-//   * every CTA streams only its half of each weight chunk: half the L2 -> SM traffic, and the same 64 KB ring now holds
-//     8 chunk halves instead of 4 chunks, so tile 0 can run up to 5 chunks ahead of tile 1 and a tile's accumulator drain
-//     hides behind the other tile's MMAs.
+//   * every CTA streams only its half of each weight chunk, so the two tiles of a CTA can take their MMA passes over a stage
+//     back to back (weights streamed once per tile, same L2 traffic per SM as the default kernel) and one tile's accumulator
+//     drain -- by all 16 epilogue warps -- hides behind the other tile's MMAs.
 //
-// Roles per CTA: 16 epilogue warps (as mlp_tc.cu), one weight producer warp (its half of every chunk), one control warp:
-// in the leader it issues the MMAs for the pair, in the peer it forwards "my operands are ready" to the leader
-// (remote mbarrier arrives).  Accumulator-full and ring-slot-empty signals come from tcgen05.commit multicast to both CTAs.
+// Roles per CTA: 16 epilogue warps (both tiles, alternating), one weight producer warp, one MMA warp (leader CTA only).
+// Cross-CTA signalling without a forwarding hop:
+//   * weights: cp.async.bulk.tensor ... cta_group::2 -- each CTA's TMA writes its half into its own ring slot and
+//     complete_tx's on the LEADER's full barrier, which therefore counts the bytes of both halves;
+//   * accumulator-full and ring-slot-empty: tcgen05.commit ... multicast::cluster to the barrier at the same offset in both CTAs;
+//   * "the peer's A operand is written": remote mbarrier arrives from the peer's epilogue warps (one per warp) on a leader
+//     barrier, with CTA-scope semantics (cluster-scope acquire / release compile to MEMBAR.ALL.GPU + CCTL.IVALL: +40 %).
 //
 // Weight image: tp_tc_pair_weights re-orders the standard image so that rank r's half of chunk c is contiguous at
-// c * 16 KB + r * 8 KB  ([k8][128 rows][8] for the 256-row chunks, [32 k8][8 rows][8] for the N=16 chunks).
+// c * 16 KB + r * 8 KB  ([k8][128 rows][8] for the 256-row chunks, [32 k8][8 rows][8] for the N=16 chunks); the kernel sees it
+// through a 2-D tensor map of 2 KB rows.
+#include <cuda.h>          // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include "mlp_tc_shared.cuh"
 #include "mlp_tc_epilogue.cuh"
 #include "../../include/texpose_b200.h"
@@ -34,7 +41,7 @@
 namespace tc3 {
 using namespace tc;
 
-constexpr int kThreads = 19 * 32;              // 16 epilogue warps, producer warp, control warp, gate warp
+constexpr int kThreads = 18 * 32;              // 16 epilogue warps, producer warp, MMA warp (leader only)
 constexpr int kRing = 4;
 constexpr uint32_t kHalfBytes = 8192;          // one chunk half
 constexpr uint32_t kSlotBytes = 2 * kHalfBytes; // a ring slot holds the halves of two consecutive chunks of a pass
@@ -79,6 +86,14 @@ __device__ __forceinline__ void mbar_wait2(uint32_t bar_a, uint32_t parity_a, ui
       "r"(parity_a), "r"(bar_b), "r"(parity_b)
       : "memory");
 }
+// TMA tile load whose completion is signalled on a barrier of the LEADER CTA of the pair (cta_group::2): both CTAs' weight
+// halves complete_tx on the one barrier the MMA warp waits on -- no forwarding hop for the weights
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst_smem, const CUtensorMap* map, int x, int y, uint32_t leader_bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst_smem),
+      "l"(map), "r"(leader_bar), "r"(x), "r"(y)
+      : "memory");
+}
 // low descriptor word; inside a cluster a shared::cta address carries the CTA rank above bit 18: mask it off
 __device__ __forceinline__ uint32_t dlo(uint32_t addr, uint32_t lbo) { return ((addr & 0x3FFFFu) >> 4) | ((lbo >> 4) << 16); }
 __device__ __forceinline__ void umma2_bf16_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
@@ -99,17 +114,9 @@ __device__ __forceinline__ void umma2_commit_both(uint32_t bar) {
                : "memory");
 }
 
-// chunk groups of a (stage, tile) pass: the first chunk alone (so the stage starts as soon as the A operand is ready), then
-// groups of four; the peer forwards "my weight halves landed" once per group, the leader's gate releases a group at a time
-// (in units of ring slots = chunk pairs: the first slot alone, then pairs of slots -- half the 4-slot ring, so the other
-// half keeps prefetching)
-__device__ __forceinline__ bool group_start(int sl) { return sl == 0 || (sl & 1) == 1; }
-__device__ __forceinline__ bool group_end(int sl, int nsl) { return sl == 0 || (sl & 1) == 0 || sl == nsl - 1; }
-// a role can run at most kRing chunks = kRing groups ahead of its consumer: 2 * kRing barriers per kind rule out a phase overrun
-constexpr int kPeerBars = 16;
-
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nerf_stl_forward_pair_kernel(const Params p, int iters) {
-  constexpr int kProducerWarp = 16, kCtrlWarp = 17, kGateWarp = 18;
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nerf_stl_forward_pair_kernel(const Params p, int iters, const __grid_constant__ CUtensorMap wmap8,
+                                                                                                   const __grid_constant__ CUtensorMap wmap4) {
+  constexpr int kProducerWarp = 16, kCtrlWarp = 17;
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
@@ -125,9 +132,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nerf_st
   auto bar_ready = [&](int t) { return bar0 + 8 * (2 * kRing + 2 + t); };
   auto bar_reload = [&](int t) { return bar0 + 8 * (2 * kRing + 4 + t); };
   auto bar_pready = [&](int t) { return bar0 + 8 * (2 * kRing + 6 + t); };    // leader: the peer's A operand of tile t is written
-  auto bar_peer = [&](int g) { return bar0 + 8 * (2 * kRing + 8 + g); };      // leader: the peer's weight halves of group g landed
-  auto bar_go = [&](int g) { return bar0 + 8 * (2 * kRing + 8 + kPeerBars + g); };   // leader: group g is in place in both CTAs
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBar + 8 * (2 * kRing + 8 + 2 * kPeerBars));
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBar + 8 * (2 * kRing + 8));
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kRing; ++s) {
@@ -139,10 +144,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nerf_st
       mbar_init(bar_ready(t), 16);         // one arrive per epilogue warp
       mbar_init(bar_reload(t), 1);
       mbar_init(bar_pready(t), 16);        // the peer's 16 epilogue warps arrive remotely
-    }
-    for (int g = 0; g < kPeerBars; ++g) {
-      mbar_init(bar_peer(g), 1);
-      mbar_init(bar_go(g), 1);
     }
     fence_barrier_init();
   }
@@ -162,6 +163,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nerf_st
     // streamed once per tile (tile 0's pass over a stage, then tile 1's): the two tiles do not share ring slots, so a whole
     // stage of MMAs of one tile is contiguous and the other tile's accumulator drain hides behind it
     uint32_t cnt = 0;
+    const uint32_t full_leader = map_to_rank(bar_full(0), 0);      // the leader's full barriers (own address in the leader)
     for (int it = 0; it < iters; ++it) {
       int c0 = 0;
       for (int L = 0; L < kNumLayers; ++L) {
@@ -178,11 +180,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nerf_st
             }
             mbar_wait(bar_empty(stage), phase ^ 1);
             if (elect_one_sync()) {
-              mbar_expect_tx(bar_full(stage), bytes[0] + bytes[1]);
+              // the leader's barrier counts the bytes of BOTH CTAs' halves (the tx-count may dip below zero until it arrives)
+              if (rank == 0) mbar_expect_tx(bar_full(stage), 2 * (bytes[0] + bytes[1]));
               for (int k = 0; k < 2; ++k)
-                if (bytes[k])
-                  bulk_g2s(sbase + kOffRing + stage * kSlotBytes + k * kHalfBytes,
-                           p.packed + (size_t)(c0 + 2 * sl + k) * kChunkBytes + rank * kHalfBytes, bytes[k], bar_full(stage));
+                if (bytes[k]) {
+                  const int row = ((c0 + 2 * sl + k) * 2 + (int)rank) * 4;     // rows of 2 KB (256 x u64) in the pair image
+                  tma_load_2d_pair(sbase + kOffRing + stage * kSlotBytes + k * kHalfBytes, bytes[k] == kHalfBytes ? &wmap8 : &wmap4,
+                                   0, row, full_leader + 8 * stage);
+                }
             }
             __syncwarp();
           }
@@ -190,63 +195,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nerf_st
         c0 += nch;
       }
     }
-  } else if (warp == kGateWarp || (warp == kCtrlWarp && rank != 0)) {
-    // ================================================================ gate warp (leader) / forwarder (peer's control warp)
-    // Walks (stage, tile, chunk) and collects the preconditions of every chunk: weight half landed (full), at the first chunk
-    // of a stage the tile's A operand written (ready, reload).  The peer forwards them to the leader once per group of kGroup
-    // chunks (remote arrive); the leader's gate warp adds the peer's signal and raises ONE barrier per chunk (go), so the MMA
-    // warp spends a single wait per chunk and the waits of the three roles overlap instead of adding up.
-    if (warp == kGateWarp && rank != 0) {
-      // the peer has no gate work
-    } else {
-      uint32_t cnt = 0, gcnt = 0, ready_ph = 0, reload_ph = 0;
-      const uint32_t peer_base = map_to_rank(bar_peer(0), 0);
-      for (int it = 0; it < iters; ++it) {
-        for (int L = 0; L < kNumLayers; ++L) {
-          const Layer ly = kLayers[L];
-          const int nch = ly.small ? 1 : ly.a_chunks + ly.e_chunks + ly.bias_chunk;
-#pragma unroll 1
-          for (int t = 0; t < 2; ++t) {
-            const int nsl = (nch + 1) / 2;
-            for (int sl = 0; sl < nsl; ++sl, ++cnt) {
-              const uint32_t stage = cnt % kRing, phase = (cnt / kRing) & 1u;
-              mbar_wait(bar_full(stage), phase);
-              if (sl == 0 && ly.reload) {
-                mbar_wait(bar_reload(t), (reload_ph >> t) & 1u);
-                reload_ph ^= 1u << t;
-              }
-              if (rank != 0) {
-                // peer: weight halves of the group landed (its A-operand readiness goes to the leader directly from the
-                // epilogue warps, bar_pready)
-                if (group_end(sl, nsl)) {
-                  if (elect_one_sync()) mbar_arrive_remote(peer_base + 8 * (gcnt % kPeerBars));
-                  __syncwarp();
-                  ++gcnt;
-                }
-              } else {
-                if (sl == 0) {
-                  mbar_wait(bar_ready(t), (ready_ph >> t) & 1u);
-                  PP(if (lane == 0) { PTRACE(L, t, 6); })
-                  mbar_wait(bar_pready(t), (ready_ph >> t) & 1u);
-                  ready_ph ^= 1u << t;
-                  PP(if (lane == 0) { PTRACE(L, t, 4); })
-                }
-                if (group_start(sl)) mbar_wait_cluster(bar_peer(gcnt % kPeerBars), (gcnt / kPeerBars) & 1u);
-                if (group_end(sl, nsl)) {        // every chunk of the group is in place in both CTAs: release it to the MMA warp
-                  if (elect_one_sync()) mbar_arrive(bar_go(gcnt % kPeerBars));
-                  __syncwarp();
-                  PP(if (lane == 0 && sl == 0) { PTRACE(L, t, 5); })
-                  ++gcnt;
-                }
-              }
-            }
-          }
-        }
-      }
-    }
+  } else if (warp == kCtrlWarp && rank != 0) {
+    // the peer's control warp has nothing to do: its weight halves signal the leader's barriers directly (TMA, cta_group::2),
+    // its A-operand readiness arrives remotely from its epilogue warps
   } else if (warp == kCtrlWarp) {
-    // ================================================================ MMA issuer (leader only): one wait per group of slots
-    uint32_t cnt = 0, gcnt = 0;
+    // ================================================================ MMA issuer (leader only): one wait per ring slot
+    uint32_t cnt = 0, ready_ph = 0, reload_ph = 0;
     const uint32_t idesc256 = umma_idesc(256, 256), idesc16 = umma_idesc(256, 16);
     constexpr uint32_t kHi = (128u >> 4) | (1u << 14);   // SBO = 128 B, descriptor version 1
     PP(long long pf_full = 0, pf_ready[2] = {0, 0}, pf_peer[2] = {0, 0}, pf_issue = 0; const long long pf_t0 = clock64();)
@@ -260,11 +214,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nerf_st
           for (int sl = 0; sl < nsl; ++sl, ++cnt) {
             const uint32_t stage = cnt % kRing;
             PP(long long pa = clock64();)
-            if (group_start(sl)) {
-              mbar_wait(bar_go(gcnt % kPeerBars), (gcnt / kPeerBars) & 1u);
-              ++gcnt;
-              tc_fence_after();
+            mbar_wait(bar_full(stage), (cnt / kRing) & 1u);      // both CTAs' halves of this slot landed
+            PP(const long long pw = clock64(); pf_peer[0] += pw - pa;)
+            if (sl == 0) {                                        // the A operand of tile t is written in both CTAs
+              mbar_wait(bar_ready(t), (ready_ph >> t) & 1u);
+              PP(const long long pr = clock64(); pf_peer[1] += pr - pw; PTRACE(L, t, 6);)
+              mbar_wait(bar_pready(t), (ready_ph >> t) & 1u);
+              PP(PTRACE(L, t, 4); PTRACE(L, t, 5);)
+              ready_ph ^= 1u << t;
+              if (ly.reload) {
+                mbar_wait(bar_reload(t), (reload_ph >> t) & 1u);
+                reload_ph ^= 1u << t;
+              }
             }
+            tc_fence_after();
             PP(long long pb = clock64(); pf_full += pb - pa;)
             PP(if (lane == 0 && sl == 0) { PTRACE(L, t, 0); })
             const uint32_t d_tmem = tmem_base + t * 256;
@@ -457,7 +420,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) nerf_st
             __syncwarp();                // every lane's st.shared + proxy fence precede the warp's single arrive
             if (lane == 0) {
               if (rank == 0) mbar_arrive(bar_ready(t));
-              else mbar_arrive_remote(pready_remote + 8 * t);
+              else {
+                // the next stage's A operand is the feature tile coming back by TMA: the peer vouches for its own reload
+                if (kLayers[L + 1].reload) mbar_wait(bar_reload(t), it & 1u);
+                mbar_arrive_remote(pready_remote + 8 * t);
+              }
             }
           }
           PP(pe_work += clock64() - eb;)
@@ -525,17 +492,41 @@ TP_API int tp_tc_pair_weights(const void* packed, void* pair_packed, void* strea
   return tp_launch_status();
 }
 
+// Tensor map over the pair image seen as rows of 2 KB (256 x u64): a chunk half is a box of 4 rows (8 KB) or 2 rows (4 KB).
+// cuTensorMapEncodeTiled comes from the driver through the runtime (no link against libcuda).
+static int make_weight_map(CUtensorMap* map, const void* base, int box_rows) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess) return (int)e;
+  if (!fn || qres != cudaDriverEntryPointSuccess) return (int)cudaErrorNotSupported;
+  const cuuint64_t dims[2] = {256, (cuuint64_t)tc::kNumChunks * 8};       // 8 rows of 2 KB per 16 KB chunk
+  const cuuint64_t strides[1] = {2048};
+  const cuuint32_t box[2] = {256, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = reinterpret_cast<EncodeFn>(fn)(map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, const_cast<void*>(base), dims, strides, box,
+                                                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                    CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : TP_ERR_BAD_ARG;
+}
+
 // dispatched from tp_tc_nerf_stl_forward (flags bit 10); p.packed must be the pair image (tp_tc_pair_weights)
 int tp_tc_pair_launch(const tc::Params& p, cudaStream_t stream) {
   cudaError_t e = cudaFuncSetAttribute(tc3::nerf_stl_forward_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)tc3::kSmemBytes);
   if (e != cudaSuccess) return (int)e;
+  alignas(64) CUtensorMap wmap8, wmap4;
+  if (int rc = make_weight_map(&wmap8, p.packed, 4)) return rc;
+  if (int rc = make_weight_map(&wmap4, p.packed, 2)) return rc;
   const long long n_super = (p.S + 255) / 256;
   int grid = (tp_num_sms() / 2) * 2;
   const long long need = ((n_super + 1) / 2) * 2;
   if (need < grid) grid = (int)need;
   const long long per_pass = grid;                          // super-tiles per pass = CTAs
   const int iters = (int)((n_super + per_pass - 1) / per_pass);
-  tc3::nerf_stl_forward_pair_kernel<<<grid, tc3::kThreads, tc3::kSmemBytes, stream>>>(p, iters);
+  tc3::nerf_stl_forward_pair_kernel<<<grid, tc3::kThreads, tc3::kSmemBytes, stream>>>(p, iters, wmap8, wmap4);
   return tp_launch_status();
 }
