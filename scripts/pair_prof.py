@@ -32,13 +32,12 @@ stages = lead[:, 7] * 17
 f = lambda t, i: (t[:, i] / stages).mean().item()
 print("flags", flags, "per stage (both tiles), leader ctrl warp: total %.0f | wait go %.0f | in elect: MMA issue %.0f commits %.0f | wait weights %.0f, own A %.0f | issue window %.0f"
       % tuple(f(lead, i) for i in range(7)))
-print("   peer ctrl warp: wait weights %.0f | wait own A t0 %.0f t1 %.0f" % (f(peer, 1), f(peer, 2), f(peer, 3)))
 print("   epilogue warp 0 (both tiles): leader wait acc %.0f work %.0f | peer wait acc %.0f work %.0f" % (f(lead, 8), f(lead, 9), f(peer, 8), f(peer, 9)))
 
 tr = out[3].view(-1).view(torch.int64)[148 * 16:148 * 16 + 2 * 17 * 2 * 8].view(2, 17, 2, 8).cpu()
 lead = tr[0]
 base = int(lead[1, 0, 0])
-print("leader CTA, iteration 3, cycles relative to stage 1 / tile 0 first MMA.  columns: first MMA | last issue | epilogue woke | drain done | gate saw own ready | gate saw peer ready | go raised")
+print("leader CTA, iteration 3, cycles relative to stage 1 / tile 0 first MMA.  columns: first MMA | last issue | epilogue woke | drain done | own A ready seen | peer A ready seen")
 for L in range(1, 12):
     for t in range(2):
         e = lead[L, t] - base

@@ -66,25 +66,12 @@ __device__ __forceinline__ uint32_t map_to_rank(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
-// Remote arrive / wait with the default (.release / .acquire at CTA scope) semantics, as CUTLASS' ClusterBarrier does: the
+// Remote arrive with the default (.release / .acquire at CTA scope) semantics, as CUTLASS' ClusterBarrier does: the
 // operands the signal stands for never cross CTAs through the generic proxy -- each SM's tensor core reads its OWN shared
 // memory, and the peer's writers ordered their st.shared before the local barrier with fence.proxy.async.  Cluster-scope
 // acquire / release would compile to MEMBAR.ALL.GPU + CCTL.IVALL on every chunk (measured: +60 % kernel time).
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); }
-// two barriers in one spin loop: the try_waits issue back to back, so their latencies overlap
-__device__ __forceinline__ void mbar_wait2(uint32_t bar_a, uint32_t parity_a, uint32_t bar_b, uint32_t parity_b) {
-  asm volatile(
-      "{\n\t.reg .pred pa, pb;\n\t"
-      "WAIT2_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 pa, [%0], %1;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 pb, [%2], %3;\n\t"
-      "and.pred pa, pa, pb;\n\t"
-      "@!pa bra WAIT2_%=;\n\t}" ::"r"(bar_a),
-      "r"(parity_a), "r"(bar_b), "r"(parity_b)
-      : "memory");
 }
 // TMA tile load whose completion is signalled on a barrier of the LEADER CTA of the pair (cta_group::2): both CTAs' weight
 // halves complete_tx on the one barrier the MMA warp waits on -- no forwarding hop for the weights
