@@ -14,7 +14,7 @@
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 8, NT = 256, PAD = 4;
+constexpr int BM = 128, BN = 128, BK = 16, NT = 256, PAD = 4;
 
 struct Segs {
   const float* ptr[4];
@@ -22,10 +22,16 @@ struct Segs {
   long long group[4];
   int begin[5];   // column range of segment i is [begin[i], begin[i+1])
   int n;
+  // group == 1 (per-sample tensors, the common case) needs no division; the others divide in 32 bits when the row fits
   __device__ __forceinline__ float at(long long row, int col) const {
 #pragma unroll
     for (int i = 0; i < 4; ++i)
-      if (i < n && col < begin[i + 1]) return ptr[i][(row / group[i]) * ld[i] + (col - begin[i])];
+      if (i < n && col < begin[i + 1]) {
+        long long r = row;
+        if (group[i] != 1)
+          r = (row < 0x7fffffffLL && group[i] < 0x7fffffffLL) ? (long long)((unsigned)row / (unsigned)group[i]) : row / group[i];
+        return ptr[i][r * ld[i] + (col - begin[i])];
+      }
     return 0.f;
   }
 };
@@ -100,12 +106,16 @@ struct EpiPartial {
   }
 };
 
-// C[M,N] tile kernel: 256 threads, 128x128x8 tiles, 8x8 register micro-tile split 4+4 in both dims.
+// C[M,N] tile kernel: 256 threads, 128x128x16 tiles, 8x8 register micro-tile split 4+4 in both dims.  The operands of
+// k-tile i+1 are fetched into registers before the FMAs of k-tile i and stored to shared memory after them (software
+// pipelining: one global-memory round trip per k-tile is hidden behind 1024 FMAs per thread).
 // A_KFAST / B_KFAST select which tile dimension consecutive threads walk so that global reads are coalesced.
+// The k order of every accumulator is ascending and independent of the tile size -> results are bit-identical to a plain loop.
 template <bool A_KFAST, bool B_KFAST, class FA, class FB, class Epi>
 __global__ void __launch_bounds__(NT) sgemm_kernel(FA fa, FB fb, Epi epi, long long Kred, long long k_per_split) {
   __shared__ float As[BK][BM + PAD];
   __shared__ float Bs[BK][BN + PAD];
+  constexpr int kLoadsA = (BM * BK) / NT, kLoadsB = (BN * BK) / NT;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const long long m0 = (long long)blockIdx.x * BM, n0 = (long long)blockIdx.y * BN;
   const long long kb = (long long)blockIdx.z * k_per_split;
@@ -116,24 +126,47 @@ __global__ void __launch_bounds__(NT) sgemm_kernel(FA fa, FB fb, Epi epi, long l
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
 
-  for (long long k0 = kb; k0 < ke; k0 += BK) {
+  float ra[kLoadsA], rb[kLoadsB];
+  auto fetch = [&](long long k0) {
 #pragma unroll
-    for (int i = 0; i < (BM * BK) / NT; ++i) {
+    for (int i = 0; i < kLoadsA; ++i) {
       int mm, kk;
-      if (A_KFAST) { kk = tid & (BK - 1); mm = (tid >> 3) + i * (NT / BK); }
-      else { mm = tid & (BM - 1); kk = (tid >> 7) + i * (NT / BM); }
+      if (A_KFAST) { kk = tid & (BK - 1); mm = (tid / BK) + i * (NT / BK); }
+      else { mm = tid & (BM - 1); kk = (tid / BM) + i * (NT / BM); }
       const long long k = k0 + kk;
-      As[kk][mm] = (k < ke) ? fa(m0 + mm, k) : 0.f;
+      ra[i] = (k < ke) ? fa(m0 + mm, k) : 0.f;
     }
 #pragma unroll
-    for (int i = 0; i < (BN * BK) / NT; ++i) {
+    for (int i = 0; i < kLoadsB; ++i) {
       int nn, kk;
-      if (B_KFAST) { kk = tid & (BK - 1); nn = (tid >> 3) + i * (NT / BK); }
-      else { nn = tid & (BN - 1); kk = (tid >> 7) + i * (NT / BN); }
+      if (B_KFAST) { kk = tid & (BK - 1); nn = (tid / BK) + i * (NT / BK); }
+      else { nn = tid & (BN - 1); kk = (tid / BN) + i * (NT / BN); }
       const long long k = k0 + kk;
-      Bs[kk][nn] = (k < ke) ? fb(k, n0 + nn) : 0.f;
+      rb[i] = (k < ke) ? fb(k, n0 + nn) : 0.f;
     }
+  };
+  auto stash = [&]() {
+#pragma unroll
+    for (int i = 0; i < kLoadsA; ++i) {
+      int mm, kk;
+      if (A_KFAST) { kk = tid & (BK - 1); mm = (tid / BK) + i * (NT / BK); }
+      else { mm = tid & (BM - 1); kk = (tid / BM) + i * (NT / BM); }
+      As[kk][mm] = ra[i];
+    }
+#pragma unroll
+    for (int i = 0; i < kLoadsB; ++i) {
+      int nn, kk;
+      if (B_KFAST) { kk = tid & (BK - 1); nn = (tid / BK) + i * (NT / BK); }
+      else { nn = tid & (BN - 1); kk = (tid / BN) + i * (NT / BN); }
+      Bs[kk][nn] = rb[i];
+    }
+  };
+
+  if (kb < ke) fetch(kb);
+  for (long long k0 = kb; k0 < ke; k0 += BK) {
+    stash();
     __syncthreads();
+    if (k0 + BK < ke) fetch(k0 + BK);          // in flight during the FMAs below
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
       float a[8], b[8];
