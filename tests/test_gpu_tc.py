@@ -197,3 +197,30 @@ def test_backward_falls_back_when_images_are_tiny():
         res[prec] = [lt.grad, ll.grad] + [p.grad for p in list(m.mlp_rgb.parameters()) + list(m.mlp_trans.parameters())]
     for a, b in zip(res["bf16"], res["fp32"]):
         assert (a - b).abs().max() <= max(1e-3, 0.02 * b.abs().max().item())
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("flags,name", [(128, "single-tile kernel"), (384, "single-tile kernel, 2-CTA cluster multicast"),
+                                        (1024, "CTA-pair kernel, tcgen05 cta_group::2")])
+def test_kernel_variants_are_bit_identical(flags, name):
+    """The experimental forward kernels behind `flags` (kept as measured alternatives, DESIGN.md 4 / profiles r01b 5) must
+    reproduce the default kernel bit for bit: same MMA shapes per row, same K order, same epilogue arithmetic.  Ragged sizes:
+    an odd number of 128-sample tiles and a partial last tile (the pair kernel then runs a dead super-tile in one CTA)."""
+    from texpose_b200 import mlp_tc
+    from texpose_b200.layers import _common
+    opt, m = _module("bf16")
+    for R, N in ((37, 128), (301, 48)):
+        g = torch.Generator().manual_seed(4)
+        center = (torch.randn(1, R, 3, generator=g) * 0.02 + torch.tensor([0.3, 0.2, -0.8])).to(DEV)
+        ray = (torch.randn(1, R, 3, generator=g) * 0.1 + torch.tensor([0.0, 0.0, 1.0])).to(DEV)
+        depth = ((torch.rand(1, R, N, 1, generator=g) + torch.arange(N)[None, None, :, None]) / N * 1.2 + 0.2).to(DEV)
+        lt, ll = [t.to(DEV) for t in synth.latents(1)]
+        cfg = m._config(opt, "val")
+        geom = _common.ray_geometry(cfg, center, ray, depth)
+        pairs = lambda ml: [(l.weight.detach(), l.bias.detach()) for l in ml]
+        args = (cfg, geom, lt, ll, pairs(m.mlp_feat), pairs(m.mlp_rgb), pairs(m.mlp_trans))
+        ref = mlp_tc.forward(*args, flags=0)
+        got = mlp_tc.forward(*args, flags=flags)
+        torch.cuda.synchronize()
+        for a, b in zip(ref, got):
+            assert torch.equal(a, b), (name, R, N)
