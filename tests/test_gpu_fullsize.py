@@ -73,3 +73,37 @@ def test_fp32_and_bf16_agree_on_a_frame_strip():
     assert (a.depth - b.depth)[:, box].abs().max() <= 1e-2
     assert (a.opacity - b.opacity).abs().max() <= 1e-2
     assert ((a.depth - b.depth)[:, ~box].abs() / 30).max() <= 1e-2       # background rays sample depths in [0, 30]
+
+
+def test_c3_backward_is_linear_in_the_upstream_gradient():
+    """Size-independent property at the full C3 shape (16 patches x 256 rays x 128 samples): the tensor-core backward is a
+    linear map of the loss seeds, and scaling by a power of two is exact in bf16 and fp32 alike -- so doubling the loss must
+    double every gradient BIT FOR BIT (dz tiles, thin-gradient MMAs, dW GEMMs, fixed-order reductions)."""
+    B, R, N = 16, 256, 128
+    opt = adapt_gan_opt(H=128, W=128, sample_intvs=N, device=DEV)
+    opt.b200 = AttrDict(mlp="bf16")
+    torch.manual_seed(0)
+    g = Graph(opt, n_train_images=8).to(DEV)
+    gen = torch.Generator().manual_seed(3)
+    center = (torch.randn(B, R, 3, generator=gen) * 0.02 + torch.tensor([0.3, 0.2, -0.8])).to(DEV)
+    ray = (torch.randn(B, R, 3, generator=gen) * 0.1 + torch.tensor([0.0, 0.0, 1.0])).to(DEV)
+    depth = ((torch.rand(B, R, N, 1, generator=gen) + torch.arange(N)[None, None, :, None]) / N * 1.2 + 0.2).to(DEV)
+    idx = torch.arange(B, device=DEV) % 8
+    target = torch.rand(B, R, 3, generator=gen).to(DEV)
+    params = [p for p in g.parameters() if p.requires_grad]
+
+    def grads(scale):
+        for p in params:
+            p.grad = None
+        lt, ll = g.latent_vars_trans.weight[idx], g.latent_vars_light.weight[idx]
+        out = g.nerf.forward_samples(opt, center, ray, depth, lt, ll, mode="train")
+        comp = g.nerf.composite(opt, ray, *out[:2], depth, out[2])
+        loss = ((target - comp[0]) ** 2 / comp[8] ** 2).mean() + torch.log(comp[8] ** 2).mean() + 0.01 * out[1][..., -1].mean()
+        (loss * scale).backward()
+        return [p.grad.clone() for p in params if p.grad is not None]
+
+    g1, g2 = grads(1.0), grads(2.0)
+    assert len(g1) == len(g2) and len(g1) >= 18
+    for a, b in zip(g1, g2):
+        assert torch.isfinite(a).all() and a.abs().max() > 0
+        assert torch.equal(2 * a, b)
