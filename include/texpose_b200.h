@@ -276,6 +276,34 @@ int tp_eval_epilogue(const float* rgb, const float* depth, const float* image, c
                      float depth_scale, float* rgb_map, float* depth_map, float* image_masked, float* mse, float* psnr,
                      float* workspace, int64_t workspace_floats, void* stream);
 
+/* ---- gradient exchange over NVLink peer memory ------------------------------------------------------- */
+
+/* The one exchange of the path: mean over the ranks of the flat fp32 gradient bucket (heads + latent embeddings, ~1.7 MB;
+ * the reference is single-GPU, options.py:112, so this replaces what DistributedDataParallel's bucket allreduce would do).
+ * One kernel over CUDA-IPC peer windows instead of a library allreduce: publish "my gradients of step `epoch` are in place"
+ * into every peer's window header (NVLink stores), wait on the local header, read all `world` buffers (peer loads) and add
+ * them in rank order -> bit-identical result on every rank.
+ * Window layout: [1 KB header | data buffer 0 | data buffer 1], each buffer tp_peer_capacity_bytes(n) long; the caller
+ * writes its gradients into buffer (epoch & 1) of its OWN window (offset tp_peer_data_offset) before the call; epochs count
+ * 1, 2, 3, ... identically on every rank.
+ * The window is the only driver object the library creates (set-up time, host calls): create = cudaMalloc + zero,
+ * export/import = the 64-byte CUDA IPC handle a peer process opens, release/destroy undo them.
+ * windows: HOST array of `world` device pointers (windows[rank] = the local window, the others imported, same order on
+ * every rank; a single process may pass windows of one device to exercise the protocol).  out: local, >= n rounded up to
+ * 4 floats, 16-byte aligned.  grid_ctas 0 = default.  A peer that does not arrive within timeout_ms (0 = 10 s) leaves `out`
+ * untouched and stores `epoch` in the window's status word (tp_peer_status: host call, synchronising copy, 0 = healthy). */
+int64_t tp_peer_capacity_bytes(int64_t n_floats);
+int64_t tp_peer_window_bytes(int64_t n_floats);
+int64_t tp_peer_data_offset(int64_t n_floats, int parity);
+int tp_peer_window_create(int64_t bytes, void** window_out);
+int tp_peer_window_destroy(void* window);
+int tp_peer_window_export(const void* window, void* handle64);
+int tp_peer_window_import(const void* handle64, void** window_out);
+int tp_peer_window_release(void* imported_window);
+int tp_peer_allreduce_mean(void* const* windows, int world, int rank, int64_t n_floats, uint32_t epoch, float* out,
+                           int grid_ctas, int64_t timeout_ms, void* stream);
+int tp_peer_status(const void* window, uint32_t* status_host);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,7 +16,7 @@ ROOT = os.path.dirname(_HERE)
 HEADER = os.path.join(ROOT, "include", "texpose_b200.h")
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libtexpose_b200.so")
-SOURCES = ["api.cu", "rays.cu", "composite.cu", "mlp_simt.cu", "mlp_tc.cu", "mlp_tc_v2.cu", "mlp_tc_pair.cu", "mlp_tc_bwd.cu", "loss.cu"]
+SOURCES = ["api.cu", "rays.cu", "composite.cu", "mlp_simt.cu", "mlp_tc.cu", "mlp_tc_v2.cu", "mlp_tc_pair.cu", "mlp_tc_bwd.cu", "loss.cu", "peer.cu"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -53,7 +53,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 _CTYPE = {"int": ctypes.c_int, "int64_t": ctypes.c_int64, "uint64_t": ctypes.c_uint64, "float": ctypes.c_float,
-          "int32_t": ctypes.c_int32}
+          "int32_t": ctypes.c_int32, "uint32_t": ctypes.c_uint32}
 
 
 def declared_prototypes():

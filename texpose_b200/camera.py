@@ -81,7 +81,9 @@ def view_matrices(pose_, intr):
         dev = pose_.device
         return (intr.detach().cpu().float().inverse().contiguous().to(dev),
                 Pose().invert(pose_.detach().cpu().float()).contiguous().to(dev))
-    return intr.float().inverse().contiguous(), Pose().invert(pose_.float()).contiguous()
+    # inv_ex == inverse() bit for bit, minus its error check: that check reads `info` back and would stall the launch
+    # queue once per frame (the calibration matrix is never singular; a singular one yields inf/nan rays as before)
+    return torch.linalg.inv_ex(intr.float())[0].contiguous(), Pose().invert(pose_.float()).contiguous()
 
 
 def get_center_and_ray(opt, pose_, intr=None, H=None, W=None, ray_idx=None):

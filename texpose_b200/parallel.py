@@ -3,16 +3,22 @@
 The reference is single-GPU (options.py:112).  The path shards naturally:
   * rendering: views (or contiguous row blocks of one frame) are partitioned across ranks, no exchange;
     an optional all_gather collects the 56 B/ray outputs;
-  * training: data-parallel over patches; ONE exchange per step -- a sum-allreduce of a flat fp32 buffer with
-    the head + embedding gradients (~1.7 MB), then a divide by the world size.
+  * training: data-parallel over patches; ONE exchange per step -- the mean over the ranks of a flat fp32 buffer with
+    the head + embedding gradients (~1.7 MB).  Two implementations with the same interface:
+      GradBucket        torch.distributed allreduce (NCCL on GPUs; gloo in the CPU tests),
+      PeerGradExchange  one kernel over CUDA-IPC peer windows (NVLink loads/stores, csrc/peer.cu): ranks of ONE node,
+                        result bit-identical on every rank (fixed rank-order sum).
 Samples of one ray are never split (scan dependence).
 """
 from __future__ import annotations
 
-from typing import Iterable, List, Sequence, Tuple
+import ctypes
+from typing import Iterable, List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
+
+from . import _C
 
 
 def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
@@ -44,9 +50,11 @@ class GradBucket:
         dev = self.params[0].device if self.params else torch.device("cpu")
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
 
-    def pack(self):
+    def pack(self, into: Optional[torch.Tensor] = None):
         """One launch: concatenate the gradients into the flat buffer (missing gradients count as zero)."""
-        base = self.flat.untyped_storage().data_ptr()
+        if into is None:
+            into = self.flat
+        base = into.untyped_storage().data_ptr()
         parts = []
         for p in self.params:
             g = p.grad if p.grad is not None else torch.zeros_like(p)
@@ -54,8 +62,8 @@ class GradBucket:
                 g = g.clone()
             parts.append(g.reshape(-1))
         if parts:
-            torch.cat(parts, out=self.flat)
-        return self.flat
+            torch.cat(parts, out=into)
+        return into
 
     def unpack(self):
         """No copy back: every .grad becomes a view into the reduced flat buffer."""
@@ -78,6 +86,122 @@ class GradBucket:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
             self.flat.div_(world)
         self.unpack()
+
+
+class _DeviceSpan:
+    """fp32 view of raw device memory for torch.as_tensor (CUDA array interface); keeps the owning window alive."""
+
+    def __init__(self, ptr: int, n: int, owner):
+        self.owner = owner
+        self.__cuda_array_interface__ = dict(shape=(n,), typestr="<f4", data=(ptr, False), version=3, strides=None)
+
+
+class PeerWindow:
+    """One rank's exchange window (csrc/peer.cu): [1 KB header | data buffer 0 | data buffer 1] in cudaMalloc'ed memory that
+    peer processes open through its 64-byte CUDA IPC handle.  `buffers[k]` are fp32 tensors over the two data buffers."""
+
+    def __init__(self, n_floats: int, device):
+        lib = _C.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("PeerWindow lives in GPU memory (texpose_b200 has no CPU path)")
+        self.n = int(n_floats)
+        self.bytes = int(lib.tp_peer_window_bytes(self.n))
+        ptr = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _C.check(lib.tp_peer_window_create(self.bytes, ctypes.byref(ptr)), "tp_peer_window_create")
+        self.ptr = int(ptr.value)
+        self._imported = []
+        self.buffers = [torch.as_tensor(_DeviceSpan(self.ptr + int(lib.tp_peer_data_offset(self.n, k)), max(self.n, 1), self),
+                                        device=self.device)[:self.n] for k in (0, 1)]
+
+    def handle(self) -> bytes:
+        buf = ctypes.create_string_buffer(64)
+        with torch.cuda.device(self.device):
+            _C.check(_C.load().tp_peer_window_export(self.ptr, buf), "tp_peer_window_export")
+        return buf.raw
+
+    def open_peer(self, handle: bytes) -> int:
+        """Device pointer of a peer process' window in this process (peer access is enabled on first use)."""
+        out = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _C.check(_C.load().tp_peer_window_import(ctypes.create_string_buffer(handle, 64), ctypes.byref(out)),
+                     "tp_peer_window_import")
+        self._imported.append(int(out.value))
+        return int(out.value)
+
+    def status(self) -> int:
+        """0 = healthy; otherwise the epoch at which a peer failed to arrive within the timeout (synchronising read)."""
+        st = ctypes.c_uint32(0)
+        with torch.cuda.device(self.device):
+            _C.check(_C.load().tp_peer_status(self.ptr, ctypes.byref(st)), "tp_peer_status")
+        return int(st.value)
+
+    def close(self):
+        lib = _C.load()
+        if self.ptr:
+            with torch.cuda.device(self.device):
+                torch.cuda.synchronize()
+                for q in self._imported:
+                    lib.tp_peer_window_release(q)
+                lib.tp_peer_window_destroy(self.ptr)
+            self.ptr, self._imported, self.buffers = 0, [], []
+
+
+def peer_allreduce_mean(window_ptrs: Sequence[int], rank: int, n_floats: int, epoch: int, out: torch.Tensor,
+                        grid_ctas: int = 0, timeout_ms: int = 0, stream=None):
+    """out[:n] = mean over the windows of data buffer (epoch & 1), summed in rank order (tp_peer_allreduce_mean)."""
+    if not out.is_cuda or out.dtype != torch.float32 or out.numel() < (n_floats + 3) // 4 * 4:
+        raise RuntimeError("peer_allreduce_mean: `out` must be a CUDA fp32 tensor of at least n rounded up to 4 floats")
+    arr = (ctypes.c_void_p * len(window_ptrs))(*window_ptrs)
+    st = stream if stream is not None else torch.cuda.current_stream(out.device)
+    with torch.cuda.device(out.device):
+        _C.call("tp_peer_allreduce_mean", arr, len(window_ptrs), rank, n_floats, epoch, out.data_ptr(), grid_ctas,
+                timeout_ms, st.cuda_stream)
+
+
+class PeerGradExchange(GradBucket):
+    """GradBucket whose exchange is ONE kernel over NVLink peer memory instead of a library allreduce.
+
+    Set-up (once): every rank creates a window, the 64-byte IPC handles travel through `all_gather_object`, every rank opens
+    its peers' windows.  Per step: one `cat` packs the gradients into the local window's buffer of the step's parity, one
+    launch publishes / waits / reduces, `.grad`s become views of the reduced buffer.  All ranks must sit on one node with
+    peer access (NVLink / NVSwitch); anything else raises at set-up -- there is no silent fallback to the allreduce."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], group=None, timeout_ms: int = 10000):
+        super().__init__(params)
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("PeerGradExchange needs an initialised process group (use GradBucket for a single process)")
+        dev = self.flat.device
+        self.group, self.timeout_ms = group, int(timeout_ms)
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.n = self.flat.numel()
+        self.window = PeerWindow(self.n, dev)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, self.window.handle(), group=group)
+        self.ptrs = [self.window.ptr if r == self.rank else self.window.open_peer(h) for r, h in enumerate(handles)]
+        self.flat = torch.zeros((self.n + 3) // 4 * 4, dtype=torch.float32, device=dev)    # the reduced gradients land here
+        self.epoch = 0
+        torch.cuda.synchronize(dev)
+        dist.barrier(group)          # every window exists, is zeroed and is open everywhere before the first publish
+
+    def allreduce_mean(self, group=None):
+        self.epoch += 1
+        self.pack(into=self.window.buffers[self.epoch & 1])
+        peer_allreduce_mean(self.ptrs, self.rank, self.n, self.epoch, self.flat, timeout_ms=self.timeout_ms)
+        self.unpack()
+
+    def check(self):
+        """Raises if a peer ever missed an exchange (reads one status word back: call it off the hot path)."""
+        bad = self.window.status()
+        if bad:
+            raise RuntimeError(f"PeerGradExchange: a peer did not arrive at epoch {bad} within {self.timeout_ms} ms")
+
+    def close(self):
+        if dist.is_initialized():
+            torch.cuda.synchronize(self.flat.device)
+            dist.barrier(self.group)     # nobody unmaps a window a peer may still be reading
+        self.window.close()
 
 
 def gather_ray_outputs(local: torch.Tensor, sizes: Sequence[int], group=None) -> torch.Tensor:
