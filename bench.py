@@ -387,26 +387,44 @@ def bench_train(args, g, opt, dev, world, timed):
     image = torch.rand(B, 3, 128, 128, device=dev)
     mask = (torch.rand(B, 128, 128, device=dev) > 0.3).float()
     params = [p for p in g.parameters() if p.requires_grad]
-    bucket = parallel.GradBucket(params)
+    # the one exchange of the path: N > 1 -> one kernel over NVLink peer windows (csrc/peer.cu); the NCCL allreduce of the same
+    # bucket is timed beside it
+    exchange = parallel.PeerGradExchange(params) if world > 1 else parallel.GradBucket(params)
     g.train()
 
-    def step():
-        for p in params:
-            p.grad = None
-        ret = g.render(opt_t, pose, intr=intr, ray_idx=coords, depth_range=(zn[:, :, None], zf[:, :, None]),
-                       sample_idx=idx, mode="train")
-        var = AttrDict(idx=idx, image=image, obj_mask=mask, ray_idx=coords)
-        var.update(ret)
-        loss = g.compute_loss(opt_t, var, mode="train")      # patch gather + render / uncert / trans_reg terms + seeds, fused
-        loss["all"].backward()
-        bucket.allreduce_mean()
+    def make_step(bucket):
+        def step():
+            for p in params:
+                p.grad = None
+            ret = g.render(opt_t, pose, intr=intr, ray_idx=coords, depth_range=(zn[:, :, None], zf[:, :, None]),
+                           sample_idx=idx, mode="train")
+            var = AttrDict(idx=idx, image=image, obj_mask=mask, ray_idx=coords)
+            var.update(ret)
+            loss = g.compute_loss(opt_t, var, mode="train")      # patch gather + render / uncert / trans_reg terms + seeds, fused
+            loss["all"].backward()
+            bucket.allreduce_mean()
+        return step
 
-    ms, _ = timed(step, max(3, args.steps // 2), 2)
-    g.eval()
+    n_steps = max(3, args.steps // 2)
+    ms, _ = timed(make_step(exchange), n_steps, 3)
     samples = B * P * P * NS
-    return dict(workload="C3 train step fwd+bwd, 4096 rays x 128 samples per GPU, fused patch loss, bf16 tcgen05 fwd + bwd (dX chain with thin gradients, dW GEMMs), grad allreduce",
-                value=world * samples / (ms * 1e-3), unit="samples/s", ms_per_step=ms, grad_allreduce_bytes=bucket.flat.numel() * 4,
-                tflops_per_gpu=FLOP_PER_SAMPLE_FWD_BWD * samples / (ms * 1e-3) / 1e12, flop_per_sample=FLOP_PER_SAMPLE_FWD_BWD)
+    out = dict(workload="C3 train step fwd+bwd, 4096 rays x 128 samples per GPU, fused patch loss, bf16 tcgen05 fwd + bwd (dX chain with thin gradients, dW GEMMs), grad exchange",
+               value=world * samples / (ms * 1e-3), unit="samples/s", ms_per_step=ms, grad_exchange_bytes=exchange.flat.numel() * 4,
+               grad_exchange="none (1 GPU)" if world == 1 else "one-kernel rank-order mean over CUDA-IPC peer windows (NVLink)",
+               tflops_per_gpu=FLOP_PER_SAMPLE_FWD_BWD * samples / (ms * 1e-3) / 1e12, flop_per_sample=FLOP_PER_SAMPLE_FWD_BWD)
+    if world > 1:
+        exchange.check()
+        ms_nccl, _ = timed(make_step(parallel.GradBucket(params)), n_steps, 3)
+        out["ms_per_step_nccl_allreduce"] = ms_nccl
+        # the exchange alone, back to back (gradients already in place): device time per call, max over ranks
+        for p in params:
+            p.grad = torch.ones_like(p)
+        out["exchange_only_us"] = {"peer": 1e3 * timed(exchange.allreduce_mean, 50, 5)[0],
+                                   "nccl": 1e3 * timed(parallel.GradBucket(params).allreduce_mean, 50, 5)[0]}
+        exchange.check()
+        exchange.close()
+    g.eval()
+    return out
 
 
 def main():

@@ -225,20 +225,27 @@ __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_ke
         if (ly.epi == EPI_HIDDEN) {
           float* dbg_row = ((L == p.dbg_layer) && live && p.dbg_out) ? p.dbg_out + s * 256 + half * kCols : nullptr;
           const uint32_t a_row = a_smem + half * (kCols / 8) * 2048 + row * 16;
-          const int mslot = p.bits ? kMaskBitSlot[L] : -1;
-          if (mslot >= 0) {
-            // training: h1 / h2 of either head also leave a ReLU bitmask [128 rows][256 bits] for the backward chain
-            // word planes [8][128 rows]: plane = 32-column slab, so a warp's store of one slab is 128 contiguous bytes
-            uint32_t* words = reinterpret_cast<uint32_t*>(p.bits + ((size_t)(st * 2 + t) * 4 + mslot) * kMaskBitBytes) +
-                              half * (kCols / 32) * 128 + row;
+          const bool train_stage = p.save && L != kSpillLayer && kSaveSlot[L] >= 0;
+          if (train_stage) {
+            // training: h1 / h2 of either head also leave a ReLU bitmask [128 rows][256 bits] for the backward chain (word
+            // planes [8][128 rows]: plane = 32-column slab, so a warp's store of one slab is 128 contiguous bytes), and the
+            // activations go straight from the registers to their saved tile image (the backward's operands): a warp's
+            // 16-byte groups cover 512 contiguous bytes and nothing re-reads the A tile
+            const int mslot = (p.dbg_save & 2) ? -1 : kMaskBitSlot[L];
+            uint32_t* words = mslot < 0 ? nullptr
+                                        : reinterpret_cast<uint32_t*>(p.bits + ((size_t)(st * 2 + t) * 4 + mslot) * kMaskBitBytes) +
+                                              half * (kCols / 32) * 128 + row;
+            uint8_t* g_row = (p.dbg_save & 1) ? nullptr
+                                              : p.save + ((size_t)(st * 2 + t) * kSaveSlots + kSaveSlot[L]) * kABytes +
+                                                    half * (kCols / 8) * 2048 + row * 16;
             if (ly.bias_kind == BIAS_MMA) {
-              hidden_epilogue<false, kCols / 32, true>(tmem_d, nullptr, a_row, dbg_row, words);
+              hidden_epilogue<false, kCols / 32, true>(tmem_d, nullptr, a_row, dbg_row, words, g_row);
             } else if (warp_bias) {
-              hidden_epilogue_wbias<kCols / 32, true>(tmem_d, wb, a_row, dbg_row, words);
+              hidden_epilogue_wbias<kCols / 32, true>(tmem_d, wb, a_row, dbg_row, words, g_row);
             } else {
               const float* bias = (ly.bias_kind == BIAS_RAY ? p.raybias + (s / p.N) * 256 : p.imgbias + (s / p.per_image) * 256) +
                                   half * kCols;
-              hidden_epilogue<true, kCols / 32, true>(tmem_d, bias, a_row, dbg_row, words);
+              hidden_epilogue<true, kCols / 32, true>(tmem_d, bias, a_row, dbg_row, words, g_row);
             }
           } else if (p.dbg_drain == 1 || p.dbg_drain == 2) {
             hidden_epilogue_experiment<kCols / 32>(tmem_d, a_row, p.dbg_drain);
@@ -252,9 +259,9 @@ __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_ke
             hidden_epilogue<true, kCols / 32>(tmem_d, bias, a_row, dbg_row);
           }
           fence_proxy_async_smem();
-          if (L == kSpillLayer || (p.save && kSaveSlot[L] >= 0)) {
-            // park the trunk feature (bf16 tile image) in the L2 scratch; in training mode every head activation is
-            // saved the same way -- the store overlaps the next stage's MMAs
+          if (L == kSpillLayer) {
+            // park the trunk feature (bf16 tile image) in the L2 scratch (training: in its slot of the save buffer, where
+            // the backward also reads it) -- the bulk store overlaps the next stage's MMAs
             named_bar_sync(1 + t, kTileThreads);
             if (row == 0 && half == 0) {
               uint8_t* dst = p.save ? p.save + ((size_t)(st * 2 + t) * kSaveSlots + kSaveSlot[L]) * kABytes : my_scratch;
@@ -489,6 +496,7 @@ TP_API int tp_tc_nerf_stl_forward(const float* center, const float* ray, const f
   p.bits = save ? p.save + ((S + 255) / 256) * 2 * tc::kSaveSlots * (size_t)tc::kABytes : nullptr;
   if (save && (flags & 128)) return TP_ERR_BAD_ARG;           // the experimental kernel does not write the ReLU bitmasks
   p.dbg_layer = dbg_layer; p.dbg_out = dbg_out; p.dbg_drain = (flags >> 2) & 7;
+  p.dbg_save = (flags >> 14) & 3;
   p.skew = ((flags >> 5) & 3) ? ((flags >> 5) & 3) - 1 : 1;      // default skew 1; flags bits 5-6 = skew+1 override (A/B)
   if (flags & 128) return tp_tc_v2_launch(p, flags, (cudaStream_t)stream);   // experimental single-tile / cluster kernel
   if (flags & 1024) {     // CTA-pair kernel (cta_group::2); `packed` must be the pair image; flags bits 11-13 = skew + 1 (default 4)

@@ -71,6 +71,8 @@ struct Params {
   int dbg_layer;
   float* dbg_out;            // [S,256] post-activation of stage dbg_layer (debug only)
   int skew;                  // weight chunks tile 0 runs ahead of tile 1 inside a stage (0..2)
+  int dbg_save;              // timing experiments only (wrong training results): bit 0 = skip the activation-save bulk stores,
+                             // bit 1 = skip the ReLU bitmasks
   int dbg_drain;             // timing experiments only (wrong results): 1 = convert/store every other slab, 2 = also skip its TMEM load
 };
 
