@@ -105,4 +105,4 @@ if os.environ.get("TP_TORCH_PROFILE"):
         for _ in range(3):
             train()
         torch.cuda.synchronize()
-    print(prof.key_averages().table(sort_by="self_cpu_time_total", row_limit=40, max_name_column_width=60))
+    print(prof.key_averages().table(sort_by="self_cuda_time_total", row_limit=32, max_name_column_width=60))

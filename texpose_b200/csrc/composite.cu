@@ -162,6 +162,131 @@ composite_stl_fwd_kernel(const float* __restrict__ ray, const float* __restrict_
   }
 }
 
+// Vectorised forward for N = 32 * K (K = 2, 4: the yaml's 64 / 128 samples): lane l owns the K CONSECUTIVE samples
+// l*K .. l*K+K-1, so every per-sample tensor moves as 128-bit (K = 2: 64-bit for the 4-byte streams) loads / stores that a
+// warp issues as one contiguous 256 B .. 3 KB block, all of them in flight before the first use; the three exclusive
+// cumulative sums are a K-step serial prefix inside the lane plus ONE warp scan of the lane totals per chain (3 scans per
+// ray instead of 3 per 32-sample chunk).
+template <int K>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+composite_stl_fwd_vec_kernel(const float* __restrict__ ray, const float* __restrict__ rgb,
+                             const float* __restrict__ density, const float* __restrict__ depth,
+                             const float* __restrict__ uncert, long long R, float min_uncert,
+                             float* __restrict__ o_rgb, float* __restrict__ o_rgb_s, float* __restrict__ o_rgb_t,
+                             float* __restrict__ o_depth, float* __restrict__ o_op, float* __restrict__ o_op_s,
+                             float* __restrict__ o_op_t, float* __restrict__ o_prob, float* __restrict__ o_unc,
+                             float* __restrict__ o_as, float* __restrict__ o_at) {
+  constexpr int N = 32 * K;
+  static_assert(K == 2 || K == 4, "K");
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
+  for (long long r = warp0; r < R; r += nwarps) {
+    const long long s0 = r * N + lane * K;      // first sample of this lane
+    float c[6 * K], sg[2 * K], d[K], u[K];
+    if (K == 4) {
+#pragma unroll
+      for (int v = 0; v < 6; ++v) {
+        const float4 q = __ldcs(reinterpret_cast<const float4*>(rgb + s0 * 6) + v);
+        c[4 * v] = q.x; c[4 * v + 1] = q.y; c[4 * v + 2] = q.z; c[4 * v + 3] = q.w;
+      }
+#pragma unroll
+      for (int v = 0; v < 2; ++v) {
+        const float4 q = __ldcs(reinterpret_cast<const float4*>(density + s0 * 2) + v);
+        sg[4 * v] = q.x; sg[4 * v + 1] = q.y; sg[4 * v + 2] = q.z; sg[4 * v + 3] = q.w;
+      }
+      const float4 qd = __ldcs(reinterpret_cast<const float4*>(depth + s0));
+      d[0] = qd.x; d[1] = qd.y; d[K - 2] = qd.z; d[K - 1] = qd.w;
+      const float4 qu = __ldcs(reinterpret_cast<const float4*>(uncert + s0));
+      u[0] = qu.x; u[1] = qu.y; u[K - 2] = qu.z; u[K - 1] = qu.w;
+    } else {
+#pragma unroll
+      for (int v = 0; v < 3; ++v) {
+        const float4 q = __ldcs(reinterpret_cast<const float4*>(rgb + s0 * 6) + v);
+        c[4 * v] = q.x; c[4 * v + 1] = q.y; c[4 * v + 2] = q.z; c[4 * v + 3] = q.w;
+      }
+      const float4 q = __ldcs(reinterpret_cast<const float4*>(density + s0 * 2));
+      sg[0] = q.x; sg[1] = q.y; sg[2] = q.z; sg[3] = q.w;
+      const float2 qd = __ldcs(reinterpret_cast<const float2*>(depth + s0));
+      d[0] = qd.x; d[1] = qd.y;
+      const float2 qu = __ldcs(reinterpret_cast<const float2*>(uncert + s0));
+      u[0] = qu.x; u[1] = qu.y;
+    }
+    const float len = ray_len(ray, r);
+    const float d_next = __shfl_down_sync(kFull, d[0], 1);      // first depth of the next lane's run
+    float sds[K], sdt[K], sdj[K];
+    float tj = 0.f, ts = 0.f, tt = 0.f;      // lane totals
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const float nxt = k + 1 < K ? d[k + 1] : d_next;
+      const float gap = (k + 1 < K || lane < 31) ? __fsub_rn(nxt, d[k]) : 1e10f;
+      const float dist = __fmul_rn(gap, len);
+      sds[k] = __fmul_rn(sg[2 * k], dist);
+      sdt[k] = __fmul_rn(sg[2 * k + 1], dist);
+      sdj[k] = __fadd_rn(sds[k], sdt[k]);
+      tj += sdj[k];
+      ts += sds[k];
+      tt += sdt[k];
+    }
+    // exclusive prefix of the lane totals
+    float ej = __shfl_up_sync(kFull, warp_scan(tj, lane), 1), es = __shfl_up_sync(kFull, warp_scan(ts, lane), 1),
+          et = __shfl_up_sync(kFull, warp_scan(tt, lane), 1);
+    if (lane == 0) ej = es = et = 0.f;
+    float acc[14];
+#pragma unroll
+    for (int k = 0; k < 14; ++k) acc[k] = 0.f;
+    float pr[K], as_[K], at_[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const float Es = expf(-sds[k]), Et = expf(-sdt[k]), E = expf(-sdj[k]);
+      const float T = expf(-ej), Ts = expf(-es), Tt = expf(-et);
+      ej += sdj[k];
+      es += sds[k];
+      et += sdt[k];
+      const float as = 1.f - Es, at = 1.f - Et, a = 1.f - E;
+      const float ps = T * as, pt = T * at, p = T * a, qs = Ts * as, qt = Tt * at;
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) {
+        const float cs = c[6 * k + 2 * ch], ct = c[6 * k + 2 * ch + 1];
+        acc[ch] += cs * ps + ct * pt;
+        acc[3 + ch] += qs * cs;
+        acc[6 + ch] += qt * ct;
+      }
+      acc[9] += d[k] * qs;
+      acc[10] += p;
+      acc[11] += qs;
+      acc[12] += qt;
+      acc[13] += u[k] * pt;
+      pr[k] = p;
+      as_[k] = as;
+      at_[k] = at;
+    }
+    if (K == 4) {
+      __stcs(reinterpret_cast<float4*>(o_prob + s0), make_float4(pr[0], pr[1], pr[K - 2], pr[K - 1]));
+      __stcs(reinterpret_cast<float4*>(o_as + s0), make_float4(as_[0], as_[1], as_[K - 2], as_[K - 1]));
+      __stcs(reinterpret_cast<float4*>(o_at + s0), make_float4(at_[0], at_[1], at_[K - 2], at_[K - 1]));
+    } else {
+      __stcs(reinterpret_cast<float2*>(o_prob + s0), make_float2(pr[0], pr[1]));
+      __stcs(reinterpret_cast<float2*>(o_as + s0), make_float2(as_[0], as_[1]));
+      __stcs(reinterpret_cast<float2*>(o_at + s0), make_float2(at_[0], at_[1]));
+    }
+#pragma unroll
+    for (int k = 0; k < 14; ++k) acc[k] = warp_sum(acc[k]);
+    if (lane < 3) {
+      o_rgb[r * 3 + lane] = acc[lane];
+      o_rgb_s[r * 3 + lane] = acc[3 + lane];
+      o_rgb_t[r * 3 + lane] = acc[6 + lane];
+    }
+    if (lane == 0) {
+      o_depth[r] = acc[9];
+      o_op[r] = acc[10];
+      o_op_s[r] = acc[11];
+      o_op_t[r] = acc[12];
+      o_unc[r] = acc[13] + min_uncert;
+    }
+  }
+}
+
 struct StlGrads {   // upstream gradients of one ray (zeros where the caller passed no tensor)
   float rgb[3], rs[3], rt[3], d, o, os, ot, u;
 };
@@ -391,9 +516,20 @@ TP_API int tp_composite_stl_forward(const float* ray, const float* rgb, const fl
     return TP_ERR_BAD_ARG;
   if (R < 0 || N < 1) return TP_ERR_BAD_SHAPE;
   if (R == 0) return TP_OK;
-  composite_stl_fwd_kernel<<<grid_for_rays(R), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
-      ray, rgb, density, depth, uncert, R, N, min_uncert, o_rgb, o_rgb_static, o_rgb_transient, o_depth, o_opacity,
-      o_opacity_static, o_opacity_transient, o_prob, o_uncert, o_alpha_static, o_alpha_transient);
+  const bool aligned = (((uintptr_t)rgb | (uintptr_t)density | (uintptr_t)depth | (uintptr_t)uncert | (uintptr_t)o_prob |
+                         (uintptr_t)o_alpha_static | (uintptr_t)o_alpha_transient) & 15) == 0;
+  if (aligned && N == 128)
+    composite_stl_fwd_vec_kernel<4><<<grid_for_rays(R), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+        ray, rgb, density, depth, uncert, R, min_uncert, o_rgb, o_rgb_static, o_rgb_transient, o_depth, o_opacity,
+        o_opacity_static, o_opacity_transient, o_prob, o_uncert, o_alpha_static, o_alpha_transient);
+  else if (aligned && N == 64)
+    composite_stl_fwd_vec_kernel<2><<<grid_for_rays(R), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+        ray, rgb, density, depth, uncert, R, min_uncert, o_rgb, o_rgb_static, o_rgb_transient, o_depth, o_opacity,
+        o_opacity_static, o_opacity_transient, o_prob, o_uncert, o_alpha_static, o_alpha_transient);
+  else
+    composite_stl_fwd_kernel<<<grid_for_rays(R), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+        ray, rgb, density, depth, uncert, R, N, min_uncert, o_rgb, o_rgb_static, o_rgb_transient, o_depth, o_opacity,
+        o_opacity_static, o_opacity_transient, o_prob, o_uncert, o_alpha_static, o_alpha_transient);
   return tp_launch_status();
 }
 
