@@ -357,44 +357,70 @@ __global__ void image_bias_kernel(const float* __restrict__ W, long long ldw, in
 }
 
 // out[r, n] = imgbias[r / rays_per_image, n] + sum_j W[n, col0 + j] * viewenc(r)[j];  viewenc = [u, enc(u)], u = ray/|ray|.
-// One CTA = kRaysPerBlock rays: all encodings first (one barrier), then thread n keeps its weight column in registers
-// and streams the rays; stores are 1 KB-coalesced rows.
+// Thread n keeps its weight row in registers; a CTA strides over groups of kRaysPerBlock rays: all encodings of the group first
+// (one thread per ray and coordinate), then every thread streams the group's rays; stores are 1 KB-coalesced rows.
 constexpr int kRaysPerBlock = 64;
 __global__ void __launch_bounds__(256) ray_bias_kernel(const float* __restrict__ ray, long long R, long long rays_per_image,
                                                        int L, const float* __restrict__ W, long long ldw, int col0,
                                                        const float* __restrict__ imgbias, float* __restrict__ out) {
-  __shared__ float enc[kRaysPerBlock][28];
+  __shared__ __align__(16) float enc[kRaysPerBlock][28];      // rows of 7 float4: the inner product reads them as broadcast LDS.128
   const int vc = 3 + 6 * L;     // <= 27 (L_view <= 4)
-  const long long r0 = (long long)blockIdx.x * kRaysPerBlock;
-  for (int i = threadIdx.x; i < kRaysPerBlock * vc; i += blockDim.x) {
-    const int rr = i / vc, c = i - rr * vc;
-    const long long r = r0 + rr;
-    float val = 0.f;
-    if (r < R) {
-      const float x = ray[r * 3], y = ray[r * 3 + 1], z = ray[r * 3 + 2];
-      const float len = fmaxf(sqrtf(x * x + y * y + z * z), 1e-12f);
-      const float u[3] = {x / len, y / len, z / len};
-      if (c < 3) val = u[c];
-      else {
-        const int e = c - 3, cc = e / (2 * L), k = e % (2 * L);
-        const float arg = __fmul_rn(u[cc], ldexpf(3.14159265358979323846f, k < L ? k : k - L));
-        val = k < L ? sinf(arg) : cosf(arg);
-      }
-    }
-    enc[rr][c] = val;
-  }
+  // the thread's weight row (27 strided, uncoalesced loads) is fetched ONCE: the CTA then strides over groups of rays
   float w[27];
   const int n = threadIdx.x;
 #pragma unroll
   for (int j = 0; j < 27; ++j) w[j] = j < vc ? W[n * ldw + col0 + j] : 0.f;
-  __syncthreads();
-  for (int rr = 0; rr < kRaysPerBlock; ++rr) {
-    const long long r = r0 + rr;
-    if (r >= R) break;
-    float acc = imgbias[(r / rays_per_image) * 256 + n];
+  const long long n_groups = (R + kRaysPerBlock - 1) / kRaysPerBlock;
+  for (long long grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+    const long long r0 = grp * kRaysPerBlock;
+    __syncthreads();      // the previous group's encodings are no longer read
+    if (threadIdx.x < kRaysPerBlock * 3) {      // one thread per (ray, coordinate): unit component, then its 2L encodings
+      const int rr = threadIdx.x / 3, cc = threadIdx.x - rr * 3;
+      const long long r = r0 + rr;
+      const bool live = r < R;
+      float uc = 0.f;
+      if (live) {
+        const float x = ray[r * 3], y = ray[r * 3 + 1], z = ray[r * 3 + 2];
+        const float len = fmaxf(sqrtf(x * x + y * y + z * z), 1e-12f);
+        uc = (cc == 0 ? x : (cc == 1 ? y : z)) / len;
+      }
+      enc[rr][cc] = uc;
+      for (int k = 0; k < L; ++k) {
+        const float arg = __fmul_rn(uc, ldexpf(3.14159265358979323846f, k));
+        enc[rr][3 + cc * 2 * L + k] = live ? sinf(arg) : 0.f;
+        enc[rr][3 + cc * 2 * L + L + k] = live ? cosf(arg) : 0.f;
+      }
+    } else {      // the other threads clear the pad columns (vc .. 27)
+      for (int i = threadIdx.x - kRaysPerBlock * 3; i < kRaysPerBlock * (28 - vc); i += blockDim.x - kRaysPerBlock * 3)
+        enc[i / (28 - vc)][vc + i % (28 - vc)] = 0.f;
+    }
+    __syncthreads();
+    // four rays per iteration: four independent fma chains per thread (the 27-long chain of one ray is latency-bound)
+    const long long img_first = r0 / rays_per_image;
+    for (int rr = 0; rr < kRaysPerBlock; rr += 4) {
+      float acc[4];
 #pragma unroll
-    for (int j = 0; j < 27; ++j) acc = fmaf(w[j], enc[rr][j], acc);
-    out[r * 256 + n] = acc;
+      for (int q = 0; q < 4; ++q) {
+        const long long r = r0 + rr + q;
+        long long img = img_first;
+        while (r >= (img + 1) * rays_per_image) ++img;
+        acc[q] = r < R ? imgbias[img * 256 + n] : 0.f;
+      }
+#pragma unroll
+      for (int j4 = 0; j4 < 7; ++j4) {      // per ray the same fma order as column by column (the pad column is skipped)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 e = reinterpret_cast<const float4*>(enc[rr + q])[j4];
+          acc[q] = fmaf(w[4 * j4], e.x, acc[q]);
+          acc[q] = fmaf(w[4 * j4 + 1], e.y, acc[q]);
+          acc[q] = fmaf(w[4 * j4 + 2], e.z, acc[q]);
+          if (j4 < 6) acc[q] = fmaf(w[4 * j4 + 3], e.w, acc[q]);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (r0 + rr + q < R) __stcs(out + (r0 + rr + q) * 256 + n, acc[q]);      // 315 MB per frame, read once by the fused kernel
+    }
   }
 }
 
@@ -466,7 +492,8 @@ TP_API int tp_tc_ray_bias(const float* ray, int64_t R, int64_t rays_per_image, i
   if (!ray || !W || !imgbias || !out) return TP_ERR_BAD_ARG;
   if (R < 0 || rays_per_image < 1 || L_view < 0 || L_view > 4) return TP_ERR_BAD_SHAPE;
   if (R == 0) return TP_OK;
-  tc::ray_bias_kernel<<<(unsigned)((R + tc::kRaysPerBlock - 1) / tc::kRaysPerBlock), 256, 0, (cudaStream_t)stream>>>(
+  const long long n_groups = (R + tc::kRaysPerBlock - 1) / tc::kRaysPerBlock, cap = (long long)tp_num_sms() * 6;
+  tc::ray_bias_kernel<<<(unsigned)(n_groups < cap ? n_groups : cap), 256, 0, (cudaStream_t)stream>>>(
       ray, R, rays_per_image, L_view, W, ldw, col0, imgbias, out);
   return tp_launch_status();
 }

@@ -181,13 +181,21 @@ __global__ void sample_depth_philox_kernel(const float* __restrict__ z_near, con
     const uint4 x = tp_philox((uint32_t)q, (uint32_t)(q >> 32), (uint32_t)seed, (uint32_t)(seed >> 32));
     const uint32_t w[4] = {x.x, x.y, x.z, x.w};
     float d[4];
+    if ((N & 3) == 0) {      // the four samples share the ray: one 64-bit division and one bounds fetch per quad
+      const long long r = (q * 4) / N;
+      const int k0 = (int)(q * 4 - r * N);
+      const float lo = z_near[r], hi = z_far[r];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const long long i = q * 4 + e;
-      if (i < total) {
-        const long long r = i / N;
-        d[e] = stratified_depth(tp_u01(w[e]), (int)(i - r * N), fn, z_near[r], z_far[r]);
-      } else d[e] = 0.f;
+      for (int e = 0; e < 4; ++e) d[e] = stratified_depth(tp_u01(w[e]), k0 + e, fn, lo, hi);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const long long i = q * 4 + e;
+        if (i < total) {
+          const long long r = i / N;
+          d[e] = stratified_depth(tp_u01(w[e]), (int)(i - r * N), fn, z_near[r], z_far[r]);
+        } else d[e] = 0.f;
+      }
     }
     if (q * 4 + 3 < total) *reinterpret_cast<float4*>(out + q * 4) = make_float4(d[0], d[1], d[2], d[3]);
     else
