@@ -217,6 +217,18 @@ def _inputs_from_images(cfg: MLPConfig, sv: _Saved, S: int, per_image: int):
     sv.images = None
 
 
+def run_mlp(cfg: MLPConfig, geom, lat_trans, lat_light, *params):
+    """NerfMLP.apply, except that an empty sample set (an eval frame whose mask prior selects no pixel, an empty shard)
+    returns empty outputs of the reference's shapes without a launch -- as the reference's torch ops do."""
+    if geom["S"] == 0:
+        shape, dev = geom["shape"], params[0].device
+        if cfg.stl:
+            return (torch.empty(*shape, 3, 2, device=dev), torch.empty(*shape, 2, device=dev),
+                    torch.empty(*shape, 1, device=dev))
+        return torch.empty(*shape, 3, device=dev), torch.empty(*shape, device=dev)
+    return NerfMLP.apply(cfg, geom, lat_trans, lat_light, *params)
+
+
 class NerfMLP(torch.autograd.Function):
     """(enc inputs, latents, *weights) -> (rgb, density[, uncert]) per sample, with the fused backward."""
 

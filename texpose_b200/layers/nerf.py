@@ -5,7 +5,7 @@ import torch
 
 from .. import ops
 from . import _common
-from ._mlp import MLPConfig, NerfMLP
+from ._mlp import MLPConfig, NerfMLP, run_mlp
 
 
 class NeRF(torch.nn.Module):
@@ -54,13 +54,13 @@ class NeRF(torch.nn.Module):
         """layers/nerf.py:61-99 -> rgb [B,HW,N,3], density [B,HW,N]."""
         cfg = self._config(opt, mode)
         geom = _common.point_geometry(cfg, points_3D, ray_unit)
-        return NerfMLP.apply(cfg, geom, None, None, *_common.flat_params(self.mlp_feat, self.mlp_rgb))
+        return run_mlp(cfg, geom, None, None, *_common.flat_params(self.mlp_feat, self.mlp_rgb))
 
     def forward_samples(self, opt, center, ray, depth_samples, mode=None):
         """layers/nerf.py:101-115."""
         cfg = self._config(opt, mode)
         geom = _common.ray_geometry(cfg, center, ray, depth_samples)
-        return NerfMLP.apply(cfg, geom, None, None, *_common.flat_params(self.mlp_feat, self.mlp_rgb))
+        return run_mlp(cfg, geom, None, None, *_common.flat_params(self.mlp_feat, self.mlp_rgb))
 
     @staticmethod
     def composite(opt, ray, rgb_samples, density_samples, depth_samples):

@@ -10,7 +10,7 @@ import torch
 
 from .. import ops
 from . import _common
-from ._mlp import MLPConfig, NerfMLP
+from ._mlp import MLPConfig, NerfMLP, run_mlp
 
 
 class NeRF(torch.nn.Module):
@@ -87,7 +87,7 @@ class NeRF(torch.nn.Module):
 
     def _run(self, cfg, geom, latent_variable_trans, latent_variable_light):
         params = _common.flat_params(self.mlp_feat, self.mlp_rgb, self.mlp_trans)
-        return NerfMLP.apply(cfg, geom, latent_variable_trans, latent_variable_light, *params)
+        return run_mlp(cfg, geom, latent_variable_trans, latent_variable_light, *params)
 
     # ------------------------------------------------------------------ reference interface
     def forward(self, opt, points_3D, ray_unit=None, latent_variable_trans=None, latent_variable_light=None, mode=None):

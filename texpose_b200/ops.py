@@ -31,8 +31,20 @@ def _f32(t: Optional[Tensor]) -> Optional[Tensor]:
     return t.contiguous()
 
 
+_EMPTY_ADDR = {}
+
+
 def _p(t: Optional[Tensor]):
-    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+    """Device address for the C-ABI.  NULL means "argument absent" there, and an empty tensor has no storage (data_ptr 0):
+    empty tensors are passed as the address of a small per-device dummy buffer, which a zero-sized call never touches."""
+    if t is None:
+        return None
+    if t.numel() == 0:
+        buf = _EMPTY_ADDR.get(t.device)
+        if buf is None:
+            buf = _EMPTY_ADDR[t.device] = torch.zeros(256, dtype=torch.uint8, device=t.device)
+        return ctypes.c_void_p(buf.data_ptr())
+    return ctypes.c_void_p(t.data_ptr())
 
 
 def _stream():
