@@ -211,6 +211,8 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's own banner / debug output (NCCL_DEBUG=VERSION prints to stdout) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     _C.build()
     pk = peaks()
@@ -405,7 +407,7 @@ def bench_train(args, g, opt, dev, world, timed):
             bucket.allreduce_mean()
         return step
 
-    n_steps = max(3, args.steps // 2)
+    n_steps = max(10, args.steps)       # 2.5 ms each: enough steps for the max-over-ranks time to settle
     ms, _ = timed(make_step(exchange), n_steps, 3)
     samples = B * P * P * NS
     out = dict(workload="C3 train step fwd+bwd, 4096 rays x 128 samples per GPU, fused patch loss, bf16 tcgen05 fwd + bwd (dX chain with thin gradients, dW GEMMs), grad exchange",
