@@ -224,3 +224,44 @@ def test_kernel_variants_are_bit_identical(flags, name):
         torch.cuda.synchronize()
         for a, b in zip(ref, got):
             assert torch.equal(a, b), (name, R, N)
+
+
+@pytest.mark.parametrize("layers_rgb", [[None, 128, 3], [None, 256, 256, 256, 3], [None, 192, 96, 3]])
+def test_plain_nerf_renders_on_tensor_cores(layers_rgb):
+    """layers/nerf.py in rendering mode (no gradient): the plain model runs through the fused tcgen05 kernel as a padded
+    static/transient/light layer image (identity pass-through layers, zero transient head) and stays within the bf16
+    contract (<= 1e-2 on rendered rgb / depth / opacity) of its own fp32 kernels; with gradients enabled it keeps using them."""
+    from texpose_b200.config import env_opt
+    from texpose_b200.layers.nerf import NeRF as PlainNeRF
+    opt = env_opt(device=DEV, sample_intvs=64)
+    opt.arch.layers_rgb = layers_rgb
+    opt.b200 = AttrDict(mlp="bf16")
+    torch.manual_seed(1)
+    m = PlainNeRF(opt).to(DEV)
+    with torch.no_grad():
+        for l in list(m.mlp_feat) + list(m.mlp_rgb):
+            l.bias.normal_(0.0, 0.05)
+    B, R, N = 2, 150, 64
+    g = torch.Generator().manual_seed(9)
+    center = (torch.randn(B, R, 3, generator=g) * 0.02 + torch.tensor([0.3, 0.2, -8.0])).to(DEV)
+    ray = (torch.randn(B, R, 3, generator=g) * 0.05 + torch.tensor([0.0, 0.0, 1.0])).to(DEV)
+    depth = ((torch.rand(B, R, N, 1, generator=g) + torch.arange(N)[None, None, :, None]) / N * 2.5 + 6.7).to(DEV)
+    assert not m.uses_tensor_cores(opt)                     # parameters want gradients and grad mode is on
+    with torch.no_grad():
+        assert m.uses_tensor_cores(opt)
+        rgb_s, den = m.forward_samples(opt, center, ray, depth, mode="val")
+        out = m.composite(opt, ray, rgb_s, den, depth)
+        opt32 = env_opt(device=DEV, sample_intvs=64)
+        opt32.arch.layers_rgb = layers_rgb
+        opt32.b200 = AttrDict(mlp="fp32")
+        rgb_32, den_32 = m.forward_samples(opt32, center, ray, depth, mode="val")
+        out32 = m.composite(opt32, ray, rgb_32, den_32, depth)
+    assert rgb_s.shape == (B, R, N, 3) and den.shape == (B, R, N) and rgb_s.is_contiguous()
+    for k in range(3):                                      # rgb, depth, opacity
+        assert (out[k] - out32[k]).abs().max() <= 1e-2, (k, (out[k] - out32[k]).abs().max())
+    assert (rgb_s - rgb_32).abs().max() <= 3e-2
+    # a parameter update must reach the packed image
+    with torch.no_grad():
+        m.mlp_rgb[-1].bias.add_(0.5)
+        rgb_2, _ = m.forward_samples(opt, center, ray, depth, mode="val")
+    assert (rgb_2 - rgb_s).abs().max() > 1e-3

@@ -38,6 +38,8 @@ class NeRF(torch.nn.Module):
             self.mlp_rgb.append(lin)
         if opt.c2f is not None:
             self.progress = torch.nn.Parameter(torch.tensor(0.))
+        self._packed = None     # (version key, packed bf16 weight image) for the tcgen05 kernel
+        self._tc_image = None   # (version key, padded head parameters), see _tc_parameters
 
     def _config(self, opt, mode) -> MLPConfig:
         if opt.arch.density_activ != "softplus":
@@ -57,10 +59,74 @@ class NeRF(torch.nn.Module):
         return run_mlp(cfg, geom, None, None, *_common.flat_params(self.mlp_feat, self.mlp_rgb))
 
     def forward_samples(self, opt, center, ray, depth_samples, mode=None):
-        """layers/nerf.py:101-115."""
+        """layers/nerf.py:101-115.  Rendering (no gradient needed) with opt.b200.mlp 'bf16' / 'auto' runs on the fused
+        tcgen05 kernel; training the plain model needs the trunk's backward and stays on the fp32 kernels."""
         cfg = self._config(opt, mode)
         geom = _common.ray_geometry(cfg, center, ray, depth_samples)
+        if geom["S"] > 0 and self.uses_tensor_cores(opt):
+            return self._forward_tc(cfg, geom)
         return run_mlp(cfg, geom, None, None, *_common.flat_params(self.mlp_feat, self.mlp_rgb))
+
+    # ------------------------------------------------------------------ tensor-core rendering path
+    def uses_tensor_cores(self, opt) -> bool:
+        """True when forward_samples will take the fused tcgen05 kernel: precision bf16 / auto, no gradient wanted, and
+        the architecture is the 8 x 256 trunk (skip 4, L = 10 / <= 4) with an rgb head of 1-3 hidden layers <= 256 wide."""
+        if _common.mlp_precision(opt) == "fp32":
+            return False
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            return False
+        if not (opt.nerf.view_dep and opt.arch.posenc and opt.arch.posenc.L_3D == 10 and 0 <= opt.arch.posenc.L_view <= 4
+                and tuple(opt.arch.skip) == (4,)):
+            return False
+        want_f = [(256, 63)] + [(256, 256)] * 3 + [(256, 319)] + [(256, 256)] * 2 + [(257, 256)]
+        if [tuple(l.weight.shape) for l in self.mlp_feat] != want_f:
+            return False
+        n = len(self.mlp_rgb)
+        widths = [l.weight.shape[0] for l in self.mlp_rgb]
+        return 2 <= n <= 4 and all(w <= 256 for w in widths[:-1]) and widths[-1] == 3
+
+    def _tc_parameters(self):
+        """The plain model expressed in the layer layout the fused kernel streams (static / transient / light model of
+        options/nerf_lm_adapt_gan.yaml): hidden layers zero-padded to 256 x 256, missing hidden layers replaced by the
+        identity (exact: their input is a ReLU output already rounded to bf16), no latents, an all-zero transient head whose
+        outputs are dropped.  Rebuilt when a parameter changes."""
+        params = [p for l in list(self.mlp_feat) + list(self.mlp_rgb) for p in (l.weight, l.bias)]
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        if self._tc_image is not None and self._tc_image[0] == key:
+            return self._tc_image[1]
+        dev = self.mlp_feat[0].weight.device
+        z = lambda *shape: torch.zeros(*shape, device=dev)
+        feat_p = [(l.weight.detach().float().contiguous(), l.bias.detach().float().contiguous()) for l in self.mlp_feat]
+        layers = [(l.weight.detach().float(), l.bias.detach().float()) for l in self.mlp_rgb]
+        k0 = layers[0][0].shape[1]
+        rgb_p = []
+        for li in range(3):
+            W, b = z(256, k0 if li == 0 else 256), z(256)
+            if li < len(layers) - 1:
+                w_src, b_src = layers[li]
+                W[:w_src.shape[0], :w_src.shape[1]] = w_src
+                b[:b_src.shape[0]] = b_src
+            else:
+                W += torch.eye(256, device=dev)      # pass-through layer
+            rgb_p.append((W, b))
+        w_out, b_out = layers[-1]
+        W = z(3, 256)
+        W[:, :w_out.shape[1]] = w_out
+        rgb_p.append((W, b_out.contiguous()))
+        trans_p = [(z(256, 256), z(256)), (z(256, 256), z(256)), (z(256, 256), z(256)), (z(5, 256), z(5))]
+        self._tc_image = (key, (feat_p, rgb_p, trans_p))
+        return self._tc_image[1]
+
+    def _forward_tc(self, cfg, geom):
+        from .. import mlp_tc
+        feat_p, rgb_p, trans_p = self._tc_parameters()
+        B, R, N = geom["shape"]
+        dev = geom["depth"].device
+        stl = MLPConfig(L_3D=cfg.L_3D, L_view=cfg.L_view, skip=cfg.skip, view_dep=True, n_feat=8, n_rgb=4, n_trans=4,
+                        n_latent_light=0, n_latent_trans=0, precision="bf16", save_for_backward=False, packed=self)
+        none = torch.zeros(B, 0, device=dev)
+        rgb, density, _ = mlp_tc.forward(stl, geom, none, none, feat_p, rgb_p, trans_p)
+        return rgb.view(B, R, N, 3, 2)[..., 0].contiguous(), density.view(B, R, N, 2)[..., 0].contiguous()
 
     @staticmethod
     def composite(opt, ray, rgb_samples, density_samples, depth_samples):
