@@ -944,23 +944,56 @@ __global__ void __launch_bounds__(256) bwd_finish2_kernel(const FinishParams f) 
   } else {
     for (int j = 0; j < 5; ++j) g[6][j * 256 + n] = f.tot[(kXwt + j) * 256 + n];
   }
+  // db3: warp j sums column j of the per-warp partials -- every lane a contiguous block in order, lane 0 the 32 block sums in
+  // order (fixed order, 19 instead of 592 dependent loads)
   const int nb = trans ? 5 : 3, off = trans ? 3 : 0;
-  if (n < nb) {
+  const int wj = n >> 5, ln = n & 31;
+  if (wj < nb) {
+    const int items = f.grid * 4, per = (items + 31) / 32;
     float acc = 0.f;
-    for (int i = 0; i < f.grid * 4; ++i) acc += f.thin_sums[(size_t)i * 8 + off + n];
-    g[7][n] = acc;                                               // db3
+    for (int i = ln * per; i < (ln + 1) * per && i < items; ++i) acc += f.thin_sums[(size_t)i * 8 + off + wj];
+    float tot = 0.f;
+    for (int l = 0; l < 32; ++l) tot += __shfl_sync(0xffffffffu, acc, l);
+    if (ln == 0) g[7][wj] = tot;                                 // db3
   }
 }
 
 // second stage of the weight-gradient GEMMs, writing each job with its own leading dimension (no torch.cat afterwards)
 struct DwOut { float* ptr[kDwMaxJobs]; long long ld[kDwMaxJobs]; };
 __global__ void dw_reduce_kernel(const float* __restrict__ partial, int splits, int n_jobs, const DwOut o) {
-  const long long total = (long long)n_jobs * 65536;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int job = (int)(i >> 16), rc = (int)(i & 65535);
-    float acc = 0.f;
-    for (int z = 0; z < splits; ++z) acc += partial[((size_t)z * n_jobs + job) * 65536 + rc];
-    o.ptr[job][(size_t)(rc >> 8) * o.ld[job] + (rc & 255)] = acc;
+  // one thread = four consecutive columns of one row: 16-byte loads of the (L2-resident) partials, eight splits in flight,
+  // every element still summed in split order (bit-identical to the scalar loop)
+  const long long total4 = (long long)n_jobs * 16384;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    const int job = (int)(i >> 14), rc = (int)(i & 16383) * 4;
+    const float4* src = reinterpret_cast<const float4*>(partial + (size_t)job * 65536 + rc);
+    const size_t zstride = (size_t)n_jobs * 16384;      // float4 units between splits
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int z = 0;
+    for (; z + 8 <= splits; z += 8) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldcs(src + (size_t)(z + u) * zstride);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        acc.x += v[u].x;
+        acc.y += v[u].y;
+        acc.z += v[u].z;
+        acc.w += v[u].w;
+      }
+    }
+    for (; z < splits; ++z) {
+      const float4 v = __ldcs(src + (size_t)z * zstride);
+      acc.x += v.x;
+      acc.y += v.y;
+      acc.z += v.z;
+      acc.w += v.w;
+    }
+    float* dst = o.ptr[job] + (size_t)(rc >> 8) * o.ld[job] + (rc & 255);      // rows of the rgb-0 / trans-0 gradients are only 8 B aligned
+    dst[0] = acc.x;
+    dst[1] = acc.y;
+    dst[2] = acc.z;
+    dst[3] = acc.w;
   }
 }
 
@@ -1286,6 +1319,6 @@ TP_API int tp_tc_heads_backward(const float* dz_rgb, const float* dz_trans, int6
   for (int j = 0; j < 6; ++j) { o.ptr[j] = grads[gidx[j]]; o.ld[j] = 256; }
   o.ld[2] = ld_r0; o.ld[5] = ld_t0;
   for (int j = 6; j < tcb::kDwMaxJobs; ++j) { o.ptr[j] = nullptr; o.ld[j] = 0; }
-  tcb::dw_reduce_kernel<<<tp_grid_for(6 * 65536, 256, 4), 256, 0, st>>>(partial, p.splits, 6, o);
+  tcb::dw_reduce_kernel<<<tp_grid_for(6 * 16384, 256, 4), 256, 0, st>>>(partial, p.splits, 6, o);
   return tp_launch_status();
 }
