@@ -187,7 +187,11 @@ int tp_tc_ray_bias(const float* ray, int64_t R, int64_t rays_per_image, int L_vi
  * biasbuf: 16 floats {trunk7 b[0], rgb3 b[0:3], trans3 b[0:5], 0...} (the 256-wide stages' biases live in `packed`).
  * Outputs rgb [S,3,2], density [S,2], uncert [S].  save: NULL, or tp_tc_save_bytes(S) bytes receiving, per 128-sample
  * tile, the bf16 tile images [7][32 k8][128 rows][8] of {trunk feature, rgb hidden 1-3, transient hidden 1-3} that the
- * backward consumes (training).  dbg_layer/dbg_out/flags: debugging aids (pass -1, NULL, 0). */
+ * backward consumes (training).  dbg_layer/dbg_out: debugging aids (pass -1, NULL).  flags: 0 = default; bit 17 (0x20000) =
+ * static-only rendering (inference launch only): the stage list stops after the rgb head, so the launch does 78 % of the work;
+ * rgb[:, :, 1], density[:, 1] and uncert are written as zeros -- for callers that use only the static outputs (rgb_static /
+ * depth / opacity_static of Model.evaluate_full, model/nerf_adapt_st_gan.py:341-362) and for the plain layers/nerf.py model;
+ * the other bits select measured kernel variants / timing experiments. */
 int tp_tc_nerf_stl_forward(const float* center, const float* ray, const float* depth, int64_t S, int N,
                            int64_t per_image, const void* packed, const float* biasbuf, const float* raybias,
                            const float* imgbias, float* rgb, float* density, float* uncert, void* scratch,

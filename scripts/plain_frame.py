@@ -38,3 +38,30 @@ for mlp, reps in (("bf16", 5), ("fp32", 1)):
     e1.record()
     torch.cuda.synchronize()
     print(f"plain NeRF, mlp={mlp}: {e0.elapsed_time(e1) / reps:.1f} ms per 480x640x128 frame")
+
+# static / transient / light model, eval mode: full launch vs static-only (opt.b200.static_only)
+from texpose_b200 import synth  # noqa: E402
+from texpose_b200.config import adapt_gan_opt  # noqa: E402
+from texpose_b200.layers.nerf_static_transient_light import NeRF as StlNeRF  # noqa: E402
+
+lt, ll = [t.to(DEV) for t in synth.latents(1)]
+for static_only in (False, True):
+    opt = adapt_gan_opt(device=DEV, sample_intvs=N)
+    opt.b200 = AttrDict(mlp="bf16", static_only=static_only)
+    torch.manual_seed(0)
+    m = StlNeRF(opt).to(DEV)
+
+    def frame():
+        with torch.no_grad():
+            out = m.forward_samples(opt, center, ray, depth, lt, ll, mode="eval")
+            m.composite(opt, ray, out[0], out[1], depth, out[2])
+
+    frame()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        frame()
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"static/transient/light model, eval, static_only={static_only}: {e0.elapsed_time(e1) / 5:.1f} ms per 480x640x128 frame")

@@ -265,3 +265,30 @@ def test_plain_nerf_renders_on_tensor_cores(layers_rgb):
         m.mlp_rgb[-1].bias.add_(0.5)
         rgb_2, _ = m.forward_samples(opt, center, ray, depth, mode="val")
     assert (rgb_2 - rgb_s).abs().max() > 1e-3
+
+
+def test_static_only_eval_render_matches_the_static_outputs_bit_for_bit():
+    """opt.b200.static_only (honoured in mode='eval' on the fused kernel): the stage list stops after the rgb head.  The static
+    per-sample outputs and everything composited from them (rgb_static, depth, opacity_static -- what Model.evaluate_full
+    uses, model/nerf_adapt_st_gan.py:341-362) are bit-identical to the full launch; the transient outputs are zeros."""
+    opt, m = _module("bf16")
+    B, R, N = 2, 333, opt.nerf.sample_intvs
+    g = torch.Generator().manual_seed(21)
+    center = (torch.randn(B, R, 3, generator=g) * 0.02 + torch.tensor([0.3, 0.2, -8.0])).to(DEV)
+    ray = (torch.randn(B, R, 3, generator=g) * 0.05 + torch.tensor([0.0, 0.0, 1.0])).to(DEV)
+    depth = ((torch.rand(B, R, N, 1, generator=g) + torch.arange(N)[None, None, :, None]) / N * 2.5 + 6.7).to(DEV)
+    lt, ll = [t.to(DEV) for t in synth.latents(B)]
+    opt_s, _ = _module("bf16")
+    opt_s.b200.static_only = True
+    with torch.no_grad():
+        full = m.forward_samples(opt, center, ray, depth, lt, ll, mode="eval")
+        stat = m.forward_samples(opt_s, center, ray, depth, lt, ll, mode="eval")
+        val = m.forward_samples(opt_s, center, ray, depth, lt, ll, mode="val")       # only eval honours the switch
+        c_full = m.composite(opt, ray, *full[:2], depth, full[2])
+        c_stat = m.composite(opt_s, ray, *stat[:2], depth, stat[2])
+    assert torch.equal(val[0], full[0]) and torch.equal(val[2], full[2])
+    assert torch.equal(stat[0][..., 0], full[0][..., 0]) and torch.equal(stat[1][..., 0], full[1][..., 0])
+    assert float(stat[0][..., 1].abs().max()) == 0.0 and float(stat[1][..., 1].abs().max()) == 0.0
+    assert float(stat[2].abs().max()) == 0.0
+    for k in (1, 3, 5):          # rgb_static, depth, opacity_static
+        assert torch.equal(c_stat[k], c_full[k]), k

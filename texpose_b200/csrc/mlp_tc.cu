@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_ke
       uint32_t stage = 0, phase = 0;
       for (long long st = blockIdx.x; st < n_super; st += gridDim.x) {
         int c = 0;
-        for (int L = 0; L < kNumLayers; ++L) {
+        for (int L = 0; L < p.n_layers; ++L) {
           const Layer ly = kLayers[L];
           const int nch = ly.small ? 1 : ly.a_chunks + ly.e_chunks + ly.bias_chunk;
           for (int j = 0; j < nch; ++j, ++c) {
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_ke
       const uint32_t idesc256 = umma_idesc(128, 256), idesc16 = umma_idesc(128, 16);
       constexpr uint32_t kHi = (128u >> 4) | (1u << 14);   // SBO = 128 B, descriptor version 1
       for (long long st = blockIdx.x; st < n_super; st += gridDim.x) {
-        for (int L = 0; L < kNumLayers; ++L) {
+        for (int L = 0; L < p.n_layers; ++L) {
           const Layer ly = kLayers[L];
           const int nch = ly.small ? 1 : ly.a_chunks + ly.e_chunks + ly.bias_chunk;
           const int skew = p.skew < nch ? p.skew : nch;
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_ke
       if (lane == 0) mbar_arrive(bar_ready(t));
 
       float sigma_s = 0.f, rgb_s[3] = {0.f, 0.f, 0.f};
-      for (int L = 0; L < kNumLayers; ++L) {
+      for (int L = 0; L < p.n_layers; ++L) {
         const Layer ly = kLayers[L];
         // table biases (per ray / per image): when every row of this warp shares the bias row, each lane fetches its
         // float4 slice(s) now -- the L2 latency hides behind the MMAs of this stage
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_ke
           named_bar_sync(1 + t, kTileThreads);
           store_pending = false;
         }
-        if (L == kReloadIssueLayer && row == 0 && half == 0) {
+        if (L == kReloadIssueLayer && p.n_layers > kStaticLayers && row == 0 && half == 0) {
           // every MMA that reads A_t has retired (acc barrier) -> bring the trunk feature back for the transient head
           bulk_wait_all();
           fence_proxy_async_all();
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_ke
             hidden_epilogue<true, kCols / 32>(tmem_d, bias, a_row, dbg_row);
           }
           fence_proxy_async_smem();
-          if (L == kSpillLayer) {
+          if (L == kSpillLayer && p.n_layers > kStaticLayers) {      // static only: no second head, nothing to park
             // park the trunk feature (bf16 tile image) in the L2 scratch (training: in its slot of the save buffer, where
             // the backward also reads it) -- the bulk store overlaps the next stage's MMAs
             named_bar_sync(1 + t, kTileThreads);
@@ -280,6 +280,12 @@ __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_ke
           } else if (ly.epi == EPI_RGB_OUT) {
 #pragma unroll
             for (int c = 0; c < 3; ++c) rgb_s[c] = tp_sigmoid(__uint_as_float(v[c]) + sb[1 + c]);
+            if (p.n_layers == kStaticLayers && live) {      // static only: this is the last stage; transient outputs are zeros
+#pragma unroll
+              for (int c = 0; c < 3; ++c) *reinterpret_cast<float2*>(p.rgb + s * 6 + c * 2) = make_float2(rgb_s[c], 0.f);
+              *reinterpret_cast<float2*>(p.density + s * 2) = make_float2(sigma_s, 0.f);
+              p.uncert[s] = 0.f;
+            }
           } else {
             float rgb_t[3];
 #pragma unroll
@@ -295,7 +301,7 @@ __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_ke
             }
           }
         }
-        if (L != kNumLayers - 1) {   // the next super-tile's encode arrival covers the last stage
+        if (L != p.n_layers - 1) {   // the next super-tile's encode arrival covers the last stage
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_ready(t));
@@ -524,6 +530,8 @@ TP_API int tp_tc_nerf_stl_forward(const float* center, const float* ray, const f
   if (save && (flags & 128)) return TP_ERR_BAD_ARG;           // the experimental kernel does not write the ReLU bitmasks
   p.dbg_layer = dbg_layer; p.dbg_out = dbg_out; p.dbg_drain = (flags >> 2) & 7;
   p.dbg_save = (flags >> 14) & 3;
+  p.n_layers = (flags & (1 << 17)) ? tc::kStaticLayers : tc::kNumLayers;      // flags bit 17: static-only rendering
+  if ((flags & (1 << 17)) && (save || (flags & (128 | 1024)))) return TP_ERR_BAD_ARG;      // inference launch of the default kernel only
   p.skew = ((flags >> 5) & 3) ? ((flags >> 5) & 3) - 1 : 1;      // default skew 1; flags bits 5-6 = skew+1 override (A/B)
   if (flags & 128) return tp_tc_v2_launch(p, flags, (cudaStream_t)stream);   // experimental single-tile / cluster kernel
   if (flags & 1024) {     // CTA-pair kernel (cta_group::2); `packed` must be the pair image; flags bits 11-13 = skew + 1 (default 4)

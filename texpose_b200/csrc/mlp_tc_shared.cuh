@@ -41,6 +41,7 @@ static __constant__ Layer kLayers[kNumLayers] = {
     {8, 0, 1, EPI_TRANS_OUT, BIAS_SMALL, 0, 0}   // trans 3  -> sigmoid x3, softplus x2
 };
 constexpr int kSpillLayer = 8, kReloadIssueLayer = 12;
+constexpr int kStaticLayers = 13;      // stages 0..12: trunk, density, feature, rgb head
 constexpr int kSaveSlots = 7;
 // activation-save slot of each stage (training): feat, rgb h1..h3, trans h1..h3; -1 = not saved
 static __constant__ int kSaveSlot[kNumLayers] = {-1, -1, -1, -1, -1, -1, -1, -1, 0, 1, 2, 3, -1, 4, 5, 6, -1};
@@ -71,6 +72,8 @@ struct Params {
   int dbg_layer;
   float* dbg_out;            // [S,256] post-activation of stage dbg_layer (debug only)
   int skew;                  // weight chunks tile 0 runs ahead of tile 1 inside a stage (0..2)
+  int n_layers;              // 17 = all stages; 13 = static only (rendering that needs neither the transient head nor uncert):
+                             // the stage list stops after the rgb output, transient outputs are written as zeros
   int dbg_save;              // timing experiments only (wrong training results): bit 0 = skip the activation-save bulk stores,
                              // bit 1 = skip the ReLU bitmasks
   int dbg_drain;             // timing experiments only (wrong results): 1 = convert/store every other slab, 2 = also skip its TMEM load

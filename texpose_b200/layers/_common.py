@@ -40,6 +40,13 @@ def mlp_precision(opt) -> str:
     return p
 
 
+def b200_option(opt, name, default=None):
+    """opt.b200.<name> (the extension block of the options; absent in the reference yamls)."""
+    b = opt.get("b200") if hasattr(opt, "get") else None
+    v = b.get(name) if b else None
+    return default if v is None else v
+
+
 def flat_params(*module_lists):
     out = []
     for ml in module_lists:

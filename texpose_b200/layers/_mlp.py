@@ -35,6 +35,7 @@ class MLPConfig:
     precision: str = "fp32"     # "fp32" | "bf16" | "auto" (bf16 when the fused kernel implements the architecture)
     save_for_backward: bool = True
     packed: object = None       # bf16 weight image for the tcgen05 kernel (mlp_tc.pack), or None
+    static_only: bool = False   # rendering only: skip the transient head (its outputs come back as zeros), fused kernel only
 
     @property
     def stl(self) -> bool:
@@ -251,7 +252,8 @@ class NerfMLP(torch.autograd.Function):
         if use_tc:
             from .. import mlp_tc
             if sv is None:
-                rgb, density, uncert = mlp_tc.forward(cfg, geom, lt, ll, feat_p, rgb_p, trans_p)
+                rgb, density, uncert = mlp_tc.forward(cfg, geom, lt, ll, feat_p, rgb_p, trans_p,
+                                                      static_only=cfg.static_only)      # sv is None: no backward will run
             else:
                 # training: the kernel also stores the head activations it computed (bf16 tile images); the backward
                 # consumes exactly those -- nothing is re-materialised

@@ -88,8 +88,8 @@ class NeRF(torch.nn.Module):
     def _tc_parameters(self):
         """The plain model expressed in the layer layout the fused kernel streams (static / transient / light model of
         options/nerf_lm_adapt_gan.yaml): hidden layers zero-padded to 256 x 256, missing hidden layers replaced by the
-        identity (exact: their input is a ReLU output already rounded to bf16), no latents, an all-zero transient head whose
-        outputs are dropped.  Rebuilt when a parameter changes."""
+        identity (exact: their input is a ReLU output already rounded to bf16), no latents; the launch is static-only
+        (flags bit 17), so the (all-zero) transient head of the image is never streamed.  Rebuilt when a parameter changes."""
         params = [p for l in list(self.mlp_feat) + list(self.mlp_rgb) for p in (l.weight, l.bias)]
         key = tuple((p.data_ptr(), p._version) for p in params)
         if self._tc_image is not None and self._tc_image[0] == key:
@@ -123,9 +123,10 @@ class NeRF(torch.nn.Module):
         B, R, N = geom["shape"]
         dev = geom["depth"].device
         stl = MLPConfig(L_3D=cfg.L_3D, L_view=cfg.L_view, skip=cfg.skip, view_dep=True, n_feat=8, n_rgb=4, n_trans=4,
-                        n_latent_light=0, n_latent_trans=0, precision="bf16", save_for_backward=False, packed=self)
+                        n_latent_light=0, n_latent_trans=0, precision="bf16", save_for_backward=False, packed=self,
+                        static_only=True)
         none = torch.zeros(B, 0, device=dev)
-        rgb, density, _ = mlp_tc.forward(stl, geom, none, none, feat_p, rgb_p, trans_p)
+        rgb, density, _ = mlp_tc.forward(stl, geom, none, none, feat_p, rgb_p, trans_p, static_only=True)
         return rgb.view(B, R, N, 3, 2)[..., 0].contiguous(), density.view(B, R, N, 2)[..., 0].contiguous()
 
     @staticmethod

@@ -73,7 +73,8 @@ class NeRF(torch.nn.Module):
                          view_dep=bool(opt.nerf.view_dep), n_feat=len(self.mlp_feat), n_rgb=len(self.mlp_rgb),
                          n_trans=len(self.mlp_trans), n_latent_light=opt.nerf.N_latent_light,
                          n_latent_trans=opt.nerf.N_latent_trans, precision=_common.mlp_precision(opt),
-                         save_for_backward=torch.is_grad_enabled(), packed=self)
+                         save_for_backward=torch.is_grad_enabled(), packed=self,
+                         static_only=bool(mode == "eval" and _common.b200_option(opt, "static_only", False)))
 
     def uses_tensor_cores(self, opt, mode="val") -> bool:
         """True when forward_samples of this module will take the fused tcgen05 path under `opt` (opt.b200.mlp)."""

@@ -14,6 +14,7 @@ from . import _C, ops
 
 _F = 256
 PAIR_KERNEL = 1024      # tp_tc_nerf_stl_forward flags bit 10: cta_group::2 kernel over CTA pairs (csrc/mlp_tc_pair.cu)
+STATIC_ONLY = 1 << 17   # flags bit 17: stop after the rgb head (rendering that uses only the static outputs)
 
 
 def supported(cfg, feat_p, rgb_p, trans_p) -> bool:
@@ -135,8 +136,10 @@ def _scratch_for(dev):
     return _scratch[k]
 
 
-def forward(cfg, geom, lat_trans, lat_light, feat_p, rgb_p, trans_p, dbg_layer=-1, flags=0, save=False):
+def forward(cfg, geom, lat_trans, lat_light, feat_p, rgb_p, trans_p, dbg_layer=-1, flags=0, save=False, static_only=False):
     flags = flags or int(os.environ.get("TEXPOSE_TC_FLAGS", "0"))     # bit 1: 8-epilogue-warp kernel variant (A/B)
+    if static_only and not save and not (flags & (128 | PAIR_KERNEL)):
+        flags |= STATIC_ONLY
     if geom.get("mode") != "rays":
         raise NotImplementedError("the fused bf16 kernel is ray-parameterised (forward_samples)")
     if not supported(cfg, feat_p, rgb_p, trans_p):
