@@ -46,6 +46,24 @@ def test_host_side_helpers_without_gpu():
     assert lib.tp_tc_heads_backward_supported(0, 128) == 0
 
 
+def test_peer_window_layout_helpers_without_gpu():
+    """Pure host arithmetic of the gradient-exchange window (csrc/peer.cu): [1 KB header | buffer 0 | buffer 1], buffers
+    padded to 256 B; argument errors are reported before any CUDA call."""
+    import ctypes
+    lib = _C.load()
+    for n in (0, 1, 63, 64, 65, 421385):
+        cap = lib.tp_peer_capacity_bytes(n)
+        assert cap % 256 == 0 and cap >= 4 * n and cap < 4 * n + 256
+        assert lib.tp_peer_window_bytes(n) == 1024 + 2 * cap
+        assert lib.tp_peer_data_offset(n, 0) == 1024 and lib.tp_peer_data_offset(n, 1) == 1024 + cap
+        assert lib.tp_peer_data_offset(n, 2) == 1024
+    out = ctypes.c_void_p()
+    assert lib.tp_peer_window_create(16, ctypes.byref(out)) == -1            # smaller than the header
+    assert lib.tp_peer_window_export(None, None) == -1 and lib.tp_peer_window_import(None, None) == -1
+    assert lib.tp_peer_allreduce_mean(None, 2, 0, 8, 1, None, 0, 0, None) == -1
+    assert lib.tp_peer_window_destroy(None) == 0 and lib.tp_peer_window_release(None) == 0
+
+
 def test_flex_patch_sampler_matches_oracle_on_cpu():
     """FlexPatchSampler is host logic (three torch.rand draws): identical to the oracle restatement for the same RNG state,
     and the coordinates stay inside [-1, 1] (tools/patch_sampler.py:100-110)."""

@@ -51,7 +51,7 @@ __device__ __forceinline__ unsigned long long global_ns() {
 }
 
 template <int kWorld>
-__device__ __forceinline__ void reduce_slices(const Windows& w, int64_t data_off, int64_t n4, float inv_is_div, float* out) {
+__device__ __forceinline__ void reduce_slices(const Windows& w, int64_t data_off, int64_t n4, float divisor, float* out) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     float4 v[kWorld];
@@ -65,10 +65,10 @@ __device__ __forceinline__ void reduce_slices(const Windows& w, int64_t data_off
       a.z = __fadd_rn(a.z, v[p].z);
       a.w = __fadd_rn(a.w, v[p].w);
     }
-    a.x = __fdiv_rn(a.x, inv_is_div);
-    a.y = __fdiv_rn(a.y, inv_is_div);
-    a.z = __fdiv_rn(a.z, inv_is_div);
-    a.w = __fdiv_rn(a.w, inv_is_div);
+    a.x = __fdiv_rn(a.x, divisor);
+    a.y = __fdiv_rn(a.y, divisor);
+    a.z = __fdiv_rn(a.z, divisor);
+    a.w = __fdiv_rn(a.w, divisor);
     reinterpret_cast<float4*>(out)[i] = a;
   }
 }
