@@ -5,7 +5,7 @@ import torch
 
 from .. import ops
 from . import _common
-from ._mlp import MLPConfig, NerfMLP, run_mlp
+from ._mlp import MLPConfig, run_mlp
 
 
 class NeRF(torch.nn.Module):

@@ -5,7 +5,6 @@ parameter's `_version` changes ("re-packed when param._version cha
 """
 from __future__ import annotations
 
-import ctypes
 import os
 
 import torch

@@ -17,7 +17,6 @@ import torch
 from .. import camera, ops
 from ..config import AttrDict
 from ..layers.nerf_static_transient_light import NeRF
-from ..layers import _common
 from ..tools.ray_sampler import RaySampler
 from ..tools.patch_sampler import FlexPatchSampler
 

@@ -6,7 +6,7 @@ hot path runs in libtexpose_b200.so.  CPU tensors are rejected (no CPU fallback)
 from __future__ import annotations
 
 import ctypes
-from typing import List, Optional, Sequence, Tuple
+from typing import Optional, Sequence, Tuple
 
 import torch
 
