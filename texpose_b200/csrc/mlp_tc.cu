@@ -37,7 +37,9 @@ constexpr int kStages = 4;
 constexpr uint32_t kOffA = 0, kOffE = 2 * kABytes, kOffRing = kOffE + 2 * kEBytes;
 constexpr uint32_t kOffBar = kOffRing + kStages * kChunkBytes;
 constexpr uint32_t kSmemBytes = kOffBar + 128;
-template <int kHalves>
+// kNL: number of stages run (kNumLayers = all; kStaticLayers = static-only rendering).  A template parameter, not a field of
+// Params: a run-time stage count costs 0.3 ms per C2 frame (same-box A/B).
+template <int kHalves, int kNL = kNumLayers>
 __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_kernel(const Params p) {
   constexpr int kEpiWarps = 8 * kHalves, kProducerWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
   constexpr int kTileThreads = 128 * kHalves;     // epilogue threads working on one tile
@@ -84,7 +86,7 @@ __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_ke
       uint32_t stage = 0, phase = 0;
       for (long long st = blockIdx.x; st < n_super; st += gridDim.x) {
         int c = 0;
-        for (int L = 0; L < p.n_layers; ++L) {
+        for (int L = 0; L < kNL; ++L) {
           const Layer ly = kLayers[L];
           const int nch = ly.small ? 1 : ly.a_chunks + ly.e_chunks + ly.bias_chunk;
           for (int j = 0; j < nch; ++j, ++c) {
@@ -111,7 +113,7 @@ __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_ke
       const uint32_t idesc256 = umma_idesc(128, 256), idesc16 = umma_idesc(128, 16);
       constexpr uint32_t kHi = (128u >> 4) | (1u << 14);   // SBO = 128 B, descriptor version 1
       for (long long st = blockIdx.x; st < n_super; st += gridDim.x) {
-        for (int L = 0; L < p.n_layers; ++L) {
+        for (int L = 0; L < kNL; ++L) {
           const Layer ly = kLayers[L];
           const int nch = ly.small ? 1 : ly.a_chunks + ly.e_chunks + ly.bias_chunk;
           const int skew = p.skew < nch ? p.skew : nch;
@@ -195,7 +197,7 @@ __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_ke
       if (lane == 0) mbar_arrive(bar_ready(t));
 
       float sigma_s = 0.f, rgb_s[3] = {0.f, 0.f, 0.f};
-      for (int L = 0; L < p.n_layers; ++L) {
+      for (int L = 0; L < kNL; ++L) {
         const Layer ly = kLayers[L];
         // table biases (per ray / per image): when every row of this warp shares the bias row, each lane fetches its
         // float4 slice(s) now -- the L2 latency hides behind the MMAs of this stage
@@ -215,7 +217,7 @@ __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_ke
           named_bar_sync(1 + t, kTileThreads);
           store_pending = false;
         }
-        if (L == kReloadIssueLayer && p.n_layers > kStaticLayers && row == 0 && half == 0) {
+        if (L == kReloadIssueLayer && kNL > kStaticLayers && row == 0 && half == 0) {
           // every MMA that reads A_t has retired (acc barrier) -> bring the trunk feature back for the transient head
           bulk_wait_all();
           fence_proxy_async_all();
@@ -259,7 +261,7 @@ __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_ke
             hidden_epilogue<true, kCols / 32>(tmem_d, bias, a_row, dbg_row);
           }
           fence_proxy_async_smem();
-          if (L == kSpillLayer && p.n_layers > kStaticLayers) {      // static only: no second head, nothing to park
+          if (L == kSpillLayer && kNL > kStaticLayers) {      // static only: no second head, nothing to park
             // park the trunk feature (bf16 tile image) in the L2 scratch (training: in its slot of the save buffer, where
             // the backward also reads it) -- the bulk store overlaps the next stage's MMAs
             named_bar_sync(1 + t, kTileThreads);
@@ -280,7 +282,7 @@ __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_ke
           } else if (ly.epi == EPI_RGB_OUT) {
 #pragma unroll
             for (int c = 0; c < 3; ++c) rgb_s[c] = tp_sigmoid(__uint_as_float(v[c]) + sb[1 + c]);
-            if (p.n_layers == kStaticLayers && live) {      // static only: this is the last stage; transient outputs are zeros
+            if (kNL == kStaticLayers && live) {      // static only: this is the last stage; transient outputs are zeros
 #pragma unroll
               for (int c = 0; c < 3; ++c) *reinterpret_cast<float2*>(p.rgb + s * 6 + c * 2) = make_float2(rgb_s[c], 0.f);
               *reinterpret_cast<float2*>(p.density + s * 2) = make_float2(sigma_s, 0.f);
@@ -301,7 +303,7 @@ __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_ke
             }
           }
         }
-        if (L != p.n_layers - 1) {   // the next super-tile's encode arrival covers the last stage
+        if (L != kNL - 1) {   // the next super-tile's encode arrival covers the last stage
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_ready(t));
@@ -539,12 +541,12 @@ TP_API int tp_tc_nerf_stl_forward(const float* center, const float* ray, const f
     return tp_tc_pair_launch(p, (cudaStream_t)stream);
   }
   const bool wide = (flags & 2) == 0;       // default: 16 epilogue warps; flags bit 1 selects the 8-warp variant
-  cudaError_t e = wide ? cudaFuncSetAttribute(tc::nerf_stl_forward_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              (int)tc::kSmemBytes)
-                       : cudaFuncSetAttribute(tc::nerf_stl_forward_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              (int)tc::kSmemBytes);
+  const bool stat = p.n_layers == tc::kStaticLayers;
+  void (*kern)(const tc::Params) =
+      wide ? (stat ? tc::nerf_stl_forward_kernel<2, tc::kStaticLayers> : tc::nerf_stl_forward_kernel<2, tc::kNumLayers>)
+           : (stat ? tc::nerf_stl_forward_kernel<1, tc::kStaticLayers> : tc::nerf_stl_forward_kernel<1, tc::kNumLayers>);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes);
   if (e != cudaSuccess) return (int)e;
-  if (wide) tc::nerf_stl_forward_kernel<2><<<grid, tc::num_threads<2>(), tc::kSmemBytes, (cudaStream_t)stream>>>(p);
-  else tc::nerf_stl_forward_kernel<1><<<grid, tc::num_threads<1>(), tc::kSmemBytes, (cudaStream_t)stream>>>(p);
+  kern<<<grid, wide ? tc::num_threads<2>() : tc::num_threads<1>(), tc::kSmemBytes, (cudaStream_t)stream>>>(p);
   return tp_launch_status();
 }

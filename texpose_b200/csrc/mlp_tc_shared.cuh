@@ -73,7 +73,8 @@ struct Params {
   float* dbg_out;            // [S,256] post-activation of stage dbg_layer (debug only)
   int skew;                  // weight chunks tile 0 runs ahead of tile 1 inside a stage (0..2)
   int n_layers;              // 17 = all stages; 13 = static only (rendering that needs neither the transient head nor uncert):
-                             // the stage list stops after the rgb output, transient outputs are written as zeros
+                             // the stage list stops after the rgb output, transient outputs are written as zeros.  Host side only:
+                             // it selects the kernel instantiation (the default kernel takes the count as a template parameter)
   int dbg_save;              // timing experiments only (wrong training results): bit 0 = skip the activation-save bulk stores,
                              // bit 1 = skip the ReLU bitmasks
   int dbg_drain;             // timing experiments only (wrong results): 1 = convert/store every other slab, 2 = also skip its TMEM load
