@@ -39,8 +39,13 @@ constexpr uint32_t kOffBar = kOffRing + kStages * kChunkBytes;
 constexpr uint32_t kSmemBytes = kOffBar + 128;
 // kNL: number of stages run (kNumLayers = all; kStaticLayers = static-only rendering).  A template parameter, not a field of
 // Params: a run-time stage count costs 0.3 ms per C2 frame (same-box A/B).
-template <int kHalves, int kNL = kNumLayers>
+// kLean: the plain inference launch (no activation save, no debug taps or timing experiments, default tile skew): every such
+// branch is compiled out of the instantiation the render runs.
+template <int kHalves, int kNL = kNumLayers, bool kLean = false>
 __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_kernel(const Params p) {
+  const int p_skew = kLean ? 1 : p.skew;
+  const int p_dbg_drain = kLean ? 0 : p.dbg_drain;
+  uint8_t* const p_save = kLean ? nullptr : p.save;
   constexpr int kEpiWarps = 8 * kHalves, kProducerWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
   constexpr int kTileThreads = 128 * kHalves;     // epilogue threads working on one tile
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -116,7 +121,7 @@ __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_ke
         for (int L = 0; L < kNL; ++L) {
           const Layer ly = kLayers[L];
           const int nch = ly.small ? 1 : ly.a_chunks + ly.e_chunks + ly.bias_chunk;
-          const int skew = p.skew < nch ? p.skew : nch;
+          const int skew = p_skew < nch ? p_skew : nch;
           for (int step = 0; step < nch + skew; ++step) {
 #pragma unroll
             for (int t = 0; t < 2; ++t) {
@@ -184,7 +189,7 @@ __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_ke
     uint32_t acc_ph = 0;
     // all 32 rows of a warp share the ray (and image) when N is a multiple of 32; tail rows are clamped to the last
     // sample, which then belongs to the same ray as the warp's live rows
-    const bool warp_bias = (p.N % 32 == 0) && !(p.dbg_drain & 4);
+    const bool warp_bias = (p.N % 32 == 0) && !(p_dbg_drain & 4);
     bool store_pending = false;      // a bulk store of A_t (feature park / activation save) may still be reading it
     for (long long st = blockIdx.x; st < n_super; st += gridDim.x) {
       const long long s_raw = (st * 2 + t) * 128 + row;
@@ -222,12 +227,12 @@ __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_ke
           bulk_wait_all();
           fence_proxy_async_all();
           mbar_expect_tx(bar_reload(t), kABytes);
-          bulk_g2s(a_smem, p.save ? p.save + ((size_t)(st * 2 + t) * kSaveSlots) * kABytes : my_scratch, kABytes, bar_reload(t));
+          bulk_g2s(a_smem, p_save ? p_save + ((size_t)(st * 2 + t) * kSaveSlots) * kABytes : my_scratch, kABytes, bar_reload(t));
         }
         if (ly.epi == EPI_HIDDEN) {
-          float* dbg_row = ((L == p.dbg_layer) && live && p.dbg_out) ? p.dbg_out + s * 256 + half * kCols : nullptr;
+          float* dbg_row = (!kLean && (L == p.dbg_layer) && live && p.dbg_out) ? p.dbg_out + s * 256 + half * kCols : nullptr;
           const uint32_t a_row = a_smem + half * (kCols / 8) * 2048 + row * 16;
-          const bool train_stage = p.save && L != kSpillLayer && kSaveSlot[L] >= 0;
+          const bool train_stage = p_save && L != kSpillLayer && kSaveSlot[L] >= 0;
           if (train_stage) {
             // training: h1 / h2 of either head also leave a ReLU bitmask [128 rows][256 bits] for the backward chain (word
             // planes [8][128 rows]: plane = 32-column slab, so a warp's store of one slab is 128 contiguous bytes), and the
@@ -238,7 +243,7 @@ __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_ke
                                         : reinterpret_cast<uint32_t*>(p.bits + ((size_t)(st * 2 + t) * 4 + mslot) * kMaskBitBytes) +
                                               half * (kCols / 32) * 128 + row;
             uint8_t* g_row = (p.dbg_save & 1) ? nullptr
-                                              : p.save + ((size_t)(st * 2 + t) * kSaveSlots + kSaveSlot[L]) * kABytes +
+                                              : p_save + ((size_t)(st * 2 + t) * kSaveSlots + kSaveSlot[L]) * kABytes +
                                                     half * (kCols / 8) * 2048 + row * 16;
             if (ly.bias_kind == BIAS_MMA) {
               hidden_epilogue<false, kCols / 32, true>(tmem_d, nullptr, a_row, dbg_row, words, g_row);
@@ -249,9 +254,9 @@ __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_ke
                                   half * kCols;
               hidden_epilogue<true, kCols / 32, true>(tmem_d, bias, a_row, dbg_row, words, g_row);
             }
-          } else if (p.dbg_drain == 1 || p.dbg_drain == 2) {
-            hidden_epilogue_experiment<kCols / 32>(tmem_d, a_row, p.dbg_drain);
-          } else if (ly.bias_kind == BIAS_MMA || p.dbg_drain == 3) {   // 3: timing experiment, bias tables ignored
+          } else if (p_dbg_drain == 1 || p_dbg_drain == 2) {
+            hidden_epilogue_experiment<kCols / 32>(tmem_d, a_row, p_dbg_drain);
+          } else if (ly.bias_kind == BIAS_MMA || p_dbg_drain == 3) {   // 3: timing experiment, bias tables ignored
             hidden_epilogue<false, kCols / 32>(tmem_d, nullptr, a_row, dbg_row);
           } else if (warp_bias) {
             hidden_epilogue_wbias<kCols / 32>(tmem_d, wb, a_row, dbg_row);
@@ -266,7 +271,7 @@ __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_ke
             // the backward also reads it) -- the bulk store overlaps the next stage's MMAs
             named_bar_sync(1 + t, kTileThreads);
             if (row == 0 && half == 0) {
-              uint8_t* dst = p.save ? p.save + ((size_t)(st * 2 + t) * kSaveSlots + kSaveSlot[L]) * kABytes : my_scratch;
+              uint8_t* dst = p_save ? p_save + ((size_t)(st * 2 + t) * kSaveSlots + kSaveSlot[L]) * kABytes : my_scratch;
               bulk_s2g(dst, a_smem, kABytes);
               bulk_commit();
             }
@@ -542,9 +547,11 @@ TP_API int tp_tc_nerf_stl_forward(const float* center, const float* ray, const f
   }
   const bool wide = (flags & 2) == 0;       // default: 16 epilogue warps; flags bit 1 selects the 8-warp variant
   const bool stat = p.n_layers == tc::kStaticLayers;
+  const bool lean = wide && !save && dbg_layer < 0 && !dbg_out && p.dbg_drain == 0 && p.skew == 1;
   void (*kern)(const tc::Params) =
-      wide ? (stat ? tc::nerf_stl_forward_kernel<2, tc::kStaticLayers> : tc::nerf_stl_forward_kernel<2, tc::kNumLayers>)
-           : (stat ? tc::nerf_stl_forward_kernel<1, tc::kStaticLayers> : tc::nerf_stl_forward_kernel<1, tc::kNumLayers>);
+      lean ? (stat ? tc::nerf_stl_forward_kernel<2, tc::kStaticLayers, true> : tc::nerf_stl_forward_kernel<2, tc::kNumLayers, true>)
+      : wide ? (stat ? tc::nerf_stl_forward_kernel<2, tc::kStaticLayers> : tc::nerf_stl_forward_kernel<2, tc::kNumLayers>)
+             : (stat ? tc::nerf_stl_forward_kernel<1, tc::kStaticLayers> : tc::nerf_stl_forward_kernel<1, tc::kNumLayers>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes);
   if (e != cudaSuccess) return (int)e;
   kern<<<grid, wide ? tc::num_threads<2>() : tc::num_threads<1>(), tc::kSmemBytes, (cudaStream_t)stream>>>(p);
