@@ -39,13 +39,15 @@ constexpr uint32_t kOffBar = kOffRing + kStages * kChunkBytes;
 constexpr uint32_t kSmemBytes = kOffBar + 128;
 // kNL: number of stages run (kNumLayers = all; kStaticLayers = static-only rendering).  A template parameter, not a field of
 // Params: a run-time stage count costs 0.3 ms per C2 frame (same-box A/B).
-// kLean: the plain inference launch (no activation save, no debug taps or timing experiments, default tile skew): every such
-// branch is compiled out of the instantiation the render runs.
-template <int kHalves, int kNL = kNumLayers, bool kLean = false>
+// kMode: 0 = general (debug taps, timing experiments, any tile skew); 1 = the plain inference launch (no activation save);
+// 2 = the plain training launch (activation save + ReLU bitmasks).  Modes 1 and 2 have every debug branch compiled out and the
+// default tile skew as a constant: the same code with those decisions left to run time is 6 % slower (same-box A/B).
+template <int kHalves, int kNL = kNumLayers, int kMode = 0>
 __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_kernel(const Params p) {
-  const int p_skew = kLean ? 1 : p.skew;
-  const int p_dbg_drain = kLean ? 0 : p.dbg_drain;
-  uint8_t* const p_save = kLean ? nullptr : p.save;
+  const int p_skew = kMode ? 1 : p.skew;
+  const int p_dbg_drain = kMode ? 0 : p.dbg_drain;
+  const int p_dbg_save = kMode ? 0 : p.dbg_save;
+  uint8_t* const p_save = kMode == 1 ? nullptr : p.save;
   constexpr int kEpiWarps = 8 * kHalves, kProducerWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
   constexpr int kTileThreads = 128 * kHalves;     // epilogue threads working on one tile
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -230,7 +232,7 @@ __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_ke
           bulk_g2s(a_smem, p_save ? p_save + ((size_t)(st * 2 + t) * kSaveSlots) * kABytes : my_scratch, kABytes, bar_reload(t));
         }
         if (ly.epi == EPI_HIDDEN) {
-          float* dbg_row = (!kLean && (L == p.dbg_layer) && live && p.dbg_out) ? p.dbg_out + s * 256 + half * kCols : nullptr;
+          float* dbg_row = (kMode == 0 && (L == p.dbg_layer) && live && p.dbg_out) ? p.dbg_out + s * 256 + half * kCols : nullptr;
           const uint32_t a_row = a_smem + half * (kCols / 8) * 2048 + row * 16;
           const bool train_stage = p_save && L != kSpillLayer && kSaveSlot[L] >= 0;
           if (train_stage) {
@@ -238,11 +240,11 @@ __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_ke
             // planes [8][128 rows]: plane = 32-column slab, so a warp's store of one slab is 128 contiguous bytes), and the
             // activations go straight from the registers to their saved tile image (the backward's operands): a warp's
             // 16-byte groups cover 512 contiguous bytes and nothing re-reads the A tile
-            const int mslot = (p.dbg_save & 2) ? -1 : kMaskBitSlot[L];
+            const int mslot = (p_dbg_save & 2) ? -1 : kMaskBitSlot[L];
             uint32_t* words = mslot < 0 ? nullptr
                                         : reinterpret_cast<uint32_t*>(p.bits + ((size_t)(st * 2 + t) * 4 + mslot) * kMaskBitBytes) +
                                               half * (kCols / 32) * 128 + row;
-            uint8_t* g_row = (p.dbg_save & 1) ? nullptr
+            uint8_t* g_row = (p_dbg_save & 1) ? nullptr
                                               : p_save + ((size_t)(st * 2 + t) * kSaveSlots + kSaveSlot[L]) * kABytes +
                                                     half * (kCols / 8) * 2048 + row * 16;
             if (ly.bias_kind == BIAS_MMA) {
@@ -547,11 +549,12 @@ TP_API int tp_tc_nerf_stl_forward(const float* center, const float* ray, const f
   }
   const bool wide = (flags & 2) == 0;       // default: 16 epilogue warps; flags bit 1 selects the 8-warp variant
   const bool stat = p.n_layers == tc::kStaticLayers;
-  const bool lean = wide && !save && dbg_layer < 0 && !dbg_out && p.dbg_drain == 0 && p.skew == 1;
+  const bool plain = wide && dbg_layer < 0 && !dbg_out && p.dbg_drain == 0 && p.dbg_save == 0 && p.skew == 1;
   void (*kern)(const tc::Params) =
-      lean ? (stat ? tc::nerf_stl_forward_kernel<2, tc::kStaticLayers, true> : tc::nerf_stl_forward_kernel<2, tc::kNumLayers, true>)
-      : wide ? (stat ? tc::nerf_stl_forward_kernel<2, tc::kStaticLayers> : tc::nerf_stl_forward_kernel<2, tc::kNumLayers>)
-             : (stat ? tc::nerf_stl_forward_kernel<1, tc::kStaticLayers> : tc::nerf_stl_forward_kernel<1, tc::kNumLayers>);
+      plain && !save ? (stat ? tc::nerf_stl_forward_kernel<2, tc::kStaticLayers, 1> : tc::nerf_stl_forward_kernel<2, tc::kNumLayers, 1>)
+      : plain        ? tc::nerf_stl_forward_kernel<2, tc::kNumLayers, 2>
+      : wide         ? (stat ? tc::nerf_stl_forward_kernel<2, tc::kStaticLayers> : tc::nerf_stl_forward_kernel<2, tc::kNumLayers>)
+                     : (stat ? tc::nerf_stl_forward_kernel<1, tc::kStaticLayers> : tc::nerf_stl_forward_kernel<1, tc::kNumLayers>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes);
   if (e != cudaSuccess) return (int)e;
   kern<<<grid, wide ? tc::num_threads<2>() : tc::num_threads<1>(), tc::kSmemBytes, (cudaStream_t)stream>>>(p);

@@ -47,7 +47,6 @@ struct BwdParams {
   const uint8_t* packed;      // kBwdChunks x 16 KB transposed weight images
   const uint8_t* saved;       // forward activations [tiles][7][64 KB]
   uint8_t* dz_out;            // [tiles][6][64 KB]: rgb dz2,dz1,dz0, trans dz2,dz1,dz0
-  int l2_hints;               // bulk copies carry L2 policies: dz image stores / h3 tile loads evict-first, weight chunks evict-last
 };
 
 __global__ void __launch_bounds__(kThreads, 1) backward_chain_kernel(const BwdParams p) {
@@ -386,8 +385,7 @@ __global__ void __launch_bounds__(kFThreads, 1) backward_chain_fused_kernel(cons
           mbar_wait(bar_empty(stage), phase ^ 1);
           if (elect_one_sync()) {
             mbar_expect_tx(bar_full(stage), bytes);
-            if (p.l2_hints) bulk_g2s_hint(sbase + kOffRingF + stage * kChunkBytes, p.packed + (size_t)c * kChunkBytes, bytes, bar_full(stage), l2_policy_evict_last());
-            else bulk_g2s(sbase + kOffRingF + stage * kChunkBytes, p.packed + (size_t)c * kChunkBytes, bytes, bar_full(stage));
+            bulk_g2s_hint(sbase + kOffRingF + stage * kChunkBytes, p.packed + (size_t)c * kChunkBytes, bytes, bar_full(stage), l2_policy_evict_last());
           }
           __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -498,8 +496,7 @@ __global__ void __launch_bounds__(kFThreads, 1) backward_chain_fused_kernel(cons
     TP_PF(long long pe_acc = 0, pe_mask = 0, pe_store = 0, pe_conv = 0, pe_bar = 0;)
     if (threadIdx.x == 32) {
       mbar_expect_tx(bar_mask, kABytes);
-      if (p.l2_hints) bulk_g2s_hint(m_smem, p.saved + ((size_t)t0 * kFwdSlots + kMaskSlot[0]) * kABytes, kABytes, bar_mask, l2_policy_evict_first());
-      else bulk_g2s(m_smem, p.saved + ((size_t)t0 * kFwdSlots + kMaskSlot[0]) * kABytes, kABytes, bar_mask);
+      bulk_g2s_hint(m_smem, p.saved + ((size_t)t0 * kFwdSlots + kMaskSlot[0]) * kABytes, kABytes, bar_mask, l2_policy_evict_first());
     }
     // one 32-column slab: mask, bf16, store as 4 core-matrix rows of the dz tile (= next A operand / dz image)
     auto convert_slab = [&](const uint32_t (&v)[32], int k8_0, bool tile_mask, uint32_t word) {
@@ -604,8 +601,7 @@ __global__ void __launch_bounds__(kFThreads, 1) backward_chain_fused_kernel(cons
         named_bar_sync(1, kFEpiThreads);  // every thread finished reading M and writing A
         TP_PF(pe_bar += clock64() - pe_a;)
         if (threadIdx.x == 0) {
-          if (p.l2_hints) bulk_s2g_hint(p.dz_out + ((size_t)tile * kDzSlots + s) * kABytes, a_smem, kABytes, l2_policy_evict_first());
-          else bulk_s2g(p.dz_out + ((size_t)tile * kDzSlots + s) * kABytes, a_smem, kABytes);
+          bulk_s2g_hint(p.dz_out + ((size_t)tile * kDzSlots + s) * kABytes, a_smem, kABytes, l2_policy_evict_first());
           bulk_commit();
         }
         store_pending = true;
@@ -613,8 +609,7 @@ __global__ void __launch_bounds__(kFThreads, 1) backward_chain_fused_kernel(cons
           const long long nt = s == 3 ? tile + 1 : tile;
           if (nt < t1) {
             mbar_expect_tx(bar_mask, kABytes);
-            if (p.l2_hints) bulk_g2s_hint(m_smem, p.saved + ((size_t)nt * kFwdSlots + kMaskSlot[s == 3 ? 0 : 3]) * kABytes, kABytes, bar_mask, l2_policy_evict_first());
-            else bulk_g2s(m_smem, p.saved + ((size_t)nt * kFwdSlots + kMaskSlot[s == 3 ? 0 : 3]) * kABytes, kABytes, bar_mask);
+            bulk_g2s_hint(m_smem, p.saved + ((size_t)nt * kFwdSlots + kMaskSlot[s == 3 ? 0 : 3]) * kABytes, kABytes, bar_mask, l2_policy_evict_first());
           }
         }
         if (s != kNumStagesPerTile - 1) {
@@ -1139,7 +1134,6 @@ TP_API int tp_tc_backward_chain(const float* dz_rgb, const float* dz_trans, int6
   p.packed = reinterpret_cast<const uint8_t*>(packed_bwd);
   p.saved = reinterpret_cast<const uint8_t*>(saved);
   p.dz_out = reinterpret_cast<uint8_t*>(dz_images);
-  p.l2_hints = 0;
   const long long n_tiles = (S + 127) / 128;
   int grid = tp_num_sms();
   if (n_tiles < grid) grid = (int)n_tiles;
@@ -1280,7 +1274,6 @@ TP_API int tp_tc_heads_backward(const float* dz_rgb, const float* dz_trans, int6
   fp.b.packed = reinterpret_cast<const uint8_t*>(packed_bwd);
   fp.b.saved = reinterpret_cast<const uint8_t*>(saved);
   fp.b.dz_out = reinterpret_cast<uint8_t*>(dz_images);
-  fp.b.l2_hints = 1;      // dz images / h3 tiles pass through L2 once (evict-first), the weight image stays (evict-last): -70 us per C3 step
   fp.center = center; fp.ray = ray; fp.depth = depth; fp.N = N; fp.per_image = per_image; fp.L_view = L_view;
   fp.extras = extras; fp.thin_sums = thin_sums;
   // debugging aid: a workspace with 2*16*grid extra floats receives the MMA warp's cycle counters in its tail
