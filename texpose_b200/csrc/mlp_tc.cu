@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_ke
     uint32_t acc_ph = 0;
     // all 32 rows of a warp share the ray (and image) when N is a multiple of 32; tail rows are clamped to the last
     // sample, which then belongs to the same ray as the warp's live rows
-    const bool warp_bias = (p.N % 32 == 0) && !(p_dbg_drain & 4);
+    const bool warp_bias = kMode ? true : (p.N % 32 == 0) && !(p_dbg_drain & 4);      // modes 1 / 2 are launched only when N % 32 == 0
     bool store_pending = false;      // a bulk store of A_t (feature park / activation save) may still be reading it
     for (long long st = blockIdx.x; st < n_super; st += gridDim.x) {
       const long long s_raw = (st * 2 + t) * 128 + row;
@@ -549,7 +549,7 @@ TP_API int tp_tc_nerf_stl_forward(const float* center, const float* ray, const f
   }
   const bool wide = (flags & 2) == 0;       // default: 16 epilogue warps; flags bit 1 selects the 8-warp variant
   const bool stat = p.n_layers == tc::kStaticLayers;
-  const bool plain = wide && dbg_layer < 0 && !dbg_out && p.dbg_drain == 0 && p.dbg_save == 0 && p.skew == 1;
+  const bool plain = wide && dbg_layer < 0 && !dbg_out && p.dbg_drain == 0 && p.dbg_save == 0 && p.skew == 1 && N % 32 == 0;
   void (*kern)(const tc::Params) =
       plain && !save ? (stat ? tc::nerf_stl_forward_kernel<2, tc::kStaticLayers, 1> : tc::nerf_stl_forward_kernel<2, tc::kNumLayers, 1>)
       : plain        ? tc::nerf_stl_forward_kernel<2, tc::kNumLayers, 2>
