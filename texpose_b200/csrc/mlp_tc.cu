@@ -547,16 +547,17 @@ TP_API int tp_tc_nerf_stl_forward(const float* center, const float* ray, const f
     p.skew = ((flags >> 11) & 7) ? ((flags >> 11) & 7) - 1 : 4;
     return tp_tc_pair_launch(p, (cudaStream_t)stream);
   }
-  // drain width: 8 epilogue warps (256 accumulator columns per thread, 168 registers) for inference launches -- 2 % faster than
-  // 16 warps under the power cap (same-box A/B, profiles/r01f_summary.md section 8) --, 16 warps (128 columns per thread) for
-  // training launches, whose drains also carry the activation-save stores.  flags bit 1 selects the other width (A/B).
-  const bool wide = save ? (flags & 2) == 0 : (flags & 2) != 0;
+  // drain width: 8 epilogue warps (256 accumulator columns per thread, 168 registers, 320 threads per CTA) by default -- same
+  // tensor-pipe time as 16 warps, but the narrower CTA draws less power and the capped clock settles higher: 2 % faster for
+  // the C2 frame, 1.7 % for the C3 training step (same-box A/B, profiles/r01f_summary.md section 9).  flags bit 1 selects 16 warps.
+  const bool wide = (flags & 2) != 0;
   const bool stat = p.n_layers == tc::kStaticLayers;
   const bool plain = dbg_layer < 0 && !dbg_out && p.dbg_drain == 0 && p.dbg_save == 0 && p.skew == 1 && N % 32 == 0;
   void (*kern)(const tc::Params) =
       plain && !save && !wide ? (stat ? tc::nerf_stl_forward_kernel<1, tc::kStaticLayers, 1> : tc::nerf_stl_forward_kernel<1, tc::kNumLayers, 1>)
       : plain && !save        ? (stat ? tc::nerf_stl_forward_kernel<2, tc::kStaticLayers, 1> : tc::nerf_stl_forward_kernel<2, tc::kNumLayers, 1>)
       : plain && wide         ? tc::nerf_stl_forward_kernel<2, tc::kNumLayers, 2>
+      : plain                 ? tc::nerf_stl_forward_kernel<1, tc::kNumLayers, 2>
       : wide ? (stat ? tc::nerf_stl_forward_kernel<2, tc::kStaticLayers> : tc::nerf_stl_forward_kernel<2, tc::kNumLayers>)
              : (stat ? tc::nerf_stl_forward_kernel<1, tc::kStaticLayers> : tc::nerf_stl_forward_kernel<1, tc::kNumLayers>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes);

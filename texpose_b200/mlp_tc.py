@@ -136,7 +136,7 @@ def _scratch_for(dev):
 
 
 def forward(cfg, geom, lat_trans, lat_light, feat_p, rgb_p, trans_p, dbg_layer=-1, flags=0, save=False, static_only=False):
-    flags = flags or int(os.environ.get("TEXPOSE_TC_FLAGS", "0"))     # bit 1: the other drain width (A/B; default 8 epilogue warps for inference, 16 for training)
+    flags = flags or int(os.environ.get("TEXPOSE_TC_FLAGS", "0"))     # bit 1: 16-epilogue-warp drain instead of the default 8 (A/B)
     if static_only and not save and not (flags & (128 | PAIR_KERNEL)):
         flags |= STATIC_ONLY
     if geom.get("mode") != "rays":
