@@ -385,6 +385,7 @@ def bench_train(args, g, opt, dev, world, timed):
     import torch
     from texpose_b200 import compute_box, parallel, synth
     from texpose_b200.config import AttrDict, adapt_gan_opt
+    from texpose_b200.model.base import summarize_loss
     B, P = 16, 16
     opt_t = adapt_gan_opt(H=128, W=128, sample_intvs=NS, device=str(dev))
     opt_t.b200 = AttrDict(mlp="bf16", rng="philox")
@@ -412,8 +413,8 @@ def bench_train(args, g, opt, dev, world, timed):
                            sample_idx=idx, mode="train")
             var = AttrDict(idx=idx, image=image, obj_mask=mask, ray_idx=coords)
             var.update(ret)
-            loss = g.compute_loss(opt_t, var, mode="train")      # patch gather + render / uncert / trans_reg terms + seeds, fused
-            loss["all"].backward()
+            loss = g.compute_loss(opt_t, var, mode="train")      # patch gather + render / uncert / trans_reg terms, fused
+            summarize_loss(opt_t, var, loss)["all"].backward()   # seeds formed on the device in the backward
             bucket.allreduce_mean()
         return step
 

@@ -262,12 +262,21 @@ int tp_tc_pack_images(const float* in, int64_t S, void* images, int slot, int n_
  * (uncertainty-weighted masked MSE), bit 1 uncert (5 + mean log u^2 / 2), bit 2 trans_reg (mean transient density); w_* =
  * 10^loss_weight.  Writes image_sample [B,3,R] (bilinear, align_corners=True), mask_sample [B,R] (nearest,
  * align_corners=False), losses[4] = {render, uncert, trans_reg, all}, and d(all)/d{rgb, uncert, density} (g_density [B*R*N,2]
- * may be NULL).  Deterministic (fixed-order reductions).  workspace >= tp_patch_loss_workspace() floats. */
+ * may be NULL; g_rgb = g_uncert = g_density = NULL computes the scalars only and leaves the seeds to tp_patch_loss_backward).
+ * Deterministic (fixed-order reductions).  workspace >= tp_patch_loss_workspace() floats. */
 int64_t tp_patch_loss_workspace(void);
 int tp_patch_loss(const float* image, const float* obj_mask, const float* coords, int B, int R, int H, int W,
                   const float* rgb, const float* uncert, const float* density, int N, float w_render, float w_uncert,
                   float w_trans_reg, int terms, float* image_sample, float* mask_sample, float* losses, float* g_rgb,
                   float* g_uncert, float* g_density, float* workspace, int64_t workspace_floats, void* stream);
+/* Backward of tp_patch_loss for arbitrary upstream gradients g_losses[4] (DEVICE memory: no host sync) of {render, uncert,
+ * trans_reg, all} -- autograd of model/nerf_adapt_st_gan.py:747-763 whichever way the caller combines the terms (the reference
+ * engine backpropagates the `all` that Model.summarize_loss builds, model/base.py:145-157: g = {10^w_r, 10^w_u, 10^w_t, 0}).
+ * image_sample, mask_sample and workspace are the forward call's outputs; same B, R, N, weights and terms. */
+int tp_patch_loss_backward(const float* g_losses, const float* image_sample, const float* mask_sample, int B, int R,
+                           const float* rgb, const float* uncert, int N, float w_render, float w_uncert, float w_trans_reg,
+                           int terms, float* g_rgb, float* g_uncert, float* g_density, const float* workspace,
+                           int64_t workspace_floats, void* stream);
 
 /* ---- eval-frame epilogue --------------------------------------------------------------------------- */
 

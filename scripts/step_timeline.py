@@ -15,6 +15,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from texpose_b200 import _C, compute_box, synth  # noqa: E402
 from texpose_b200.config import AttrDict, adapt_gan_opt  # noqa: E402
 from texpose_b200.model.nerf_adapt_st_gan import Graph  # noqa: E402
+from texpose_b200.model.base import summarize_loss  # noqa: E402
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 10
 dev = torch.device("cuda:0")
@@ -95,7 +96,7 @@ def train():
                    sample_idx=idx, mode="train")
     v = AttrDict(idx=idx, image=image, obj_mask=mask, ray_idx=coords)
     v.update(ret)
-    g.compute_loss(opt_t, v, mode="train")["all"].backward()
+    summarize_loss(opt_t, v, g.compute_loss(opt_t, v, mode="train"))["all"].backward()
 
 
 measure("C3 train", train, steps)

@@ -8,6 +8,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from texpose_b200 import compute_box, synth  # noqa: E402
 from texpose_b200.config import AttrDict, adapt_gan_opt  # noqa: E402
 from texpose_b200.model.nerf_adapt_st_gan import Graph  # noqa: E402
+from texpose_b200.model.base import summarize_loss  # noqa: E402
 
 dev = torch.device("cuda:0")
 B, P, NS = 16, 16, 128
@@ -30,7 +31,7 @@ for it in range(int(sys.argv[1]) if len(sys.argv) > 1 else 3):
     ret = g.render(opt, pose, intr=intr, ray_idx=coords, depth_range=(zn[:, :, None], zf[:, :, None]), sample_idx=idx, mode="train")
     var = AttrDict(idx=idx, image=image, obj_mask=mask, ray_idx=coords)
     var.update(ret)
-    loss = g.compute_loss(opt, var, mode="train")["all"]
+    loss = summarize_loss(opt, var, g.compute_loss(opt, var, mode="train"))["all"]
     loss.backward()
 torch.cuda.synchronize()
 print("ok", float(loss))

@@ -77,3 +77,23 @@ def test_flex_patch_sampler_matches_oracle_on_cpu():
         got = FlexPatchSampler()(nbatch=B, patch_size=P, device="cpu")
         assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
         assert got[0].shape == (B, P, P, 2) and got[0].abs().max() <= 1.0
+
+
+def test_patch_sampler_anneals_like_the_reference():
+    """Graph builds FlexPatchSampler(scale_anneal=0.0002) (model/nerf_adapt_st_gan.py:424) and the engine
+    feeds it `iterations` (:185): min_scale = min(0.8, max(0.25, exp(-it * 2e-4))) (tools/patch_sampler.py:85-89)."""
+    import math
+    import torch
+    from texpose_b200.config import adapt_gan_opt
+    from texpose_b200.model.nerf_adapt_st_gan import Graph
+    opt = adapt_gan_opt(H=32, W=32)
+    g = Graph(opt, n_train_images=2)
+    ps = g.patch_sampler
+    assert ps.scale_anneal == 0.0002 and ps.min_scale == 0.25 and ps.max_scale == 1.0
+    for it, want in ((0, 0.8), (1000, 0.8), (2000, math.exp(-0.4)), (5000, math.exp(-1.0)), (100000, 0.25)):
+        ps.iterations = it
+        torch.manual_seed(3)
+        coords, scales = ps(nbatch=64, patch_size=4, device="cpu")
+        assert abs(ps.scales_curr[0] - want) < 1e-12 and ps.scales_curr[1] == 1.0
+        assert float(scales.min()) >= want - 1e-6 and float(scales.max()) <= 1.0
+        assert coords.abs().max() <= 1.0 + 1e-6

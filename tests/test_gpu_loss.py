@@ -76,7 +76,8 @@ def test_graph_compute_loss_and_patch_sampler():
     var.rgb = torch.rand(4, 64, 3, generator=gen).to(DEV).requires_grad_(True)
     var.uncert = (torch.rand(4, 64, 1, generator=gen) + 0.05).to(DEV).requires_grad_(True)
     var.density = torch.rand(4, 64, 16, 2, generator=gen).to(DEV).requires_grad_(True)
-    loss = g.compute_loss(opt, var, mode="train")
+    from texpose_b200.model.base import summarize_loss
+    loss = summarize_loss(opt, var, g.compute_loss(opt, var, mode="train"))
     ref = O.patch_losses(var.image.cpu(), var.obj_mask.cpu(), var.ray_idx.cpu(), var.rgb.detach().cpu(), var.uncert.detach().cpu(),
                          var.density.detach().cpu(), 0, 0, -2)
     for k in ("render", "uncert", "trans_reg", "all"):

@@ -2,7 +2,7 @@
 
 The protocol is exercised three ways: (1) several "ranks" of ONE process on one device, each on its own stream (the
 kernels wait for each other exactly as ranks on different GPUs do, minus NVLink); (2) a rank that never shows up -> bounded
-wait, status word, output untouched; (3) two PROCESSES exchanging through real CUDA IPC handles (on two GPUs when the box has
+wait, status word, output poisoned with NaN; (3) two PROCESSES exchanging through real CUDA IPC handles (on two GPUs when the box has
 them, else both on cuda:0) against the torch.distributed allreduce of the same gradients."""
 import os
 import socket
@@ -50,6 +50,13 @@ def test_rank_order_mean_bit_exact(world, n, grid):
     _ranks_in_one_process(world, n, epochs=4, grid=grid if grid else 16)
 
 
+def test_no_cta_waits_for_its_own_grid():
+    """A grid far larger than one resident wave (1 rank: nothing to wait for; 2 ranks on one device, launched back to back):
+    no CTA depends on CTA 0 of its own grid being resident, so the exchange completes whatever the grid size."""
+    _ranks_in_one_process(1, 1 << 20, epochs=2, grid=4096)
+    _ranks_in_one_process(2, 1 << 18, epochs=2, grid=64)
+
+
 def test_missing_peer_times_out_and_reports():
     dev = torch.device("cuda:0")
     n = 4096
@@ -60,7 +67,7 @@ def test_missing_peer_times_out_and_reports():
         parallel.peer_allreduce_mean([w.ptr for w in wins], 0, n, 1, out, grid_ctas=4, timeout_ms=50)
         torch.cuda.synchronize()
         assert wins[0].status() == 1 and wins[1].status() == 0
-        assert torch.equal(out, torch.full((n,), 3.0, device=dev))
+        assert torch.isnan(out).all()        # poisoned: stale / partial gradients can never reach an optimizer step unnoticed
     finally:
         for w in wins:
             w.close()

@@ -40,6 +40,8 @@ struct LossParams {
   float* g_density;        // [S,2] or NULL
   float* partial;          // [blocks][4]
   int blocks;
+  const float* g_losses;   // device [4] or NULL: upstream gradients of {render, uncert, trans_reg, all} (NULL = {0,0,0,1})
+  int write_losses;        // 0 in the backward launch (tp_patch_loss_backward): the scalars were written by the forward
 };
 
 __device__ __forceinline__ float block_sum(float v, float* sm) {
@@ -105,7 +107,7 @@ __global__ void __launch_bounds__(kLossThreads) patch_loss_grad_kernel(const Los
   __syncthreads();
   const long long rays = (long long)p.B * p.R;
   const float denom = tot[1] + 1e-5f;
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
+  if (p.write_losses && blockIdx.x == 0 && threadIdx.x == 0) {
     const float l_r = tot[0] / denom, l_u = 5.f + tot[2] / (float)rays / 2.f, l_t = p.S > 0 ? tot[3] / (float)p.S : 0.f;
     float all = 0.f;
     if (p.terms & 1) all += p.w_render * l_r;
@@ -116,8 +118,13 @@ __global__ void __launch_bounds__(kLossThreads) patch_loss_grad_kernel(const Los
     p.losses[2] = (p.terms & 4) ? l_t : 0.f;
     p.losses[3] = all;
   }
-  const float kr = (p.terms & 1) ? p.w_render / denom : 0.f;
-  const float ku = (p.terms & 2) ? p.w_uncert / (float)rays : 0.f;
+  if (!p.g_rgb) return;      // forward launch of the autograd function: scalars only, the seeds are formed in the backward
+  // d(sum_k g_k * loss_k)/d{.} with g = upstream gradients of the four outputs: `all` is sum_k w_k * term_k, so term k
+  // carries g_k + g_all * w_k (the reference engine backpropagates `all` built by Model.summarize_loss: g = {w_r, w_u, w_t, 0})
+  const float g0 = p.g_losses ? p.g_losses[0] : 0.f, g1 = p.g_losses ? p.g_losses[1] : 0.f, g2 = p.g_losses ? p.g_losses[2] : 0.f,
+              g3 = p.g_losses ? p.g_losses[3] : 1.f;
+  const float kr = (p.terms & 1) ? (g0 + g3 * p.w_render) / denom : 0.f;
+  const float ku = (p.terms & 2) ? (g1 + g3 * p.w_uncert) / (float)rays : 0.f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < rays; i += (long long)gridDim.x * blockDim.x) {
     const int b = (int)(i / p.R);
     const long long r = i - (long long)b * p.R;
@@ -133,7 +140,7 @@ __global__ void __launch_bounds__(kLossThreads) patch_loss_grad_kernel(const Los
     p.g_uncert[i] = -2.f * kr * m * e2 * iu2 / u + ku / u;
   }
   if (p.g_density) {
-    const float gt = (p.terms & 4) && p.S > 0 ? p.w_trans / (float)p.S : 0.f;
+    const float gt = (p.terms & 4) && p.S > 0 ? (g2 + g3 * p.w_trans) / (float)p.S : 0.f;
     float2* g = reinterpret_cast<float2*>(p.g_density);
     for (long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x; s < p.S; s += (long long)gridDim.x * blockDim.x)
       g[s] = make_float2(0.f, gt);
@@ -148,9 +155,9 @@ TP_API int tp_patch_loss(const float* image, const float* obj_mask, const float*
                          const float* rgb, const float* uncert, const float* density, int N, float w_render, float w_uncert,
                          float w_trans_reg, int terms, float* image_sample, float* mask_sample, float* losses, float* g_rgb,
                          float* g_uncert, float* g_density, float* workspace, int64_t workspace_floats, void* stream) {
-  if (!image || !obj_mask || !coords || !rgb || !uncert || !image_sample || !mask_sample || !losses || !g_rgb || !g_uncert ||
-      !workspace)
+  if (!image || !obj_mask || !coords || !rgb || !uncert || !image_sample || !mask_sample || !losses || !workspace)
     return TP_ERR_BAD_ARG;
+  if ((g_rgb == nullptr) != (g_uncert == nullptr) || (!g_rgb && g_density)) return TP_ERR_BAD_ARG;      // seeds: all or none
   if ((terms & 4) && !density) return TP_ERR_BAD_ARG;
   if (B < 1 || R < 1 || H < 2 || W < 2 || N < 0 || (terms & ~7)) return TP_ERR_BAD_SHAPE;
   if (((uintptr_t)g_density & 7)) return TP_ERR_ALIGN;
@@ -160,13 +167,38 @@ TP_API int tp_patch_loss(const float* image, const float* obj_mask, const float*
   p.w_render = w_render; p.w_uncert = w_uncert; p.w_trans = w_trans_reg; p.terms = terms;
   p.image_sample = image_sample; p.mask_sample = mask_sample; p.losses = losses;
   p.g_rgb = g_rgb; p.g_uncert = g_uncert; p.g_density = g_density; p.partial = workspace;
+  p.g_losses = nullptr; p.write_losses = 1;
   const long long work = (terms & 4) ? p.S : (long long)B * R;
   p.blocks = tp_grid_for(work > (long long)B * R ? work : (long long)B * R, kLossThreads, 2);
   if (workspace_floats < (int64_t)p.blocks * 4) return TP_ERR_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
   patch_loss_partial_kernel<<<p.blocks, kLossThreads, 0, st>>>(p);
   if (int rc = tp_launch_status()) return rc;
-  patch_loss_grad_kernel<<<p.blocks, kLossThreads, 0, st>>>(p);
+  patch_loss_grad_kernel<<<g_rgb ? p.blocks : 1, kLossThreads, 0, st>>>(p);      // without seeds: one block for the scalars
+  return tp_launch_status();
+}
+
+// Backward of tp_patch_loss for arbitrary upstream gradients of its four scalars (g_losses: DEVICE pointer, so no host sync):
+// re-reduces the forward's partials in the same fixed order and writes the seeds.  image_sample / mask_sample / workspace are
+// the forward's outputs, unchanged.
+TP_API int tp_patch_loss_backward(const float* g_losses, const float* image_sample, const float* mask_sample, int B, int R,
+                                  const float* rgb, const float* uncert, int N, float w_render, float w_uncert,
+                                  float w_trans_reg, int terms, float* g_rgb, float* g_uncert, float* g_density,
+                                  const float* workspace, int64_t workspace_floats, void* stream) {
+  if (!g_losses || !image_sample || !mask_sample || !rgb || !uncert || !g_rgb || !g_uncert || !workspace) return TP_ERR_BAD_ARG;
+  if (B < 1 || R < 1 || N < 0 || (terms & ~7)) return TP_ERR_BAD_SHAPE;
+  if (((uintptr_t)g_density & 7)) return TP_ERR_ALIGN;
+  LossParams p;
+  p.image = nullptr; p.obj_mask = nullptr; p.coords = nullptr; p.B = B; p.R = R; p.H = 0; p.W = 0;
+  p.rgb = rgb; p.uncert = uncert; p.density = nullptr; p.S = (long long)B * R * N;
+  p.w_render = w_render; p.w_uncert = w_uncert; p.w_trans = w_trans_reg; p.terms = terms;
+  p.image_sample = const_cast<float*>(image_sample); p.mask_sample = const_cast<float*>(mask_sample); p.losses = nullptr;
+  p.g_rgb = g_rgb; p.g_uncert = g_uncert; p.g_density = g_density; p.partial = const_cast<float*>(workspace);
+  p.g_losses = g_losses; p.write_losses = 0;
+  const long long work = (terms & 4) ? p.S : (long long)B * R;      // the forward's grid: same number of partials
+  p.blocks = tp_grid_for(work > (long long)B * R ? work : (long long)B * R, kLossThreads, 2);
+  if (workspace_floats < (int64_t)p.blocks * 4) return TP_ERR_WORKSPACE;
+  patch_loss_grad_kernel<<<p.blocks, kLossThreads, 0, (cudaStream_t)stream>>>(p);
   return tp_launch_status();
 }
 

@@ -9,7 +9,8 @@
 //   step e (e = 1, 2, ...), on every rank, on the caller's stream:
 //     1. the caller packs its gradients into data buffer e&1 of its OWN window (ordinary local writes);
 //     2. CTA 0 publishes: st.release.sys  arrive[rank] = e  into every peer's header (NVLink stores);
-//     3. every CTA waits on its LOCAL header until all arrive[p] have reached e (ld.acquire.sys, bounded by a timeout);
+//     3. every CTA waits on its LOCAL header until arrive[p] of every peer p has reached e (ld.acquire.sys, bounded by a
+//        timeout; on a timeout the status word is set and `out` is filled with NaN);
 //     4. every CTA reads its slice of all `world` buffers (own HBM + NVLink peer loads, 16 B vectors, all loads of a
 //        slice in flight together), adds them in rank order 0..world-1 and divides by world -> `out` (local).
 //   The rank order makes the result bit-identical on every rank and run to run.  Buffers alternate with the epoch's
@@ -81,9 +82,11 @@ __global__ void __launch_bounds__(256) peer_allreduce_mean_kernel(const Windows 
     __threadfence_system();
     st_release_sys(reinterpret_cast<uint32_t*>(w.base[threadIdx.x]) + rank, epoch);
   }
-  // 3. wait on the local header (every CTA; no CTA waits for another CTA of this grid)
+  // 3. wait on the local header for every PEER (every CTA).  The own slot is not waited on: this rank's buffer was written
+  // by earlier work on this stream, and only CTA 0 publishes it -- waiting for it would make the other CTAs depend on CTA 0
+  // being resident, which a grid larger than one wave does not guarantee.
   int failed = 0;
-  if (threadIdx.x < world) {
+  if (threadIdx.x < world && threadIdx.x != rank) {
     const uint32_t* flag = my_hdr + threadIdx.x;
     const unsigned long long t0 = global_ns();
     while ((int32_t)(ld_acquire_sys(flag) - epoch) < 0) {
@@ -95,8 +98,14 @@ __global__ void __launch_bounds__(256) peer_allreduce_mean_kernel(const Windows 
     }
   }
   failed = __syncthreads_or(failed);
-  if (failed) {   // a peer never arrived: report, leave `out` untouched
+  if (failed) {
+    // a peer never arrived: report through the status word AND poison this CTA's slice of `out` with NaN, so a caller that
+    // does not poll tp_peer_status cannot step the optimizer on stale or partially reduced gradients without noticing
     if (threadIdx.x == 0) atomicMax(my_hdr + kStatusWord, epoch);
+    const float nan = __int_as_float(0x7fc00000);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride)
+      reinterpret_cast<float4*>(out)[i] = make_float4(nan, nan, nan, nan);
     return;
   }
   // 4. reduce in rank order

@@ -83,11 +83,15 @@ class NeRF(torch.nn.Module):
             return False
         from .. import mlp_tc
         pairs = lambda ml: [(l.weight, l.bias) for l in ml]
-        ok = mlp_tc.supported(cfg, pairs(self.mlp_feat), pairs(self.mlp_rgb), pairs(self.mlp_trans))
-        return ok and not any(p.requires_grad for p in self.mlp_feat.parameters())
+        return mlp_tc.supported(cfg, pairs(self.mlp_feat), pairs(self.mlp_rgb), pairs(self.mlp_trans))
 
     def _run(self, cfg, geom, latent_variable_trans, latent_variable_light):
-        params = _common.flat_params(self.mlp_feat, self.mlp_rgb, self.mlp_trans)
+        # The reference runs the trunk and the static density under torch.no_grad() (:87-101): the static scene never
+        # receives a gradient, whatever requires_grad says -- its engine calls toggle_grad(nerf, True) before every
+        # nerf_trainstep (model/nerf_adapt_st_gan.py:110).  The trunk parameters therefore enter the autograd function
+        # detached: no trunk gradient is computed, none is returned, and the fused bf16 path stays selected.
+        trunk = [p.detach() for p in _common.flat_params(self.mlp_feat)]
+        params = trunk + _common.flat_params(self.mlp_rgb, self.mlp_trans)
         return run_mlp(cfg, geom, latent_variable_trans, latent_variable_light, *params)
 
     # ------------------------------------------------------------------ reference interface

@@ -34,7 +34,10 @@ class Graph(torch.nn.Module):
         super().__init__()
         self.nerf = NeRF(opt)
         self.ray_sampler = RaySampler(opt)
-        self.patch_sampler = FlexPatchSampler(random_shift=True, random_scale=True, min_scale=0.25, max_scale=1.0)   # :424
+        # :424 builds FlexPatchSampler(opt, scale_anneal=0.0002) (`opt` lands in random_shift: truthy); the engine keeps
+        # `patch_sampler.iterations = self.it` up to date (:185), so min_scale anneals 0.8 -> 0.25 as exp(-it * 2e-4)
+        self.patch_sampler = FlexPatchSampler(random_shift=True, random_scale=True, min_scale=0.25, max_scale=1.0,
+                                              scale_anneal=0.0002)
         if n_train_images is not None:      # the reference attaches these in Model.build_networks (:56-59)
             self.latent_vars_trans = torch.nn.Embedding(n_train_images, opt.nerf.N_latent_trans)
             torch.nn.init.normal_(self.latent_vars_trans.weight)
@@ -60,10 +63,13 @@ class Graph(torch.nn.Module):
         return var
 
     def compute_loss(self, opt, var, mode=None, train_step="nerf"):
-        """Ray-wise terms of model/nerf_adapt_st_gan.py:712-763 (render / uncert / trans_reg) fused with the patch gather and
-        their backward seeds (csrc/loss.cu).  `loss.all` (Model.summarize_loss, model/base.py:145-157) is computed in the same
-        pass; backpropagate it.  The VGG / Lab / GAN terms need the engine's pretrained nets and stay with it (they read
-        var.image_sample / var.mask_sample, which are filled here as in the reference)."""
+        """Ray-wise terms of model/nerf_adapt_st_gan.py:712-763 (render / uncert / trans_reg) fused with the patch gather
+        (csrc/loss.cu).  Returns the reference's dict -- one differentiable scalar per enabled term and NO `all` key, so an
+        unmodified Model.summarize_loss (model/base.py:145-157, which asserts "all" not in loss) accepts it; the backward forms
+        the seeds on the device from whatever upstream gradients arrive.  The weighted sum the same pass already computed is
+        left in `var.loss_all_fused` for texpose_b200.model.base.summarize_loss (no extra launches, no host sync).  The
+        VGG / Lab / GAN terms need the engine's pretrained nets and stay with it (they read var.image_sample /
+        var.mask_sample, which are filled here as in the reference)."""
         if train_step != "nerf":
             raise NotImplementedError("discriminator losses stay with the engine (out of the hot path, SURVEY.md 8)")
         lw = opt.loss_weight
@@ -91,7 +97,7 @@ class Graph(torch.nn.Module):
         for i, k in enumerate(("render", "uncert", "trans_reg")):
             if weights[i] is not None:
                 loss[k] = losses[i]
-        loss["all"] = losses[3]
+        var.loss_all_fused = losses[3]
         return loss
 
     # ---------------------------------------------------------------- reference interface
@@ -153,10 +159,17 @@ class Graph(torch.nn.Module):
             if opt.render.transient == "zero":
                 lat_trans = torch.zeros(B, opt.nerf.N_latent_trans, device=ray.device)
             elif opt.render.transient == "sample":
-                lat_trans = self.latent_vars_trans.weight[sample_idx][None]
+                lat_trans = self.latent_vars_trans.weight[sample_idx].reshape(-1, opt.nerf.N_latent_trans)
             else:
                 raise NotImplementedError
-            lat_light = self.latent_vars_light.weight[sample_idx][None]
+            lat_light = self.latent_vars_light.weight[sample_idx].reshape(-1, opt.nerf.N_latent_light)
+        # the kernels index the latents by image: a single row is broadcast to every view of the batch, as the
+        # reference's `.expand(B, ...)` does (layers/nerf_static_transient_light.py:113,127)
+        if lat_trans.shape[0] != B or lat_light.shape[0] != B:
+            if lat_trans.shape[0] not in (1, B) or lat_light.shape[0] not in (1, B):
+                raise ValueError(f"latents must have 1 or {B} rows, got {lat_trans.shape[0]} / {lat_light.shape[0]}")
+            lat_trans = lat_trans.expand(B, -1).contiguous()
+            lat_light = lat_light.expand(B, -1).contiguous()
 
         rgb_samples, density_samples, uncert_samples = self.nerf.forward_samples(
             opt, center=center, ray=ray, depth_samples=depth_samples, latent_variable_trans=lat_trans,

@@ -276,23 +276,29 @@ class PatchLoss(torch.autograd.Function):
         img_s = torch.empty(B, 3, h, w, device=dev)
         mask_s = torch.empty(B, 1, h, w, device=dev)
         losses = torch.empty(4, device=dev)
-        g_rgb, g_unc = torch.empty_like(rgb_c), torch.empty_like(unc_c)
-        g_den = torch.empty_like(den_c) if (den_c is not None and density.requires_grad) else None
         ws = torch.empty(_C.load().tp_patch_loss_workspace(), device=dev)
         _C.call("tp_patch_loss", _p(_f32(image)), _p(_f32(obj_mask)), _p(_f32(coords)), B, R, H, W, _p(rgb_c), _p(unc_c),
-                _p(den_c), N, lin[0], lin[1], lin[2], terms, _p(img_s), _p(mask_s), _p(losses), _p(g_rgb), _p(g_unc),
-                _p(g_den), _p(ws), ws.numel(), _stream())
-        ctx.seeds = (g_rgb, g_unc, g_den)
+                _p(den_c), N, lin[0], lin[1], lin[2], terms, _p(img_s), _p(mask_s), _p(losses), None, None, None, _p(ws),
+                ws.numel(), _stream())
+        ctx.saved = (rgb_c, unc_c, img_s, mask_s, ws)
+        ctx.meta = (B, R, N, lin, terms, den_c is not None and density.requires_grad, den_c.shape if den_c is not None else None)
         ctx.mark_non_differentiable(img_s, mask_s)
         return losses, img_s, mask_s
 
     @staticmethod
     def backward(ctx, g_losses, _gi, _gm):
-        g_rgb, g_unc, g_den = ctx.seeds
-        ctx.seeds = None
-        # the seeds are d(all)/d(.): exact when the caller backpropagates losses[3] (Model.summarize_loss' `all`)
-        s = g_losses[3]
-        return g_rgb * s, g_unc * s, (g_den * s if g_den is not None else None), None, None, None, None
+        """All four scalars are differentiable: the seeds are formed on the device from the upstream gradient vector, so
+        `losses[3].backward()`, the reference's `summarize_loss(...).all.backward()` and any re-weighting of the individual
+        terms give the right gradients (no host sync)."""
+        rgb_c, unc_c, img_s, mask_s, ws = ctx.saved
+        ctx.saved = None
+        B, R, N, lin, terms, want_den, den_shape = ctx.meta
+        g = _f32(g_losses)
+        g_rgb, g_unc = torch.empty_like(rgb_c), torch.empty_like(unc_c)
+        g_den = torch.empty(den_shape, device=rgb_c.device) if want_den else None
+        _C.call("tp_patch_loss_backward", _p(g), _p(img_s), _p(mask_s), B, R, _p(rgb_c), _p(unc_c), N, lin[0], lin[1], lin[2],
+                terms, _p(g_rgb), _p(g_unc), _p(g_den), _p(ws), ws.numel(), _stream())
+        return g_rgb, g_unc, g_den, None, None, None, None
 
 
 # ------------------------------------------------------------------------------------------------- fp32 MLP layers
