@@ -294,7 +294,7 @@ def run_ours(args, rank, world, local_rank):
     orig_call = _C.call
 
     def timing_call(name, *a):
-        if name == "tp_tc_nerf_stl_forward":
+        if name in ("tp_tc_nerf_stl_forward", "tp_render_fused_forward"):
             a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a0.record()
             orig_call(name, *a)

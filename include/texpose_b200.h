@@ -167,12 +167,10 @@ int64_t tp_tc_scratch_bytes(void);
 
 /* Packs fp32 nn.Linear weights (and the static biases, which ride on a constant-1 input column) into the bf16 SMEM
  * images of the chunks.  chunk_desc: DEVICE int64 [n_chunks,10] rows {W device pointer (0 = none), ld, row0, rows_valid,
- * col0, cols_valid, n_layout (256|16), bias device pointer (0 = none), bias k-column, 0}; packed: n_chunks*chunk_bytes. */
+ * col0, cols_valid, n_layout (256|16), bias device pointer (0 = none), bias k-column, transpose}; packed: n_chunks*chunk_bytes.
+ * n_layout 16 (the output stages, <= 8 rows): rows 0..7 of the chunk hold bf16(W), rows 8..15 bf16(W - bf16(W)); the kernel
+ * adds the two accumulator columns, so the output layers see their weights to ~16 mantissa bits. */
 int tp_tc_pack_weights(const int64_t* chunk_desc, int n_chunks, void* packed, void* stream);
-
-/* Re-orders a tp_tc_pack_weights image for the CTA-pair kernel (tp_tc_nerf_stl_forward flags bit 10: tcgen05 cta_group::2 over
- * clusters of two CTAs, each SM holding half of every weight chunk): rank r's half of chunk c at c*16 KB + r*8 KB. */
-int tp_tc_pair_weights(const void* packed, void* pair_packed, void* stream);
 
 /* out[b,:] = bias + W[:, col0:col0+ncols] latent[b]   (per-image constants folded into a bias; fp32) */
 int tp_tc_image_bias(const float* W, int64_t ldw, int col0, int ncols, const float* bias, const float* latent, int B,
@@ -191,12 +189,37 @@ int tp_tc_ray_bias(const float* ray, int64_t R, int64_t rays_per_image, int L_vi
  * static-only rendering (inference launch only): the stage list stops after the rgb head, so the launch does 78 % of the work;
  * rgb[:, :, 1], density[:, 1] and uncert are written as zeros -- for callers that use only the static outputs (rgb_static /
  * depth / opacity_static of Model.evaluate_full, model/nerf_adapt_st_gan.py:341-362) and for the plain layers/nerf.py model;
- * the other bits select measured kernel variants / timing experiments. */
+ * bit 1 = 16 epilogue warps instead of 8, bits 5-6 = tile skew + 1 (A/B switches). */
 int tp_tc_nerf_stl_forward(const float* center, const float* ray, const float* depth, int64_t S, int N,
                            int64_t per_image, const void* packed, const float* biasbuf, const float* raybias,
                            const float* imgbias, float* rgb, float* density, float* uncert, void* scratch,
                            int64_t scratch_bytes, void* save, int dbg_layer, float* dbg_out, int flags, void* stream);
 int64_t tp_tc_save_bytes(int64_t S);
+
+/* Graph.render after ray selection (model/nerf_adapt_st_gan.py:565-631: get_center_and_ray + ray_batch_sample, sample_depth,
+ * forward_samples, composite) as ONE launch of the fused kernel, for inference (no gradient).  Per ray the kernel reads its
+ * pixel index (8 B, optional) and its bounds (8 B) and writes 56 B; no depth, point, bias-table, rgb-sample or uncertainty
+ * tensor exists in HBM.
+ *   kinv [B,9], pose_inv [B,12]: K^-1 and pose^-1 per view (the reference's own host-side inverses, camera.py:292-314);
+ *   ray_idx [B,R] int64 pixel indices (p = y*W + x), or NULL: ray r of every view is pixel ray0 + r (a row block of the frame);
+ *   z_near / z_far [B,H*W]: full-frame sample bounds, read at the ray's pixel (Graph.ray_batch_sample, :702-710);
+ *   N in {32, 64, 128} samples per ray; depth_mode 0 = injected jitter rand [B,R,N] (the reference's torch.rand draw),
+ *   1 = midpoints (sample_stratified false), 2 = in-kernel Philox keyed by seed (same stream as tp_sample_depth mode 2);
+ *   packed / biasbuf as for tp_tc_nerf_stl_forward; wview [3+6*L_view,256] = columns 256.. of mlp_rgb[0].weight transposed
+ *   (view-direction inputs, layers/nerf_static_transient_light.py:111-117); imgbias_rgb / imgbias_trans [B,256] from
+ *   tp_tc_image_bias (per-image latents folded into the layer-0 biases).
+ * Outputs (any may be NULL = not materialised): rgb, rgb_static, rgb_transient [B*R,3]; depth, opacity, opacity_static,
+ * opacity_transient, uncert [B*R] (uncert includes + min_uncert, layers/..light.py:207); alpha_static, alpha_transient [B*R*N];
+ * density [B*R*N,2].  Output pointers may address a peer GPU's memory (NVLink stores: the one-frame multi-GPU gather).
+ * flags: bit 17 = static only (transient terms zero).  scratch >= tp_tc_scratch_bytes(). */
+int tp_render_fused_forward(const float* kinv, const float* pose_inv, int B, int H, int W, float pix_offset,
+                            const int64_t* ray_idx, int64_t R, int64_t ray0, const float* z_near, const float* z_far, int N,
+                            int depth_mode, const float* rand, uint64_t seed, const void* packed, const float* biasbuf,
+                            const float* wview, int L_view, const float* imgbias_rgb, const float* imgbias_trans,
+                            float min_uncert, float* rgb, float* rgb_static, float* rgb_transient, float* depth,
+                            float* opacity, float* opacity_static, float* opacity_transient, float* uncert,
+                            float* alpha_static, float* alpha_transient, float* density, void* scratch,
+                            int64_t scratch_bytes, int flags, void* stream);
 /* One slot of the saved tile images -> row-major fp32 [S,256]. */
 int tp_tc_unpack_images(const void* images, int slot, int n_slots, int64_t S, float* out, void* stream);
 

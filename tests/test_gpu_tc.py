@@ -53,7 +53,7 @@ def test_c1_forward_render_bf16_vs_oracle():
     print("bf16 render max-abs errors:", {k: f"{v:.2e}" for k, v in errs.items()})
     for k in ("rgb", "rgb_static", "rgb_transient", "depth", "opacity", "opacity_static", "opacity_transient"):
         assert errs[k] <= TOL, (k, errs[k])
-    assert errs["uncert"] <= 2e-2, errs["uncert"]      # SURVEY probe: uncert is borderline (1.1e-2) with bf16 operands
+    assert errs["uncert"] <= TOL, errs["uncert"]       # (1.2e-2 before the output layers carried hi + lo weight rows)
     # per-sample head outputs: bounded quantities within 1e-2, raw densities within 2 % of their range
     assert (got_s[0].cpu() - ref_s[0]).abs().max() <= 2e-2
     assert (got_s[1].cpu() - ref_s[1]).abs().max() <= 0.02 * ref_s[1].abs().max()
@@ -130,11 +130,12 @@ def test_c3_shape_gradients_bf16():
         print(f"  {n:22s} |grad|max {mag:9.3e}  max-abs err {err:9.3e}  ({100 * err / max(mag, 1e-12):5.2f} % of max)")
         worst, gmax = max(worst, err), max(gmax, mag)
     print(f"bf16 fwd gradient max-abs error {worst:.2e} (largest gradient entry {gmax:.2e})")
-    # north_star: 1e-2 max-abs with the bf16 MLP path, for gradients of the reference's mean-normalised losses; the one
-    # tensor whose entries exceed 1 (mlp_trans.3.weight, the log-uncertainty term) is held to 1.5 % of its largest entry
+    # north_star: 1e-2 max-abs with the bf16 MLP path, for gradients of the reference's mean-normalised losses -- every tensor,
+    # no relative carve-out (the output layers carry their weights as bf16 hi + lo rows: the systematic rounding of those few
+    # rows was the dominant term for mlp_trans.3.weight, whose entries reach 1.86)
     for n, a, b in pairs:
-        err, mag = (a - b).abs().max().item(), b.abs().max().item()
-        assert err <= max(TOL, 0.015 * mag), (n, err, mag)
+        err = (a - b).abs().max().item()
+        assert err <= TOL, (n, err)
 
 
 @pytest.mark.parametrize("B,R,N", [(3, 50, 48), (2, 1200, 32), (16, 256, 128)])
@@ -197,33 +198,6 @@ def test_backward_falls_back_when_images_are_tiny():
         res[prec] = [lt.grad, ll.grad] + [p.grad for p in list(m.mlp_rgb.parameters()) + list(m.mlp_trans.parameters())]
     for a, b in zip(res["bf16"], res["fp32"]):
         assert (a - b).abs().max() <= max(1e-3, 0.02 * b.abs().max().item())
-
-
-@pytest.mark.timeout(120)
-@pytest.mark.parametrize("flags,name", [(128, "single-tile kernel"), (384, "single-tile kernel, 2-CTA cluster multicast"),
-                                        (1024, "CTA-pair kernel, tcgen05 cta_group::2")])
-def test_kernel_variants_are_bit_identical(flags, name):
-    """The experimental forward kernels behind `flags` (kept as measured alternatives, DESIGN.md 4 / profiles r01b 5) must
-    reproduce the default kernel bit for bit: same MMA shapes per row, same K order, same epilogue arithmetic.  Ragged sizes:
-    an odd number of 128-sample tiles and a partial last tile (the pair kernel then runs a dead super-tile in one CTA)."""
-    from texpose_b200 import mlp_tc
-    from texpose_b200.layers import _common
-    opt, m = _module("bf16")
-    for R, N in ((37, 128), (301, 48)):
-        g = torch.Generator().manual_seed(4)
-        center = (torch.randn(1, R, 3, generator=g) * 0.02 + torch.tensor([0.3, 0.2, -0.8])).to(DEV)
-        ray = (torch.randn(1, R, 3, generator=g) * 0.1 + torch.tensor([0.0, 0.0, 1.0])).to(DEV)
-        depth = ((torch.rand(1, R, N, 1, generator=g) + torch.arange(N)[None, None, :, None]) / N * 1.2 + 0.2).to(DEV)
-        lt, ll = [t.to(DEV) for t in synth.latents(1)]
-        cfg = m._config(opt, "val")
-        geom = _common.ray_geometry(cfg, center, ray, depth)
-        pairs = lambda ml: [(l.weight.detach(), l.bias.detach()) for l in ml]
-        args = (cfg, geom, lt, ll, pairs(m.mlp_feat), pairs(m.mlp_rgb), pairs(m.mlp_trans))
-        ref = mlp_tc.forward(*args, flags=0)
-        got = mlp_tc.forward(*args, flags=flags)
-        torch.cuda.synchronize()
-        for a, b in zip(ref, got):
-            assert torch.equal(a, b), (name, R, N)
 
 
 @pytest.mark.parametrize("layers_rgb", [[None, 128, 3], [None, 256, 256, 256, 3], [None, 192, 96, 3]])

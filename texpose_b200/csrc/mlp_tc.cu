@@ -14,11 +14,17 @@
 //   * 8 epilogue warps (one TMEM lane quarter each, 4 per tile): tcgen05.ld -> +bias -> ReLU -> bf16 ->
 //     st.shared straight into the K-major core-matrix layout the next stage's A descriptor reads;
 //   * per-ray constants (view-direction encoding, light latent) and per-image constants (transient latent)
-//     are folded into bias tables by two tiny fp32 pre-kernels, so they cost no MMA work per sample;
+//     are folded into fp32 biases, so they cost no MMA work per sample: per-image rows by a tiny pre-kernel, the per-ray
+//     row by a pre-kernel table (per-sample launches) or by the tile's own warps (render launch);
+//   * render launch (tp_render_fused_forward, Graph.render model/nerf_adapt_st_gan.py:565-631 as ONE kernel): the tile's
+//     rows generate their ray from the pixel index, their sample depth from the ray's bounds (midpoint / injected rand /
+//     Philox), and the last stage's epilogue composites the tile's rays (row = sample: warp scan + cross-warp carry) --
+//     no depth, bias-table, rgb or uncertainty tensor ever exists in HBM; per ray 8 B in, 56 B out (+ 16 B per sample for
+//     the API's alpha / density tensors);
 //   * the trunk feature (needed by both heads) is parked in an L2-resident scratch with a bulk store after
 //     the last trunk layer and bulk-loaded back before the transient head.
 //
-// SMEM (bytes): A0 64K | A1 64K | E0 16K | E1 16K | ring 4x16K | barriers = 229 504 (<= 227 KB opt-in).
+// SMEM (bytes): A0 64K | A1 64K | E0 16K | E1 16K | ring 4x16K | barriers 128 | compositing scratch 1 088 = 230 592 (<= 227 KB).
 // TMEM: 512 columns = two 128x256 fp32 accumulators.
 //
 // Operand layout (no swizzle, K-major "interleave" canonical layout): element (row r, col k) of a tile with
@@ -36,18 +42,198 @@ template <int kHalves> constexpr int num_threads() { return (8 * kHalves + 2) * 
 constexpr int kStages = 4;
 constexpr uint32_t kOffA = 0, kOffE = 2 * kABytes, kOffRing = kOffE + 2 * kEBytes;
 constexpr uint32_t kOffBar = kOffRing + kStages * kChunkBytes;
-constexpr uint32_t kSmemBytes = kOffBar + 128;
+// compositing scratch of the render launch: [parity 2][tile 2][ warp totals 4 x 3 | warp partial sums 4 x 14 ] floats
+constexpr int kCompFloats = 4 * 3 + 4 * 14;
+constexpr uint32_t kOffComp = kOffBar + 128;
+constexpr uint32_t kSmemBytes = kOffComp + 2 * 2 * kCompFloats * 4;
+static_assert(kSmemBytes <= 232448, "227 KB of shared memory per CTA");
+constexpr unsigned kFullMask = 0xffffffffu;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_scan(float v, int lane) {      // inclusive
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float n = __shfl_up_sync(kFullMask, v, o);
+    if (lane >= o) v += n;
+  }
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------ fused render pieces (mode 3)
+// One sample of the render launch: its ray is generated from the pixel index (camera.py:292-314, same arithmetic as
+// tp_raygen), its depth from the ray's bounds (model/nerf_adapt_st_gan.py:682-700, same arithmetic and Philox stream as
+// tp_sample_depth), the interval to the next sample of the ray for the compositing, and its encoding goes into the E tile.
+struct RenderSample {
+  long long ray;      // ray index within the launch (clamped to the last ray for dead rows)
+  int k;              // sample index within the ray
+  int img;            // view
+  float d, dist;      // depth, (d_{k+1} - d_k) * |ray|  (1e10 * |ray| for the last sample: layers/..light.py:169-175)
+  float dir[3];
+  bool live;
+};
+
+__device__ __forceinline__ float render_jitter(const Params& p, long long s) {
+  if (p.depth_mode == 0) return p.rand[s];
+  if (p.depth_mode == 1) return 0.5f;
+  const long long qd = s >> 2;
+  const uint4 x = tp_philox((uint32_t)qd, (uint32_t)(qd >> 32), (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+  const int e = (int)(s & 3);
+  return tp_u01(e == 0 ? x.x : e == 1 ? x.y : e == 2 ? x.z : x.w);
+}
+
+__device__ __forceinline__ RenderSample render_encode(const Params& p, long long tile, int row, int lane, uint32_t e_smem) {
+  RenderSample o;
+  const int N = p.N;                                      // divides 128: a tile holds 128 / N whole rays
+  o.k = row % N;
+  const long long n_rays = p.S / N, ray_raw = tile * (128 / N) + row / N;
+  o.live = ray_raw < n_rays;
+  o.ray = o.live ? ray_raw : n_rays - 1;
+  const long long s = o.ray * N + o.k;
+  const long long b = o.ray / p.R;
+  o.img = (int)b;
+  const long long pix = p.ray_idx ? p.ray_idx[o.ray] : p.ray0 + (o.ray - b * p.R);
+  float c[3];
+  unproject(p.kinv + b * 9, p.pinv + b * 12, __fadd_rn((float)(pix % p.W), p.pix_offset),
+            __fadd_rn((float)(pix / p.W), p.pix_offset), c, o.dir);
+  const long long zi = b * (long long)p.H * p.W + pix;
+  const float lo = p.z_near[zi], hi = p.z_far[zi];
+  const float u0 = render_jitter(p, s);
+  float u1 = __shfl_down_sync(kFullMask, u0, 1);           // the next sample of the ray sits in the next lane ...
+  if (lane == 31 && o.k + 1 < N) u1 = render_jitter(p, s + 1);      // ... or in the next warp
+  const float fn = (float)N;
+  o.d = stratified_depth(u0, o.k, fn, lo, hi);
+  const float dn = stratified_depth(u1, o.k + 1, fn, lo, hi);
+  const float len = sqrtf(o.dir[0] * o.dir[0] + o.dir[1] * o.dir[1] + o.dir[2] * o.dir[2]);
+  o.dist = __fmul_rn(o.k + 1 < N ? __fsub_rn(dn, o.d) : 1e10f, len);
+  encode_point(c, o.dir, o.d, e_smem, row);
+  return o;
+}
+
+// rgb-0 bias row of the warp's ray: imgbias_rgb[view] + W_view [u, enc(u)], u = ray / |ray| (layers/..light.py:104-117,155-157),
+// in the distributed layout hidden_epilogue_wbias reads (lane l: columns 4l..4l+3 and 128+4l..).  Same operation order as
+// tp_tc_ray_bias, whose 315 MB table this replaces: lane j holds element j of the 3+6L encoding, 27 shuffles feed 8 fma chains.
+__device__ __forceinline__ void render_view_bias(const Params& p, const RenderSample& rs, int lane, float4 (&wb)[2]) {
+  const float len = fmaxf(sqrtf(rs.dir[0] * rs.dir[0] + rs.dir[1] * rs.dir[1] + rs.dir[2] * rs.dir[2]), 1e-12f);
+  const int L = p.L_view, vc = 3 + 6 * L;
+  float e = 0.f;
+  if (lane < vc) {
+    const int jj = lane - 3, cc = lane < 3 ? lane : jj / (2 * L);
+    const float uc = (cc == 0 ? rs.dir[0] : cc == 1 ? rs.dir[1] : rs.dir[2]) / len;
+    e = uc;
+    if (lane >= 3) {
+      const int rem = jj - cc * 2 * L, k = rem < L ? rem : rem - L;
+      const float arg = __fmul_rn(uc, ldexpf(3.14159265358979323846f, k));
+      e = rem < L ? sinf(arg) : cosf(arg);
+    }
+  }
+  const float* brow = p.imgbias_rgb + (long long)rs.img * 256;
+  float4 a0 = __ldg(reinterpret_cast<const float4*>(brow) + lane), a1 = __ldg(reinterpret_cast<const float4*>(brow + 128) + lane);
+#pragma unroll
+  for (int j = 0; j < 27; ++j) {
+    if (j < vc) {
+      const float ej = __shfl_sync(kFullMask, e, j);
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.wview + j * 256) + lane);
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.wview + j * 256 + 128) + lane);
+      a0.x = fmaf(w0.x, ej, a0.x); a0.y = fmaf(w0.y, ej, a0.y); a0.z = fmaf(w0.z, ej, a0.z); a0.w = fmaf(w0.w, ej, a0.w);
+      a1.x = fmaf(w1.x, ej, a1.x); a1.y = fmaf(w1.y, ej, a1.y); a1.z = fmaf(w1.z, ej, a1.z); a1.w = fmaf(w1.w, ej, a1.w);
+    }
+  }
+  wb[0] = a0;
+  wb[1] = a1;
+}
+
+// Compositing of the tile's rays as the epilogue of the last stage (layers/nerf_static_transient_light.py:168-212, SURVEY
+// appendix C; arithmetic of csrc/composite.cu): row = sample, so the three exclusive cumulative sums are a warp scan plus the
+// totals of the ray's earlier warps (N / 32 warps per ray, exchanged through `sc`), and the 14 per-ray sums a warp reduction
+// plus the same exchange.  Per sample it writes alpha_static, alpha_transient and density (16 B), per ray 14 floats.
+__device__ __forceinline__ void render_composite(const Params& p, float* sc, int t, int q, int lane, const RenderSample& rs,
+                                                 float sig_s, float sig_t, const float (&cs)[3], const float (&ct)[3], float u) {
+  float* tot = sc;             // [4 warps][3]
+  float* red = sc + 12;        // [4 warps][14]
+  const float sd_s = __fmul_rn(sig_s, rs.dist), sd_t = __fmul_rn(sig_t, rs.dist), sd = __fadd_rn(sd_s, sd_t);
+  const float in_j = warp_scan(sd, lane), in_s = warp_scan(sd_s, lane), in_t = warp_scan(sd_t, lane);
+  if (lane == 31) {
+    tot[q * 3] = in_j;
+    tot[q * 3 + 1] = in_s;
+    tot[q * 3 + 2] = in_t;
+  }
+  const float pj = __shfl_up_sync(kFullMask, in_j, 1), ps_ = __shfl_up_sync(kFullMask, in_s, 1), pt_ = __shfl_up_sync(kFullMask, in_t, 1);
+  named_bar_sync(1 + t, 128);
+  const int wpr = p.N >> 5, q0 = q & ~(wpr - 1);      // warps per ray (1, 2, 4), first warp of this ray
+  float ex_j = lane ? pj : 0.f, ex_s = lane ? ps_ : 0.f, ex_t = lane ? pt_ : 0.f;
+  {
+    float cj = 0.f, c_s = 0.f, c_t = 0.f;
+    for (int w = q0; w < q; ++w) {
+      cj += tot[w * 3];
+      c_s += tot[w * 3 + 1];
+      c_t += tot[w * 3 + 2];
+    }
+    ex_j += cj;
+    ex_s += c_s;
+    ex_t += c_t;
+  }
+  const float Es = expf(-sd_s), Et = expf(-sd_t), E = expf(-sd);
+  const float T = expf(-ex_j), Ts = expf(-ex_s), Tt = expf(-ex_t);
+  const float as = 1.f - Es, at = 1.f - Et, a = 1.f - E;
+  const float w_ps = T * as, w_pt = T * at, w_p = T * a, w_qs = Ts * as, w_qt = Tt * at;
+  float acc[14];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    acc[c] = cs[c] * w_ps + ct[c] * w_pt;
+    acc[3 + c] = w_qs * cs[c];
+    acc[6 + c] = w_qt * ct[c];
+  }
+  acc[9] = rs.d * w_qs;
+  acc[10] = w_p;
+  acc[11] = w_qs;
+  acc[12] = w_qt;
+  acc[13] = u * w_pt;
+#pragma unroll
+  for (int i = 0; i < 14; ++i) acc[i] = warp_sum(acc[i]);
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < 14; ++i) red[q * 14 + i] = acc[i];
+  }
+  if (rs.live) {
+    const long long s = rs.ray * p.N + rs.k;
+    if (p.o_as) __stcs(p.o_as + s, as);
+    if (p.o_at) __stcs(p.o_at + s, at);
+    if (p.density) __stcs(reinterpret_cast<float2*>(p.density) + s, make_float2(sig_s, sig_t));
+  }
+  named_bar_sync(1 + t, 128);
+  if (q == q0 && lane < 14 && rs.live) {
+    float v = 0.f;
+    for (int w = q0; w < q0 + wpr; ++w) v += red[w * 14 + lane];
+    const long long r = rs.ray;
+    float* dst = lane < 3 ? (p.o_rgb ? p.o_rgb + r * 3 + lane : nullptr)
+               : lane < 6 ? (p.o_rgb_s ? p.o_rgb_s + r * 3 + lane - 3 : nullptr)
+               : lane < 9 ? (p.o_rgb_t ? p.o_rgb_t + r * 3 + lane - 6 : nullptr)
+               : lane == 9 ? (p.o_depth ? p.o_depth + r : nullptr)
+               : lane == 10 ? (p.o_op ? p.o_op + r : nullptr)
+               : lane == 11 ? (p.o_op_s ? p.o_op_s + r : nullptr)
+               : lane == 12 ? (p.o_op_t ? p.o_op_t + r : nullptr)
+                            : (p.o_unc ? p.o_unc + r : nullptr);
+    if (lane == 13) v += p.min_uncert;
+    if (dst) *dst = v;
+  }
+}
+
 // kNL: number of stages run (kNumLayers = all; kStaticLayers = static-only rendering).  A template parameter, not a field of
 // Params: a run-time stage count costs 0.3 ms per C2 frame (same-box A/B).
-// kMode: 0 = general (debug taps, timing experiments, any tile skew); 1 = the plain inference launch (no activation save);
-// 2 = the plain training launch (activation save + ReLU bitmasks).  Modes 1 and 2 have every debug branch compiled out and the
-// default tile skew as a constant: the same code with those decisions left to run time is 6 % slower (same-box A/B).
+// kMode: 0 = general (debug tap, any tile skew, any N); 1 = the plain inference launch (per-sample outputs, no activation save);
+// 2 = the plain training launch (activation save + ReLU bitmasks); 3 = the fused render launch (rays, depths, view bias and
+// compositing in-kernel; per-ray outputs).  Modes 1-3 have every debug branch compiled out and the default tile skew as a
+// constant: the same code with those decisions left to run time is 6 % slower (same-box A/B).
 template <int kHalves, int kNL = kNumLayers, int kMode = 0>
 __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_kernel(const Params p) {
+  constexpr bool kRender = kMode == 3;
+  static_assert(!kRender || kHalves == 1, "the render launch uses the 8-warp drain");
   const int p_skew = kMode ? 1 : p.skew;
-  const int p_dbg_drain = kMode ? 0 : p.dbg_drain;
-  const int p_dbg_save = kMode ? 0 : p.dbg_save;
-  uint8_t* const p_save = kMode == 1 ? nullptr : p.save;
+  uint8_t* const p_save = (kMode == 1 || kRender) ? nullptr : p.save;
   constexpr int kEpiWarps = 8 * kHalves, kProducerWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
   constexpr int kTileThreads = 128 * kHalves;     // epilogue threads working on one tile
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -191,30 +377,40 @@ __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_ke
     uint32_t acc_ph = 0;
     // all 32 rows of a warp share the ray (and image) when N is a multiple of 32; tail rows are clamped to the last
     // sample, which then belongs to the same ray as the warp's live rows
-    const bool warp_bias = kMode ? true : (p.N % 32 == 0) && !(p_dbg_drain & 4);      // modes 1 / 2 are launched only when N % 32 == 0
+    const bool warp_bias = kMode ? true : (p.N % 32 == 0);      // modes 1-3 are launched only when N % 32 == 0
     bool store_pending = false;      // a bulk store of A_t (feature park / activation save) may still be reading it
-    for (long long st = blockIdx.x; st < n_super; st += gridDim.x) {
+    RenderSample rs = {};            // render launch: the sample this row holds
+    int iter = 0;
+    for (long long st = blockIdx.x; st < n_super; st += gridDim.x, ++iter) {
       const long long s_raw = (st * 2 + t) * 128 + row;
       const bool live = s_raw < p.S;
       const long long s = live ? s_raw : p.S - 1;
-      if (half == 0) encode_sample(p, s, e_smem, row);
-      fence_proxy_async_smem();
-      tc_fence_before();
-      __syncwarp();                    // every lane's st.shared + proxy fence precede the warp's single arrive
-      if (lane == 0) mbar_arrive(bar_ready(t));
+      if (!kRender || iter == 0) {     // (the render launch encodes the next super-tile at the end of the last stage, below)
+        if (kRender) rs = render_encode(p, st * 2 + t, row, lane, e_smem);
+        else if (half == 0) encode_sample(p, s, e_smem, row);
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();                    // every lane's st.shared + proxy fence precede the warp's single arrive
+        if (lane == 0) mbar_arrive(bar_ready(t));
+      }
 
       float sigma_s = 0.f, rgb_s[3] = {0.f, 0.f, 0.f};
       for (int L = 0; L < kNL; ++L) {
         const Layer ly = kLayers[L];
         // table biases (per ray / per image): when every row of this warp shares the bias row, each lane fetches its
-        // float4 slice(s) now -- the L2 latency hides behind the MMAs of this stage
+        // float4 slice(s) now -- the L2 latency hides behind the MMAs of this stage.  The render launch computes the per-ray
+        // row here instead of reading a table.
         float4 wb[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
         const bool table_bias = ly.epi == EPI_HIDDEN && ly.bias_kind != BIAS_MMA;
         if (table_bias && warp_bias) {
-          const float* brow = (ly.bias_kind == BIAS_RAY ? p.raybias + (s / p.N) * 256 : p.imgbias + (s / p.per_image) * 256) +
-                              half * kCols;
-          wb[0] = __ldg(reinterpret_cast<const float4*>(brow) + lane);
-          if (kCols == 256) wb[1] = __ldg(reinterpret_cast<const float4*>(brow + 128) + lane);
+          if (kRender && ly.bias_kind == BIAS_RAY) {
+            render_view_bias(p, rs, lane, wb);
+          } else {
+            const long long img = kRender ? (long long)rs.img : s / p.per_image;
+            const float* brow = (ly.bias_kind == BIAS_RAY ? p.raybias + (s / p.N) * 256 : p.imgbias + img * 256) + half * kCols;
+            wb[0] = __ldg(reinterpret_cast<const float4*>(brow) + lane);
+            if (kCols == 256) wb[1] = __ldg(reinterpret_cast<const float4*>(brow + 128) + lane);
+          }
         }
         mbar_wait(bar_acc(t), acc_ph);
         acc_ph ^= 1;
@@ -240,13 +436,11 @@ __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_ke
             // planes [8][128 rows]: plane = 32-column slab, so a warp's store of one slab is 128 contiguous bytes), and the
             // activations go straight from the registers to their saved tile image (the backward's operands): a warp's
             // 16-byte groups cover 512 contiguous bytes and nothing re-reads the A tile
-            const int mslot = (p_dbg_save & 2) ? -1 : kMaskBitSlot[L];
+            const int mslot = kMaskBitSlot[L];
             uint32_t* words = mslot < 0 ? nullptr
                                         : reinterpret_cast<uint32_t*>(p.bits + ((size_t)(st * 2 + t) * 4 + mslot) * kMaskBitBytes) +
                                               half * (kCols / 32) * 128 + row;
-            uint8_t* g_row = (p_dbg_save & 1) ? nullptr
-                                              : p_save + ((size_t)(st * 2 + t) * kSaveSlots + kSaveSlot[L]) * kABytes +
-                                                    half * (kCols / 8) * 2048 + row * 16;
+            uint8_t* g_row = p_save + ((size_t)(st * 2 + t) * kSaveSlots + kSaveSlot[L]) * kABytes + half * (kCols / 8) * 2048 + row * 16;
             if (ly.bias_kind == BIAS_MMA) {
               hidden_epilogue<false, kCols / 32, true>(tmem_d, nullptr, a_row, dbg_row, words, g_row);
             } else if (warp_bias) {
@@ -256,9 +450,7 @@ __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_ke
                                   half * kCols;
               hidden_epilogue<true, kCols / 32, true>(tmem_d, bias, a_row, dbg_row, words, g_row);
             }
-          } else if (p_dbg_drain == 1 || p_dbg_drain == 2) {
-            hidden_epilogue_experiment<kCols / 32>(tmem_d, a_row, p_dbg_drain);
-          } else if (ly.bias_kind == BIAS_MMA || p_dbg_drain == 3) {   // 3: timing experiment, bias tables ignored
+          } else if (ly.bias_kind == BIAS_MMA) {
             hidden_epilogue<false, kCols / 32>(tmem_d, nullptr, a_row, dbg_row);
           } else if (warp_bias) {
             hidden_epilogue_wbias<kCols / 32>(tmem_d, wb, a_row, dbg_row);
@@ -280,31 +472,41 @@ __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_ke
             store_pending = true;
           }
         } else if (half == 0) {
-          uint32_t v[8];
-          TP_TMEM_LD8(tmem_row, v);
-          TP_TMEM_WAIT8(v);
+          // N=16 output stage: columns 0..7 = x . bf16(W rows), columns 8..15 = x . bf16(W - bf16(W)) of the same rows
+          uint32_t v[16];
+          TP_TMEM_LD16(tmem_row, v);
+          TP_TMEM_WAIT16(v);
           const float* sb = p.biasbuf + kSmallBiasOffset;
+          auto out = [&](int c) { return __uint_as_float(v[c]) + __uint_as_float(v[c + 8]); };
+          float rgb_t[3] = {0.f, 0.f, 0.f}, sigma_t = 0.f, unc = 0.f;
           if (ly.epi == EPI_DENSITY) {
-            sigma_s = tp_softplus(__uint_as_float(v[0]) + sb[0]);
+            sigma_s = tp_softplus(out(0) + sb[0]);
           } else if (ly.epi == EPI_RGB_OUT) {
 #pragma unroll
-            for (int c = 0; c < 3; ++c) rgb_s[c] = tp_sigmoid(__uint_as_float(v[c]) + sb[1 + c]);
-            if (kNL == kStaticLayers && live) {      // static only: this is the last stage; transient outputs are zeros
-#pragma unroll
-              for (int c = 0; c < 3; ++c) *reinterpret_cast<float2*>(p.rgb + s * 6 + c * 2) = make_float2(rgb_s[c], 0.f);
-              *reinterpret_cast<float2*>(p.density + s * 2) = make_float2(sigma_s, 0.f);
-              p.uncert[s] = 0.f;
-            }
+            for (int c = 0; c < 3; ++c) rgb_s[c] = tp_sigmoid(out(c) + sb[1 + c]);
           } else {
-            float rgb_t[3];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) rgb_t[c] = tp_sigmoid(__uint_as_float(v[c]) + sb[4 + c]);
-            const float sigma_t = tp_softplus(__uint_as_float(v[3]) + sb[7]);
-            const float unc = tp_softplus(__uint_as_float(v[4]) + sb[8]);
-            if (live) {
+            for (int c = 0; c < 3; ++c) rgb_t[c] = tp_sigmoid(out(c) + sb[4 + c]);
+            sigma_t = tp_softplus(out(3) + sb[7]);
+            unc = tp_softplus(out(4) + sb[8]);
+          }
+          if (L == kNL - 1) {      // last stage (static only: the rgb output; the transient values stay zero)
+            if (kRender) {
+              // hand the tile on first: the next super-tile's samples are encoded and its first MMAs released before this
+              // one is composited, so the compositing overlaps tensor work instead of leaving the pipe idle
+              const RenderSample cur = rs;
+              if (st + gridDim.x < n_super) {
+                rs = render_encode(p, (st + gridDim.x) * 2 + t, row, lane, e_smem);
+                fence_proxy_async_smem();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_ready(t));
+              }
+              float* sc = reinterpret_cast<float*>(smem + kOffComp) + ((iter & 1) * 2 + t) * kCompFloats;
+              render_composite(p, sc, t, q, lane, cur, sigma_s, sigma_t, rgb_s, rgb_t, unc);
+            } else if (live) {
 #pragma unroll
-              for (int c = 0; c < 3; ++c)
-                *reinterpret_cast<float2*>(p.rgb + s * 6 + c * 2) = make_float2(rgb_s[c], rgb_t[c]);
+              for (int c = 0; c < 3; ++c) *reinterpret_cast<float2*>(p.rgb + s * 6 + c * 2) = make_float2(rgb_s[c], rgb_t[c]);
               *reinterpret_cast<float2*>(p.density + s * 2) = make_float2(sigma_s, sigma_t);
               p.uncert[s] = unc;
             }
@@ -351,10 +553,15 @@ __global__ void pack_weights_kernel(const long long* __restrict__ desc, __nv_bfl
       n = (e >> 3) & 15;
       in_layout = e < 4096;
     }
+    // N=16 output chunks carry every weight row twice: rows 0..7 = bf16(W), rows 8..15 = bf16(W - bf16(W)) (the epilogue
+    // adds accumulator columns c and c + 8)
+    const bool lo_part = n_layout == 16 && n >= 8;
+    if (n_layout == 16) n &= 7;
     float v = 0.f;
     if (in_layout && W && n < rows_valid && kl < cols_valid)
       v = transpose ? W[(col0 + kl) * ld + row0 + n] : W[(row0 + n) * ld + col0 + kl];
     if (in_layout && bias && kl == bias_k && n < rows_valid) v = bias[n];
+    if (lo_part) v -= __bfloat162float(__float2bfloat16_rn(v));
     o[e] = __float2bfloat16_rn(v);
   }
 }
@@ -465,9 +672,6 @@ __global__ void unpack_images_kernel(const uint8_t* __restrict__ images, int slo
 
 }  // namespace tc
 
-int tp_tc_v2_launch(const tc::Params& p, int flags, cudaStream_t stream);   // mlp_tc_v2.cu
-int tp_tc_pair_launch(const tc::Params& p, cudaStream_t stream);            // mlp_tc_pair.cu
-
 TP_API int tp_tc_num_chunks(void) { return tc::kNumChunks; }
 TP_API int64_t tp_tc_chunk_bytes(void) { return tc::kChunkBytes; }
 TP_API int64_t tp_tc_scratch_bytes(void) { return (int64_t)tp_num_sms() * 2 * tc::kABytes; }
@@ -513,6 +717,13 @@ TP_API int tp_tc_ray_bias(const float* ray, int64_t R, int64_t rays_per_image, i
   return tp_launch_status();
 }
 
+static int tc_launch(void (*kern)(const tc::Params), const tc::Params& p, int grid, int threads, cudaStream_t stream) {
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes);
+  if (e != cudaSuccess) return (int)e;
+  kern<<<grid, threads, tc::kSmemBytes, stream>>>(p);
+  return tp_launch_status();
+}
+
 TP_API int tp_tc_nerf_stl_forward(const float* center, const float* ray, const float* depth, int64_t S, int N,
                                   int64_t per_image, const void* packed, const float* biasbuf, const float* raybias,
                                   const float* imgbias, float* rgb, float* density, float* uncert, void* scratch,
@@ -521,38 +732,31 @@ TP_API int tp_tc_nerf_stl_forward(const float* center, const float* ray, const f
     return TP_ERR_BAD_ARG;
   if (S < 0 || N < 1 || per_image < 1) return TP_ERR_BAD_SHAPE;
   if (((uintptr_t)packed & 15) || ((uintptr_t)scratch & 15) || ((uintptr_t)biasbuf & 15) || ((uintptr_t)raybias & 15) ||
-      ((uintptr_t)imgbias & 15) || ((uintptr_t)rgb & 7) || ((uintptr_t)density & 7))
+      ((uintptr_t)imgbias & 15) || ((uintptr_t)rgb & 7) || ((uintptr_t)density & 7) || ((uintptr_t)save & 15))
     return TP_ERR_ALIGN;
+  if (flags & ~((1 << 1) | (3 << 5) | (1 << 17))) return TP_ERR_BAD_ARG;
   if (!tp_device_is_sm100()) return TP_ERR_ARCH;
   if (S == 0) return TP_OK;
   const long long n_super = (S + 255) / 256;
   int grid = tp_num_sms();
   if (n_super < grid) grid = (int)n_super;
   if (scratch_bytes < (int64_t)grid * 2 * tc::kABytes) return TP_ERR_WORKSPACE;
-  tc::Params p;
+  tc::Params p = {};
   p.center = center; p.ray = ray; p.depth = depth; p.S = S; p.N = N; p.per_image = per_image;
   p.packed = reinterpret_cast<const uint8_t*>(packed); p.biasbuf = biasbuf; p.raybias = raybias; p.imgbias = imgbias;
   p.rgb = rgb; p.density = density; p.uncert = uncert; p.scratch = reinterpret_cast<uint8_t*>(scratch);
   p.save = reinterpret_cast<uint8_t*>(save);
-  if (((uintptr_t)save & 15)) return TP_ERR_ALIGN;
   p.bits = save ? p.save + ((S + 255) / 256) * 2 * tc::kSaveSlots * (size_t)tc::kABytes : nullptr;
-  if (save && (flags & 128)) return TP_ERR_BAD_ARG;           // the experimental kernel does not write the ReLU bitmasks
-  p.dbg_layer = dbg_layer; p.dbg_out = dbg_out; p.dbg_drain = (flags >> 2) & 7;
-  p.dbg_save = (flags >> 14) & 3;
+  p.dbg_layer = dbg_layer; p.dbg_out = dbg_out;
   p.n_layers = (flags & (1 << 17)) ? tc::kStaticLayers : tc::kNumLayers;      // flags bit 17: static-only rendering
-  if ((flags & (1 << 17)) && (save || (flags & (128 | 1024)))) return TP_ERR_BAD_ARG;      // inference launch of the default kernel only
+  if ((flags & (1 << 17)) && save) return TP_ERR_BAD_ARG;                     // inference launches only
   p.skew = ((flags >> 5) & 3) ? ((flags >> 5) & 3) - 1 : 1;      // default skew 1; flags bits 5-6 = skew+1 override (A/B)
-  if (flags & 128) return tp_tc_v2_launch(p, flags, (cudaStream_t)stream);   // experimental single-tile / cluster kernel
-  if (flags & 1024) {     // CTA-pair kernel (cta_group::2); `packed` must be the pair image; flags bits 11-13 = skew + 1 (default 4)
-    p.skew = ((flags >> 11) & 7) ? ((flags >> 11) & 7) - 1 : 4;
-    return tp_tc_pair_launch(p, (cudaStream_t)stream);
-  }
-  // drain width: 8 epilogue warps (256 accumulator columns per thread, 168 registers, 320 threads per CTA) by default -- same
-  // tensor-pipe time as 16 warps, but the narrower CTA draws less power and the capped clock settles higher: 2 % faster for
-  // the C2 frame, 1.7 % for the C3 training step (same-box A/B, profiles/r01f_summary.md section 9).  flags bit 1 selects 16 warps.
+  // drain width: 8 epilogue warps (256 accumulator columns per thread, 320 threads per CTA) by default -- same tensor-pipe
+  // time as 16 warps, but the narrower CTA draws less power and the capped clock settles higher: 2 % faster for the C2 frame,
+  // 1.7 % for the C3 training step (same-box A/B, profiles/r01f_summary.md section 9).  flags bit 1 selects 16 warps.
   const bool wide = (flags & 2) != 0;
   const bool stat = p.n_layers == tc::kStaticLayers;
-  const bool plain = dbg_layer < 0 && !dbg_out && p.dbg_drain == 0 && p.dbg_save == 0 && p.skew == 1 && N % 32 == 0;
+  const bool plain = dbg_layer < 0 && !dbg_out && p.skew == 1 && N % 32 == 0;
   void (*kern)(const tc::Params) =
       plain && !save && !wide ? (stat ? tc::nerf_stl_forward_kernel<1, tc::kStaticLayers, 1> : tc::nerf_stl_forward_kernel<1, tc::kNumLayers, 1>)
       : plain && !save        ? (stat ? tc::nerf_stl_forward_kernel<2, tc::kStaticLayers, 1> : tc::nerf_stl_forward_kernel<2, tc::kNumLayers, 1>)
@@ -560,8 +764,48 @@ TP_API int tp_tc_nerf_stl_forward(const float* center, const float* ray, const f
       : plain                 ? tc::nerf_stl_forward_kernel<1, tc::kNumLayers, 2>
       : wide ? (stat ? tc::nerf_stl_forward_kernel<2, tc::kStaticLayers> : tc::nerf_stl_forward_kernel<2, tc::kNumLayers>)
              : (stat ? tc::nerf_stl_forward_kernel<1, tc::kStaticLayers> : tc::nerf_stl_forward_kernel<1, tc::kNumLayers>);
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes);
-  if (e != cudaSuccess) return (int)e;
-  kern<<<grid, wide ? tc::num_threads<2>() : tc::num_threads<1>(), tc::kSmemBytes, (cudaStream_t)stream>>>(p);
-  return tp_launch_status();
+  return tc_launch(kern, p, grid, wide ? tc::num_threads<2>() : tc::num_threads<1>(), (cudaStream_t)stream);
+}
+
+// Graph.render after ray selection (model/nerf_adapt_st_gan.py:565-631) as ONE launch.
+TP_API int tp_render_fused_forward(const float* kinv, const float* pose_inv, int B, int H, int W, float pix_offset,
+                                   const int64_t* ray_idx, int64_t R, int64_t ray0, const float* z_near, const float* z_far,
+                                   int N, int depth_mode, const float* rand, uint64_t seed, const void* packed,
+                                   const float* biasbuf, const float* wview, int L_view, const float* imgbias_rgb,
+                                   const float* imgbias_trans, float min_uncert, float* rgb, float* rgb_static,
+                                   float* rgb_transient, float* depth, float* opacity, float* opacity_static,
+                                   float* opacity_transient, float* uncert, float* alpha_static, float* alpha_transient,
+                                   float* density, void* scratch, int64_t scratch_bytes, int flags, void* stream) {
+  if (!kinv || !pose_inv || !z_near || !z_far || !packed || !biasbuf || !wview || !imgbias_rgb || !imgbias_trans || !scratch)
+    return TP_ERR_BAD_ARG;
+  if (B < 1 || H < 1 || W < 1 || R < 0 || L_view < 0 || L_view > 4) return TP_ERR_BAD_SHAPE;
+  if (N != 32 && N != 64 && N != 128) return TP_ERR_BAD_SHAPE;      // a 128-row tile holds whole rays
+  if (depth_mode < 0 || depth_mode > 2 || (depth_mode == 0 && !rand)) return TP_ERR_BAD_ARG;
+  if (!ray_idx && (ray0 < 0 || ray0 + R > (int64_t)H * W)) return TP_ERR_BAD_SHAPE;
+  if (flags & ~(1 << 17)) return TP_ERR_BAD_ARG;
+  if (((uintptr_t)packed & 15) || ((uintptr_t)scratch & 15) || ((uintptr_t)wview & 15) || ((uintptr_t)imgbias_rgb & 15) ||
+      ((uintptr_t)imgbias_trans & 15) || ((uintptr_t)density & 7))
+    return TP_ERR_ALIGN;
+  if (!tp_device_is_sm100()) return TP_ERR_ARCH;
+  const int64_t S = (int64_t)B * R * N;
+  if (S == 0) return TP_OK;
+  const long long n_super = (S + 255) / 256;
+  int grid = tp_num_sms();
+  if (n_super < grid) grid = (int)n_super;
+  if (scratch_bytes < (int64_t)grid * 2 * tc::kABytes) return TP_ERR_WORKSPACE;
+  tc::Params p = {};
+  p.S = S; p.N = N; p.per_image = R * N;
+  p.packed = reinterpret_cast<const uint8_t*>(packed); p.biasbuf = biasbuf; p.imgbias = imgbias_trans;
+  p.density = density; p.scratch = reinterpret_cast<uint8_t*>(scratch);
+  p.dbg_layer = -1; p.skew = 1;
+  p.n_layers = (flags & (1 << 17)) ? tc::kStaticLayers : tc::kNumLayers;
+  p.kinv = kinv; p.pinv = pose_inv; p.H = H; p.W = W; p.pix_offset = pix_offset;
+  p.ray_idx = reinterpret_cast<const long long*>(ray_idx); p.R = R; p.ray0 = ray0;
+  p.z_near = z_near; p.z_far = z_far; p.rand = rand; p.depth_mode = depth_mode; p.seed = seed;
+  p.wview = wview; p.L_view = L_view; p.imgbias_rgb = imgbias_rgb; p.min_uncert = min_uncert;
+  p.o_rgb = rgb; p.o_rgb_s = rgb_static; p.o_rgb_t = rgb_transient; p.o_depth = depth; p.o_op = opacity;
+  p.o_op_s = opacity_static; p.o_op_t = opacity_transient; p.o_unc = uncert; p.o_as = alpha_static; p.o_at = alpha_transient;
+  void (*kern)(const tc::Params) = p.n_layers == tc::kStaticLayers ? tc::nerf_stl_forward_kernel<1, tc::kStaticLayers, 3>
+                                                                   : tc::nerf_stl_forward_kernel<1, tc::kNumLayers, 3>;
+  return tc_launch(kern, p, grid, tc::num_threads<1>(), (cudaStream_t)stream);
 }

@@ -1,4 +1,4 @@
-// Accumulator-drain helpers of the fused forward kernels (mlp_tc.cu: one CTA per SM; mlp_tc_pair.cu: CTA pairs, cta_group::2):
+// Accumulator-drain helpers of the fused forward kernel (mlp_tc.cu):
 // TMEM -> registers -> (+bias) ReLU -> bf16 -> SMEM A operand of the next stage, optionally emitting the ReLU bitmask.
 #pragma once
 #include "mlp_tc_shared.cuh"
@@ -102,19 +102,6 @@ __device__ __forceinline__ void hidden_epilogue_wbias(uint32_t tmem_d, const flo
 
 // Whole 128x256 accumulator row of one thread: TMEM loads are software-pipelined (slab j+1 in flight while slab j is
 // converted), ping-ponging two register slabs.
-// timing experiment (results are wrong on purpose): what bounds the drain -- the TMEM read or the convert/store?
-template <int kSlabs>
-__device__ __noinline__ void hidden_epilogue_experiment(uint32_t tmem_d, uint32_t a_row, int mode) {
-  uint32_t v[32];
-  for (int j = 0; j < kSlabs; ++j) {
-    if (mode == 2 && (j & 1)) continue;
-    TP_TMEM_LD32(tmem_d + j * 32, v);
-    TP_TMEM_WAIT32(v);
-    if (j & 1) continue;
-    hidden_slab<false>(v, nullptr, a_row + j * 4 * 2048, nullptr);
-  }
-}
-
 template <bool kBias, int kSlabs, bool kBits = false>
 __device__ __forceinline__ void hidden_epilogue(uint32_t tmem_d, const float* bias, uint32_t a_row, float* dbg_row,
                                                 uint32_t* words = nullptr, uint8_t* g_row = nullptr) {

@@ -1,7 +1,8 @@
-// Stage table, kernel parameters and the per-sample encoder shared by the fused forward kernels (mlp_tc.cu: two lock-stepped
-// tiles per CTA; mlp_tc_v2.cu: one tile per CTA, cluster-multicast weights).  Both consume the same packed weight image.
+// Stage table, kernel parameters and the per-sample encoder of the fused forward kernel (mlp_tc.cu: two lock-stepped tiles
+// per CTA) and its accumulator-drain helpers (mlp_tc_epilogue.cuh).
 #pragma once
 #include "tc_common.cuh"
+#include "rays.cuh"
 
 namespace tc {
 
@@ -16,6 +17,9 @@ constexpr int kNumChunks = 122;
 // chunk, for the others as one extra K=16 step on E columns 48..63 with an 8 KB weight chunk that is zero except for
 // that column (BIAS_MMA).  Their epilogue is then a pure convert.  Per-ray / per-image biases (fp32 tables) and the
 // three N=16 output stages add their bias in the epilogue.
+// The N=16 output stages carry their weight rows TWICE: rows 0..7 = bf16(W), rows 8..15 = bf16(W - bf16(W)) -- the epilogue
+// adds column c and column c + 8, so the output layers see ~16 mantissa bits of their weights at no extra MMA (the systematic
+// rounding of these few rows was the largest term of the bf16 gradient error: DESIGN.md section 2).
 enum Epi : int { EPI_HIDDEN = 0, EPI_DENSITY = 1, EPI_RGB_OUT = 2, EPI_TRANS_OUT = 3 };
 enum BiasKind : int { BIAS_MMA = 0, BIAS_RAY = 1, BIAS_IMAGE = 2, BIAS_SMALL = 3 };
 struct Layer {
@@ -53,15 +57,15 @@ constexpr uint32_t kMaskBitBytes = 4096;
 constexpr int kSmallBiasOffset = 0;            // biasbuf: [density b, rgb3 b(3), trans3 b(5)] (fp32, 16 floats)
 
 struct Params {
-  const float* center;       // [rays,3]
+  const float* center;       // [rays,3]                              (per-sample launches; the render launch generates rays)
   const float* ray;          // [rays,3]
   const float* depth;        // [S]
   long long S;
   int N;                     // samples per ray
   long long per_image;       // samples per image
   const uint8_t* packed;     // kNumChunks x 16 KB weight image
-  const float* biasbuf;      // 12 x 256 static biases + 16 small
-  const float* raybias;      // [rays,256]  rgb-0 bias incl. view encoding + light latent
+  const float* biasbuf;      // 16 floats: biases of the three N=16 output stages
+  const float* raybias;      // [rays,256]  rgb-0 bias incl. view encoding + light latent (per-sample launches)
   const float* imgbias;      // [images,256] trans-0 bias incl. transient latent
   float* rgb;                // [S,3,2]
   float* density;            // [S,2]
@@ -74,21 +78,43 @@ struct Params {
   int skew;                  // weight chunks tile 0 runs ahead of tile 1 inside a stage (0..2)
   int n_layers;              // 17 = all stages; 13 = static only (rendering that needs neither the transient head nor uncert):
                              // the stage list stops after the rgb output, transient outputs are written as zeros.  Host side only:
-                             // it selects the kernel instantiation (the default kernel takes the count as a template parameter)
-  int dbg_save;              // timing experiments only (wrong training results): bit 0 = skip the activation-save bulk stores,
-                             // bit 1 = skip the ReLU bitmasks
-  int dbg_drain;             // timing experiments only (wrong results): 1 = convert/store every other slab, 2 = also skip its TMEM load
+                             // it selects the kernel instantiation (the kernel takes the count as a template parameter)
+  // ---- fused render launch (mode 3, tp_render_fused_forward): rays, sample depths, the view-direction bias and the
+  // compositing all happen in the kernel; per ray it reads 8 B (+ 8 B of ray index) and writes 56 B
+  const float* kinv;         // [B,9]  K^-1 per view (camera.py:292-314; host-side inverses as in the reference)
+  const float* pinv;         // [B,12] pose^-1 per view
+  int H, W;
+  float pix_offset;          // 0.5 (camera.py:301-302)
+  const long long* ray_idx;  // [B,R] pixel index of each ray, or NULL: ray r of a view is pixel ray0 + r
+  long long R, ray0;
+  const float* z_near;       // [B,H*W] full-frame sample bounds (data/lm.py:316-365), read at the ray's pixel
+  const float* z_far;
+  const float* rand;         // [S] injected stratified jitter (depth_mode 0), else NULL
+  int depth_mode;            // 0 = injected rand, 1 = midpoints, 2 = in-kernel Philox (same stream as tp_sample_depth)
+  unsigned long long seed;
+  const float* wview;        // [3+6L][256] fp32: columns 256.. of mlp_rgb[0].weight, transposed (view-direction inputs)
+  int L_view;
+  const float* imgbias_rgb;  // [B,256] rgb-0 bias + light-latent part (tp_tc_image_bias)
+  float min_uncert;
+  float* o_rgb;              // per-ray outputs (any may be NULL): [B*R,3] x 3, [B*R] x 5
+  float* o_rgb_s;
+  float* o_rgb_t;
+  float* o_depth;
+  float* o_op;
+  float* o_op_s;
+  float* o_op_t;
+  float* o_unc;
+  float* o_as;               // per-sample outputs (any may be NULL): alpha_static [S], alpha_transient [S]; `density` [S,2]
+  float* o_at;
 };
 
-// positional encoding of one sample into the E tile (bf16): [x,y,z, per coord sin(2^k pi x) k<10, cos(...) k<10, 1].
+// positional encoding of one point into the E tile (bf16): [x,y,z, per coord sin(2^k pi x) k<10, cos(...) k<10, 1].
 // sincospif gives the exact-argument octave 0; higher octaves by the double-angle recurrence (error << bf16 ulp).
-__device__ __forceinline__ void encode_sample(const Params& p, long long s, uint32_t e_smem, int row) {
-  const long long r = s / p.N;
-  const float d = p.depth[s];
+__device__ __forceinline__ void encode_point(const float (&c)[3], const float (&r)[3], float d, uint32_t e_smem, int row) {
   float v[64];
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
-    const float x = __fadd_rn(p.center[r * 3 + j], __fmul_rn(p.ray[r * 3 + j], d));
+    const float x = __fadd_rn(c[j], __fmul_rn(r[j], d));
     v[j] = x;
     float sn, cs;
     sincospif(x, &sn, &cs);
@@ -108,5 +134,11 @@ __device__ __forceinline__ void encode_sample(const Params& p, long long s, uint
                  pack_bf16(v[k8 * 8 + 4], v[k8 * 8 + 5]), pack_bf16(v[k8 * 8 + 6], v[k8 * 8 + 7]));
 }
 
+__device__ __forceinline__ void encode_sample(const Params& p, long long s, uint32_t e_smem, int row) {
+  const long long r = s / p.N;
+  const float c[3] = {p.center[r * 3], p.center[r * 3 + 1], p.center[r * 3 + 2]};
+  const float ry[3] = {p.ray[r * 3], p.ray[r * 3 + 1], p.ray[r * 3 + 2]};
+  encode_point(c, ry, p.depth[s], e_smem, row);
+}
 
 }  // namespace tc

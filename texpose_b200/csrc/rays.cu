@@ -10,34 +10,12 @@
 //   compute_box.py:266-271 + data/lm.py:349-356.
 #include "common.cuh"
 #include "bilinear.cuh"
+#include "rays.cuh"
 #include "../../include/texpose_b200.h"
 
 namespace {
 
 constexpr int kThreads = 256;
-
-// [u,v,1] @ Kinv^T then [cam,1] @ pose_inv^T, ray = grid - center.  The reference evaluates both
-// products with torch.matmul; its fp32 result equals a sequential mul,fma,fma(,fma) chain over k
-// (verified bit-for-bit against the reference on CPU, tests/golden/rays.npz).
-__device__ __forceinline__ void unproject(const float* __restrict__ kinv, const float* __restrict__ pinv,
-                                          float u, float v, float c[3], float d[3]) {
-  float cam[3];
-#pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    float acc = __fmul_rn(u, kinv[j * 3 + 0]);
-    acc = __fmaf_rn(v, kinv[j * 3 + 1], acc);
-    cam[j] = __fmaf_rn(1.0f, kinv[j * 3 + 2], acc);
-  }
-#pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    float acc = __fmul_rn(cam[0], pinv[j * 4 + 0]);
-    acc = __fmaf_rn(cam[1], pinv[j * 4 + 1], acc);
-    acc = __fmaf_rn(cam[2], pinv[j * 4 + 2], acc);
-    acc = __fmaf_rn(1.0f, pinv[j * 4 + 3], acc);
-    c[j] = pinv[j * 4 + 3];  // 0*R + 1*t == t exactly
-    d[j] = __fsub_rn(acc, c[j]);
-  }
-}
 
 __global__ void raygen_kernel(const float* __restrict__ kinv, const float* __restrict__ pinv, int B, int H, int W,
                               float pix_offset, const long long* __restrict__ ray_idx, int R,
@@ -154,11 +132,6 @@ __global__ void aabb_kernel(const float* __restrict__ amin, const float* __restr
 // d_i = (u_i + i) / N * (far - near) + near, one rounding per reference op (model/nerf_adapt_st_gan.py:690-697).
 // IEEE division as torch's CPU kernel does (the pinned oracle); torch's CUDA kernel multiplies by fl(1/N) instead,
 // identical for the power-of-two N the yamls use (64, 128) and 1 ulp apart otherwise.
-__device__ __forceinline__ float stratified_depth(float u, int k, float fn, float lo, float hi) {
-  const float t = __fdiv_rn(__fadd_rn(u, (float)k), fn);
-  return __fadd_rn(__fmul_rn(t, __fsub_rn(hi, lo)), lo);
-}
-
 __global__ void sample_depth_kernel(const float* __restrict__ z_near, const float* __restrict__ z_far,
                                     const float* __restrict__ rand, long long n_rays, int N, int mode,
                                     float* __restrict__ out) {

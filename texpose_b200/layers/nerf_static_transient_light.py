@@ -112,6 +112,30 @@ class NeRF(torch.nn.Module):
         geom = _common.ray_geometry(cfg, center, ray, depth_samples)
         return self._run(cfg, geom, latent_variable_trans, latent_variable_light)
 
+    def fused_render_applies(self, opt, mode) -> bool:
+        """True when Graph.render may run as ONE launch (tp_render_fused_forward): inference (no gradient recorded), the fused
+        kernel's architecture and precision, 32 / 64 / 128 samples per ray.  opt.b200.fused_render = False switches it off."""
+        from .. import mlp_tc
+        if mode == "train" or torch.is_grad_enabled() or not _common.b200_option(opt, "fused_render", True):
+            return False
+        if opt.nerf.sample_intvs not in mlp_tc.FUSED_N or opt.nerf.depth.param != "metric" or opt.camera.ndc:
+            return False
+        return self.uses_tensor_cores(opt, mode)
+
+    def render_rays(self, opt, kinv, pinv, ray_idx, ray0, R, z_near, z_far, latent_variable_trans, latent_variable_light,
+                    mode=None, rand=None, seed=0, want=None, out_ptrs=None):
+        """get_center_and_ray + ray_batch_sample + sample_depth + forward_samples + composite (model/nerf_adapt_st_gan.py:565-631)
+        in one launch; returns the dict of the eleven outputs of Graph.render."""
+        from .. import mlp_tc
+        cfg = self._config(opt, mode)
+        pairs = lambda ml: [(l.weight.detach(), l.bias.detach()) for l in ml]
+        lt = ops._f32(latent_variable_trans.detach())
+        ll = ops._f32(latent_variable_light.detach())
+        return mlp_tc.render_fused(cfg, kinv, pinv, opt.H, opt.W, ray_idx, ray0, R, ops._f32(z_near), ops._f32(z_far),
+                                   opt.nerf.sample_intvs, lt, ll, pairs(self.mlp_feat), pairs(self.mlp_rgb), pairs(self.mlp_trans),
+                                   float(opt.nerf.min_uncert), rand=rand, stratified=bool(opt.nerf.sample_stratified), seed=seed,
+                                   static_only=cfg.static_only, want=want or mlp_tc.RENDER_KEYS, out_ptrs=out_ptrs)
+
     @staticmethod
     def composite(opt, ray, rgb_samples, density_samples, depth_samples, uncert_samples=None):
         """layers/nerf_static_transient_light.py:168-212; returns the reference's 11-tuple."""

@@ -12,8 +12,8 @@ import torch
 from . import _C, ops
 
 _F = 256
-PAIR_KERNEL = 1024      # tp_tc_nerf_stl_forward flags bit 10: cta_group::2 kernel over CTA pairs (csrc/mlp_tc_pair.cu)
 STATIC_ONLY = 1 << 17   # flags bit 17: stop after the rgb head (rendering that uses only the static outputs)
+FUSED_N = (32, 64, 128)  # samples per ray the fused render launch takes (a 128-row tile holds whole rays)
 
 
 def supported(cfg, feat_p, rgb_p, trans_p) -> bool:
@@ -88,7 +88,7 @@ def _chunk_table(cfg, feat_p, rgb_p, trans_p):
 
 
 class Packed:
-    __slots__ = ("key", "weights", "weights_pair", "biasbuf", "keep")
+    __slots__ = ("key", "weights", "wview", "biasbuf", "keep")
 
 
 def _version_key(params):
@@ -117,7 +117,9 @@ def pack(cfg, holder, feat_p, rgb_p, trans_p, params_for_key) -> Packed:
     biasbuf[4:9] = tb[3]
     out = Packed()
     out.key, out.weights, out.biasbuf = key, weights, biasbuf
-    out.weights_pair = None                    # built on first use of the CTA-pair kernel (flags bit 10)
+    # view-direction columns of mlp_rgb[0] ([unit dir, posenc]: layers/nerf_static_transient_light.py:111-117), transposed to
+    # [3+6L, 256] so a warp of the render launch reads one input's 256 weights as two coalesced 512 B rows (a copy, no arithmetic)
+    out.wview = rgb_p[0][0][:, 256:256 + cfg.view_cols].t().contiguous()
     out.keep = (desc, keep)
     if holder is not None:
         holder._packed = out
@@ -135,9 +137,25 @@ def _scratch_for(dev):
     return _scratch[k]
 
 
+def image_biases(cfg, B, lat_trans, lat_light, rgb_p, trans_p):
+    """Per-image constants folded into the layer-0 biases of the two heads (latents x their weight columns + bias): [B,256] each."""
+    dev = rgb_p[0][0].device
+    W_r0, b_r0 = rgb_p[0]
+    W_t0, b_t0 = trans_p[0]
+    if lat_trans.shape[0] != B or lat_light.shape[0] != B:
+        raise ValueError(f"latents must have one row per image ({B}); got {tuple(lat_trans.shape)} / {tuple(lat_light.shape)}")
+    img_r = torch.empty(B, _F, device=dev)
+    img_t = torch.empty(B, _F, device=dev)
+    _C.call("tp_tc_image_bias", ops._p(W_r0), W_r0.stride(0), 256 + cfg.view_cols + 3, cfg.n_latent_light, ops._p(b_r0),
+            ops._p(lat_light), B, _F, ops._p(img_r), ops._stream())
+    _C.call("tp_tc_image_bias", ops._p(W_t0), W_t0.stride(0), 256, cfg.n_latent_trans, ops._p(b_t0), ops._p(lat_trans),
+            B, _F, ops._p(img_t), ops._stream())
+    return img_r, img_t
+
+
 def forward(cfg, geom, lat_trans, lat_light, feat_p, rgb_p, trans_p, dbg_layer=-1, flags=0, save=False, static_only=False):
     flags = flags or int(os.environ.get("TEXPOSE_TC_FLAGS", "0"))     # bit 1: 16-epilogue-warp drain instead of the default 8 (A/B)
-    if static_only and not save and not (flags & (128 | PAIR_KERNEL)):
+    if static_only and not save:
         flags |= STATIC_ONLY
     if geom.get("mode") != "rays":
         raise NotImplementedError("the fused bf16 kernel is ray-parameterised (forward_samples)")
@@ -150,14 +168,8 @@ def forward(cfg, geom, lat_trans, lat_light, feat_p, rgb_p, trans_p, dbg_layer=-
     dev = depth.device
     flat = [t for pair in (feat_p + rgb_p + trans_p) for t in pair]
     pk = pack(cfg, cfg.packed, feat_p, rgb_p, trans_p, flat)
-    W_r0, b_r0 = rgb_p[0]
-    W_t0, b_t0 = trans_p[0]
-    img_r = torch.empty(B, _F, device=dev)
-    img_t = torch.empty(B, _F, device=dev)
-    _C.call("tp_tc_image_bias", ops._p(W_r0), W_r0.stride(0), 256 + cfg.view_cols + 3, cfg.n_latent_light, ops._p(b_r0),
-            ops._p(lat_light), B, _F, ops._p(img_r), ops._stream())
-    _C.call("tp_tc_image_bias", ops._p(W_t0), W_t0.stride(0), 256, cfg.n_latent_trans, ops._p(b_t0), ops._p(lat_trans),
-            B, _F, ops._p(img_t), ops._stream())
+    W_r0 = rgb_p[0][0]
+    img_r, img_t = image_biases(cfg, B, lat_trans, lat_light, rgb_p, trans_p)
     raybias = torch.empty(B * R, _F, device=dev)
     _C.call("tp_tc_ray_bias", ops._p(ray), B * R, R, cfg.L_view, ops._p(W_r0), W_r0.stride(0), 256, ops._p(img_r),
             ops._p(raybias), ops._stream())
@@ -167,13 +179,7 @@ def forward(cfg, geom, lat_trans, lat_light, feat_p, rgb_p, trans_p, dbg_layer=-
     scratch = _scratch_for(dev)
     dbg = torch.zeros(S, _F, device=dev) if dbg_layer >= 0 else None
     images = torch.empty(_C.load().tp_tc_save_bytes(S), dtype=torch.uint8, device=dev) if save else None
-    weights = pk.weights
-    if flags & PAIR_KERNEL:
-        if pk.weights_pair is None:
-            pk.weights_pair = torch.empty_like(pk.weights)
-            _C.call("tp_tc_pair_weights", ops._p(pk.weights), ops._p(pk.weights_pair), ops._stream())
-        weights = pk.weights_pair
-    _C.call("tp_tc_nerf_stl_forward", ops._p(center), ops._p(ray), ops._p(depth), S, N, per_image, ops._p(weights),
+    _C.call("tp_tc_nerf_stl_forward", ops._p(center), ops._p(ray), ops._p(depth), S, N, per_image, ops._p(pk.weights),
             ops._p(pk.biasbuf), ops._p(raybias), ops._p(img_t), ops._p(rgb), ops._p(density), ops._p(uncert),
             ops._p(scratch), scratch.numel(), ops._p(images), dbg_layer, ops._p(dbg), flags, ops._stream())
     if dbg_layer >= 0:
@@ -181,6 +187,59 @@ def forward(cfg, geom, lat_trans, lat_light, feat_p, rgb_p, trans_p, dbg_layer=-
     if save:
         return rgb, density, uncert, images
     return rgb, density, uncert
+
+
+RENDER_KEYS = ("rgb", "rgb_static", "rgb_transient", "depth", "opacity", "opacity_static", "opacity_transient", "uncert",
+               "alpha_static", "alpha_transient", "density")
+
+
+def render_fused(cfg, kinv, pinv, H, W, ray_idx, ray0, R, z_near, z_far, N, lat_trans, lat_light, feat_p, rgb_p, trans_p,
+                 min_uncert, rand=None, stratified=True, seed=0, static_only=False, want=RENDER_KEYS, out_ptrs=None):
+    """Graph.render after ray selection (model/nerf_adapt_st_gan.py:565-631) as ONE launch: tp_render_fused_forward.
+
+    ray_idx: [B,R] int64 pixel indices, or None for the row block [ray0, ray0+R) of every view.  z_near / z_far: [B,H*W].
+    want: which of the reference's eleven outputs are materialised.  out_ptrs: {key: raw device address} overriding the
+    destination of an output (e.g. a row block of a frame buffer in a peer GPU's window: the stores then travel over NVLink);
+    such outputs are not returned.  Returns the dict of allocated outputs in the reference's shapes."""
+    if N not in FUSED_N:
+        raise NotImplementedError(f"the fused render launch takes {FUSED_N} samples per ray")
+    if not supported(cfg, feat_p, rgb_p, trans_p):
+        raise NotImplementedError("bf16 tensor-core path implements the nerf_lm_adapt_gan.yaml architecture only")
+    B = kinv.shape[0]
+    dev = kinv.device
+    flat = [t for pair in (feat_p + rgb_p + trans_p) for t in pair]
+    pk = pack(cfg, cfg.packed, feat_p, rgb_p, trans_p, flat)
+    img_r, img_t = image_biases(cfg, B, lat_trans, lat_light, rgb_p, trans_p)
+    shapes = dict(rgb=(B, R, 3), rgb_static=(B, R, 3), rgb_transient=(B, R, 3), depth=(B, R, 1), opacity=(B, R, 1),
+                  opacity_static=(B, R, 1), opacity_transient=(B, R, 1), uncert=(B, R, 1), alpha_static=(B, R, N),
+                  alpha_transient=(B, R, N), density=(B, R, N, 2))
+    out_ptrs = out_ptrs or {}
+    ret = {k: torch.empty(shapes[k], device=dev) for k in want if k not in out_ptrs}
+    if B * R == 0:
+        return ret
+    import ctypes
+
+    def dst(k):
+        if k in out_ptrs:
+            return ctypes.c_void_p(int(out_ptrs[k]))
+        return ops._p(ret[k]) if k in ret else None
+
+    if rand is not None:
+        mode, rand_t = 0, ops._f32(rand)
+        assert rand_t.numel() == B * R * N
+    elif not stratified:
+        mode, rand_t = 1, None
+    else:
+        mode, rand_t = 2, None
+    if ray_idx is not None:
+        ray_idx = ray_idx.to(torch.int64).contiguous()
+        assert ray_idx.shape == (B, R)
+    scratch = _scratch_for(dev)
+    _C.call("tp_render_fused_forward", ops._p(kinv), ops._p(pinv), B, H, W, 0.5, ops._p(ray_idx), R, int(ray0), ops._p(z_near),
+            ops._p(z_far), N, mode, ops._p(rand_t), int(seed), ops._p(pk.weights), ops._p(pk.biasbuf), ops._p(pk.wview),
+            cfg.L_view, ops._p(img_r), ops._p(img_t), float(min_uncert), *[dst(k) for k in RENDER_KEYS], ops._p(scratch),
+            scratch.numel(), STATIC_ONLY if static_only else 0, ops._stream())
+    return ret
 
 
 SLOT_FEAT, SLOT_RGB_H1, SLOT_TRANS_H1, N_SLOTS = 0, 1, 4, 7

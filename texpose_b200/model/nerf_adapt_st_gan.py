@@ -128,9 +128,62 @@ class Graph(torch.nn.Module):
         var.update(ret)
         return var
 
+    def _latents(self, opt, B, sample_idx, mode, dev):
+        """Latent rows of model/nerf_adapt_st_gan.py:589-603, one row per view (a single row is broadcast as the
+        reference's `.expand(B, ...)` does, layers/nerf_static_transient_light.py:113,127)."""
+        if mode == "train":
+            lat_trans = self.latent_vars_trans.weight[sample_idx]
+            lat_light = self.latent_vars_light.weight[sample_idx]
+        elif mode == "val":
+            lat_trans = self.latent_vars_trans.weight[0][None]
+            lat_light = self.latent_vars_light.weight[0][None]
+        else:
+            if opt.render.transient == "zero":
+                lat_trans = torch.zeros(B, opt.nerf.N_latent_trans, device=dev)
+            elif opt.render.transient == "sample":
+                lat_trans = self.latent_vars_trans.weight[sample_idx].reshape(-1, opt.nerf.N_latent_trans)
+            else:
+                raise NotImplementedError
+            lat_light = self.latent_vars_light.weight[sample_idx].reshape(-1, opt.nerf.N_latent_light)
+        if lat_trans.shape[0] != B or lat_light.shape[0] != B:
+            if lat_trans.shape[0] not in (1, B) or lat_light.shape[0] not in (1, B):
+                raise ValueError(f"latents must have 1 or {B} rows, got {lat_trans.shape[0]} / {lat_light.shape[0]}")
+            lat_trans = lat_trans.expand(B, -1).contiguous()
+            lat_light = lat_light.expand(B, -1).contiguous()
+        return lat_trans, lat_light
+
+    def _render_fused(self, opt, pose, intr, ray_idx, depth_range, sample_idx, mode, want=None, out_ptrs=None):
+        """model/nerf_adapt_st_gan.py:565-631 as one launch (csrc/mlp_tc.cu, render mode): rays, depths, view-direction bias
+        and compositing happen inside the fused kernel.  ray_idx: [B,R] tensor, or a `range` = contiguous row block."""
+        B = len(pose)
+        HW = opt.H * opt.W
+        kinv, pinv = camera.view_matrices(pose, intr)
+        zn, zf = depth_range[0].reshape(B, HW), depth_range[1].reshape(B, HW)
+        if isinstance(ray_idx, range):
+            assert ray_idx.step == 1
+            idx_t, ray0, R = None, ray_idx.start, len(ray_idx)
+        else:
+            idx_t, ray0, R = ray_idx, 0, ray_idx.shape[1]
+        lat_trans, lat_light = self._latents(opt, B, sample_idx, mode, pose.device)
+        rand, seed = None, 0
+        if opt.nerf.sample_stratified:
+            if self._b200(opt, "rng", "torch") == "philox":
+                seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+            else:
+                rand = torch.rand(B, R, opt.nerf.sample_intvs, 1, device=pose.device)      # the reference's draw (:690)
+        ret = self.nerf.render_rays(opt, kinv, pinv, idx_t, ray0, R, zn, zf, lat_trans, lat_light, mode=mode, rand=rand,
+                                    seed=seed, want=want, out_ptrs=out_ptrs)
+        return AttrDict(ret)
+
     def render(self, opt, pose, intr=None, ray_idx=None, depth_range=None, sample_idx=None, mode=None):
         """model/nerf_adapt_st_gan.py:547-631 -> dict of 11 tensors."""
         depth_min, depth_max = depth_range
+        if opt.camera.ndc:
+            raise NotImplementedError("camera.ndc is false in every reference yaml; not implemented")
+        if mode != "train" and not self._b200(opt, "nan_guard", False) and self.nerf.fused_render_applies(opt, mode):
+            return self._render_fused(opt, pose, intr, ray_idx, depth_range, sample_idx, mode)
+        if isinstance(ray_idx, range):
+            ray_idx = torch.arange(ray_idx.start, ray_idx.stop, device=pose.device)[None].expand(len(pose), -1)
         if mode == "train":
             B, h, w, _ = ray_idx.shape
             center, ray = self.ray_sampler.get_rays(opt, intrinsics=intr, coords=ray_idx, pose=pose)
@@ -144,32 +197,9 @@ class Graph(torch.nn.Module):
             zf = self.ray_batch_sample(depth_max, ray_idx).squeeze(-1)
         if self._b200(opt, "nan_guard", False) and bool(ray.isnan().any()):
             raise FloatingPointError("NaN in generated rays")
-        if opt.camera.ndc:
-            raise NotImplementedError("camera.ndc is false in every reference yaml; not implemented")
-
         depth_samples = self.sample_depth(opt, B, (zn, zf), num_rays=ray.shape[1])       # [B,R,N,1]
 
-        if mode == "train":
-            lat_trans = self.latent_vars_trans.weight[sample_idx]
-            lat_light = self.latent_vars_light.weight[sample_idx]
-        elif mode == "val":
-            lat_trans = self.latent_vars_trans.weight[0][None]
-            lat_light = self.latent_vars_light.weight[0][None]
-        else:
-            if opt.render.transient == "zero":
-                lat_trans = torch.zeros(B, opt.nerf.N_latent_trans, device=ray.device)
-            elif opt.render.transient == "sample":
-                lat_trans = self.latent_vars_trans.weight[sample_idx].reshape(-1, opt.nerf.N_latent_trans)
-            else:
-                raise NotImplementedError
-            lat_light = self.latent_vars_light.weight[sample_idx].reshape(-1, opt.nerf.N_latent_light)
-        # the kernels index the latents by image: a single row is broadcast to every view of the batch, as the
-        # reference's `.expand(B, ...)` does (layers/nerf_static_transient_light.py:113,127)
-        if lat_trans.shape[0] != B or lat_light.shape[0] != B:
-            if lat_trans.shape[0] not in (1, B) or lat_light.shape[0] not in (1, B):
-                raise ValueError(f"latents must have 1 or {B} rows, got {lat_trans.shape[0]} / {lat_light.shape[0]}")
-            lat_trans = lat_trans.expand(B, -1).contiguous()
-            lat_light = lat_light.expand(B, -1).contiguous()
+        lat_trans, lat_light = self._latents(opt, B, sample_idx, mode, ray.device)
 
         rgb_samples, density_samples, uncert_samples = self.nerf.forward_samples(
             opt, center=center, ray=ray, depth_samples=depth_samples, latent_variable_trans=lat_trans,
@@ -202,7 +232,7 @@ class Graph(torch.nn.Module):
             parts = {k: [] for k in keys}
             B = len(pose)
             for c in range(0, HW, step):
-                ray_idx = torch.arange(c, min(c + step, HW), device=dev)[None].expand(B, -1)
+                ray_idx = range(c, min(c + step, HW))       # contiguous block: no index tensor (the fused launch takes ray0 + r)
                 ret = self.render(opt, pose, intr=intr, ray_idx=ray_idx, depth_range=depth_range,
                                   sample_idx=sample_idx, mode=mode)
                 for k in keys:
