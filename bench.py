@@ -4,13 +4,18 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 Workload (BASELINE.json configs[1], "C2"): LineMOD-duck-shaped synthetic full-frame render, 480x640 rays x 128
-samples, static + transient + light heads, random-init (seed 0) weights, bf16 tensor-core MLP.  One step = one
-full frame through the public API (Graph.nerf_forward(mode='val')).  With N GPUs every rank renders its own
-view (weak scaling over views, no data-path collective).  Prints ONE JSON line on rank 0.
+samples, static + transient + light heads, random-init (seed 0) weights, bf16 tensor-core MLP.  One step = ONE frame.
+  N = 1   the frame through the public API (Graph.nerf_forward(mode='val')): one fused render launch.
+  N > 1   the SAME frame, row blocks sharded over the ranks (strong scaling: BASELINE `metric` "480x640 render ms/frame
+          at 1/2/4/8 B200"): every rank's fused launch stores its 56 B/ray outputs straight into rank 0's frame buffers
+          over NVLink peer memory (parallel.FrameGather), one barrier kernel per frame; no collective.
+          The round-1 weak-scaling number (one view per GPU) is kept as the `weak_views` block.
+Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -23,8 +28,11 @@ sys.path.insert(0, ROOT)
 
 H, W, NS = 480, 640, 128
 FLOP_PER_SAMPLE_FWD = 1_821_184          # SURVEY.md 8d (dense, unpadded)
-FLOP_PER_SAMPLE_FWD_BWD = 3_220_992      # forward + backward with the trunk frozen
+FLOP_PER_SAMPLE_BWD = 1_399_808          # backward with the trunk frozen
+FLOP_PER_SAMPLE_FWD_BWD = FLOP_PER_SAMPLE_FWD + FLOP_PER_SAMPLE_BWD
 METRIC, UNIT = "ray-samples/sec", "samples/s"
+WORKLOAD = "C2 LineMOD-duck synthetic full-frame render 480x640x128, static+transient+light heads"
+REF_CHUNK0 = 230 * W                     # the reference arm's 2048-ray chunks start in the object rows of the frame
 
 
 def parse():
@@ -33,9 +41,11 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-rays", type=int, default=1024, help="rays of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-rays", type=int, default=2048, help="rays per step of the bounded CPU sample (the reference's own "
+                                                               "chunk size, opt.nerf.rand_rays)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--no-weak", action="store_true", help="N > 1: skip the one-view-per-GPU block")
     return ap.parse_args()
 
 
@@ -47,67 +57,125 @@ def peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
 
 
-# ---------------------------------------------------------------------------------------------- CPU reference arm
+def so_sha16():
+    from texpose_b200 import _C
+    try:
+        return hashlib.sha256(open(_C.LIB_PATH, "rb").read()).hexdigest()[:16]
+    except OSError:
+        return None
 
-def cpu_render_sample(n_rays, threads):
-    """Times the oracle (CPU restatement of the reference path: rays -> bounds -> depths -> MLP -> composite)
-    on a bounded sample of the C2 workload.  Returns samples/s."""
+
+# ---------------------------------------------------------------------------------------------- reference arm
+
+def frame_inputs(dev="cpu"):
+    """Seeded C2 inputs: pose seed 0, LineMOD K, AABB sample bounds of the padded duck box."""
+    from oracle import texpose_oracle as O
+    from texpose_b200 import synth
+    pose, intr = synth.poses([0]), synth.intrinsics(1)
+    c, r = O.get_center_and_ray(pose, intr, H, W)
+    lo, hi = synth.padded_aabb()
+    tn, tf, v = O.aabb_ray_intersection(lo, hi, c, r)
+    zn, zf = O.box_bounds_to_range(tn, tf, v, *synth.BG_RANGE)
+    t = lambda x: x.to(dev)
+    return t(pose), t(intr), (t(zn)[:, :, None], t(zf)[:, :, None])
+
+
+def reference_graph(device):
+    """The REAL reference (unmodified sources from /root/reference or baseline/_ref): Graph of model/nerf_adapt_st_gan.py with
+    the nerf_lm_adapt_gan.yaml options at the C2 sample count.  None when no copy of the reference is present."""
+    from oracle import ref_import
+    if not ref_import.available():
+        return None
+    ns = ref_import.load()
+    opt = ref_import.load_yaml_opt("nerf_lm_adapt_gan", H, W, device=device)
+    opt.nerf.sample_intvs = NS
+    g = ref_import.build_graph(ns, opt, n_images=8, seed=0).to(device)
+    return ns, opt, g
+
+
+def cpu_reference_step(n_rays, threads):
+    """One step of the CPU arm = one chunk of the reference's own render_by_slices loop (model/nerf_adapt_st_gan.py:640-650):
+    Graph.render(mode='val') on `n_rays` consecutive rays of the C2 frame, fp32, all host threads.  The real reference when a
+    copy is present (kind 'reference'), else the oracle port.  Returns (step, samples per step, kind, description)."""
     import torch
+    torch.set_num_threads(threads)
+    ref = reference_graph("cpu")
+    pose, intr, dr = frame_inputs("cpu")
+    state = {"c": 0}
+    if ref is not None:
+        from oracle import ref_import
+        ns, opt, g = ref
+
+        def step():
+            c0 = REF_CHUNK0 + (state["c"] % 16) * n_rays
+            state["c"] += 1
+            idx = torch.arange(c0, c0 + n_rays)[None]
+            with ref_import.cpu_shim(), torch.no_grad():
+                state["out"] = g.render(opt, pose, intr=intr, ray_idx=idx, depth_range=dr, sample_idx=None, mode="val")
+
+        return step, n_rays * NS, "reference", (f"the unmodified reference (model/nerf_adapt_st_gan.py Graph.render, mode='val') on {n_rays} "
+                                                f"consecutive rays x {NS} samples of the C2 frame per step = one chunk of its own "
+                                                f"render_by_slices loop, fp32, torch CPU ops on {threads} threads")
     from oracle import texpose_oracle as O
     from texpose_b200 import synth
     from texpose_b200.config import adapt_gan_opt
     from texpose_b200.layers.nerf_static_transient_light import NeRF
-
-    torch.set_num_threads(threads)
     torch.manual_seed(0)
     m = NeRF(adapt_gan_opt())
     L = lambda ml: [(l.weight.detach(), l.bias.detach()) for l in ml]
     feat, rgb, trans = L(m.mlp_feat), L(m.mlp_rgb), L(m.mlp_trans)
-    pose, intr = synth.poses([0]), synth.intrinsics(1)
-    lo, hi = synth.padded_aabb()
     lt, ll = synth.latents(1)
-    state = {}
 
     def step():
+        c0 = REF_CHUNK0 + (state["c"] % 16) * n_rays
+        state["c"] += 1
         with torch.no_grad():
             c, r = O.get_center_and_ray(pose, intr, H, W)
-            tn, tf, v = O.aabb_ray_intersection(lo, hi, c, r)
-            zn, zf = O.box_bounds_to_range(tn, tf, v, *synth.BG_RANGE)
-            idx = torch.linspace(0, H * W - 1, n_rays).long()[None]
-            c, r = O.gather_rays(c, idx), O.gather_rays(r, idx)
-            zn, zf = zn[:, idx[0]], zf[:, idx[0]]
+            idx = torch.arange(c0, c0 + n_rays)[None]
             rand = torch.rand(1, n_rays, NS, 1)
-            state["out"] = O.render_stl(c, r, zn, zf, rand, NS, lt, ll, feat, rgb, trans)
+            state["out"] = O.render_stl(O.gather_rays(c, idx), O.gather_rays(r, idx), dr[0][:, idx[0], 0], dr[1][:, idx[0], 0], rand, NS,
+                                        lt, ll, feat, rgb, trans)
 
-    return step, n_rays * NS
+    return step, n_rays * NS, "port", (f"oracle port of the reference path (no copy of the reference on this box) on {n_rays} consecutive rays x "
+                                      f"{NS} samples per step, fp32, {threads} threads")
 
 
-def eager_gpu_sample(dev, n_chunks=8, chunk=2048):
-    """The reference's eager aten-op path (oracle port) run ON THE GPU in its own 2048-ray chunks (opt.nerf.rand_rays,
-    model/nerf_adapt_st_gan.py:669-679), cuBLAS fp32 -- the meaningful "before" on the same B200.  Reported as context only."""
+def eager_gpu_sample(dev, n_chunks=8):
+    """The meaningful "before" on the same B200: the reference's stock eager path (Graph.render in its own 2048-ray chunks, full-
+    frame ray generation per chunk, cuBLAS fp32) -- the real reference when a copy is present, else the oracle port."""
     import torch
-    from oracle import texpose_oracle as O
-    from texpose_b200 import synth
-    from texpose_b200.config import adapt_gan_opt
-    from texpose_b200.layers.nerf_static_transient_light import NeRF
-    torch.manual_seed(0)
-    m = NeRF(adapt_gan_opt()).to(dev)
-    L = lambda ml: [(l.weight.detach(), l.bias.detach()) for l in ml]
-    feat, rgb, trans = L(m.mlp_feat), L(m.mlp_rgb), L(m.mlp_trans)
-    pose, intr = synth.poses([0]).to(dev), synth.intrinsics(1).to(dev)
-    lo, hi = [t.to(dev) for t in synth.padded_aabb()]
-    lt, ll = [t.to(dev) for t in synth.latents(1)]
+    ref = reference_graph(str(dev))
+    pose, intr, dr = frame_inputs(dev)
+    chunk = 2048
+    if ref is not None:
+        ns, opt, g = ref
+        kind = "reference"
 
-    def run():
-        with torch.no_grad():
-            for c in range(n_chunks):
-                cen, ray = O.get_center_and_ray(pose, intr, H, W)          # whole frame per chunk, as the reference does
-                tn, tf, v = O.aabb_ray_intersection(lo, hi, cen, ray)
-                zn, zf = O.box_bounds_to_range(tn, tf, v, *synth.BG_RANGE)
-                idx = torch.arange(c * chunk, (c + 1) * chunk, device=dev)[None]
-                rand = torch.rand(1, chunk, NS, 1, device=dev)
-                O.render_stl(O.gather_rays(cen, idx), O.gather_rays(ray, idx), zn[:, idx[0]], zf[:, idx[0]], rand, NS, lt, ll,
-                             feat, rgb, trans)
+        def run():
+            with torch.no_grad():
+                for c in range(n_chunks):
+                    idx = torch.arange(REF_CHUNK0 + c * chunk, REF_CHUNK0 + (c + 1) * chunk, device=dev)[None]
+                    g.render(opt, pose, intr=intr, ray_idx=idx, depth_range=dr, sample_idx=None, mode="val")
+    else:
+        from oracle import texpose_oracle as O
+        from texpose_b200 import synth
+        from texpose_b200.config import adapt_gan_opt
+        from texpose_b200.layers.nerf_static_transient_light import NeRF
+        torch.manual_seed(0)
+        m = NeRF(adapt_gan_opt()).to(dev)
+        L = lambda ml: [(l.weight.detach(), l.bias.detach()) for l in ml]
+        feat, rgb, trans = L(m.mlp_feat), L(m.mlp_rgb), L(m.mlp_trans)
+        lt, ll = [t.to(dev) for t in synth.latents(1)]
+        kind = "port"
+
+        def run():
+            with torch.no_grad():
+                for c in range(n_chunks):
+                    cen, ray = O.get_center_and_ray(pose, intr, H, W)
+                    idx = torch.arange(REF_CHUNK0 + c * chunk, REF_CHUNK0 + (c + 1) * chunk, device=dev)[None]
+                    rand = torch.rand(1, chunk, NS, 1, device=dev)
+                    O.render_stl(O.gather_rays(cen, idx), O.gather_rays(ray, idx), dr[0][:, idx[0], 0], dr[1][:, idx[0], 0], rand, NS, lt,
+                                 ll, feat, rgb, trans)
     run()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -116,9 +184,9 @@ def eager_gpu_sample(dev, n_chunks=8, chunk=2048):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
-    return dict(value=n_chunks * chunk * NS / (ms * 1e-3), unit=UNIT, kind="port",
-                sample=f"{n_chunks} chunks x {chunk} rays x {NS} samples, eager torch ops (oracle port of the reference path) on "
-                       f"this GPU, fp32 cuBLAS, full-frame ray generation per chunk as in the reference",
+    return dict(value=n_chunks * chunk * NS / (ms * 1e-3), unit=UNIT, kind=kind,
+                sample=f"{n_chunks} chunks x {chunk} rays x {NS} samples through Graph.render(mode='val') of the "
+                       f"{'unmodified reference' if kind == 'reference' else 'oracle port'}, eager torch ops on this GPU, fp32",
                 ms_per_frame_extrapolated=ms * (H * W / (n_chunks * chunk)))
 
 
@@ -127,7 +195,7 @@ def run_reference(args, rank):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    step, samples = cpu_render_sample(args.cpu_rays, threads)
+    step, samples, kind, desc = cpu_reference_step(args.cpu_rays, threads)
     for _ in range(max(1, min(args.warmup, 2))):
         step()
     t0 = time.perf_counter()
@@ -136,14 +204,10 @@ def run_reference(args, rank):
     dt = (time.perf_counter() - t0) / args.steps
     val = samples / dt
     line = dict(metric=METRIC, value=val, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-                ms_per_step=dt * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
-                data="synthetic", impl="reference",
-                config=dict(workload="C2 LineMOD-duck synthetic full-frame render 480x640x128, static+transient+light "
-                                     "heads (bounded CPU sample)", rays_per_step=args.cpu_rays, samples_per_ray=NS),
-                cpu_baseline=dict(value=val, unit=UNIT, cores=threads, kind="port",
-                                  sample=f"{args.cpu_rays} evenly spaced rays x {NS} samples of the 480x640 frame per step "
-                                         f"(oracle = CPU restatement of the reference path; the reference itself is a "
-                                         f"Python checkout that does not travel to the GPU box)"),
+                ms_per_step=dt * 1e3, higher_is_better=True, scaling="strong" if args.gpus > 1 else "weak", vs_baseline=None,
+                dtype="f32", data="synthetic", impl="reference",
+                config=dict(workload=WORKLOAD + " (bounded CPU sample)", rays_per_step=args.cpu_rays, samples_per_ray=NS),
+                cpu_baseline=dict(value=val, unit=UNIT, cores=threads, kind=kind, sample=desc),
                 e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 torch_threads=torch.get_num_threads())
     print(json.dumps(line), flush=True)
@@ -197,12 +261,48 @@ class ClockSampler:
                     samples=len(sm))
 
 
+class CallTimer:
+    """CUDA events around C-ABI calls (on the launching stream): per-entry-point device time of an instrumented pass."""
+
+    def __init__(self, names=None):
+        from texpose_b200 import _C
+        self._C, self.names, self.events, self.orig = _C, names, [], _C.call
+
+    def __enter__(self):
+        import torch
+
+        def call(name, *a):
+            if self.names is None or name in self.names:
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                self.orig(name, *a)
+                a1.record()
+                self.events.append((name, a0, a1))
+            else:
+                self.orig(name, *a)
+
+        self._C.call = call
+        return self
+
+    def __exit__(self, *exc):
+        self._C.call = self.orig
+        return False
+
+    def per_call_ms(self):
+        import torch
+        torch.cuda.synchronize()
+        out = {}
+        for name, a0, a1 in self.events:
+            out.setdefault(name, []).append(a0.elapsed_time(a1))
+        return out
+
+
 # ---------------------------------------------------------------------------------------------- our arm
 
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
-    from texpose_b200 import _C, compute_box, synth
+    from texpose_b200 import _C, compute_box, parallel, synth
     from texpose_b200.config import AttrDict, adapt_gan_opt
     from texpose_b200.model.nerf_adapt_st_gan import Graph
 
@@ -232,35 +332,13 @@ def run_ours(args, rank, world, local_rank):
     torch.manual_seed(0)
     g = Graph(opt, n_train_images=8).to(dev)
     g.eval()
-    # this rank's view: seed = rank (C4-style view sharding); inputs as the data loader would deliver them
-    pose_h = synth.poses([rank]).pin_memory()
-    intr_h = synth.intrinsics(1).pin_memory()
     lo, hi = [t.to(dev) for t in synth.padded_aabb()]
-    zn, zf = compute_box.box_range(pose_h.to(dev), intr_h.to(dev), lo, hi, H, W, *synth.BG_RANGE)
-    zn_h, zf_h = zn.cpu().pin_memory(), zf.cpu().pin_memory()
-    mask_h = torch.ones(1, H, W).pin_memory()
-    var_dev = AttrDict(pose=pose_h.to(dev), intr=intr_h.to(dev), z_near=zn, z_far=zf, obj_mask=mask_h.to(dev),
-                       idx=torch.zeros(1, dtype=torch.long, device=dev))
-    samples_per_step = H * W * NS
-    out_h = dict(rgb=torch.empty(1, H * W, 3).pin_memory(), depth=torch.empty(1, H * W, 1).pin_memory(),
-                 opacity=torch.empty(1, H * W, 1).pin_memory(), uncert=torch.empty(1, H * W, 1).pin_memory())
 
-    def step_resident():
-        with torch.no_grad():
-            return g.nerf_forward(opt, AttrDict(var_dev), mode="val")
-
-    def step_e2e():
-        with torch.no_grad():
-            var = AttrDict(pose=pose_h.to(dev, non_blocking=True), intr=intr_h.to(dev, non_blocking=True),
-                           z_near=zn_h.to(dev, non_blocking=True), z_far=zf_h.to(dev, non_blocking=True),
-                           obj_mask=mask_h.to(dev, non_blocking=True), idx=var_dev.idx)
-            ret = g.nerf_forward(opt, var, mode="val")
-            for k, buf in out_h.items():
-                buf.copy_(ret[k], non_blocking=True)
-        return ret
-
-    h2d = sum(t.numel() * t.element_size() for t in (pose_h, intr_h, zn_h, zf_h, mask_h))
-    d2h = sum(t.numel() * t.element_size() for t in out_h.values())
+    def view_inputs(seed):
+        pose_h = synth.poses([seed]).pin_memory()
+        intr_h = synth.intrinsics(1).pin_memory()
+        zn, zf = compute_box.box_range(pose_h.to(dev), intr_h.to(dev), lo, hi, H, W, *synth.BG_RANGE)
+        return pose_h, intr_h, zn, zf
 
     def barrier():
         if world > 1:
@@ -289,100 +367,168 @@ def run_ours(args, rank, world, local_rank):
             ms = t.item()
         return ms, (cs.stop(t0, t1) if cs else None)
 
-    # --- dominant kernel (fused MLP) duration: CUDA events around the C-ABI launch on the launching stream
-    kern_ms = []
-    orig_call = _C.call
+    # ---- the frame: view 0 on every rank (N > 1: the ranks share it)
+    pose_h, intr_h, zn, zf = view_inputs(0)
+    zn_h, zf_h = zn.cpu().pin_memory(), zf.cpu().pin_memory()
+    mask_h = torch.ones(1, H, W).pin_memory()
+    pose_d, intr_d = pose_h.to(dev), intr_h.to(dev)
+    idx0 = torch.zeros(1, dtype=torch.long, device=dev)
+    var_dev = AttrDict(pose=pose_d, intr=intr_d, z_near=zn, z_far=zf, obj_mask=mask_h.to(dev), idx=idx0)
+    out_h = dict(rgb=torch.empty(1, H * W, 3).pin_memory(), depth=torch.empty(1, H * W, 1).pin_memory(),
+                 opacity=torch.empty(1, H * W, 1).pin_memory(), uncert=torch.empty(1, H * W, 1).pin_memory())
+    samples_per_frame = H * W * NS
 
-    def timing_call(name, *a):
-        if name in ("tp_tc_nerf_stl_forward", "tp_render_fused_forward"):
-            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a0.record()
-            orig_call(name, *a)
-            a1.record()
-            kern_ms.append((a0, a1))
-        else:
-            orig_call(name, *a)
+    if world == 1:
+        rows = (0, H * W)
+        gather = None
+
+        def step_resident():
+            with torch.no_grad():
+                return g.nerf_forward(opt, AttrDict(var_dev), mode="val")
+
+        def step_e2e():
+            with torch.no_grad():
+                var = AttrDict(pose=pose_h.to(dev, non_blocking=True), intr=intr_h.to(dev, non_blocking=True),
+                               z_near=zn_h.to(dev, non_blocking=True), z_far=zf_h.to(dev, non_blocking=True),
+                               obj_mask=mask_h.to(dev, non_blocking=True), idx=idx0)
+                ret = g.nerf_forward(opt, var, mode="val")
+                for k, buf in out_h.items():
+                    buf.copy_(ret[k], non_blocking=True)
+            return ret
+
+        h2d = sum(t.numel() * t.element_size() for t in (pose_h, intr_h, zn_h, zf_h, mask_h))
+        d2h = sum(t.numel() * t.element_size() for t in out_h.values())
+    else:
+        gather = parallel.FrameGather(opt, device=dev)
+        rows = gather.rows
+        dr_dev = (zn[:, :, None], zf[:, :, None])
+        zn_e2e, zf_e2e = torch.zeros_like(zn), torch.zeros_like(zf)      # e2e: only this rank's rows are uploaded
+
+        def step_resident():
+            with torch.no_grad():
+                return gather.render(g, opt, pose_d, intr_d, dr_dev)
+
+        def step_e2e():
+            b, e = rows
+            with torch.no_grad():
+                p_d, i_d = pose_h.to(dev, non_blocking=True), intr_h.to(dev, non_blocking=True)
+                zn_e2e[:, b:e].copy_(zn_h[:, b:e], non_blocking=True)
+                zf_e2e[:, b:e].copy_(zf_h[:, b:e], non_blocking=True)
+                frame, _ = gather.render(g, opt, p_d, i_d, (zn_e2e[:, :, None], zf_e2e[:, :, None]))
+                if frame is not None:
+                    for k, buf in out_h.items():
+                        buf.copy_(frame[k], non_blocking=True)
+
+        h2d_local = (pose_h.numel() + intr_h.numel() + 2 * (rows[1] - rows[0])) * 4
+        t = torch.tensor([float(h2d_local)], device=dev)
+        dist.all_reduce(t)
+        h2d = int(t.item())
+        d2h = sum(t.numel() * t.element_size() for t in out_h.values())      # rank 0 reads the gathered frame back
 
     _C.launch_counts.clear()
     ms, clocks = timed(step_resident, args.steps, args.warmup, sampler=True)
-    launches = sum(_C.launch_counts.values()) * args.steps // (args.steps + args.warmup)
-    per_step = {k: v // (args.steps + args.warmup) for k, v in _C.launch_counts.items()}
-    # second pass with per-kernel events (kept out of the headline timing)
-    import texpose_b200.ops as ops_mod
-    import texpose_b200.mlp_tc as tc_mod
-    _C.call = timing_call
-    ops_mod._C.call = timing_call
-    tc_mod._C.call = timing_call
-    for _ in range(min(args.steps, 5)):
-        step_resident()
-    torch.cuda.synchronize()
-    _C.call = orig_call
-    kms = sorted(a.elapsed_time(b) for a, b in kern_ms)
+    per_step = {k: v // (args.steps + args.warmup) for k, v in _C.launch_counts.items() if v >= args.steps + args.warmup}
+    launches = sum(per_step.values()) * args.steps
+    # second pass with events around the fused launch (kept out of the headline timing)
+    with CallTimer({"tp_render_fused_forward"}) as ct:
+        for _ in range(min(args.steps, 5)):
+            step_resident()
+    kms = sorted(ct.per_call_ms()["tp_render_fused_forward"])
     k_ms = sum(kms) / len(kms)
-    achieved_tf = FLOP_PER_SAMPLE_FWD * samples_per_step / (k_ms * 1e-3) / 1e12
+    local_samples = (rows[1] - rows[0]) * NS
+    achieved_tf = FLOP_PER_SAMPLE_FWD * local_samples / (k_ms * 1e-3) / 1e12
+    if gather is not None:
+        gather.check()
 
     ms_e2e, _ = timed(step_e2e, args.steps, max(1, args.warmup // 2))
+    value = samples_per_frame / (ms * 1e-3)
+    e2e_value = samples_per_frame / (ms_e2e * 1e-3)
 
-    value = world * samples_per_step / (ms * 1e-3)
-    e2e_value = world * samples_per_step / (ms_e2e * 1e-3)
+    weak = None
+    if world > 1 and not args.no_weak:
+        # round-1 mode for continuity: every rank renders its OWN view (seed = rank), no exchange at all
+        p_h, i_h, zn_r, zf_r = view_inputs(rank)
+        var_r = AttrDict(pose=p_h.to(dev), intr=i_h.to(dev), z_near=zn_r, z_far=zf_r, obj_mask=mask_h.to(dev), idx=idx0)
+
+        def step_view():
+            with torch.no_grad():
+                return g.nerf_forward(opt, AttrDict(var_r), mode="val")
+
+        ms_w, _ = timed(step_view, max(3, args.steps // 2), 2)
+        weak = dict(workload="one 480x640x128 view per GPU per step (views sharded across ranks, no exchange)", scaling="weak",
+                    value=world * samples_per_frame / (ms_w * 1e-3), unit=UNIT, ms_per_step=ms_w)
 
     train = None
     if not args.no_train:
-        train = bench_train(args, g, opt, dev, world, timed)
+        train = bench_train(args, g, opt, dev, world, timed, pk)
+    if gather is not None:
+        gather.close()
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_tc_forward_traffic.json")
-    if os.path.exists(tpath):
+    # DRAM bytes of the fused launch from ncu (`scripts/collect_profiles.sh`), valid only for the build it was measured on
+    traffic, traffic_note = None, "no ncu capture for this build (scripts/collect_profiles.sh writes profiles/r02_render_traffic.json)"
+    tpath = os.path.join(ROOT, "profiles", "r02_render_traffic.json")
+    if os.path.exists(tpath) and world == 1:
         try:
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            tj = json.load(open(tpath))
+            if tj.get("so_sha16") == so_sha16():
+                traffic, traffic_note = tj.get("dram_bytes_per_launch"), f"ncu dram__bytes_read+write of this build ({tj.get('so_sha16')})"
+            else:
+                traffic_note = f"profiles/r02_render_traffic.json was measured on build {tj.get('so_sha16')}, this is {so_sha16()}"
         except Exception:
-            traffic = None
+            pass
 
+    sharding = "1 GPU" if world == 1 else (f"one frame, {world} row blocks of {(rows[1] - rows[0]) // W} image rows; per-ray outputs stored into "
+                                          f"rank 0's frame buffers over NVLink peer memory by the fused launch, one barrier kernel per frame")
+    l2 = ("per-frame working set 0.65 GB of per-sample outputs (alpha, density) + 20 MB per-ray I/O >> 126 MB L2: inputs larger than "
+          "L2, no flush needed") if world == 1 else ("per-ray outputs only (17 MB per frame, written once over NVLink); the 2 MB weight "
+                                                     "image stays L2-resident by design")
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
-                ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
-                impl="ours",
-                config=dict(workload="C2 LineMOD-duck synthetic full-frame render 480x640x128, static+transient+light heads, "
-                                     "1 view per GPU per step (views sharded across ranks)",
+                ms_per_step=ms, higher_is_better=True, scaling="strong" if world > 1 else "weak", vs_baseline=None, dtype="bf16",
+                data="synthetic", impl="ours",
+                config=dict(workload=WORKLOAD + f", ONE frame per step ({sharding})",
                             rays_per_step=H * W, samples_per_ray=NS, ms_per_frame=ms, mlp="bf16 tcgen05, fp32 accumulate",
-                            weights="random-init seed 0 (Xavier, as the reference)", rng="in-kernel Philox jitter",
-                            l2="per-step working set ~2.2 GB (per-sample outputs + bias table) >> 126 MB L2; no flush needed"),
+                            weights="random-init seed 0 (Xavier, as the reference)", rng="in-kernel Philox jitter", l2=l2),
                 roofline=dict(bound="tensor", achieved=achieved_tf, peak=pk["tf_sustained"], unit="TFLOP/s",
-                              frac=achieved_tf / pk["tf_sustained"], traffic=traffic, kernel="tc::nerf_stl_forward_kernel",
+                              frac=achieved_tf / pk["tf_sustained"], traffic=traffic, traffic_note=traffic_note,
+                              kernel="tc::nerf_stl_forward_kernel<1,17,3> (fused render launch)",
                               kernel_ms=k_ms, kernel_share_of_step=k_ms / ms, peak_source=f"{pk['src']} bf16 sustained",
-                              flop_per_sample=FLOP_PER_SAMPLE_FWD),
+                              flop_per_sample=FLOP_PER_SAMPLE_FWD, samples_per_launch=local_samples),
                 e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=ms_e2e),
-                gpu_launches=launches, launches_per_step=per_step, clocks=clocks)
+                gpu_launches=launches, launches_per_step=per_step, clocks=clocks, so_sha16=so_sha16())
+    if weak:
+        line["weak_views"] = weak
     if train:
         line["train_step"] = train
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         try:
             line["eager_gpu_baseline"] = eager_gpu_sample(dev)
         except Exception as e:  # noqa: BLE001  (context only; never fails the bench)
             line["eager_gpu_baseline"] = dict(error=str(e)[:200])
         threads = os.cpu_count() or 1
-        cstep, csamples = cpu_render_sample(args.cpu_rays, threads)
+        cstep, csamples, kind, desc = cpu_reference_step(args.cpu_rays, threads)
         cstep()
-        best = 1e30
-        for _ in range(2):
+        times = []
+        t_end = time.perf_counter() + 20.0
+        while len(times) < 12 and (len(times) < 3 or time.perf_counter() < t_end):
             t0 = time.perf_counter()
             cstep()
-            best = min(best, time.perf_counter() - t0)
-        line["cpu_baseline"] = dict(value=csamples / best, unit=UNIT, cores=threads, kind="port",
-                                    sample=f"{args.cpu_rays} evenly spaced rays x {NS} samples of the same frame, fp32, "
-                                           f"best of 2 after warm-up (oracle = CPU restatement of the reference path)")
+            times.append(time.perf_counter() - t0)
+        line["cpu_baseline"] = dict(value=csamples / (sum(times) / len(times)), unit=UNIT, cores=threads, kind=kind,
+                                    sample=desc + f"; mean of {len(times)} steps after one warm-up")
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def bench_train(args, g, opt, dev, world, timed):
-    """C3: texture-learner step, 16 patches of 16x16 rays x 128 samples per GPU, fwd + bwd (+ grad allreduce)."""
+def bench_train(args, g, opt, dev, world, timed, pk):
+    """C3: texture-learner step, 16 patches of 16x16 rays x 128 samples per GPU, fwd + bwd (+ grad exchange)."""
     import torch
+    import torch.distributed as dist
     from texpose_b200 import compute_box, parallel, synth
     from texpose_b200.config import AttrDict, adapt_gan_opt
     from texpose_b200.model.base import summarize_loss
@@ -415,18 +561,59 @@ def bench_train(args, g, opt, dev, world, timed):
             var.update(ret)
             loss = g.compute_loss(opt_t, var, mode="train")      # patch gather + render / uncert / trans_reg terms, fused
             summarize_loss(opt_t, var, loss)["all"].backward()   # seeds formed on the device in the backward
-            bucket.allreduce_mean()
+            if bucket is not None:
+                bucket.allreduce_mean()
         return step
 
-    n_steps = max(10, args.steps)       # 2.5 ms each: enough steps for the max-over-ranks time to settle
+    n_steps = max(10, args.steps)       # 2.4 ms each: enough steps for the max-over-ranks time to settle
     ms, _ = timed(make_step(exchange), n_steps, 3)
     samples = B * P * P * NS
-    out = dict(workload="C3 train step fwd+bwd, 4096 rays x 128 samples per GPU, fused patch loss, bf16 tcgen05 fwd + bwd (dX chain with thin gradients, dW GEMMs), grad exchange",
+    tf = FLOP_PER_SAMPLE_FWD_BWD * samples / (ms * 1e-3) / 1e12
+    out = dict(workload="C3 train step fwd+bwd, 4096 rays x 128 samples per GPU, fused patch loss, bf16 tcgen05 fwd + bwd (dX chain with thin "
+                        "gradients, dW GEMMs), grad exchange",
                value=world * samples / (ms * 1e-3), unit="samples/s", ms_per_step=ms, grad_exchange_bytes=exchange.flat.numel() * 4,
                grad_exchange="none (1 GPU)" if world == 1 else "one-kernel rank-order mean over CUDA-IPC peer windows (NVLink)",
-               tflops_per_gpu=FLOP_PER_SAMPLE_FWD_BWD * samples / (ms * 1e-3) / 1e12, flop_per_sample=FLOP_PER_SAMPLE_FWD_BWD)
+               tflops_per_gpu=tf, flop_per_sample=FLOP_PER_SAMPLE_FWD_BWD, frac_of_sustained_bf16=tf / pk["tf_sustained"])
+    # per-entry-point device time of the step (CUDA events around every C-ABI call, a pass of its own) and the roofline of the
+    # two calls that carry the work; algorithmic bytes per 128-sample tile from DESIGN.md section 4 (K2 / K2b)
+    step = make_step(None)
+    with CallTimer() as ct:
+        for _ in range(5):
+            step()
+    per = {k: sum(v) / 5 for k, v in ct.per_call_ms().items()}
+    tiles = samples / 128
+    fwd_ms, bwd_ms = per.get("tp_tc_nerf_stl_forward", 0.0), per.get("tp_tc_heads_backward", 0.0)
+    fwd_bytes = tiles * (7 * 65536 + 4 * 4096) + samples * 36               # activation save + bitmasks + per-sample outputs
+    bwd_bytes = tiles * ((2 * 65536 + 4 * 4096 + 6 * 65536) + 13 * 65536)   # chain: in + dz out; dW GEMMs: dz + activations in
+
+    def roof(entry, t_ms, flop, nbytes, bound):
+        if not t_ms:
+            return dict(entry=entry, ms=None)
+        tfs, gbs = flop * samples / (t_ms * 1e-3) / 1e12, nbytes / (t_ms * 1e-3) / 1e9
+        return dict(entry=entry, ms=t_ms, bound=bound, achieved=tfs, unit="TFLOP/s", peak=pk["tf_sustained"], frac=tfs / pk["tf_sustained"],
+                    hbm_gbs=gbs, hbm_peak=pk["hbm"], hbm_frac=gbs / pk["hbm"], algorithmic_bytes=nbytes)
+
+    out["train_roofline"] = [
+        roof("tp_tc_nerf_stl_forward (training launch: forward + activation save)", fwd_ms, FLOP_PER_SAMPLE_FWD, fwd_bytes, "tensor"),
+        roof("tp_tc_heads_backward (dX chain + thin gradients, finish, six dW GEMMs, reduce: 5 launches)", bwd_ms, FLOP_PER_SAMPLE_BWD,
+             bwd_bytes, "tensor + hbm"),
+    ]
+    out["entry_point_ms"] = {k: round(v, 4) for k, v in sorted(per.items(), key=lambda kv: -kv[1])}
     if world > 1:
         exchange.check()
+        # the exchanged gradients must equal the NCCL allreduce of the same bucket: one more step, then both exchanges
+        make_step(None)()
+        ref_bucket = parallel.GradBucket(params)
+        ref_bucket.pack()
+        dist.all_reduce(ref_bucket.flat, op=dist.ReduceOp.SUM)
+        want = ref_bucket.flat / world
+        exchange.allreduce_mean()
+        got = exchange.flat[:want.numel()]
+        err, scale = float((got - want).abs().max()), float(want.abs().max())
+        out["exchange_vs_nccl_allreduce"] = dict(max_abs_diff=err, max_abs_value=scale,
+                                                 note="peer-window rank-order mean vs NCCL SUM / world of the same packed gradients")
+        if not err <= 1e-5 * max(scale, 1e-30) + 1e-12:
+            raise RuntimeError(f"peer exchange differs from the NCCL allreduce: {err} (scale {scale})")
         ms_nccl, _ = timed(make_step(parallel.GradBucket(params)), n_steps, 3)
         out["ms_per_step_nccl_allreduce"] = ms_nccl
         # the exchange alone, back to back (gradients already in place): device time per call, max over ranks

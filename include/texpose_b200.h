@@ -326,8 +326,9 @@ int tp_eval_epilogue(const float* rgb, const float* depth, const float* image, c
  * export/import = the 64-byte CUDA IPC handle a peer process opens, release/destroy undo them.
  * windows: HOST array of `world` device pointers (windows[rank] = the local window, the others imported, same order on
  * every rank; a single process may pass windows of one device to exercise the protocol).  out: local, >= n rounded up to
- * 4 floats, 16-byte aligned.  grid_ctas 0 = default.  A peer that does not arrive within timeout_ms (0 = 10 s) leaves `out`
- * untouched and stores `epoch` in the window's status word (tp_peer_status: host call, synchronising copy, 0 = healthy). */
+ * 4 floats, 16-byte aligned.  grid_ctas 0 = default.  A peer that does not arrive within timeout_ms (0 = 10 s) makes
+ * the kernel fill `out` with NaN (stale or partial gradients can never pass for a result) and store `epoch` in the window's
+ * status word (tp_peer_status: host call, synchronising copy, 0 = healthy). */
 int64_t tp_peer_capacity_bytes(int64_t n_floats);
 int64_t tp_peer_window_bytes(int64_t n_floats);
 int64_t tp_peer_data_offset(int64_t n_floats, int parity);
@@ -339,6 +340,12 @@ int tp_peer_window_release(void* imported_window);
 int tp_peer_allreduce_mean(void* const* windows, int world, int rank, int64_t n_floats, uint32_t epoch, float* out,
                            int grid_ctas, int64_t timeout_ms, void* stream);
 int tp_peer_status(const void* window, uint32_t* status_host);
+
+/* Completion barrier over the same windows (no data): rank publishes `epoch` (1, 2, ...) to every peer's header and waits
+ * for every peer's.  Stream-ordered after a tp_render_fused_forward launch whose output pointers address the root rank's
+ * window, it makes that rank's row block of the frame visible to the root (one-frame multi-GPU render, SURVEY 8e: "row
+ * blocks of HW ... gather of 56 B/ray").  A peer that never arrives sets the status word after timeout_ms (default 10 s). */
+int tp_peer_barrier(void* const* windows, int world, int rank, uint32_t epoch, int64_t timeout_ms, void* stream);
 
 #ifdef __cplusplus
 }

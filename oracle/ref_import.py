@@ -1,8 +1,9 @@
-"""Import the REAL reference (read-only checkout at /root/reference) with stub modules.
+"""Import the REAL reference with stub modules: the read-only checkout at /root/reference in the build container, or the
+unmodified copy that `python -m oracle.install_ref` leaves in baseline/_ref (git-ignored; it travels to the GPU box).
 
-TEST INFRASTRUCTURE ONLY (see oracle/texpose_oracle.py header).  Used by
-`oracle/make_golden.py` to generate `tests/golden/*.npz` and, when /root/reference is
-present (this container only -- never the GPU box), by `tests/test_oracle_vs_reference.py`.
+TEST / BENCH INFRASTRUCTURE ONLY (see oracle/texpose_oracle.py header).  Used by `oracle/make_golden.py` to generate
+`tests/golden/*.npz`, by `bench.py --impl reference` / its eager-GPU "before" number, and by the integration tests that
+patch texpose_b200 into the reference's own Graph (INTEGRATION.md option B).
 
 The reference imports third-party packages that are not installed here (easydict, ipdb,
 termcolor, pytorch3d, open3d, kornia, lpips, visdom, matplotlib, imageio, ...).  None of them
@@ -17,7 +18,18 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("TEXPOSE_REFERENCE", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_root() -> str:
+    cands = [os.environ.get("TEXPOSE_REFERENCE"), "/root/reference", os.path.join(_REPO, "baseline", "_ref")]
+    for c in cands:
+        if c and os.path.isdir(os.path.join(c, "layers")):
+            return c
+    return "/root/reference"
+
+
+REF_ROOT = _find_root()
 
 _STUB_ROOTS = ["ipdb", "termcolor", "pytorch3d", "open3d", "kornia", "lpips", "visdom", "matplotlib",
                "mpl_toolkits", "imageio", "plyfile", "trimesh", "tensorboard"]
@@ -75,6 +87,8 @@ def _install():
     if getattr(_install, "done", False):
         return
     _install.done = True
+    if not os.path.isdir(os.path.join(REF_ROOT, "external")):      # baseline/_ref leaves out external/ (SSIM / LPIPS helpers,
+        _STUB_ROOTS.append("external")                             # not on the render path)
     sys.meta_path.append(_StubFinder)
     # easydict: attribute dict -- reuse the product's AttrDict (pure container, no arithmetic)
     from texpose_b200.config import AttrDict
@@ -149,6 +163,23 @@ def load_yaml_opt(name="nerf_lm_adapt_gan", H=480, W=640, device="cpu"):
     opt.device = device
     opt.H, opt.W = H, W
     return opt
+
+
+class cpu_shim:
+    """The reference hard-codes `.cuda()` in three places of the render path (model/nerf_adapt_st_gan.py:600,659-667,708).
+    To time its own code on the host cores, `.cuda()` is made the identity for the duration of the block -- an environment
+    shim like the import stubs above; no line of the reference changes."""
+
+    def __enter__(self):
+        import torch
+        self._orig = torch.Tensor.cuda
+        torch.Tensor.cuda = lambda t, *a, **k: t
+        return self
+
+    def __exit__(self, *exc):
+        import torch
+        torch.Tensor.cuda = self._orig
+        return False
 
 
 def build_graph(ns, opt, n_images=4, seed=0):

@@ -4,7 +4,7 @@ seeded inputs.  Shared by the C3 parity test and the data-parallel equivalence t
 import torch
 
 from oracle import texpose_oracle as O
-from texpose_b200 import compute_box, synth
+from texpose_b200 import camera, compute_box, synth
 from texpose_b200.config import AttrDict, adapt_gan_opt
 from texpose_b200.model import base
 from texpose_b200.model.nerf_adapt_st_gan import Graph
@@ -42,14 +42,21 @@ def cuda_step(opt, g, inp, images, dev, seed):
     sl = images
     pose, intr = inp.pose[sl].to(dev), inp.intr[sl].to(dev)
     lo, hi = [t.to(dev) for t in synth.padded_aabb()]
-    zn, zf = compute_box.box_range(pose, intr, lo, hi, H, W, *synth.BG_RANGE)
     coords = inp.coords[sl].to(dev)
     idx = inp.idx[sl].to(dev)
     for _, p in named_trainables(g):
         p.grad = None
     n = len(idx)
-    torch.manual_seed(seed)
-    ret = g.render(opt, pose, intr=intr, ray_idx=coords, depth_range=(zn[:, :, None], zf[:, :, None]), sample_idx=idx, mode="train")
+    # K^-1 / pose^-1 with the CPU reference's LAPACK bits, so rays and bounds are bit-identical to the oracle's (the 2^9 pi
+    # positional encoding amplifies an ulp of difference in a ray to ~1e-3 at the outputs: DESIGN.md section 2)
+    host_matrices = camera.HOST_MATRICES
+    camera.HOST_MATRICES = True
+    try:
+        zn, zf = compute_box.box_range(pose, intr, lo, hi, H, W, *synth.BG_RANGE)
+        torch.manual_seed(seed)
+        ret = g.render(opt, pose, intr=intr, ray_idx=coords, depth_range=(zn[:, :, None], zf[:, :, None]), sample_idx=idx, mode="train")
+    finally:
+        camera.HOST_MATRICES = host_matrices
     torch.manual_seed(seed)
     rand = torch.rand(n, P * P, N, 1, device=dev).cpu()          # the draw Graph.sample_depth just made (:690)
     var = AttrDict(idx=idx, image=inp.image[sl].to(dev), obj_mask=inp.mask[sl].to(dev), ray_idx=coords)

@@ -85,7 +85,8 @@ __device__ __forceinline__ float render_jitter(const Params& p, long long s) {
   return tp_u01(e == 0 ? x.x : e == 1 ? x.y : e == 2 ? x.z : x.w);
 }
 
-__device__ __forceinline__ RenderSample render_encode(const Params& p, long long tile, int row, int lane, uint32_t e_smem) {
+// (the encoding comes back in registers: the caller stores it once the E tile is free)
+__device__ __forceinline__ RenderSample render_prepare(const Params& p, long long tile, int row, int lane, uint32_t (&enc)[32]) {
   RenderSample o;
   const int N = p.N;                                      // divides 128: a tile holds 128 / N whole rays
   o.k = row % N;
@@ -109,7 +110,7 @@ __device__ __forceinline__ RenderSample render_encode(const Params& p, long long
   const float dn = stratified_depth(u1, o.k + 1, fn, lo, hi);
   const float len = sqrtf(o.dir[0] * o.dir[0] + o.dir[1] * o.dir[1] + o.dir[2] * o.dir[2]);
   o.dist = __fmul_rn(o.k + 1 < N ? __fsub_rn(dn, o.d) : 1e10f, len);
-  encode_point(c, o.dir, o.d, e_smem, row);
+  encode_regs(c, o.dir, o.d, enc);
   return o;
 }
 
@@ -379,15 +380,18 @@ __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_ke
     // sample, which then belongs to the same ray as the warp's live rows
     const bool warp_bias = kMode ? true : (p.N % 32 == 0);      // modes 1-3 are launched only when N % 32 == 0
     bool store_pending = false;      // a bulk store of A_t (feature park / activation save) may still be reading it
-    RenderSample rs = {};            // render launch: the sample this row holds
+    RenderSample rs = {}, rs_next = {};      // render launch: the sample this row holds / will hold in the next super-tile
+    uint32_t enc_next[32];                   // ... and the next sample's encoding, computed a stage early (below)
     int iter = 0;
     for (long long st = blockIdx.x; st < n_super; st += gridDim.x, ++iter) {
       const long long s_raw = (st * 2 + t) * 128 + row;
       const bool live = s_raw < p.S;
       const long long s = live ? s_raw : p.S - 1;
       if (!kRender || iter == 0) {     // (the render launch encodes the next super-tile at the end of the last stage, below)
-        if (kRender) rs = render_encode(p, st * 2 + t, row, lane, e_smem);
-        else if (half == 0) encode_sample(p, s, e_smem, row);
+        if (kRender) {
+          rs = render_prepare(p, st * 2 + t, row, lane, enc_next);
+          store_encoding(enc_next, e_smem, row);
+        } else if (half == 0) encode_sample(p, s, e_smem, row);
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();                    // every lane's st.shared + proxy fence precede the warp's single arrive
@@ -411,6 +415,13 @@ __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_ke
             wb[0] = __ldg(reinterpret_cast<const float4*>(brow) + lane);
             if (kCols == 256) wb[1] = __ldg(reinterpret_cast<const float4*>(brow + 128) + lane);
           }
+        }
+        if (kRender && L == kNL - 2 && st + gridDim.x < n_super) {
+          // the next super-tile's sample of this row -- ray, bounds, jitter, depth, interval, encoding -- is worked out NOW, in
+          // the shadow of this stage's MMAs (the warp would only wait for the accumulator); the 32 packed words wait in
+          // registers until the E tile is free, so the hand-over after the last stage is eight st.shared instead of two
+          // dependent global loads, a Philox block, two IEEE divisions and sixty sines
+          rs_next = render_prepare(p, (st + gridDim.x) * 2 + t, row, lane, enc_next);
         }
         mbar_wait(bar_acc(t), acc_ph);
         acc_ph ^= 1;
@@ -496,7 +507,8 @@ __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_ke
               // one is composited, so the compositing overlaps tensor work instead of leaving the pipe idle
               const RenderSample cur = rs;
               if (st + gridDim.x < n_super) {
-                rs = render_encode(p, (st + gridDim.x) * 2 + t, row, lane, e_smem);
+                store_encoding(enc_next, e_smem, row);
+                rs = rs_next;
                 fence_proxy_async_smem();
                 tc_fence_before();
                 __syncwarp();

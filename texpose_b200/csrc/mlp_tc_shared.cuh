@@ -108,9 +108,10 @@ struct Params {
   float* o_at;
 };
 
-// positional encoding of one point into the E tile (bf16): [x,y,z, per coord sin(2^k pi x) k<10, cos(...) k<10, 1].
-// sincospif gives the exact-argument octave 0; higher octaves by the double-angle recurrence (error << bf16 ulp).
-__device__ __forceinline__ void encode_point(const float (&c)[3], const float (&r)[3], float d, uint32_t e_smem, int row) {
+// positional encoding of one point as the 32 packed bf16x2 words of its E-tile row: [x,y,z, per coord sin(2^k pi x) k<10,
+// cos(...) k<10, 1].  sincospif gives the exact-argument octave 0; higher octaves by the double-angle recurrence (error <<
+// bf16 ulp).  Kept in registers so the arithmetic can run while the E tile is still being read by the previous super-tile.
+__device__ __forceinline__ void encode_regs(const float (&c)[3], const float (&r)[3], float d, uint32_t (&e)[32]) {
   float v[64];
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
@@ -129,9 +130,16 @@ __device__ __forceinline__ void encode_point(const float (&c)[3], const float (&
   }
   v[63] = 1.f;   // constant-1 column: carries the static biases through the MMA
 #pragma unroll
-  for (int k8 = 0; k8 < 8; ++k8)
-    st_shared_v4(e_smem + k8 * 2048 + row * 16, pack_bf16(v[k8 * 8 + 0], v[k8 * 8 + 1]), pack_bf16(v[k8 * 8 + 2], v[k8 * 8 + 3]),
-                 pack_bf16(v[k8 * 8 + 4], v[k8 * 8 + 5]), pack_bf16(v[k8 * 8 + 6], v[k8 * 8 + 7]));
+  for (int i = 0; i < 32; ++i) e[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
+}
+__device__ __forceinline__ void store_encoding(const uint32_t (&e)[32], uint32_t e_smem, int row) {
+#pragma unroll
+  for (int k8 = 0; k8 < 8; ++k8) st_shared_v4(e_smem + k8 * 2048 + row * 16, e[4 * k8], e[4 * k8 + 1], e[4 * k8 + 2], e[4 * k8 + 3]);
+}
+__device__ __forceinline__ void encode_point(const float (&c)[3], const float (&r)[3], float d, uint32_t e_smem, int row) {
+  uint32_t e[32];
+  encode_regs(c, r, d, e);
+  store_encoding(e, e_smem, row);
 }
 
 __device__ __forceinline__ void encode_sample(const Params& p, long long s, uint32_t e_smem, int row) {

@@ -5,7 +5,8 @@
 // exchange is ONE kernel over CUDA-IPC peer windows:
 //
 //   window (one per rank, cudaMalloc'ed, opened by every peer):  [ header 1 KB | data buffer 0 | data buffer 1 ]
-//     header: arrive[16] u32 (slot p = "rank p's gradients of epoch e are in place"), status u32 at byte 512
+//     header: arrive[16] u32 (slot p = "rank p's gradients of epoch e are in place"), barrier[16] u32 at byte 128
+//     (tp_peer_barrier), status u32 at byte 512
 //   step e (e = 1, 2, ...), on every rank, on the caller's stream:
 //     1. the caller packs its gradients into data buffer e&1 of its OWN window (ordinary local writes);
 //     2. CTA 0 publishes: st.release.sys  arrive[rank] = e  into every peer's header (NVLink stores);
@@ -27,6 +28,7 @@ namespace {
 constexpr int kMaxWorld = 16;
 constexpr int64_t kHeaderBytes = 1024;
 constexpr int kStatusWord = 128;   // u32 index of the status word inside the header (byte 512)
+constexpr int kBarrierSlot0 = 32;  // u32 index of the barrier slots [16] (tp_peer_barrier; separate from the exchange's arrive[16])
 
 struct Windows {
   uint8_t* base[kMaxWorld];
@@ -141,6 +143,32 @@ __global__ void __launch_bounds__(256) peer_allreduce_mean_kernel(const Windows 
   }
 }
 
+// Completion barrier over the windows' headers (no data): publish `epoch` into slot `rank` of every peer's header, then wait
+// until every peer's slot in the LOCAL header has reached it.  Used after the fused render launch whose compositing epilogue
+// stored this rank's row block of the frame straight into the root rank's window: when the root passes the barrier, every
+// rank's stores have been performed at system scope (kernel boundary + fence.sys before the release store).
+__global__ void peer_barrier_kernel(const Windows w, int world, int rank, uint32_t epoch, unsigned long long timeout_ns) {
+  uint32_t* my_hdr = reinterpret_cast<uint32_t*>(w.base[rank]);
+  int failed = 0;
+  if (threadIdx.x < world) {
+    __threadfence_system();
+    st_release_sys(reinterpret_cast<uint32_t*>(w.base[threadIdx.x]) + kBarrierSlot0 + rank, epoch);
+    if (threadIdx.x != rank) {
+      const uint32_t* flag = my_hdr + kBarrierSlot0 + threadIdx.x;
+      const unsigned long long t0 = global_ns();
+      while ((int32_t)(ld_acquire_sys(flag) - epoch) < 0) {
+        if (global_ns() - t0 > timeout_ns) {
+          failed = 1;
+          break;
+        }
+        __nanosleep(64);
+      }
+    }
+  }
+  failed = __syncthreads_or(failed);
+  if (failed && threadIdx.x == 0) atomicMax(my_hdr + kStatusWord, epoch);
+}
+
 inline int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
 
 }  // namespace
@@ -218,6 +246,18 @@ TP_API int tp_peer_allreduce_mean(void* const* windows, int world, int rank, int
   if (timeout_ms <= 0) timeout_ms = 10000;
   peer_allreduce_mean_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       w, world, rank, n4, tp_peer_capacity_bytes(n_floats), epoch, out, (unsigned long long)timeout_ms * 1000000ull);
+  return tp_launch_status();
+}
+
+TP_API int tp_peer_barrier(void* const* windows, int world, int rank, uint32_t epoch, int64_t timeout_ms, void* stream) {
+  if (windows == nullptr || world < 1 || world > kMaxWorld || rank < 0 || rank >= world || epoch == 0) return TP_ERR_BAD_ARG;
+  Windows w;
+  for (int p = 0; p < kMaxWorld; ++p) {
+    w.base[p] = p < world ? static_cast<uint8_t*>(windows[p]) : nullptr;
+    if (p < world && (w.base[p] == nullptr || (reinterpret_cast<uintptr_t>(w.base[p]) & 255u) != 0)) return TP_ERR_ALIGN;
+  }
+  if (timeout_ms <= 0) timeout_ms = 10000;
+  peer_barrier_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(w, world, rank, epoch, (unsigned long long)timeout_ms * 1000000ull);
   return tp_launch_status();
 }
 

@@ -204,6 +204,97 @@ class PeerGradExchange(GradBucket):
         self.window.close()
 
 
+PER_RAY_KEYS = ("rgb", "rgb_static", "rgb_transient", "depth", "opacity", "opacity_static", "opacity_transient", "uncert")
+_PER_RAY_CHANNELS = dict(rgb=3, rgb_static=3, rgb_transient=3, depth=1, opacity=1, opacity_static=1, opacity_transient=1, uncert=1)
+
+
+def frame_layout(n_rays: int, keys: Sequence[str] = PER_RAY_KEYS):
+    """Float offsets of the per-ray frame buffers inside one data buffer of the gather window: {key: (offset, channels)},
+    total floats.  Every buffer starts on a 64-float (256 B) boundary."""
+    off, out = 0, {}
+    for k in keys:
+        c = _PER_RAY_CHANNELS[k]
+        out[k] = (off, c)
+        off += (n_rays * c + 63) // 64 * 64
+    return out, off
+
+
+def peer_barrier(window_ptrs: Sequence[int], rank: int, epoch: int, device, timeout_ms: int = 0, stream=None):
+    arr = (ctypes.c_void_p * len(window_ptrs))(*window_ptrs)
+    st = stream if stream is not None else torch.cuda.current_stream(device)
+    with torch.cuda.device(device):
+        _C.call("tp_peer_barrier", arr, len(window_ptrs), rank, epoch, timeout_ms, st.cuda_stream)
+
+
+class FrameGather:
+    """ONE frame rendered by all ranks of a node (the north-star's 480x640x128 frame at 1/2/4/8 GPUs; the reference is
+    single-GPU, options.py:112).  Rank r renders the row block shard_rays(HW, r, world, align=W) with the fused render launch,
+    whose compositing epilogue stores the 56 B/ray outputs STRAIGHT INTO THE ROOT RANK'S FRAME BUFFERS -- a CUDA-IPC window, so
+    the stores of ranks != root travel over NVLink as they are produced: the gather is the kernel's own output write, there
+    is no collective and no staging copy.  One tiny barrier kernel per frame (tp_peer_barrier) publishes completion.
+
+    Frame e lands in data buffer e & 1 of the root's window, so the root may still read frame e while frame e+1 is rendered;
+    buffer e & 1 is rewritten by frame e+2, which no rank starts before the root has passed barrier e+1 -- i.e. after whatever
+    the root enqueued on its stream between the two barriers (its reads of frame e).  Per-sample tensors (alpha_*, density:
+    16 B/sample) are not gathered: a rank that wants them for its rows passes them in `local_keys`."""
+
+    def __init__(self, opt, keys: Sequence[str] = PER_RAY_KEYS, root: int = 0, group=None, timeout_ms: int = 10000, device=None):
+        self.keys = tuple(keys)
+        self.H, self.W = int(opt.H), int(opt.W)
+        self.HW = self.H * self.W
+        self.layout, self.n = frame_layout(self.HW, self.keys)
+        self.group, self.root, self.timeout_ms = group, int(root), int(timeout_ms)
+        distributed = dist.is_available() and dist.is_initialized()
+        self.rank = dist.get_rank(group) if distributed else 0
+        self.world = dist.get_world_size(group) if distributed else 1
+        self.device = torch.device(device if device is not None else opt.device)
+        self.window = PeerWindow(self.n, self.device)
+        if self.world > 1:
+            handles = [None] * self.world
+            dist.all_gather_object(handles, self.window.handle(), group=group)
+            self.ptrs = [self.window.ptr if r == self.rank else self.window.open_peer(h) for r, h in enumerate(handles)]
+        else:
+            self.ptrs = [self.window.ptr]
+        self.epoch = 0
+        lib = _C.load()
+        self._data_off = [int(lib.tp_peer_data_offset(self.n, k)) for k in (0, 1)]
+        self.rows = shard_rays(self.HW, self.rank, self.world, align=self.W)
+        torch.cuda.synchronize(self.device)
+        if self.world > 1:
+            dist.barrier(group)
+
+    def frame_views(self, parity: int):
+        """The root's view of one data buffer: {key: [1, HW, C] tensor} (valid on the root after the frame's barrier)."""
+        buf = self.window.buffers[parity]
+        return {k: buf[o:o + self.HW * c].view(1, self.HW, c) for k, (o, c) in self.layout.items()}
+
+    def render(self, graph, opt, pose, intr, depth_range, sample_idx=None, mode="val", local_keys: Sequence[str] = ()):
+        """Renders this rank's row block of the frame of view `pose` ([1,3,4]) and gathers it.  Returns (frame, local): `frame` =
+        {key: [1,HW,C]} on the root (None elsewhere), `local` = the `local_keys` outputs of this rank's rows."""
+        if len(pose) != 1:
+            raise ValueError("FrameGather renders one view per call")
+        self.epoch += 1
+        par = self.epoch & 1
+        b, e = self.rows
+        base = self.ptrs[self.root] + self._data_off[par]
+        out_ptrs = {k: base + 4 * (o + b * c) for k, (o, c) in self.layout.items()}
+        local = graph._render_fused(opt, pose, intr, range(b, e), depth_range, sample_idx, mode,
+                                    want=tuple(self.keys) + tuple(local_keys), out_ptrs=out_ptrs)
+        peer_barrier(self.ptrs, self.rank, self.epoch, self.device, timeout_ms=self.timeout_ms)
+        return (self.frame_views(par) if self.rank == self.root else None), local
+
+    def check(self):
+        bad = self.window.status()
+        if bad:
+            raise RuntimeError(f"FrameGather: a rank did not finish frame {bad} within {self.timeout_ms} ms")
+
+    def close(self):
+        if self.world > 1 and dist.is_initialized():
+            torch.cuda.synchronize(self.device)
+            dist.barrier(self.group)
+        self.window.close()
+
+
 def gather_ray_outputs(local: torch.Tensor, sizes: Sequence[int], group=None) -> torch.Tensor:
     """all_gather of per-ray outputs [R_local, C] from uneven contiguous shards -> [sum(sizes), C] on every rank."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
