@@ -164,6 +164,8 @@ int tp_tc_num_chunks(void);
 int64_t tp_tc_chunk_bytes(void);
 /* Bytes of L2-resident scratch the forward needs (parked trunk features: SMs x 2 tiles x 64 KB). */
 int64_t tp_tc_scratch_bytes(void);
+/* Byte offset, inside that scratch, of the cycle counters a -DTP_FWD_PROF build of the library leaves behind (debugging aid). */
+int64_t tp_tc_prof_offset(void);
 
 /* Packs fp32 nn.Linear weights (and the static biases, which ride on a constant-1 input column) into the bf16 SMEM
  * images of the chunks.  chunk_desc: DEVICE int64 [n_chunks,10] rows {W device pointer (0 = none), ld, row0, rows_valid,

@@ -98,14 +98,15 @@ def test_val_mode_broadcasts_latent_row_zero_to_every_view(precision):
     zn, zf = compute_box.box_range(pose, intr, lo, hi, H, W, *synth.BG_RANGE)
     idx = torch.arange(H * W, device=DEV)[None].expand(B, -1)
     dr = (zn[:, :, None], zf[:, :, None])
-    tol = 2e-3 if precision == "fp32" else 1e-2
+    tol = 2e-3 if precision == "fp32" else 2e-2      # relative to the quantity's range (uncert reaches ~2 with these latents)
     with torch.no_grad():
         full = g.render(opt, pose, intr=intr, ray_idx=idx, depth_range=dr, mode="val")
         for b in range(B):
             one = g.render(opt, pose[b:b + 1], intr=intr[b:b + 1], ray_idx=idx[:1], depth_range=(dr[0][b:b + 1], dr[1][b:b + 1]),
                            mode="val")
             for k in ("rgb", "uncert", "rgb_transient"):
-                assert (full[k][b] - one[k][0]).abs().max() <= tol, (b, k, float((full[k][b] - one[k][0]).abs().max()))
+                scale = max(1.0, float(one[k].abs().max()))
+                assert (full[k][b] - one[k][0]).abs().max() <= tol * scale, (b, k, float((full[k][b] - one[k][0]).abs().max()))
         # the same render with row 1's latents differs by far more than the tolerance: the check above is discriminating
         g.latent_vars_trans.weight[0], g.latent_vars_light.weight[0] = g.latent_vars_trans.weight[1].clone(), g.latent_vars_light.weight[1].clone()
         other = g.render(opt, pose[1:2], intr=intr[1:2], ray_idx=idx[:1], depth_range=(dr[0][1:2], dr[1][1:2]), mode="val")

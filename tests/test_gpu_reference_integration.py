@@ -36,7 +36,7 @@ def _problem():
     host = bcam.HOST_MATRICES
     zn, zf = compute_box.box_range(pose, intr, lo, hi, H, W, *synth.BG_RANGE)
     obj = (zf[0] < 29).nonzero()[:, 0]
-    assert len(obj) > 200
+    assert len(obj) > 100
     return ns, opt, pose, intr, (zn[:, :, None], zf[:, :, None]), obj[None]
 
 

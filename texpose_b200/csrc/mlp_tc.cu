@@ -24,7 +24,7 @@
 //   * the trunk feature (needed by both heads) is parked in an L2-resident scratch with a bulk store after
 //     the last trunk layer and bulk-loaded back before the transient head.
 //
-// SMEM (bytes): A0 64K | A1 64K | E0 16K | E1 16K | ring 4x16K | barriers 128 | compositing scratch 1 088 = 230 592 (<= 227 KB).
+// SMEM (bytes): A0 64K | A1 64K | E0 16K | E1 16K | ring 4x16K | barriers 128 | compositing scratch 544 | bias rows 2 x 1K = 232 096 (<= 227 KB).
 // TMEM: 512 columns = two 128x256 fp32 accumulators.
 //
 // Operand layout (no swizzle, K-major "interleave" canonical layout): element (row r, col k) of a tile with
@@ -42,12 +42,16 @@ template <int kHalves> constexpr int num_threads() { return (8 * kHalves + 2) * 
 constexpr int kStages = 4;
 constexpr uint32_t kOffA = 0, kOffE = 2 * kABytes, kOffRing = kOffE + 2 * kEBytes;
 constexpr uint32_t kOffBar = kOffRing + kStages * kChunkBytes;
-// compositing scratch of the render launch: [parity 2][tile 2][ warp totals 4 x 3 | warp partial sums 4 x 14 ] floats
+// compositing scratch of the render launch: [tile 2][ warp totals 4 x 3 | warp partial sums 4 x 14 ] floats, then one 1 KB
+// fp32 bias row per tile (the per-ray / per-image row of the two table-bias stages when all 128 rows of the tile share it)
 constexpr int kCompFloats = 4 * 3 + 4 * 14;
 constexpr uint32_t kOffComp = kOffBar + 128;
-constexpr uint32_t kSmemBytes = kOffComp + 2 * 2 * kCompFloats * 4;
+constexpr uint32_t kOffBias = kOffComp + 2 * kCompFloats * 4;
+constexpr uint32_t kSmemBytes = kOffBias + 2 * 1024;
+static_assert(kOffBias % 16 == 0, "bias rows are read with ld.shared.v4");
 static_assert(kSmemBytes <= 232448, "227 KB of shared memory per CTA");
 constexpr unsigned kFullMask = 0xffffffffu;
+constexpr int kViewBiasLayer = 6;      // render launch: the view-direction bias rows are computed while this stage's MMAs run
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -72,21 +76,47 @@ struct RenderSample {
   int k;              // sample index within the ray
   int img;            // view
   float d, dist;      // depth, (d_{k+1} - d_k) * |ray|  (1e10 * |ray| for the last sample: layers/..light.py:169-175)
-  float dir[3];
+  float dir[3];       // ray direction (unnormalised, camera-z = 1)
+  float xyz[3];       // the sample point c + ray * d
   bool live;
 };
 
-__device__ __forceinline__ float render_jitter(const Params& p, long long s) {
-  if (p.depth_mode == 0) return p.rand[s];
-  if (p.depth_mode == 1) return 0.5f;
-  const long long qd = s >> 2;
+// Stratified jitter of this lane's sample and of the NEXT sample of its ray (for the interval).  A warp holds 32 consecutive
+// samples = 8 Philox quads (tp_sample_depth's stream: one Philox4x32-10 block per 4 consecutive samples, counter = sample / 4):
+// lanes 0..8 evaluate quads 0..8 of the warp ONCE (quad 8 = the first sample of the next warp, lane 31's neighbour) and four
+// shuffles hand every lane its component -- one Philox evaluation per warp instead of two.
+__device__ __forceinline__ void render_jitter_pair(const Params& p, long long s, int lane, bool has_next, float& u0, float& u1) {
+  if (p.depth_mode == 1) {
+    u0 = u1 = 0.5f;
+    return;
+  }
+  if (p.depth_mode == 0) {
+    u0 = p.rand[s];
+    u1 = __shfl_down_sync(kFullMask, u0, 1);
+    if (lane == 31 && has_next) u1 = p.rand[s + 1];
+    return;
+  }
+  const long long qd = ((s - lane) >> 2) + lane;      // (s - lane) is the warp's first sample: a multiple of 32
   const uint4 x = tp_philox((uint32_t)qd, (uint32_t)(qd >> 32), (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
-  const int e = (int)(s & 3);
-  return tp_u01(e == 0 ? x.x : e == 1 ? x.y : e == 2 ? x.z : x.w);
+  const int src = lane >> 2, e = lane & 3;
+  const float c0 = __shfl_sync(kFullMask, tp_u01(x.x), src), c1 = __shfl_sync(kFullMask, tp_u01(x.y), src),
+              c2 = __shfl_sync(kFullMask, tp_u01(x.z), src), c3 = __shfl_sync(kFullMask, tp_u01(x.w), src);
+  u0 = e == 0 ? c0 : e == 1 ? c1 : e == 2 ? c2 : c3;
+  const float nq = __shfl_sync(kFullMask, tp_u01(x.x), 8);      // first component of the next warp's first quad
+  u1 = __shfl_down_sync(kFullMask, u0, 1);
+  if (lane == 31) u1 = nq;
 }
 
-// (the encoding comes back in registers: the caller stores it once the E tile is free)
-__device__ __forceinline__ RenderSample render_prepare(const Params& p, long long tile, int row, int lane, uint32_t (&enc)[32]) {
+// stratified_depth for N = 2^m: (u + k) / N is an exact scaling, so the multiplication gives the division's bits
+__device__ __forceinline__ float stratified_depth_pow2(float u, int k, float inv_n, float lo, float hi) {
+  return __fadd_rn(__fmul_rn(__fmul_rn(__fadd_rn(u, (float)k), inv_n), __fsub_rn(hi, lo)), lo);
+}
+
+// Everything of a sample but its encoding: pixel -> ray, bounds, jitter, depth, interval, point.  A call, like the other render
+// pieces: the stage loop of the epilogue warps must stay small and spill-free -- local-memory traffic and instruction fetch share
+// the SM's data paths with the MMAs' operand reads, and every build that carried this code inside the loop was slower
+// (scripts/fwd_prof.py).  It runs where both tiles and the tensor pipe wait anyway (below); the encoding follows from `xyz`.
+__device__ __noinline__ RenderSample render_fetch(const Params& p, long long tile, int row, int lane) {
   RenderSample o;
   const int N = p.N;                                      // divides 128: a tile holds 128 / N whole rays
   o.k = row % N;
@@ -102,28 +132,38 @@ __device__ __forceinline__ RenderSample render_prepare(const Params& p, long lon
             __fadd_rn((float)(pix / p.W), p.pix_offset), c, o.dir);
   const long long zi = b * (long long)p.H * p.W + pix;
   const float lo = p.z_near[zi], hi = p.z_far[zi];
-  const float u0 = render_jitter(p, s);
-  float u1 = __shfl_down_sync(kFullMask, u0, 1);           // the next sample of the ray sits in the next lane ...
-  if (lane == 31 && o.k + 1 < N) u1 = render_jitter(p, s + 1);      // ... or in the next warp
-  const float fn = (float)N;
-  o.d = stratified_depth(u0, o.k, fn, lo, hi);
-  const float dn = stratified_depth(u1, o.k + 1, fn, lo, hi);
+  float u0, u1;
+  render_jitter_pair(p, s, lane, o.k + 1 < N, u0, u1);
+  const float inv_n = 1.f / (float)N;                      // N in {32, 64, 128}: exact
+  o.d = stratified_depth_pow2(u0, o.k, inv_n, lo, hi);
+  const float dn = stratified_depth_pow2(u1, o.k + 1, inv_n, lo, hi);
   const float len = sqrtf(o.dir[0] * o.dir[0] + o.dir[1] * o.dir[1] + o.dir[2] * o.dir[2]);
   o.dist = __fmul_rn(o.k + 1 < N ? __fsub_rn(dn, o.d) : 1e10f, len);
-  encode_regs(c, o.dir, o.d, enc);
+#pragma unroll
+  for (int j = 0; j < 3; ++j) o.xyz[j] = __fadd_rn(c[j], __fmul_rn(o.dir[j], o.d));      // camera.py:317-322
   return o;
 }
+__device__ __noinline__ void render_encode(const float x, const float y, const float z, uint32_t e_smem, int row) {
+  const float xyz[3] = {x, y, z};
+  uint32_t e[32];
+  encode_xyz_regs(xyz, e);
+  store_encoding(e, e_smem, row);
+}
 
-// rgb-0 bias row of the warp's ray: imgbias_rgb[view] + W_view [u, enc(u)], u = ray / |ray| (layers/..light.py:104-117,155-157),
-// in the distributed layout hidden_epilogue_wbias reads (lane l: columns 4l..4l+3 and 128+4l..).  Same operation order as
-// tp_tc_ray_bias, whose 315 MB table this replaces: lane j holds element j of the 3+6L encoding, 27 shuffles feed 8 fma chains.
-__device__ __forceinline__ void render_view_bias(const Params& p, const RenderSample& rs, int lane, float4 (&wb)[2]) {
-  const float len = fmaxf(sqrtf(rs.dir[0] * rs.dir[0] + rs.dir[1] * rs.dir[1] + rs.dir[2] * rs.dir[2]), 1e-12f);
+// rgb-0 bias row of a ray: imgbias_rgb[view] + W_view [u, enc(u)], u = ray / |ray| (layers/..light.py:104-117,155-157).  Same
+// operation order as tp_tc_ray_bias, whose 315 MB table this replaces (one fma chain per column, inputs in ascending order), so
+// the row has the table's bits.  The ray's N / 32 warps share the row: warp w computes columns [w, w+1) * 256 / wpr, every lane
+// kC = 8 / wpr consecutive ones; lane j holds element j of the 3+6L encoding and shuffles broadcast it.  The 27 inputs are taken
+// nine at a time in the shadow of three consecutive trunk stages (the nine weight loads of a batch are independent: one L2
+// round trip per stage, 18-36 registers), the partial sums wait in registers, and the slices meet in a 1 KB slot of the CTA's
+// L2-resident scratch; at the rgb-0 stage the ray's warps read the row back exactly as the per-sample launches read the table.
+__device__ __noinline__ float render_view_element(const Params& p, const RenderSample& rs, int lane) {
+  const float len = unit_length(rs.dir[0], rs.dir[1], rs.dir[2]);
   const int L = p.L_view, vc = 3 + 6 * L;
   float e = 0.f;
   if (lane < vc) {
     const int jj = lane - 3, cc = lane < 3 ? lane : jj / (2 * L);
-    const float uc = (cc == 0 ? rs.dir[0] : cc == 1 ? rs.dir[1] : rs.dir[2]) / len;
+    const float uc = __fdiv_rn(cc == 0 ? rs.dir[0] : cc == 1 ? rs.dir[1] : rs.dir[2], len);
     e = uc;
     if (lane >= 3) {
       const int rem = jj - cc * 2 * L, k = rem < L ? rem : rem - L;
@@ -131,28 +171,48 @@ __device__ __forceinline__ void render_view_bias(const Params& p, const RenderSa
       e = rem < L ? sinf(arg) : cosf(arg);
     }
   }
-  const float* brow = p.imgbias_rgb + (long long)rs.img * 256;
-  float4 a0 = __ldg(reinterpret_cast<const float4*>(brow) + lane), a1 = __ldg(reinterpret_cast<const float4*>(brow + 128) + lane);
+  return e;
+}
+// inputs j0 .. j0+8 of columns col .. col+kC-1 (kC = 2 or 4): acc[c] = fma(W[j][col+c], e_j, acc[c]) in ascending j.  A call,
+// not inlined (the stage loop of the epilogue warps stays small; arguments and result travel in registers).
+template <int kC>
+__device__ __noinline__ float4 render_view_batch(const Params& p, float e, int col, int j0, float4 acc4) {
+  const int vc = 3 + 6 * p.L_view;
+  float acc[4] = {acc4.x, acc4.y, acc4.z, acc4.w};
+  float w[9][kC];
 #pragma unroll
-  for (int j = 0; j < 27; ++j) {
-    if (j < vc) {
-      const float ej = __shfl_sync(kFullMask, e, j);
-      const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.wview + j * 256) + lane);
-      const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.wview + j * 256 + 128) + lane);
-      a0.x = fmaf(w0.x, ej, a0.x); a0.y = fmaf(w0.y, ej, a0.y); a0.z = fmaf(w0.z, ej, a0.z); a0.w = fmaf(w0.w, ej, a0.w);
-      a1.x = fmaf(w1.x, ej, a1.x); a1.y = fmaf(w1.y, ej, a1.y); a1.z = fmaf(w1.z, ej, a1.z); a1.w = fmaf(w1.w, ej, a1.w);
+  for (int i = 0; i < 9; ++i) {
+    if (j0 + i < vc) {
+      const float* wr = p.wview + (j0 + i) * 256 + col;
+      if (kC == 2) {
+        const float2 t2 = __ldg(reinterpret_cast<const float2*>(wr));
+        w[i][0] = t2.x; w[i][1] = t2.y;
+      } else {
+        const float4 t4 = __ldg(reinterpret_cast<const float4*>(wr));
+        w[i][0] = t4.x; w[i][1] = t4.y; w[i][kC - 2] = t4.z; w[i][kC - 1] = t4.w;
+      }
     }
   }
-  wb[0] = a0;
-  wb[1] = a1;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+    const float ej = __shfl_sync(kFullMask, e, (j0 + i) & 31);
+    if (j0 + i < vc) {
+#pragma unroll
+      for (int c = 0; c < kC; ++c) acc[c] = fmaf(w[i][c], ej, acc[c]);
+    }
+  }
+  return make_float4(acc[0], acc[1], acc[2], acc[3]);
 }
 
 // Compositing of the tile's rays as the epilogue of the last stage (layers/nerf_static_transient_light.py:168-212, SURVEY
 // appendix C; arithmetic of csrc/composite.cu): row = sample, so the three exclusive cumulative sums are a warp scan plus the
 // totals of the ray's earlier warps (N / 32 warps per ray, exchanged through `sc`), and the 14 per-ray sums a warp reduction
 // plus the same exchange.  Per sample it writes alpha_static, alpha_transient and density (16 B), per ray 14 floats.
-__device__ __forceinline__ void render_composite(const Params& p, float* sc, int t, int q, int lane, const RenderSample& rs,
-                                                 float sig_s, float sig_t, const float (&cs)[3], const float (&ct)[3], float u) {
+__device__ __noinline__ void render_composite(const Params& p, float* sc, int t, int q, int lane, long long ray, int k, float d_k,
+                                              float dist, bool live, float sig_s, float sig_t, float cs0, float cs1, float cs2,
+                                              float ct0, float ct1, float ct2, float u) {
+  struct { long long ray; int k; float d, dist; bool live; } rs = {ray, k, d_k, dist, live};
+  const float cs[3] = {cs0, cs1, cs2}, ct[3] = {ct0, ct1, ct2};
   float* tot = sc;             // [4 warps][3]
   float* red = sc + 12;        // [4 warps][14]
   const float sd_s = __fmul_rn(sig_s, rs.dist), sd_t = __fmul_rn(sig_t, rs.dist), sd = __fadd_rn(sd_s, sd_t);
@@ -193,12 +253,51 @@ __device__ __forceinline__ void render_composite(const Params& p, float* sc, int
   acc[11] = w_qs;
   acc[12] = w_qt;
   acc[13] = u * w_pt;
+  // warp totals of the 14 (padded to 16) sums by recursive halving: at every step a lane keeps one half of its values and adds
+  // the partner's -- 8 + 4 + 2 + 1 + 1 = 16 shuffles instead of 14 x 5; lane l ends up with the total of value (l >> 1) & 15... see idx
+  float v16[16];
 #pragma unroll
-  for (int i = 0; i < 14; ++i) acc[i] = warp_sum(acc[i]);
-  if (lane == 0) {
+  for (int i = 0; i < 14; ++i) v16[i] = acc[i];
+  v16[14] = v16[15] = 0.f;
+  float v8[8], v4[4], v2[2];
+  {
+    const bool up = (lane & 16) != 0;
 #pragma unroll
-    for (int i = 0; i < 14; ++i) red[q * 14 + i] = acc[i];
+    for (int i = 0; i < 8; ++i) {
+      const float send = up ? v16[i] : v16[i + 8];
+      const float recv = __shfl_xor_sync(kFullMask, send, 16);
+      v8[i] = (up ? v16[i + 8] : v16[i]) + recv;
+    }
   }
+  {
+    const bool up = (lane & 8) != 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float send = up ? v8[i] : v8[i + 4];
+      const float recv = __shfl_xor_sync(kFullMask, send, 8);
+      v4[i] = (up ? v8[i + 4] : v8[i]) + recv;
+    }
+  }
+  {
+    const bool up = (lane & 4) != 0;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float send = up ? v4[i] : v4[i + 2];
+      const float recv = __shfl_xor_sync(kFullMask, send, 4);
+      v2[i] = (up ? v4[i + 2] : v4[i]) + recv;
+    }
+  }
+  float v1;
+  {
+    const bool up = (lane & 2) != 0;
+    const float send = up ? v2[0] : v2[1];
+    const float recv = __shfl_xor_sync(kFullMask, send, 2);
+    v1 = (up ? v2[1] : v2[0]) + recv;
+  }
+  v1 += __shfl_xor_sync(kFullMask, v1, 1);
+  // value index held by this lane: bit 4 of the lane chose +8, bit 3 +4, bit 2 +2, bit 1 +1
+  const int vidx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+  if ((lane & 1) == 0 && vidx < 14) red[q * 14 + vidx] = v1;
   if (rs.live) {
     const long long s = rs.ray * p.N + rs.k;
     if (p.o_as) __stcs(p.o_as + s, as);
@@ -229,10 +328,16 @@ __device__ __forceinline__ void render_composite(const Params& p, float* sc, int
 // 2 = the plain training launch (activation save + ReLU bitmasks); 3 = the fused render launch (rays, depths, view bias and
 // compositing in-kernel; per-ray outputs).  Modes 1-3 have every debug branch compiled out and the default tile skew as a
 // constant: the same code with those decisions left to run time is 6 % slower (same-box A/B).
-template <int kHalves, int kNL = kNumLayers, int kMode = 0>
+// kSmemBias: the launch has one ray per tile (N = 128, hence also one image per tile): the per-ray / per-image bias row of the
+// two table-bias stages sits in shared memory and the drain reads it with broadcast loads instead of warp shuffles.
+template <int kHalves, int kNL = kNumLayers, int kMode = 0, bool kSmemBias = false>
+// (320 threads allocate registers as 12 warps -- warps are allocated in fours -- so the cap is 168 registers per thread; the render
+// launch keeps its look-ahead state (next sample's encoding, finished sample) partly in local memory: a few dozen L1-resident
+// STL / LDL per super-tile, cheaper than recomputing it on the critical path)
 __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_kernel(const Params p) {
   constexpr bool kRender = kMode == 3;
   static_assert(!kRender || kHalves == 1, "the render launch uses the 8-warp drain");
+  static_assert(!kSmemBias || (kHalves == 1 && kMode != 0), "shared-memory bias rows: lean 8-warp launches");
   const int p_skew = kMode ? 1 : p.skew;
   uint8_t* const p_save = (kMode == 1 || kRender) ? nullptr : p.save;
   constexpr int kEpiWarps = 8 * kHalves, kProducerWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
@@ -304,6 +409,10 @@ __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_ke
     // stage -- overlap T1's MMAs / epilogue instead of leaving the tensor pipe idle.
     {
       uint32_t chunk_base = 0, ready_ph = 0, reload_ph = 0;   // per-tile phase bits (bit t)
+#ifdef TP_FWD_PROF
+      long long pf_ready[2][kNumLayers] = {}, pf_full[kNumLayers] = {}, pf_total = 0;
+      const long long pf_t0 = clock64();
+#endif
       const uint32_t idesc256 = umma_idesc(128, 256), idesc16 = umma_idesc(128, 16);
       constexpr uint32_t kHi = (128u >> 4) | (1u << 14);   // SBO = 128 B, descriptor version 1
       for (long long st = blockIdx.x; st < n_super; st += gridDim.x) {
@@ -318,9 +427,19 @@ __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_ke
               if (c < 0 || c >= nch) continue;
               const uint32_t abs_chunk = chunk_base + c;
               const uint32_t stage = abs_chunk % kStages, phase = (abs_chunk / kStages) & 1u;
+#ifdef TP_FWD_PROF
+              const long long pf_a = clock64();
+#endif
               if (t == 0) mbar_wait(bar_full(stage), phase);          // first touch of this ring slot
+#ifdef TP_FWD_PROF
+              const long long pf_b = clock64();
+              pf_full[L] += pf_b - pf_a;
+#endif
               if (c == 0) {
                 mbar_wait(bar_ready(t), (ready_ph >> t) & 1u);
+#ifdef TP_FWD_PROF
+                pf_ready[t][L] += clock64() - pf_b;
+#endif
                 ready_ph ^= 1u << t;
                 if (ly.reload) {
                   mbar_wait(bar_reload(t), (reload_ph >> t) & 1u);
@@ -365,6 +484,19 @@ __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_ke
           chunk_base += nch;
         }
       }
+#ifdef TP_FWD_PROF
+      if (lane == 0) {      // [CTA][tile][stage][4]: cycles waiting for the tile's epilogue, for a weight chunk (tile 0), total, super-tiles
+        long long* o = reinterpret_cast<long long*>(p.scratch + (size_t)p.prof_offset) + (size_t)blockIdx.x * 2 * kNumLayers * 4;
+        long long n_st = 0;
+        for (long long st = blockIdx.x; st < n_super; st += gridDim.x) ++n_st;
+        pf_total = clock64() - pf_t0;
+        for (int t = 0; t < 2; ++t)
+          for (int L = 0; L < kNumLayers; ++L) {
+            long long* r = o + (t * kNumLayers + L) * 4;
+            r[0] = pf_ready[t][L]; r[1] = t == 0 ? pf_full[L] : 0; r[2] = pf_total; r[3] = n_st;
+          }
+      }
+#endif
     }
   } else {
     // ================================================================ encode + epilogue warps
@@ -375,13 +507,22 @@ __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_ke
     const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16) + t * 256;
     const uint32_t tmem_d = tmem_row + half * kCols;
     uint8_t* my_scratch = p.scratch + ((size_t)blockIdx.x * 2 + t) * kABytes;
+    // render launch: view-bias rows of this tile's rays (<= 4 rays x 1 KB), behind the parked features of all CTAs
+    float* vb_slot = reinterpret_cast<float*>(p.scratch + (size_t)gridDim.x * 2 * kABytes) + ((size_t)blockIdx.x * 2 + t) * 4 * 256;
     uint32_t acc_ph = 0;
     // all 32 rows of a warp share the ray (and image) when N is a multiple of 32; tail rows are clamped to the last
     // sample, which then belongs to the same ray as the warp's live rows
     const bool warp_bias = kMode ? true : (p.N % 32 == 0);      // modes 1-3 are launched only when N % 32 == 0
     bool store_pending = false;      // a bulk store of A_t (feature park / activation save) may still be reading it
-    RenderSample rs = {}, rs_next = {};      // render launch: the sample this row holds / will hold in the next super-tile
-    uint32_t enc_next[32];                   // ... and the next sample's encoding, computed a stage early (below)
+    RenderSample rs = {}, nxt = {};          // render launch: the sample this row holds / will hold in the next super-tile
+    // ... and the finished sample of the previous super-tile: composited where both tiles and the tensor pipe wait anyway
+    long long done_ray = 0;
+    int done_k = 0;
+    float done_d = 0.f, done_dist = 0.f, done_v[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    bool done_live = false, have_done = false;
+    uint32_t enc_next[32];                   // per-sample launches: the next sample's encoding, computed a stage early (below)
+    float4 vb_acc = make_float4(0.f, 0.f, 0.f, 0.f);         // view-direction bias of the tile's ray(s): partial sums across three stages
+    float vb_e = 0.f;
     int iter = 0;
     for (long long st = blockIdx.x; st < n_super; st += gridDim.x, ++iter) {
       const long long s_raw = (st * 2 + t) * 128 + row;
@@ -389,9 +530,12 @@ __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_ke
       const long long s = live ? s_raw : p.S - 1;
       if (!kRender || iter == 0) {     // (the render launch encodes the next super-tile at the end of the last stage, below)
         if (kRender) {
-          rs = render_prepare(p, st * 2 + t, row, lane, enc_next);
-          store_encoding(enc_next, e_smem, row);
-        } else if (half == 0) encode_sample(p, s, e_smem, row);
+          rs = render_fetch(p, st * 2 + t, row, lane);
+          render_encode(rs.xyz[0], rs.xyz[1], rs.xyz[2], e_smem, row);
+        } else if (half == 0) {
+          if (kMode == 0 || kHalves != 1 || iter == 0) encode_sample(p, s, e_smem, row);
+          else store_encoding(enc_next, e_smem, row);      // worked out during the previous super-tile (below)
+        }
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();                    // every lane's st.shared + proxy fence precede the warp's single arrive
@@ -406,9 +550,21 @@ __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_ke
         // row here instead of reading a table.
         float4 wb[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
         const bool table_bias = ly.epi == EPI_HIDDEN && ly.bias_kind != BIAS_MMA;
-        if (table_bias && warp_bias) {
+        const uint32_t bias_sm = sbase + kOffBias + t * 1024;
+        // the render launch has produced its per-ray row in place (below); every other table row is copied in here
+        const bool copy_row = kSmemBias && table_bias && !(kRender && ly.bias_kind == BIAS_RAY);
+        if (copy_row) {
+          // 128 threads x 8 bytes: the tile's bias row -> shared memory (the loads fly during the stage's MMAs)
+          const long long img = kRender ? (long long)rs.img : s / p.per_image;
+          const float* brow = ly.bias_kind == BIAS_RAY ? p.raybias + (s / p.N) * 256 : p.imgbias + img * 256;
+          const float2 b2 = __ldg(reinterpret_cast<const float2*>(brow) + row);
+          asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(bias_sm + row * 8), "f"(b2.x), "f"(b2.y) : "memory");
+        } else if (table_bias && warp_bias && !kSmemBias) {
           if (kRender && ly.bias_kind == BIAS_RAY) {
-            render_view_bias(p, rs, lane, wb);
+            // the row its ray's warps left in the scratch slot (ordered by the tile barrier of the feature park)
+            const float* brow = vb_slot + (q / (p.N >> 5)) * 256;
+            wb[0] = __ldcg(reinterpret_cast<const float4*>(brow) + lane);
+            wb[1] = __ldcg(reinterpret_cast<const float4*>(brow + 128) + lane);
           } else {
             const long long img = kRender ? (long long)rs.img : s / p.per_image;
             const float* brow = (ly.bias_kind == BIAS_RAY ? p.raybias + (s / p.N) * 256 : p.imgbias + img * 256) + half * kCols;
@@ -416,12 +572,58 @@ __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_ke
             if (kCols == 256) wb[1] = __ldg(reinterpret_cast<const float4*>(brow + 128) + lane);
           }
         }
-        if (kRender && L == kNL - 2 && st + gridDim.x < n_super) {
-          // the next super-tile's sample of this row -- ray, bounds, jitter, depth, interval, encoding -- is worked out NOW, in
-          // the shadow of this stage's MMAs (the warp would only wait for the accumulator); the 32 packed words wait in
-          // registers until the E tile is free, so the hand-over after the last stage is eight st.shared instead of two
-          // dependent global loads, a Philox block, two IEEE divisions and sixty sines
-          rs_next = render_prepare(p, (st + gridDim.x) * 2 + t, row, lane, enc_next);
+        if (kRender && L == kSpillLayer + 1) {
+          // Right after the feature park the weight stream of this stage queues behind 128 KB of bulk stores in the SM's TMA
+          // FIFO: both tiles and the tensor pipe wait ~2 700 cycles here whatever the epilogue warps do (scripts/fwd_prof.py).
+          // The work that has no place on a tile's critical path goes into that window: the compositing of the previous
+          // super-tile's samples, and the next super-tile's rays, bounds, jitter and depths (two dependent global loads).
+          if (have_done) {
+            float* sc = reinterpret_cast<float*>(smem + kOffComp) + t * kCompFloats;      // (the park barrier separates two uses)
+            render_composite(p, sc, t, q, lane, done_ray, done_k, done_d, done_dist, done_live, done_v[0], done_v[1], done_v[2], done_v[3],
+                             done_v[4], done_v[5], done_v[6], done_v[7], done_v[8]);
+            have_done = false;
+          }
+          if (st + gridDim.x < n_super) nxt = render_fetch(p, (st + gridDim.x) * 2 + t, row, lane);
+        }
+        if (kRender) {
+          // the tile's view-direction bias row is worked out HERE, before the accumulator wait of three consecutive trunk stages
+          if (L >= kViewBiasLayer - 2 && L <= kViewBiasLayer) {
+            const int wpr = kSmemBias ? 4 : p.N >> 5;      // warps per ray: 4, 2, 1
+            float* dst = vb_slot + (q / wpr) * 256;
+            if (wpr >= 2) {                // N = 128 / 64: nine inputs per stage
+              const int col = (q & (wpr - 1)) * (256 / wpr) + lane * (8 / wpr);
+              const int j0 = (L - (kViewBiasLayer - 2)) * 9;
+              if (j0 == 0) {
+                vb_e = render_view_element(p, rs, lane);
+                const float* brow = p.imgbias_rgb + (long long)rs.img * 256 + col;
+                vb_acc.x = __ldg(brow); vb_acc.y = __ldg(brow + 1);
+                vb_acc.z = wpr == 2 ? __ldg(brow + 2) : 0.f; vb_acc.w = wpr == 2 ? __ldg(brow + 3) : 0.f;
+              }
+              if (wpr == 4) vb_acc = render_view_batch<2>(p, vb_e, col, j0, vb_acc);
+              else vb_acc = render_view_batch<4>(p, vb_e, col, j0, vb_acc);
+              if (L == kViewBiasLayer) {
+                if (kSmemBias) asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(bias_sm + col * 4), "f"(vb_acc.x), "f"(vb_acc.y) : "memory");
+                else if (wpr == 4) *reinterpret_cast<float2*>(dst + col) = make_float2(vb_acc.x, vb_acc.y);
+                else *reinterpret_cast<float4*>(dst + col) = vb_acc;
+              }
+            } else if (L == kViewBiasLayer) {      // N = 32: one warp per ray computes all 256 columns, four at a time
+              const float e = render_view_element(p, rs, lane);
+              for (int pass = 0; pass < 2; ++pass) {
+                const int col = pass * 128 + lane * 4;
+                const float* brow = p.imgbias_rgb + (long long)rs.img * 256 + col;
+                float4 acc4 = make_float4(__ldg(brow), __ldg(brow + 1), __ldg(brow + 2), __ldg(brow + 3));
+                for (int j0 = 0; j0 < 27; j0 += 9) acc4 = render_view_batch<4>(p, e, col, j0, acc4);
+                *reinterpret_cast<float4*>(dst + col) = acc4;
+              }
+            }
+          }
+        }
+        if (!kRender && kMode != 0 && kHalves == 1 && L == kNL - 2 && st + gridDim.x < n_super) {      // (8-warp drain: registers to spare)
+          // per-sample launches: the same for the next sample's loads (ray, depth) and its sixty sines
+          const long long sn_raw = ((st + gridDim.x) * 2 + t) * 128 + row, sn = sn_raw < p.S ? sn_raw : p.S - 1, rn = sn / p.N;
+          const float cn[3] = {p.center[rn * 3], p.center[rn * 3 + 1], p.center[rn * 3 + 2]};
+          const float dn[3] = {p.ray[rn * 3], p.ray[rn * 3 + 1], p.ray[rn * 3 + 2]};
+          encode_regs(cn, dn, p.depth[sn], enc_next);
         }
         mbar_wait(bar_acc(t), acc_ph);
         acc_ph ^= 1;
@@ -438,6 +640,7 @@ __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_ke
           mbar_expect_tx(bar_reload(t), kABytes);
           bulk_g2s(a_smem, p_save ? p_save + ((size_t)(st * 2 + t) * kSaveSlots) * kABytes : my_scratch, kABytes, bar_reload(t));
         }
+        if (copy_row) named_bar_sync(1 + t, kTileThreads);      // the tile's 128 threads wrote the row before the accumulator wait
         if (ly.epi == EPI_HIDDEN) {
           float* dbg_row = (kMode == 0 && (L == p.dbg_layer) && live && p.dbg_out) ? p.dbg_out + s * 256 + half * kCols : nullptr;
           const uint32_t a_row = a_smem + half * (kCols / 8) * 2048 + row * 16;
@@ -454,6 +657,8 @@ __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_ke
             uint8_t* g_row = p_save + ((size_t)(st * 2 + t) * kSaveSlots + kSaveSlot[L]) * kABytes + half * (kCols / 8) * 2048 + row * 16;
             if (ly.bias_kind == BIAS_MMA) {
               hidden_epilogue<false, kCols / 32, true>(tmem_d, nullptr, a_row, dbg_row, words, g_row);
+            } else if (kSmemBias) {
+              hidden_epilogue_sbias<kCols / 32, true>(tmem_d, bias_sm, a_row, dbg_row, words, g_row);
             } else if (warp_bias) {
               hidden_epilogue_wbias<kCols / 32, true>(tmem_d, wb, a_row, dbg_row, words, g_row);
             } else {
@@ -463,6 +668,8 @@ __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_ke
             }
           } else if (ly.bias_kind == BIAS_MMA) {
             hidden_epilogue<false, kCols / 32>(tmem_d, nullptr, a_row, dbg_row);
+          } else if (kSmemBias) {
+            hidden_epilogue_sbias<kCols / 32>(tmem_d, bias_sm, a_row, dbg_row);
           } else if (warp_bias) {
             hidden_epilogue_wbias<kCols / 32>(tmem_d, wb, a_row, dbg_row);
           } else {
@@ -481,12 +688,19 @@ __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_ke
               bulk_commit();
             }
             store_pending = true;
+          } else if (kRender && L == kSpillLayer) {
+            named_bar_sync(1 + t, kTileThreads);      // static only: nothing is parked, but the view-bias rows need the tile barrier
           }
         } else if (half == 0) {
           // N=16 output stage: columns 0..7 = x . bf16(W rows), columns 8..15 = x . bf16(W - bf16(W)) of the same rows
           uint32_t v[16];
           TP_TMEM_LD16(tmem_row, v);
           TP_TMEM_WAIT16(v);
+          if (L != kNL - 1) {      // the accumulator is in registers: release the next stage's MMAs before the softplus / sigmoid arithmetic
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_ready(t));
+          }
           const float* sb = p.biasbuf + kSmallBiasOffset;
           auto out = [&](int c) { return __uint_as_float(v[c]) + __uint_as_float(v[c + 8]); };
           float rgb_t[3] = {0.f, 0.f, 0.f}, sigma_t = 0.f, unc = 0.f;
@@ -505,17 +719,21 @@ __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_ke
             if (kRender) {
               // hand the tile on first: the next super-tile's samples are encoded and its first MMAs released before this
               // one is composited, so the compositing overlaps tensor work instead of leaving the pipe idle
-              const RenderSample cur = rs;
+              // the sample is finished: keep its nine values for the compositing (above, next super-tile), encode the next
+              // super-tile's sample (its point is known since the rgb-0 stage) and release its first MMAs
+              done_ray = rs.ray; done_k = rs.k; done_d = rs.d; done_dist = rs.dist; done_live = rs.live;
+              done_v[0] = sigma_s; done_v[1] = sigma_t; done_v[8] = unc;
+#pragma unroll
+              for (int c = 0; c < 3; ++c) { done_v[2 + c] = rgb_s[c]; done_v[5 + c] = rgb_t[c]; }
+              have_done = true;
               if (st + gridDim.x < n_super) {
-                store_encoding(enc_next, e_smem, row);
-                rs = rs_next;
+                rs = nxt;
+                render_encode(rs.xyz[0], rs.xyz[1], rs.xyz[2], e_smem, row);
                 fence_proxy_async_smem();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_ready(t));
               }
-              float* sc = reinterpret_cast<float*>(smem + kOffComp) + ((iter & 1) * 2 + t) * kCompFloats;
-              render_composite(p, sc, t, q, lane, cur, sigma_s, sigma_t, rgb_s, rgb_t, unc);
             } else if (live) {
 #pragma unroll
               for (int c = 0; c < 3; ++c) *reinterpret_cast<float2*>(p.rgb + s * 6 + c * 2) = make_float2(rgb_s[c], rgb_t[c]);
@@ -524,12 +742,17 @@ __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_ke
             }
           }
         }
-        if (L != kNL - 1) {   // the next super-tile's encode arrival covers the last stage
+        if (L != kNL - 1 && !(ly.small && half == 0)) {   // (output stages arrived above; the next super-tile's encode covers the last stage)
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_ready(t));
         }
       }
+    }
+    if (kRender && have_done) {      // the last super-tile of this CTA
+      float* sc = reinterpret_cast<float*>(smem + kOffComp) + t * kCompFloats;
+      render_composite(p, sc, t, q, lane, done_ray, done_k, done_d, done_dist, done_live, done_v[0], done_v[1], done_v[2], done_v[3],
+                       done_v[4], done_v[5], done_v[6], done_v[7], done_v[8]);
     }
     if (row == 0 && half == 0) bulk_wait_all();
   }
@@ -615,8 +838,7 @@ __global__ void __launch_bounds__(256) ray_bias_kernel(const float* __restrict__
       float uc = 0.f;
       if (live) {
         const float x = ray[r * 3], y = ray[r * 3 + 1], z = ray[r * 3 + 2];
-        const float len = fmaxf(sqrtf(x * x + y * y + z * z), 1e-12f);
-        uc = (cc == 0 ? x : (cc == 1 ? y : z)) / len;
+        uc = __fdiv_rn(cc == 0 ? x : (cc == 1 ? y : z), unit_length(x, y, z));      // same bits as the render launch's in-kernel row
       }
       enc[rr][cc] = uc;
       for (int k = 0; k < L; ++k) {
@@ -686,7 +908,10 @@ __global__ void unpack_images_kernel(const uint8_t* __restrict__ images, int slo
 
 TP_API int tp_tc_num_chunks(void) { return tc::kNumChunks; }
 TP_API int64_t tp_tc_chunk_bytes(void) { return tc::kChunkBytes; }
-TP_API int64_t tp_tc_scratch_bytes(void) { return (int64_t)tp_num_sms() * 2 * tc::kABytes; }
+// parked features (2 x 64 KB per CTA) + view-bias rows of the render launch (2 tiles x 4 rays x 1 KB per CTA) + the cycle
+// counters of a -DTP_FWD_PROF build (scripts/fwd_prof.py; [CTA][tile][stage][4] int64, untouched otherwise)
+TP_API int64_t tp_tc_scratch_bytes(void) { return (int64_t)tp_num_sms() * (2 * tc::kABytes + 2 * 4 * 1024 + 2 * tc::kNumLayers * 4 * 8); }
+TP_API int64_t tp_tc_prof_offset(void) { return (int64_t)tp_num_sms() * (2 * tc::kABytes + 2 * 4 * 1024); }
 
 // save buffer: [tiles][7][64 KB] tile images, then [tiles][4][4 KB] ReLU bitmasks (tiles rounded up to whole super-tiles)
 TP_API int64_t tp_tc_save_bytes(int64_t S) {
@@ -759,7 +984,7 @@ TP_API int tp_tc_nerf_stl_forward(const float* center, const float* ray, const f
   p.rgb = rgb; p.density = density; p.uncert = uncert; p.scratch = reinterpret_cast<uint8_t*>(scratch);
   p.save = reinterpret_cast<uint8_t*>(save);
   p.bits = save ? p.save + ((S + 255) / 256) * 2 * tc::kSaveSlots * (size_t)tc::kABytes : nullptr;
-  p.dbg_layer = dbg_layer; p.dbg_out = dbg_out;
+  p.dbg_layer = dbg_layer; p.dbg_out = dbg_out; p.prof_offset = tp_tc_prof_offset();
   p.n_layers = (flags & (1 << 17)) ? tc::kStaticLayers : tc::kNumLayers;      // flags bit 17: static-only rendering
   if ((flags & (1 << 17)) && save) return TP_ERR_BAD_ARG;                     // inference launches only
   p.skew = ((flags >> 5) & 3) ? ((flags >> 5) & 3) - 1 : 1;      // default skew 1; flags bits 5-6 = skew+1 override (A/B)
@@ -769,11 +994,13 @@ TP_API int tp_tc_nerf_stl_forward(const float* center, const float* ray, const f
   const bool wide = (flags & 2) != 0;
   const bool stat = p.n_layers == tc::kStaticLayers;
   const bool plain = dbg_layer < 0 && !dbg_out && p.skew == 1 && N % 32 == 0;
+  const bool n128 = N == 128;      // one ray (and one image) per tile: bias rows in shared memory
   void (*kern)(const tc::Params) =
-      plain && !save && !wide ? (stat ? tc::nerf_stl_forward_kernel<1, tc::kStaticLayers, 1> : tc::nerf_stl_forward_kernel<1, tc::kNumLayers, 1>)
+      plain && !save && !wide ? (stat ? (n128 ? tc::nerf_stl_forward_kernel<1, tc::kStaticLayers, 1, true> : tc::nerf_stl_forward_kernel<1, tc::kStaticLayers, 1>)
+                                      : (n128 ? tc::nerf_stl_forward_kernel<1, tc::kNumLayers, 1, true> : tc::nerf_stl_forward_kernel<1, tc::kNumLayers, 1>))
       : plain && !save        ? (stat ? tc::nerf_stl_forward_kernel<2, tc::kStaticLayers, 1> : tc::nerf_stl_forward_kernel<2, tc::kNumLayers, 1>)
       : plain && wide         ? tc::nerf_stl_forward_kernel<2, tc::kNumLayers, 2>
-      : plain                 ? tc::nerf_stl_forward_kernel<1, tc::kNumLayers, 2>
+      : plain                 ? (n128 ? tc::nerf_stl_forward_kernel<1, tc::kNumLayers, 2, true> : tc::nerf_stl_forward_kernel<1, tc::kNumLayers, 2>)
       : wide ? (stat ? tc::nerf_stl_forward_kernel<2, tc::kStaticLayers> : tc::nerf_stl_forward_kernel<2, tc::kNumLayers>)
              : (stat ? tc::nerf_stl_forward_kernel<1, tc::kStaticLayers> : tc::nerf_stl_forward_kernel<1, tc::kNumLayers>);
   return tc_launch(kern, p, grid, wide ? tc::num_threads<2>() : tc::num_threads<1>(), (cudaStream_t)stream);
@@ -804,12 +1031,12 @@ TP_API int tp_render_fused_forward(const float* kinv, const float* pose_inv, int
   const long long n_super = (S + 255) / 256;
   int grid = tp_num_sms();
   if (n_super < grid) grid = (int)n_super;
-  if (scratch_bytes < (int64_t)grid * 2 * tc::kABytes) return TP_ERR_WORKSPACE;
+  if (scratch_bytes < (int64_t)grid * (2 * tc::kABytes + 2 * 4 * 1024)) return TP_ERR_WORKSPACE;
   tc::Params p = {};
   p.S = S; p.N = N; p.per_image = R * N;
   p.packed = reinterpret_cast<const uint8_t*>(packed); p.biasbuf = biasbuf; p.imgbias = imgbias_trans;
   p.density = density; p.scratch = reinterpret_cast<uint8_t*>(scratch);
-  p.dbg_layer = -1; p.skew = 1;
+  p.dbg_layer = -1; p.skew = 1; p.prof_offset = tp_tc_prof_offset();
   p.n_layers = (flags & (1 << 17)) ? tc::kStaticLayers : tc::kNumLayers;
   p.kinv = kinv; p.pinv = pose_inv; p.H = H; p.W = W; p.pix_offset = pix_offset;
   p.ray_idx = reinterpret_cast<const long long*>(ray_idx); p.R = R; p.ray0 = ray0;
@@ -817,7 +1044,9 @@ TP_API int tp_render_fused_forward(const float* kinv, const float* pose_inv, int
   p.wview = wview; p.L_view = L_view; p.imgbias_rgb = imgbias_rgb; p.min_uncert = min_uncert;
   p.o_rgb = rgb; p.o_rgb_s = rgb_static; p.o_rgb_t = rgb_transient; p.o_depth = depth; p.o_op = opacity;
   p.o_op_s = opacity_static; p.o_op_t = opacity_transient; p.o_unc = uncert; p.o_as = alpha_static; p.o_at = alpha_transient;
-  void (*kern)(const tc::Params) = p.n_layers == tc::kStaticLayers ? tc::nerf_stl_forward_kernel<1, tc::kStaticLayers, 3>
-                                                                   : tc::nerf_stl_forward_kernel<1, tc::kNumLayers, 3>;
+  const bool stat = p.n_layers == tc::kStaticLayers, n128 = N == 128;
+  void (*kern)(const tc::Params) =
+      stat ? (n128 ? tc::nerf_stl_forward_kernel<1, tc::kStaticLayers, 3, true> : tc::nerf_stl_forward_kernel<1, tc::kStaticLayers, 3>)
+           : (n128 ? tc::nerf_stl_forward_kernel<1, tc::kNumLayers, 3, true> : tc::nerf_stl_forward_kernel<1, tc::kNumLayers, 3>);
   return tc_launch(kern, p, grid, tc::num_threads<1>(), (cudaStream_t)stream);
 }

@@ -80,6 +80,59 @@ __device__ __forceinline__ uint32_t hidden_slab_wbias(const uint32_t (&v)[32], c
   return __brev(~signs);
 }
 
+// Same with the bias row in shared memory (all 128 rows of the tile share it: one ray per tile at N = 128, one image per tile):
+// every lane reads the same 16 bytes, i.e. a broadcast ld.shared.v4 -- 2 loads per 8 columns instead of 8 shuffles.  The
+// shuffle form costs ~2 000 cycles per table-bias stage (256 warp shuffles per thread against a shuffle unit that serves one
+// warp per cycle): 4 % of a super-tile (scripts/fwd_prof.py: the MMA warp waits 2 700 cycles for the stage after each of them).
+template <bool kBits = false>
+__device__ __forceinline__ uint32_t hidden_slab_sbias(const uint32_t (&v)[32], uint32_t bias_smem, uint32_t a_dst, float* dbg_row,
+                                                      uint8_t* g_dst = nullptr) {
+  uint32_t signs = 0u;
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    float4 b0, b1;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b0.x), "=f"(b0.y), "=f"(b0.z), "=f"(b0.w) : "r"(bias_smem + i * 4));
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b1.x), "=f"(b1.y), "=f"(b1.z), "=f"(b1.w) : "r"(bias_smem + i * 4 + 16));
+    float x[8];
+    x[0] = __uint_as_float(v[i + 0]) + b0.x; x[1] = __uint_as_float(v[i + 1]) + b0.y;
+    x[2] = __uint_as_float(v[i + 2]) + b0.z; x[3] = __uint_as_float(v[i + 3]) + b0.w;
+    x[4] = __uint_as_float(v[i + 4]) + b1.x; x[5] = __uint_as_float(v[i + 5]) + b1.y;
+    x[6] = __uint_as_float(v[i + 6]) + b1.z; x[7] = __uint_as_float(v[i + 7]) + b1.w;
+    if (kBits) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) signs = __funnelshift_l(__float_as_uint(x[e]), signs, 1);
+    }
+    const uint32_t q0 = pack_relu_bf16(x[0], x[1]), q1 = pack_relu_bf16(x[2], x[3]), q2 = pack_relu_bf16(x[4], x[5]),
+                   q3 = pack_relu_bf16(x[6], x[7]);
+    st_shared_v4(a_dst + (i >> 3) * 2048, q0, q1, q2, q3);
+    if (kBits && g_dst) st_global_cs_v4(g_dst + (i >> 3) * 2048, q0, q1, q2, q3);
+    if (dbg_row) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) dbg_row[i + e] = fmaxf(x[e], 0.f);
+    }
+  }
+  return __brev(~signs);
+}
+
+template <int kSlabs, bool kBits = false>
+__device__ __forceinline__ void hidden_epilogue_sbias(uint32_t tmem_d, uint32_t bias_smem, uint32_t a_row, float* dbg_row,
+                                                      uint32_t* words = nullptr, uint8_t* g_row = nullptr) {
+  uint32_t va[32], vb[32];
+  TP_TMEM_LD32(tmem_d, va);
+#pragma unroll
+  for (int j = 0; j < kSlabs; j += 2) {
+    TP_TMEM_WAIT32(va);
+    TP_TMEM_LD32(tmem_d + (j + 1) * 32, vb);
+    const uint32_t w0 = hidden_slab_sbias<kBits>(va, bias_smem + j * 128, a_row + j * 4 * 2048, dbg_row ? dbg_row + j * 32 : nullptr,
+                                                 g_row ? g_row + j * 4 * 2048 : nullptr);
+    TP_TMEM_WAIT32(vb);
+    if (j + 2 < kSlabs) TP_TMEM_LD32(tmem_d + (j + 2) * 32, va);
+    const uint32_t w1 = hidden_slab_sbias<kBits>(vb, bias_smem + (j + 1) * 128, a_row + (j + 1) * 4 * 2048,
+                                                 dbg_row ? dbg_row + (j + 1) * 32 : nullptr, g_row ? g_row + (j + 1) * 4 * 2048 : nullptr);
+    if (kBits && words) { __stcs(words + j * 128, w0); __stcs(words + (j + 1) * 128, w1); }
+  }
+}
+
 template <int kSlabs, bool kBits = false>
 __device__ __forceinline__ void hidden_epilogue_wbias(uint32_t tmem_d, const float4 (&mine)[2], uint32_t a_row, float* dbg_row,
                                                       uint32_t* words = nullptr,        // words: plane j at words[j * 128]

@@ -76,6 +76,7 @@ struct Params {
   int dbg_layer;
   float* dbg_out;            // [S,256] post-activation of stage dbg_layer (debug only)
   int skew;                  // weight chunks tile 0 runs ahead of tile 1 inside a stage (0..2)
+  long long prof_offset;     // byte offset of the cycle counters inside `scratch` (-DTP_FWD_PROF builds only)
   int n_layers;              // 17 = all stages; 13 = static only (rendering that needs neither the transient head nor uncert):
                              // the stage list stops after the rgb output, transient outputs are written as zeros.  Host side only:
                              // it selects the kernel instantiation (the kernel takes the count as a template parameter)
@@ -111,11 +112,11 @@ struct Params {
 // positional encoding of one point as the 32 packed bf16x2 words of its E-tile row: [x,y,z, per coord sin(2^k pi x) k<10,
 // cos(...) k<10, 1].  sincospif gives the exact-argument octave 0; higher octaves by the double-angle recurrence (error <<
 // bf16 ulp).  Kept in registers so the arithmetic can run while the E tile is still being read by the previous super-tile.
-__device__ __forceinline__ void encode_regs(const float (&c)[3], const float (&r)[3], float d, uint32_t (&e)[32]) {
+__device__ __forceinline__ void encode_xyz_regs(const float (&xyz)[3], uint32_t (&e)[32]) {
   float v[64];
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
-    const float x = __fadd_rn(c[j], __fmul_rn(r[j], d));
+    const float x = xyz[j];
     v[j] = x;
     float sn, cs;
     sincospif(x, &sn, &cs);
@@ -131,6 +132,10 @@ __device__ __forceinline__ void encode_regs(const float (&c)[3], const float (&r
   v[63] = 1.f;   // constant-1 column: carries the static biases through the MMA
 #pragma unroll
   for (int i = 0; i < 32; ++i) e[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
+}
+__device__ __forceinline__ void encode_regs(const float (&c)[3], const float (&r)[3], float d, uint32_t (&e)[32]) {
+  const float xyz[3] = {__fadd_rn(c[0], __fmul_rn(r[0], d)), __fadd_rn(c[1], __fmul_rn(r[1], d)), __fadd_rn(c[2], __fmul_rn(r[2], d))};
+  encode_xyz_regs(xyz, e);      // x = c + ray * d (camera.py:317-322), one rounding per operation
 }
 __device__ __forceinline__ void store_encoding(const uint32_t (&e)[32], uint32_t e_smem, int row) {
 #pragma unroll

@@ -34,3 +34,9 @@ __device__ __forceinline__ float stratified_depth(float u, int k, float fn, floa
   return __fadd_rn(__fmul_rn(t, __fsub_rn(hi, lo)), lo);
 }
 
+
+// |ray| clamped as F.normalize does (eps 1e-12), with one rounding per operation so that every kernel that normalises a view
+// direction (the bias-table kernel, the render launch's in-kernel row) produces the same bits
+__device__ __forceinline__ float unit_length(float x, float y, float z) {
+  return fmaxf(__fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z))), 1e-12f);
+}
