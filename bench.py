@@ -441,6 +441,24 @@ def run_ours(args, rank, world, local_rank):
         gather.check()
 
     ms_e2e, _ = timed(step_e2e, args.steps, max(1, args.warmup // 2))
+    # the same frame through the multi-kernel path the fused launch replaces (raygen, gathers, depths, bias table, per-sample MLP
+    # launch, compositing: 9 launches, 4.2 GB of HBM traffic) -- reported beside the headline, same box, same process
+    multi = None
+    if world == 1:
+        opt_mk = AttrDict(opt)
+        opt_mk.b200 = AttrDict(opt.b200)
+        opt_mk.b200.fused_render = False
+
+        def step_multi():
+            with torch.no_grad():
+                return g.nerf_forward(opt_mk, AttrDict(var_dev), mode="val")
+
+        _C.launch_counts.clear()
+        ms_mk, _ = timed(step_multi, max(3, args.steps // 2), 2)
+        n_mk = max(3, args.steps // 2) + 2
+        multi = dict(ms_per_frame=ms_mk, value=samples_per_frame / (ms_mk * 1e-3), unit=UNIT,
+                     launches_per_frame=sum(v // n_mk for v in _C.launch_counts.values()),
+                     note="multi-kernel path (opt.b200.fused_render = False): per-sample tensors and the bias table go through HBM")
     value = samples_per_frame / (ms * 1e-3)
     e2e_value = samples_per_frame / (ms_e2e * 1e-3)
 
@@ -500,6 +518,8 @@ def run_ours(args, rank, world, local_rank):
                               flop_per_sample=FLOP_PER_SAMPLE_FWD, samples_per_launch=local_samples),
                 e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=ms_e2e),
                 gpu_launches=launches, launches_per_step=per_step, clocks=clocks, so_sha16=so_sha16())
+    if multi:
+        line["multi_kernel_frame"] = multi
     if weak:
         line["weak_views"] = weak
     if train:

@@ -14,7 +14,7 @@ from texpose_b200.config import AttrDict, adapt_gan_opt  # noqa: E402
 from texpose_b200.model.base import summarize_loss  # noqa: E402
 from texpose_b200.model.nerf_adapt_st_gan import Graph  # noqa: E402
 
-what = set(sys.argv[1:]) or {"render", "train", "peer"}
+what = set(sys.argv[1:]) or {"render", "train"}      # "peer" needs concurrent kernels: the tool serialises launches of one process
 dev = "cuda:0"
 H, W, N = 12, 64, 128            # 768 rays x 128 samples = 384 super-tiles: every CTA runs 2-3 of them
 opt = adapt_gan_opt(H=H, W=W, sample_intvs=N, device=dev)

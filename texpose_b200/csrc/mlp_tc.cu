@@ -572,18 +572,17 @@ __global__ void __launch_bounds__(num_threads<kHalves>(), 1) nerf_stl_forward_ke
             if (kCols == 256) wb[1] = __ldg(reinterpret_cast<const float4*>(brow + 128) + lane);
           }
         }
-        if (kRender && L == kSpillLayer + 1) {
-          // Right after the feature park the weight stream of this stage queues behind 128 KB of bulk stores in the SM's TMA
-          // FIFO: both tiles and the tensor pipe wait ~2 700 cycles here whatever the epilogue warps do (scripts/fwd_prof.py).
-          // The work that has no place on a tile's critical path goes into that window: the compositing of the previous
-          // super-tile's samples, and the next super-tile's rays, bounds, jitter and depths (two dependent global loads).
-          if (have_done) {
-            float* sc = reinterpret_cast<float*>(smem + kOffComp) + t * kCompFloats;      // (the park barrier separates two uses)
-            render_composite(p, sc, t, q, lane, done_ray, done_k, done_d, done_dist, done_live, done_v[0], done_v[1], done_v[2], done_v[3],
-                             done_v[4], done_v[5], done_v[6], done_v[7], done_v[8]);
-            have_done = false;
-          }
-          if (st + gridDim.x < n_super) nxt = render_fetch(p, (st + gridDim.x) * 2 + t, row, lane);
+        // Two windows in which both tiles and the tensor pipe wait whatever the epilogue warps do (scripts/fwd_prof.py): right after
+        // the feature park the weight stream of the rgb-0 stage queues behind 128 KB of bulk stores in the SM's TMA FIFO
+        // (~2 700 cycles), and the trans-0 stage waits for the 64 KB feature reload (~2 100 cycles).  The work that has no place on
+        // a tile's critical path goes there: the next super-tile's rays, bounds, jitter and depths (two dependent global
+        // loads) into the first, the compositing of the previous super-tile's samples into the second.
+        if (kRender && L == kSpillLayer + 1 && st + gridDim.x < n_super) nxt = render_fetch(p, (st + gridDim.x) * 2 + t, row, lane);
+        if (kRender && L == (kNL > kStaticLayers ? kReloadIssueLayer + 1 : kSpillLayer + 1) && have_done) {
+          float* sc = reinterpret_cast<float*>(smem + kOffComp) + t * kCompFloats;      // (the park barrier separates two uses)
+          render_composite(p, sc, t, q, lane, done_ray, done_k, done_d, done_dist, done_live, done_v[0], done_v[1], done_v[2], done_v[3],
+                           done_v[4], done_v[5], done_v[6], done_v[7], done_v[8]);
+          have_done = false;
         }
         if (kRender) {
           // the tile's view-direction bias row is worked out HERE, before the accumulator wait of three consecutive trunk stages
