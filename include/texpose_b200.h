@@ -41,6 +41,11 @@ int tp_device_is_sm100(void);
 
 /* ---- rays / sampling (K1) ------------------------------------------------------------------------------- */
 
+/* K^-1 [B,3,3] and pose^-1 [B,3,4] of B views in one launch (camera.py:267 `cam_intr.inverse()`, camera.py:38-44
+ * Pose.invert): intr [B,3,3], pose [B,3,4] = [R|t].  K^-1 = fp64 cofactor formula rounded to fp32 (last-bit differences from
+ * torch's LU-based inverse; the fp32 parity mode keeps torch's call); pose^-1 = [R^T | (-R^T) t]. */
+int tp_view_matrices(const float* intr, const float* pose, int B, float* kinv, float* pose_inv, void* stream);
+
 /* camera.get_center_and_ray (camera.py:292-314) + Graph.ray_batch_sample (model/nerf_adapt_st_gan.py:702-710).
  * kinv [B,3,3] = intr.inverse(), pose_inv [B,3,4] = Pose().invert(pose) (host-side torch calls, a1 in SURVEY 8a).
  * ray_idx: NULL -> all H*W pixels (R must equal H*W); else int64 [B,R] pixel indices.  pix_offset 0.5. */
@@ -177,6 +182,11 @@ int tp_tc_pack_weights(const int64_t* chunk_desc, int n_chunks, void* packed, vo
 /* out[b,:] = bias + W[:, col0:col0+ncols] latent[b]   (per-image constants folded into a bias; fp32) */
 int tp_tc_image_bias(const float* W, int64_t ldw, int col0, int ncols, const float* bias, const float* latent, int B,
                      int nout, float* out, void* stream);
+/* Both heads' image biases in one launch: out_rgb[b,:] = b_rgb + W_rgb[:, col_rgb:col_rgb+n_light] light[b],
+ * out_trans[b,:] = b_trans + W_trans[:, col_trans:col_trans+n_trans] trans[b]  (256 outputs each; same arithmetic as tp_tc_image_bias). */
+int tp_tc_image_biases(const float* W_rgb, int64_t ld_rgb, int col_rgb, int n_light, const float* b_rgb, const float* light,
+                       const float* W_trans, int64_t ld_trans, int col_trans, int n_trans, const float* b_trans,
+                       const float* trans, int B, float* out_rgb, float* out_trans, void* stream);
 /* out[r,:] = imgbias[r / rays_per_image] + W[:, col0:col0+3+6L] [u, enc(u)], u = ray[r]/|ray[r]|  (256 outputs; fp32):
  * the view-direction part of mlp_rgb[0] (layers/nerf_static_transient_light.py:104-117), once per ray. */
 int tp_tc_ray_bias(const float* ray, int64_t R, int64_t rays_per_image, int L_view, const float* W, int64_t ldw,

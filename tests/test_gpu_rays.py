@@ -134,3 +134,20 @@ def test_normals_and_guided_range(golden):
 def test_cpu_tensors_are_rejected():
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         ops.sample_depth(torch.zeros(1, 4), torch.ones(1, 4), 8, stratified=False)
+
+
+def test_view_matrices_kernel_matches_torch_to_the_last_bits():
+    """tp_view_matrices (one launch; the bf16 path's per-view constants) against torch's inverse / Pose.invert: K^-1 is the
+    fp64 cofactor formula rounded once, so it agrees with the LU-based fp32 inverse to a few ulp; so does pose^-1."""
+    from texpose_b200 import camera
+    B = 7
+    pose = synth.poses(list(range(B))).to(DEV)
+    intr = synth.intrinsics(B).to(DEV).clone()
+    intr[3:, :2] *= 0.37
+    k0, p0 = camera.view_matrices(pose, intr)
+    k1, p1 = camera.view_matrices(pose, intr, one_launch=True)
+    assert torch.equal(p0[..., :3], p1[..., :3])                                      # R^T: exact
+    assert ((p0[..., 3] - p1[..., 3]).abs() <= 4 * torch.finfo(torch.float32).eps * 10.0).all()      # -(R^T t): |t| ~ 8
+    exact = torch.linalg.inv(intr.double())
+    assert (k1.double() - exact).abs().max() <= (k0.double() - exact).abs().max() + 1e-12      # at least as close to the exact inverse
+    assert ((k1 - k0).abs() <= 4 * torch.finfo(torch.float32).eps * k0.abs().clamp(min=1e-3)).all()

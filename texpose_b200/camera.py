@@ -73,10 +73,19 @@ def cam2world(X, pose_):
 HOST_MATRICES = False   # True: invert K / the pose on the CPU (LAPACK bits == the CPU reference), costs one sync
 
 
-def view_matrices(pose_, intr):
+def view_matrices(pose_, intr, one_launch=False):
     """(K^-1 [B,3,3], pose^-1 [B,3,4]) -- the per-view constants every ray kernel takes (camera.py:267,270-277).
-    By default they are computed where `pose_` lives (no host sync).  With HOST_MATRICES the two tiny inverses run
-    on the CPU exactly as the CPU reference does, which makes generated rays bit-identical to it."""
+    By default they are computed where `pose_` lives with the torch calls the reference makes (no host sync; same bits as the
+    reference on the same device).  With HOST_MATRICES the two tiny inverses run on the CPU exactly as the CPU reference does,
+    which makes generated rays bit-identical to it.  one_launch: tp_view_matrices instead of torch's ~20 tiny launches
+    (~1.3 ms per call): K^-1 then differs from torch's LU result in the last bits, so only the bf16 path (1e-2 contract) uses it."""
+    if one_launch and pose_.is_cuda and not HOST_MATRICES:
+        B = pose_.shape[0]
+        intr_c, pose_c = ops._f32(intr.detach()).reshape(B, 9), ops._f32(pose_.detach()).reshape(B, 12)
+        kinv = torch.empty(B, 3, 3, device=pose_.device)
+        pinv = torch.empty(B, 3, 4, device=pose_.device)
+        ops._C.call("tp_view_matrices", ops._p(intr_c), ops._p(pose_c), B, ops._p(kinv), ops._p(pinv), ops._stream())
+        return kinv, pinv
     if HOST_MATRICES and pose_.is_cuda:
         dev = pose_.device
         return (intr.detach().cpu().float().inverse().contiguous().to(dev),
@@ -86,13 +95,25 @@ def view_matrices(pose_, intr):
     return torch.linalg.inv_ex(intr.float())[0].contiguous(), Pose().invert(pose_.float()).contiguous()
 
 
+def one_launch_matrices(opt) -> bool:
+    """opt.b200.view_matrices: 'kernel' (tp_view_matrices, one launch) | 'torch' (the reference's calls, its bits).  Default:
+    'torch' in the fp32 parity mode, 'kernel' wherever the MLP may take the bf16 tensor-core path (1e-2 contract)."""
+    from .layers import _common
+    v = _common.b200_option(opt, "view_matrices")
+    if v is None:
+        return _common.mlp_precision(opt) != "fp32"
+    if v not in ("kernel", "torch"):
+        raise ValueError(f"unknown opt.b200.view_matrices {v!r}")
+    return v == "kernel"
+
+
 def get_center_and_ray(opt, pose_, intr=None, H=None, W=None, ray_idx=None):
     """camera.get_center_and_ray (camera.py:292-314).  Extra `ray_idx` [B,R] fuses Graph.ray_batch_sample
     (model/nerf_adapt_st_gan.py:702-710) so only the requested pixels are ever generated."""
     assert opt.camera.model == "perspective"
     if H is None and W is None:
         H, W = opt.H, opt.W
-    kinv, pinv = view_matrices(pose_, intr)
+    kinv, pinv = view_matrices(pose_, intr, one_launch=one_launch_matrices(opt))
     return ops.raygen(kinv, pinv, H, W, 0.5, ray_idx)
 
 

@@ -812,6 +812,25 @@ __global__ void image_bias_kernel(const float* __restrict__ W, long long ldw, in
   }
 }
 
+// both heads in one launch: blocks [0, B) the rgb head's rows, [B, 2B) the transient head's
+__global__ void image_biases_kernel(const float* __restrict__ W_r, long long ld_r, int col_r, int n_r, const float* __restrict__ b_r,
+                                    const float* __restrict__ lat_r, const float* __restrict__ W_t, long long ld_t, int col_t, int n_t,
+                                    const float* __restrict__ b_t, const float* __restrict__ lat_t, int B, float* __restrict__ out_r,
+                                    float* __restrict__ out_t) {
+  const bool second = (int)blockIdx.x >= B;
+  const int b = second ? blockIdx.x - B : blockIdx.x;
+  const float* W = second ? W_t : W_r;
+  const long long ldw = second ? ld_t : ld_r;
+  const int col0 = second ? col_t : col_r, ncols = second ? n_t : n_r;
+  const float* bias = second ? b_t : b_r;
+  const float* latent = second ? lat_t : lat_r;
+  float* out = second ? out_t : out_r;
+  const int n = threadIdx.x;
+  float acc = bias ? bias[n] : 0.f;
+  for (int j = 0; j < ncols; ++j) acc = fmaf(W[n * ldw + col0 + j], latent[(long long)b * ncols + j], acc);
+  out[(long long)b * 256 + n] = acc;
+}
+
 // out[r, n] = imgbias[r / rays_per_image, n] + sum_j W[n, col0 + j] * viewenc(r)[j];  viewenc = [u, enc(u)], u = ray/|ray|.
 // Thread n keeps its weight row in registers; a CTA strides over groups of kRaysPerBlock rays: all encodings of the group first
 // (one thread per ray and coordinate), then every thread streams the group's rays; stores are 1 KB-coalesced rows.
@@ -939,6 +958,16 @@ TP_API int tp_tc_image_bias(const float* W, int64_t ldw, int col0, int ncols, co
   if (!W || !latent || !out) return TP_ERR_BAD_ARG;
   if (B < 1 || nout < 1 || ncols < 0) return TP_ERR_BAD_SHAPE;
   tc::image_bias_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(W, ldw, col0, ncols, bias, latent, nout, out);
+  return tp_launch_status();
+}
+
+TP_API int tp_tc_image_biases(const float* W_rgb, int64_t ld_rgb, int col_rgb, int n_light, const float* b_rgb, const float* light,
+                              const float* W_trans, int64_t ld_trans, int col_trans, int n_trans, const float* b_trans,
+                              const float* trans, int B, float* out_rgb, float* out_trans, void* stream) {
+  if (!W_rgb || !light || !out_rgb || !W_trans || !trans || !out_trans) return TP_ERR_BAD_ARG;
+  if (B < 1 || n_light < 0 || n_trans < 0) return TP_ERR_BAD_SHAPE;
+  tc::image_biases_kernel<<<2 * B, 256, 0, (cudaStream_t)stream>>>(W_rgb, ld_rgb, col_rgb, n_light, b_rgb, light, W_trans, ld_trans,
+                                                                col_trans, n_trans, b_trans, trans, B, out_rgb, out_trans);
   return tp_launch_status();
 }
 

@@ -266,6 +266,43 @@ __global__ void normal_kernel(const float* __restrict__ kinv, const float* __res
     if (!(cond)) return (code); \
   } while (0)
 
+// Per-view constants of every ray kernel in ONE launch: K^-1 and pose^-1 (camera.py:267 `cam_intr.inverse()`, camera.py:38-44
+// Pose.invert).  torch's GPU path spends ~20 tiny launches per call on them (batched LU + two triangular solves for the 3x3
+// inverse, transpose / neg / bmm / cat for the pose): ~1.3 ms per frame, a sixth of a frame's share at 8 GPUs.  K^-1 is the
+// cofactor formula in fp64, rounded once to fp32 (<= 0.5 ulp from the exact inverse; LU in fp32 is within a few ulp of it, so
+// the two agree to the last bits but are not bit-identical -- the fp32 parity mode keeps torch's own call, camera.view_matrices);
+// pose^-1 = [R^T | (-R^T) t] with the matmul as the sequential mul, fma, fma chain torch's fp32 matmuls reduce to.
+__global__ void view_matrices_kernel(const float* __restrict__ intr, const float* __restrict__ pose, int B,
+                                     float* __restrict__ kinv, float* __restrict__ pinv) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float* K = intr + b * 9;
+  const double a = K[0], bb = K[1], c = K[2], d = K[3], e = K[4], f = K[5], g = K[6], h = K[7], i = K[8];
+  const double A = e * i - f * h, Bc = -(d * i - f * g), C = d * h - e * g;
+  const double det = a * A + bb * Bc + c * C, inv = 1.0 / det;
+  float* o = kinv + b * 9;
+  o[0] = (float)(A * inv);              o[1] = (float)(-(bb * i - c * h) * inv); o[2] = (float)((bb * f - c * e) * inv);
+  o[3] = (float)(Bc * inv);             o[4] = (float)((a * i - c * g) * inv);   o[5] = (float)(-(a * f - c * d) * inv);
+  o[6] = (float)(C * inv);              o[7] = (float)(-(a * h - bb * g) * inv); o[8] = (float)((a * e - bb * d) * inv);
+  const float* P = pose + b * 12;       // [R | t], rows of 4
+  float* q = pinv + b * 12;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const float r0 = P[0 * 4 + r], r1 = P[1 * 4 + r], r2 = P[2 * 4 + r];      // row r of R^T
+    q[r * 4 + 0] = r0; q[r * 4 + 1] = r1; q[r * 4 + 2] = r2;
+    float acc = __fmul_rn(-r0, P[0 * 4 + 3]);
+    acc = __fmaf_rn(-r1, P[1 * 4 + 3], acc);
+    q[r * 4 + 3] = __fmaf_rn(-r2, P[2 * 4 + 3], acc);
+  }
+}
+
+TP_API int tp_view_matrices(const float* intr, const float* pose, int B, float* kinv, float* pose_inv, void* stream) {
+  TP_CHECK(intr && pose && kinv && pose_inv, TP_ERR_BAD_ARG);
+  TP_CHECK(B > 0, TP_ERR_BAD_SHAPE);
+  view_matrices_kernel<<<(B + 63) / 64, 64, 0, (cudaStream_t)stream>>>(intr, pose, B, kinv, pose_inv);
+  return tp_launch_status();
+}
+
 TP_API int tp_raygen(const float* kinv, const float* pose_inv, int B, int H, int W, float pix_offset,
                      const int64_t* ray_idx, int R, float* center, float* ray, void* stream) {
   TP_CHECK(kinv && pose_inv && center && ray, TP_ERR_BAD_ARG);

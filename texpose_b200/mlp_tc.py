@@ -144,12 +144,11 @@ def image_biases(cfg, B, lat_trans, lat_light, rgb_p, trans_p):
     W_t0, b_t0 = trans_p[0]
     if lat_trans.shape[0] != B or lat_light.shape[0] != B:
         raise ValueError(f"latents must have one row per image ({B}); got {tuple(lat_trans.shape)} / {tuple(lat_light.shape)}")
-    img_r = torch.empty(B, _F, device=dev)
-    img_t = torch.empty(B, _F, device=dev)
-    _C.call("tp_tc_image_bias", ops._p(W_r0), W_r0.stride(0), 256 + cfg.view_cols + 3, cfg.n_latent_light, ops._p(b_r0),
-            ops._p(lat_light), B, _F, ops._p(img_r), ops._stream())
-    _C.call("tp_tc_image_bias", ops._p(W_t0), W_t0.stride(0), 256, cfg.n_latent_trans, ops._p(b_t0), ops._p(lat_trans),
-            B, _F, ops._p(img_t), ops._stream())
+    img = torch.empty(2, B, _F, device=dev)
+    _C.call("tp_tc_image_biases", ops._p(W_r0), W_r0.stride(0), 256 + cfg.view_cols + 3, cfg.n_latent_light, ops._p(b_r0),
+            ops._p(lat_light), ops._p(W_t0), W_t0.stride(0), 256, cfg.n_latent_trans, ops._p(b_t0), ops._p(lat_trans), B,
+            ops._p(img[0]), ops._p(img[1]), ops._stream())
+    img_r, img_t = img[0], img[1]
     return img_r, img_t
 
 

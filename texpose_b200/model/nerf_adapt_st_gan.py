@@ -157,7 +157,7 @@ class Graph(torch.nn.Module):
         and compositing happen inside the fused kernel.  ray_idx: [B,R] tensor, or a `range` = contiguous row block."""
         B = len(pose)
         HW = opt.H * opt.W
-        kinv, pinv = camera.view_matrices(pose, intr)
+        kinv, pinv = camera.view_matrices(pose, intr, one_launch=camera.one_launch_matrices(opt))
         zn, zf = depth_range[0].reshape(B, HW), depth_range[1].reshape(B, HW)
         if isinstance(ray_idx, range):
             assert ray_idx.step == 1

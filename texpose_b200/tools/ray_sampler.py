@@ -35,5 +35,5 @@ class RaySampler(object):
         """tools/ray_sampler.py:39-69 -> center, ray [B,h,w,3]."""
         H, W = RaySampler._hw(opt, H, W)
         with torch.no_grad():
-            kinv, pinv = camera.view_matrices(pose, intrinsics)
+            kinv, pinv = camera.view_matrices(pose, intrinsics, one_launch=camera.one_launch_matrices(opt))
             return ops.patch_rays(kinv, pinv, coords, H, W)
