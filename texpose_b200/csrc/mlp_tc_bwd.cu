@@ -488,7 +488,6 @@ __global__ void __launch_bounds__(kFThreads, 1) backward_chain_fused_kernel(cons
     const uint32_t a_smem = sbase + kOffA, m_smem = sbase + kOffM;
     const uint32_t tmem_d = tmem_base + ((uint32_t)(q * 32) << 16) + cq * 64;
     uint32_t acc_ph = 0, mask_ph = 0;
-    bool store_pending = false;
     const long long img0 = (t0 * 128) / fp.per_image;
     // ReLU bitmasks of h1 / h2 (written by the forward behind the tile images): word planes [8][128 rows] per tile and slot
     const uint8_t* bits = p.saved + ((p.S + 255) / 256) * 2 * (size_t)kFwdSlots * kABytes;
@@ -499,7 +498,10 @@ __global__ void __launch_bounds__(kFThreads, 1) backward_chain_fused_kernel(cons
       bulk_g2s_hint(m_smem, p.saved + ((size_t)t0 * kFwdSlots + kMaskSlot[0]) * kABytes, kABytes, bar_mask, l2_policy_evict_first());
     }
     // one 32-column slab: mask, bf16, store as 4 core-matrix rows of the dz tile (= next A operand / dz image)
-    auto convert_slab = [&](const uint32_t (&v)[32], int k8_0, bool tile_mask, uint32_t word) {
+    // ... and straight from the registers to the dz image in HBM (streaming 16-byte stores, a warp covers 512 contiguous bytes):
+    // a 64 KB bulk store per stage would re-read the A tile through the shared-memory pipe the MMAs load, queue in the SM's TMA
+    // FIFO in front of the next stage's weight chunks, and need a CTA barrier + wait before A may be overwritten
+    auto convert_slab = [&](const uint32_t (&v)[32], int k8_0, bool tile_mask, uint32_t word, uint8_t* g_tile) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const uint32_t off = (uint32_t)(k8_0 + i) * 2048 + row * 16;
@@ -524,6 +526,7 @@ __global__ void __launch_bounds__(kFThreads, 1) backward_chain_fused_kernel(cons
           }
         }
         st_shared_v4(a_smem + off, o[0], o[1], o[2], o[3]);
+        st_global_cs_v4(g_tile + off, o[0], o[1], o[2], o[3]);
       }
     };
     for (long long tile = t0; tile < t1; ++tile) {
@@ -577,18 +580,14 @@ __global__ void __launch_bounds__(kFThreads, 1) backward_chain_fused_kernel(cons
         // (18 warps leave 96 registers per thread: one slab in flight per thread, four warps per scheduler hide the latency)
         uint32_t va[32];
         TP_TMEM_LD32(tmem_d, va);
-        if (store_pending) {          // the previous dz image store must have finished reading A
-          if (threadIdx.x == 0) bulk_wait_read();
-          named_bar_sync(1, kFEpiThreads);
-          store_pending = false;
-        }
+        uint8_t* g_tile = p.dz_out + ((size_t)tile * kDzSlots + s) * kABytes;
         TP_PF(pe_b = clock64();)
         TP_PF(pe_store += pe_b - pe_a;)
         TP_TMEM_WAIT32(va);
-        convert_slab(va, cq * 8, tile_mask, w0);
+        convert_slab(va, cq * 8, tile_mask, w0, g_tile);
         TP_TMEM_LD32(tmem_d + 32, va);
         TP_TMEM_WAIT32(va);
-        convert_slab(va, cq * 8 + 4, tile_mask, w1);
+        convert_slab(va, cq * 8 + 4, tile_mask, w1, g_tile);
         if (cq == 1 && s % 3 != 2) {       // the 1-column of block S for the dz tile just written: column = dz slot
           const uint32_t one = 0x3F80u << ((s & 1) * 16);
           const int w = s >> 1;
@@ -598,13 +597,8 @@ __global__ void __launch_bounds__(kFThreads, 1) backward_chain_fused_kernel(cons
         fence_proxy_async_smem();
         TP_PF(pe_a = clock64();)
         TP_PF(pe_conv += pe_a - pe_b;)
-        named_bar_sync(1, kFEpiThreads);  // every thread finished reading M and writing A
+        if (tile_mask) named_bar_sync(1, kFEpiThreads);  // every thread finished reading M (the next h3 tile may land in it)
         TP_PF(pe_bar += clock64() - pe_a;)
-        if (threadIdx.x == 0) {
-          bulk_s2g_hint(p.dz_out + ((size_t)tile * kDzSlots + s) * kABytes, a_smem, kABytes, l2_policy_evict_first());
-          bulk_commit();
-        }
-        store_pending = true;
         if (threadIdx.x == 32 && tile_mask) {    // M is free again: fetch the next h3 tile (trans h3 of this tile / rgb h3 of the next)
           const long long nt = s == 3 ? tile + 1 : tile;
           if (nt < t1) {
