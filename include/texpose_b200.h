@@ -232,6 +232,31 @@ int tp_render_fused_forward(const float* kinv, const float* pose_inv, int B, int
                             float* opacity, float* opacity_static, float* opacity_transient, float* uncert,
                             float* alpha_static, float* alpha_transient, float* density, void* scratch,
                             int64_t scratch_bytes, int flags, void* stream);
+/* ---- fp32-parity mode on the tensor cores (K2 split-bf16, csrc/mlp_tc_split.cu) --------------------------------
+ * NeRF.forward_samples (layers/nerf_static_transient_light.py:76-166; layers/nerf.py:61-99 as a padded layer list) with every
+ * operand carried as hi + lo bf16 and three tcgen05.mma passes per K step (A_hi W_hi + A_hi W_lo + A_lo W_hi, fp32 accumulate):
+ * ~16 mantissa bits per operand, for the <= 1e-4 contract the bf16 kernel cannot meet.  The positional encoding is the
+ * reference's fp32 arithmetic (sin / cos of the rounded product x * fl(2^k pi)), biases are added in fp32.
+ *   image: n_slots x tp_tc32_slot_bytes() from tp_tc32_pack_weights; slot_desc: DEVICE int64 [n_slots,8] rows {W device
+ *   pointer (0 = zeros), ld, row0, rows_valid, col0, cols_valid, kind (256: one K = 16 step of a 256-row layer, hi | lo;
+ *   16: an output layer of <= 8 rows over K = 256, hi rows 0..7 / lo rows 8..15), 0} in consumption order;
+ *   stages: HOST int32 [n_stages,6] rows {a_steps (0 | 16: K steps read from the activation tile), e_steps (0..4: K steps
+ *   read from the encoding tile [xyz, enc(xyz)], taken first), kind (0 hidden 256-wide + ReLU, 1 density: softplus of row 0,
+ *   2 rgb: sigmoid of rows 0..2, 3 transient: sigmoid x3, softplus x2), bias kind (0 static: bias + bias_off, 1 per ray:
+ *   raybias row, 2 per image: imgbias row), bias_off (floats, multiple of 4), flags (1 = reads the activation tile the previous
+ *   hidden stage wrote, 2 = reads the parked trunk feature, 4 = its output is the trunk feature (parked), 8 = last stage that
+ *   reads the encoding tile)}; the list is validated (TP_ERR_BAD_ARG / TP_ERR_BAD_SHAPE) before the launch;
+ *   bias: fp32 static biases; raybias [rays,256] from tp_tc_ray_bias, imgbias [images,256] from tp_tc_image_bias.
+ * Outputs rgb [S,3,2], density [S,2], uncert [S] as tp_tc_nerf_stl_forward.  scratch >= tp_tc32_scratch_bytes(). */
+int64_t tp_tc32_slot_bytes(void);
+int64_t tp_tc32_scratch_bytes(void);
+int tp_tc32_max_stages(void);
+int tp_tc32_pack_weights(const int64_t* slot_desc, int n_slots, void* image, void* stream);
+int tp_tc32_forward(const float* center, const float* ray, const float* depth, int64_t S, int N, int64_t per_image,
+                    const void* image, int n_slots, const int32_t* stages, int n_stages, const float* bias,
+                    const float* raybias, const float* imgbias, float* rgb, float* density, float* uncert, void* scratch,
+                    int64_t scratch_bytes, void* stream);
+
 /* One slot of the saved tile images -> row-major fp32 [S,256]. */
 int tp_tc_unpack_images(const void* images, int slot, int n_slots, int64_t S, float* out, void* stream);
 

@@ -1,4 +1,5 @@
-"""Frame time of the fp32 (<= 1e-4 parity) mode on the C2 frame, for the record.  Never a benchmark."""
+"""Frame time of the fp32 (<= 1e-4 parity) mode on the C2 frame -- split-bf16 tensor-core kernel vs the SIMT kernels -- beside the
+bf16 modes, for the record.  Never a benchmark."""
 import os, sys, time
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -7,9 +8,9 @@ from texpose_b200.config import AttrDict, adapt_gan_opt
 from texpose_b200.model.nerf_adapt_st_gan import Graph
 dev = torch.device("cuda:0")
 H, W, NS = 480, 640, 128
-for mode in ("fp32", "bf16", None):
+for mode, engine in (("fp32", "auto"), ("fp32", "simt"), ("bf16", "auto"), (None, "auto")):
     opt = adapt_gan_opt(H=H, W=W, sample_intvs=NS, device=str(dev))
-    opt.b200 = AttrDict(rng="philox") if mode is None else AttrDict(mlp=mode, rng="philox")
+    opt.b200 = AttrDict(rng="philox", fp32_engine=engine) if mode is None else AttrDict(mlp=mode, rng="philox", fp32_engine=engine)
     torch.manual_seed(0)
     g = Graph(opt, n_train_images=8).to(dev).eval()
     pose, intr = synth.poses([0]).to(dev), synth.intrinsics(1).to(dev)
@@ -21,4 +22,4 @@ for mode in ("fp32", "bf16", None):
             torch.cuda.synchronize(); t0 = time.perf_counter()
             out = g.nerf_forward(opt, AttrDict(var), mode="val")
             torch.cuda.synchronize(); dt = time.perf_counter() - t0
-    print(f"{mode}: {dt * 1e3:.1f} ms/frame ({H * W * NS / dt / 1e6:.1f} M samples/s), rgb mean {out.rgb.mean().item():.4f}")
+    print(f"{mode} (fp32 engine {engine}): {dt * 1e3:.1f} ms/frame ({H * W * NS / dt / 1e6:.1f} M samples/s), rgb mean {out.rgb.mean().item():.4f}")

@@ -5,7 +5,9 @@ model, trunk under no_grad) and layers/nerf.py:61-99 (plain model, trunk trainab
 reference are never materialised: each layer reads a *segmented* input (see tp_linear_forward).
 
 Two arithmetic modes:
-  fp32  -- SIMT FFMA kernels (mlp_simt.cu), the <=1e-4 parity mode, forward and backward;
+  fp32  -- the <=1e-4 parity mode: SIMT FFMA kernels (mlp_simt.cu), forward and backward; calls that record no gradient
+           (rendering) run on the tensor cores with split-bf16 operands instead (mlp_tc_split.cu, three MMA passes per K
+           step), for any 256-wide static/transient/light architecture (opt.b200.fp32_engine = 'simt' keeps them on SIMT);
   bf16  -- fused tcgen05/TMEM forward (mlp_tc.cu) for the static/transient/light model; in training it also saves
            the head activations (bf16 tile images) that the backward consumes.
 """
@@ -36,6 +38,7 @@ class MLPConfig:
     save_for_backward: bool = True
     packed: object = None       # bf16 weight image for the tcgen05 kernel (mlp_tc.pack), or None
     static_only: bool = False   # rendering only: skip the transient head (its outputs come back as zeros), fused kernel only
+    fp32_tc: bool = True        # fp32 mode, no gradient wanted: split-bf16 tensor-core kernel (mlp_tc32) instead of SIMT FFMA
 
     @property
     def stl(self) -> bool:
@@ -249,7 +252,13 @@ class NerfMLP(torch.autograd.Function):
         if cfg.precision == "auto" and cfg.stl and not trunk_grad and geom.get("mode") == "rays":
             from .. import mlp_tc
             use_tc = mlp_tc.supported(cfg, feat_p, rgb_p, trans_p)
-        if use_tc:
+        use_tc32 = False
+        if not use_tc and sv is None and cfg.stl and cfg.fp32_tc and geom.get("mode") == "rays":
+            from .. import mlp_tc32
+            use_tc32 = mlp_tc32.supported(cfg, feat_p, rgb_p, trans_p)
+        if use_tc32:
+            rgb, density, uncert = mlp_tc32.forward(cfg, geom, lt, ll, feat_p, rgb_p, trans_p, static_only=cfg.static_only)
+        elif use_tc:
             from .. import mlp_tc
             if sv is None:
                 rgb, density, uncert = mlp_tc.forward(cfg, geom, lt, ll, feat_p, rgb_p, trans_p,
