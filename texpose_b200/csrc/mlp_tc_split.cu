@@ -24,6 +24,7 @@
 //     architecture, not from a table compiled into the kernel.
 //
 // SMEM: A_hi 64K | A_lo 64K | E_hi 16K | E_lo 16K | ring 4 x 16K | barriers = 229 632 B.  TMEM: 512 columns.
+#include <cuda_fp16.h>
 #include "tc_common.cuh"
 #include "../../include/texpose_b200.h"
 
@@ -73,10 +74,20 @@ struct Params {
   Stage st[kMaxStages];
 };
 
-// hi / lo words of two fp32 values (x0 in the low half)
+// hi / lo fp16 words of two fp32 values (x0 in the low half): hi = fp16(x), lo = fp16(x - hi) -> x to ~22 mantissa bits
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
 __device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
-  hi = pack_bf16(x0, x1);
-  lo = pack_bf16(x0 - __uint_as_float(hi << 16), x1 - __uint_as_float(hi & 0xffff0000u));
+  hi = pack_f16(x0, x1);
+  const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  lo = pack_f16(x0 - h.x, x1 - h.y);
+}
+// instruction descriptor, kind::f16 with FP16 operands (format fields 0), fp32 accumulate, both K-major
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 __device__ __forceinline__ void umma3(uint32_t d, uint32_t ah, uint32_t al, uint32_t a_hi, uint32_t bh, uint32_t bl, uint32_t b_hi,
@@ -152,7 +163,7 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_forward_split_kernel(const P
   } else if (warp == kMmaWarp) {
     // ================================================================ MMA issuer
     uint32_t slot = 0, phase = 0, ready_ph = 0, reload_ph = 0, enc_ph = 0, out_ph = 0;
-    const uint32_t idesc256 = umma_idesc(128, 256), idesc16 = umma_idesc(128, 16);
+    const uint32_t idesc256 = umma_idesc_f16(128, 256), idesc16 = umma_idesc_f16(128, 16);
     constexpr uint32_t kHi = (128u >> 4) | (1u << 14);      // SBO = 128 B, descriptor version 1
     bool first_tile = true;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -377,11 +388,11 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_forward_split_kernel(const P
 // slot_desc row: [W ptr, ld, row0, rows_valid, col0, cols_valid, kind (256 | 16), unused]
 //   kind 256: slot = [hi | lo], each [2 k8][256 rows][8]: element (n, kl) = W[row0 + n][col0 + kl], kl < 16
 //   kind 16:  first 8 KB = [32 k8][16 rows][8]: rows 0..7 hi, rows 8..15 lo of W[row0 + (n & 7)][col0 + kl], kl < 256
-__global__ void pack_split_kernel(const long long* __restrict__ desc, __nv_bfloat16* __restrict__ out) {
+__global__ void pack_split_kernel(const long long* __restrict__ desc, __half* __restrict__ out) {
   const long long* d = desc + (long long)blockIdx.x * 8;
   const float* W = reinterpret_cast<const float*>(d[0]);
   const long long ld = d[1], row0 = d[2], rows_valid = d[3], col0 = d[4], cols_valid = d[5], kind = d[6];
-  __nv_bfloat16* o = out + (long long)blockIdx.x * (kSlotBytes / 2);
+  __half* o = out + (long long)blockIdx.x * (kSlotBytes / 2);
   for (int e = threadIdx.x; e < (int)(kSlotBytes / 2); e += blockDim.x) {
     int n, kl;
     bool lo_part, in_layout = true;
@@ -399,8 +410,8 @@ __global__ void pack_split_kernel(const long long* __restrict__ desc, __nv_bfloa
     }
     float v = 0.f;
     if (in_layout && W && n < rows_valid && kl < cols_valid) v = W[(row0 + n) * ld + col0 + kl];
-    if (lo_part) v -= __bfloat162float(__float2bfloat16_rn(v));
-    o[e] = __float2bfloat16_rn(v);
+    if (lo_part) v -= __half2float(__float2half_rn(v));
+    o[e] = __float2half_rn(v);
   }
 }
 
@@ -414,7 +425,7 @@ TP_API int tp_tc32_pack_weights(const int64_t* slot_desc, int n_slots, void* ima
   if (!slot_desc || !image) return TP_ERR_BAD_ARG;
   if (n_slots < 1) return TP_ERR_BAD_SHAPE;
   tcs::pack_split_kernel<<<n_slots, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const long long*>(slot_desc),
-                                                                   reinterpret_cast<__nv_bfloat16*>(image));
+                                                                   reinterpret_cast<__half*>(image));
   return tp_launch_status();
 }
 
