@@ -45,6 +45,7 @@ def parse():
                                                                "chunk size, opt.nerf.rand_rays)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--no-parity-frame", action="store_true", help="skip the fp32-parity-mode frame (split-fp16 kernel vs SIMT)")
     ap.add_argument("--no-weak", action="store_true", help="N > 1: skip the one-view-per-GPU block")
     return ap.parse_args()
 
@@ -459,6 +460,32 @@ def run_ours(args, rank, world, local_rank):
         multi = dict(ms_per_frame=ms_mk, value=samples_per_frame / (ms_mk * 1e-3), unit=UNIT,
                      launches_per_frame=sum(v // n_mk for v in _C.launch_counts.values()),
                      note="multi-kernel path (opt.b200.fused_render = False): per-sample tensors and the bias table go through HBM")
+    # the same frame in the fp32-parity mode (<= 1e-4 against the reference): split-fp16 tensor-core kernel (three MMA passes per
+    # K step, csrc/mlp_tc_split.cu) against the SIMT FFMA kernels it replaces for rendering -- same box, same process
+    parity = None
+    if world == 1 and not args.no_parity_frame:
+        def parity_step(engine):
+            o = AttrDict(opt)
+            o.b200 = AttrDict(opt.b200)
+            o.b200.mlp, o.b200.fp32_engine = "fp32", engine
+
+            def step():
+                with torch.no_grad():
+                    return g.nerf_forward(o, AttrDict(var_dev), mode="val")
+            return step
+
+        ms_tc, _ = timed(parity_step("auto"), 3, 1)
+        with CallTimer({"tp_tc32_forward"}) as ct32:
+            parity_step("auto")()
+        k32 = sum(ct32.per_call_ms()["tp_tc32_forward"])
+        ms_simt, _ = timed(parity_step("simt"), 1, 1)
+        tf32 = 3 * FLOP_PER_SAMPLE_FWD * samples_per_frame / (k32 * 1e-3) / 1e12
+        parity = dict(ms_per_frame=ms_tc, value=samples_per_frame / (ms_tc * 1e-3), unit=UNIT, simt_ms_per_frame=ms_simt,
+                      speedup_vs_simt=ms_simt / ms_tc, kernel="tcs::nerf_forward_split_kernel", kernel_ms_per_frame=k32,
+                      launches_of_kernel_per_frame=len(ct32.per_call_ms()["tp_tc32_forward"]),
+                      executed_tflops=tf32, frac_of_sustained_tensor_peak=tf32 / pk["tf_sustained"],
+                      note="fp32-parity mode: operands carried as hi + lo fp16, three tcgen05 passes per K step (executed FLOPs = 3 x "
+                           "algorithmic); tolerance 1e-4 (tests/test_gpu_tc32.py)")
     value = samples_per_frame / (ms * 1e-3)
     e2e_value = samples_per_frame / (ms_e2e * 1e-3)
 
@@ -520,6 +547,8 @@ def run_ours(args, rank, world, local_rank):
                 gpu_launches=launches, launches_per_step=per_step, clocks=clocks, so_sha16=so_sha16())
     if multi:
         line["multi_kernel_frame"] = multi
+    if parity:
+        line["fp32_parity_frame"] = parity
     if weak:
         line["weak_views"] = weak
     if train:

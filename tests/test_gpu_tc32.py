@@ -163,3 +163,35 @@ def test_stage_list_is_validated():
     assert run([[0, 1, 0, 0, 0, 8], [16, 0, 0, 0, 0, 2], [16, 0, 2, 0, 256, 1]], 18) == -1      # reload without a parked feature
     assert run([[0, 1, 0, 0, 0, 0], [16, 0, 2, 0, 256, 1]], 2) == -1            # nobody marks the last reader of the encoding
     torch.cuda.synchronize()
+
+
+def test_plain_model_renders_on_the_split_kernel():
+    """layers/nerf.py (nerf_lm_env.yaml: 128-wide rgb head, no latents) in the fp32 mode, no gradient: the split kernel with the
+    head zero-padded to 256 columns, within 1e-4 of the oracle; with gradients wanted the SIMT kernels stay."""
+    from texpose_b200 import _C
+    from texpose_b200.config import env_opt
+    from texpose_b200.layers.nerf import NeRF as PlainNeRF
+    center, ray, depth = _c1_inputs(R=200, N=48)
+    opt = env_opt(device=DEV)
+    opt.b200 = AttrDict(mlp="fp32")
+    torch.manual_seed(0)
+    m = PlainNeRF(opt).to(DEV)
+    gen = torch.Generator().manual_seed(5)
+    with torch.no_grad():
+        for lin in list(m.mlp_feat) + list(m.mlp_rgb):
+            lin.bias.copy_(torch.randn(lin.bias.shape, generator=gen).mul_(0.3).to(DEV))
+    cpu_layers = lambda ml: [(l.weight.detach().cpu(), l.bias.detach().cpu()) for l in ml]
+    pts = O.points_from_depth(center, ray, depth)
+    unit = torch.nn.functional.normalize(ray, dim=-1)[..., None, :].expand_as(pts)
+    ref_rgb, ref_sigma = O.nerf_plain_forward(pts, unit, cpu_layers(m.mlp_feat), cpu_layers(m.mlp_rgb))
+    _C.launch_counts.clear()
+    with torch.no_grad():
+        rgb, sigma = m.forward_samples(opt, center.to(DEV), ray.to(DEV), depth.to(DEV), mode="val")
+    assert _C.launch_counts.get("tp_tc32_forward") == 1 and "tp_linear_forward" not in _C.launch_counts
+    assert rgb.shape == ref_rgb.shape and sigma.shape == ref_sigma.shape
+    assert (rgb.cpu() - ref_rgb).abs().max() <= TOL
+    assert (sigma.cpu() - ref_sigma).abs().max() <= TOL * max(1.0, ref_sigma.abs().max().item())
+    _C.launch_counts.clear()
+    rgb_g, _ = m.forward_samples(opt, center.to(DEV), ray.to(DEV), depth.to(DEV), mode="train")
+    assert "tp_tc32_forward" not in _C.launch_counts
+    assert (rgb_g - rgb).abs().max() <= TOL

@@ -39,7 +39,8 @@ class NeRF(torch.nn.Module):
         if opt.c2f is not None:
             self.progress = torch.nn.Parameter(torch.tensor(0.))
         self._packed = None     # (version key, packed bf16 weight image) for the tcgen05 kernel
-        self._tc_image = None   # (version key, padded head parameters), see _tc_parameters
+        self._tc_image = None
+        self._tc32_image = None   # (version key, padded head parameters), see _tc_parameters
 
     def _config(self, opt, mode) -> MLPConfig:
         if opt.arch.density_activ != "softplus":
@@ -65,6 +66,8 @@ class NeRF(torch.nn.Module):
         geom = _common.ray_geometry(cfg, center, ray, depth_samples)
         if geom["S"] > 0 and self.uses_tensor_cores(opt):
             return self._forward_tc(cfg, geom)
+        if geom["S"] > 0 and self.uses_split_tensor_cores(opt):
+            return self._forward_tc32(cfg, geom)
         return run_mlp(cfg, geom, None, None, *_common.flat_params(self.mlp_feat, self.mlp_rgb))
 
     # ------------------------------------------------------------------ tensor-core rendering path
@@ -127,6 +130,61 @@ class NeRF(torch.nn.Module):
                         static_only=True)
         none = torch.zeros(B, 0, device=dev)
         rgb, density, _ = mlp_tc.forward(stl, geom, none, none, feat_p, rgb_p, trans_p, static_only=True)
+        return rgb.view(B, R, N, 3, 2)[..., 0].contiguous(), density.view(B, R, N, 2)[..., 0].contiguous()
+
+    # ------------------------------------------------------------------ fp32-parity rendering on the tensor cores
+    def uses_split_tensor_cores(self, opt) -> bool:
+        """True when forward_samples will take the split-fp16 kernel (csrc/mlp_tc_split.cu, <= 1e-4): no gradient wanted, the
+        bf16 kernel not selected (opt.b200.mlp = 'fp32', or an architecture it does not implement), 256-wide trunk of any depth /
+        skip set, rgb head of any depth <= 256 wide, L_3D = 10.  opt.b200.fp32_engine = 'simt' keeps the SIMT kernels."""
+        if _common.b200_option(opt, "fp32_engine", "auto") == "simt":
+            return False
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            return False
+        if not (opt.nerf.view_dep and opt.arch.posenc and opt.arch.posenc.L_3D == 10 and 0 <= (opt.arch.posenc.L_view or 0) <= 4):
+            return False
+        nf, skip = len(self.mlp_feat), set(opt.arch.skip)
+        if nf < 2 or 0 in skip or nf - 1 in skip or len(self.mlp_rgb) < 2:
+            return False
+        for li, l in enumerate(self.mlp_feat):
+            k = 63 if li == 0 else 256 + (63 if li in skip else 0)
+            if tuple(l.weight.shape) != ((257 if li == nf - 1 else 256), k):
+                return False
+        widths = [l.weight.shape[0] for l in self.mlp_rgb]
+        return all(w <= 256 for w in widths[:-1]) and widths[-1] == 3 and nf + 1 + len(widths) <= 24
+
+    def _tc32_parameters(self):
+        """The plain model as the layer list mlp_tc32 builds its stages from: rgb hidden layers zero-padded to 256 wide (exact),
+        no latents, a dummy transient head that the static-only stage list never streams."""
+        params = [p for l in list(self.mlp_feat) + list(self.mlp_rgb) for p in (l.weight, l.bias)]
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        if self._tc32_image is not None and self._tc32_image[0] == key:
+            return self._tc32_image[1]
+        dev = self.mlp_feat[0].weight.device
+        z = lambda *shape: torch.zeros(*shape, device=dev)
+        feat_p = [(l.weight.detach().float().contiguous(), l.bias.detach().float().contiguous()) for l in self.mlp_feat]
+        layers = [(l.weight.detach().float(), l.bias.detach().float()) for l in self.mlp_rgb]
+        rgb_p = []
+        for li, (w_src, b_src) in enumerate(layers):
+            last = li == len(layers) - 1
+            W, b = z(3 if last else 256, w_src.shape[1] if li == 0 else 256), z(3 if last else 256)
+            W[:w_src.shape[0], :w_src.shape[1]] = w_src
+            b[:b_src.shape[0]] = b_src
+            rgb_p.append((W, b))
+        trans_p = [(z(256, 256), z(256)), (z(5, 256), z(5))]
+        self._tc32_image = (key, (feat_p, rgb_p, trans_p))
+        return self._tc32_image[1]
+
+    def _forward_tc32(self, cfg, geom):
+        from .. import mlp_tc32
+        feat_p, rgb_p, trans_p = self._tc32_parameters()
+        B, R, N = geom["shape"]
+        dev = geom["depth"].device
+        stl = MLPConfig(L_3D=cfg.L_3D, L_view=cfg.L_view, skip=cfg.skip, view_dep=True, n_feat=len(feat_p), n_rgb=len(rgb_p),
+                        n_trans=2, n_latent_light=0, n_latent_trans=0, precision="fp32", save_for_backward=False, packed=self,
+                        static_only=True)
+        none = torch.zeros(B, 0, device=dev)
+        rgb, density, _ = mlp_tc32.forward(stl, geom, none, none, feat_p, rgb_p, trans_p, static_only=True)
         return rgb.view(B, R, N, 3, 2)[..., 0].contiguous(), density.view(B, R, N, 2)[..., 0].contiguous()
 
     @staticmethod
