@@ -340,6 +340,14 @@ int tp_patch_loss_backward(const float* g_losses, const float* image_sample, con
 
 /* ---- eval-frame epilogue --------------------------------------------------------------------------- */
 
+/* Latent rows of a training batch (model/nerf_adapt_st_gan.py:589-603): out_a[b,:] = table_a[idx[b],:], out_b likewise -- both
+ * embedding tables in one launch; idx DEVICE int64 [B].  The backward writes the dense table gradients: d_table[r,:] = sum of
+ * g[b,:] over the b with idx[b] == r, in ascending b (deterministic); untouched rows are zero. */
+int tp_latent_rows(const float* table_a, int cols_a, const float* table_b, int cols_b, const int64_t* idx, int B,
+                   float* out_a, float* out_b, void* stream);
+int tp_latent_rows_backward(const float* g_a, int cols_a, int64_t rows_a, const float* g_b, int cols_b, int64_t rows_b,
+                            const int64_t* idx, int B, float* d_table_a, float* d_table_b, void* stream);
+
 /* Model.evaluate_full per frame (model/nerf_adapt_st_gan.py:341-362) for B views at once, no host sync: rgb [B,HW,3]
  * (rgb_static of the render) -> rgb_map [B,3,HW]; depth [B,HW] -> depth_map = depth / depth_scale; image [B,3,HW] * mask
  * [B,HW] -> image_masked; mse[b] = mean((rgb_map - image_masked)^2), psnr[b] = -10 log10(mse[b]) stay on the device.

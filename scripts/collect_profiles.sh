@@ -31,6 +31,10 @@ out = dict(so_sha16=sha, dram_bytes_per_launch=int(m["dram__bytes_read.sum"] + m
 json.dump(out, open("gpurun_out/${T}_render_traffic.json", "w"), indent=1)
 print(out)
 PY
+# (4b) the split-fp16 kernel of the fp32-parity mode: one launch (2^21 samples of the C2 frame), tensor pipe + traffic
+timeout -k 10 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed,gpu__time_duration.sum,sm__cycles_elapsed.avg.per_second,lts__t_bytes.sum \
+    --clock-control none -k regex:nerf_forward_split -s 2 -c 1 --csv --log-file gpurun_out/${T}_split_kernel_metrics.csv \
+    env TP_SPLIT_ONLY=1 python scripts/fp32_frame.py > /dev/null 2>&1; echo "ncu split rc=$?" | tee -a gpurun_out/${T}_rc.txt
 # (5) training step: launch list + per-kernel DRAM traffic / tensor pipe
 timeout -k 10 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file gpurun_out/${T}_launches_train_step.csv python scripts/train_profile.py 3 > /dev/null 2>&1
 timeout -k 10 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed \
@@ -38,7 +42,7 @@ timeout -k 10 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__
     python scripts/train_profile.py 2 > /dev/null 2>&1
 # (6) sanitizers on smoke-sized launches of every hand-written synchronisation protocol (peer kernels: scripts/gpu_round2_n2.sh, two GPUs)
 for tool in memcheck racecheck synccheck; do
-  timeout -k 10 900 compute-sanitizer --tool $tool --print-limit 40 python scripts/sanitize_target.py render train > gpurun_out/${T}_sanitizer_${tool}.log 2>&1
+  timeout -k 10 900 compute-sanitizer --tool $tool --print-limit 40 python scripts/sanitize_target.py render train split > gpurun_out/${T}_sanitizer_${tool}.log 2>&1
   echo "$tool rc=$?" | tee -a gpurun_out/${T}_rc.txt
 done
 cat gpurun_out/${T}_rc.txt; tail -4 gpurun_out/${T}_pytest.log; head -c 700 gpurun_out/${T}_bench_n1.json

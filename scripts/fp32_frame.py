@@ -8,7 +8,8 @@ from texpose_b200.config import AttrDict, adapt_gan_opt
 from texpose_b200.model.nerf_adapt_st_gan import Graph
 dev = torch.device("cuda:0")
 H, W, NS = 480, 640, 128
-for mode, engine in (("fp32", "auto"), ("fp32", "simt"), ("bf16", "auto"), (None, "auto")):
+modes = (("fp32", "auto"),) if os.environ.get("TP_SPLIT_ONLY") else (("fp32", "auto"), ("fp32", "simt"), ("bf16", "auto"), (None, "auto"))
+for mode, engine in modes:
     opt = adapt_gan_opt(H=H, W=W, sample_intvs=NS, device=str(dev))
     opt.b200 = AttrDict(rng="philox", fp32_engine=engine) if mode is None else AttrDict(mlp=mode, rng="philox", fp32_engine=engine)
     torch.manual_seed(0)

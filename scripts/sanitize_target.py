@@ -2,7 +2,7 @@
 the fused forward kernel in its three launch kinds (render <1,17,3>, per-sample inference <1,17,1>, training <1,17,2> with the
 activation save), the static-only instantiations, the fused backward chain + dW GEMM kernels, the fused loss, and the peer-window
 exchange / barrier kernels with two "ranks" on one device.
-usage: compute-sanitizer --tool racecheck python scripts/sanitize_target.py [what ...]   (what: render train peer; default all)"""
+usage: compute-sanitizer --tool racecheck python scripts/sanitize_target.py [what ...]   (what: render train split peer; default render train split)"""
 import os
 import sys
 
@@ -14,7 +14,7 @@ from texpose_b200.config import AttrDict, adapt_gan_opt  # noqa: E402
 from texpose_b200.model.base import summarize_loss  # noqa: E402
 from texpose_b200.model.nerf_adapt_st_gan import Graph  # noqa: E402
 
-what = set(sys.argv[1:]) or {"render", "train"}      # "peer" needs concurrent kernels: the tool serialises launches of one process
+what = set(sys.argv[1:]) or {"render", "train", "split"}      # "peer" needs concurrent kernels: the tool serialises launches of one process
 dev = "cuda:0"
 H, W, N = 12, 64, 128            # 768 rays x 128 samples = 384 super-tiles: every CTA runs 2-3 of them
 opt = adapt_gan_opt(H=H, W=W, sample_intvs=N, device=dev)
@@ -38,6 +38,16 @@ if "render" in what:
         d = g.render(opt64, pose, intr=intr, ray_idx=torch.randperm(H * W, device=dev)[None, :300].expand(2, -1).contiguous(), depth_range=dr, mode="val")   # 2 rays per tile
     torch.cuda.synchronize()
     print("render ok", float(a.rgb.sum()), float(b.rgb.sum()), float(c.rgb_static.sum()), float(d.rgb.sum()))
+
+if "split" in what:
+    # fp32-parity split-fp16 kernel (csrc/mlp_tc_split.cu): full stage list (park + reload), static-only list, ragged tail tile
+    o32 = AttrDict(opt); o32.b200 = AttrDict(mlp="fp32", rng="philox")
+    with torch.no_grad():
+        a = g.render(o32, pose, intr=intr, ray_idx=range(0, H * W), depth_range=dr, mode="val")
+        o33 = AttrDict(o32); o33.b200 = AttrDict(o32.b200); o33.b200.static_only = True
+        b = g.render(o33, pose[:1], intr=intr[:1], ray_idx=range(0, H * W - 5), depth_range=(dr[0][:1], dr[1][:1]), sample_idx=torch.tensor(0, device=dev), mode="eval")
+    torch.cuda.synchronize()
+    print("split ok", float(a.rgb.sum()), float(b.rgb_static.sum()))
 
 if "train" in what:
     B, P = 4, 16

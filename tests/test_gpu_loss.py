@@ -84,3 +84,22 @@ def test_graph_compute_loss_and_patch_sampler():
         assert abs(loss[k].item() - float(ref[k])) <= 1e-5 * max(1.0, abs(float(ref[k]))), k
     loss["all"].backward()
     assert var.rgb.grad is not None and var.uncert.grad is not None and var.density.grad is not None
+
+
+def test_latent_rows_match_embedding_indexing_forward_and_backward():
+    """ops.LatentRows == (weight_t[idx], weight_l[idx]) of model/nerf_adapt_st_gan.py:589-603, duplicates included; the table
+    gradients equal torch's index backward (sum over the samples of a row) and untouched rows get zeros."""
+    from texpose_b200 import ops
+    torch.manual_seed(3)
+    wt = torch.randn(9, 16, device=DEV, requires_grad=True)
+    wl = torch.randn(9, 48, device=DEV, requires_grad=True)
+    idx = torch.tensor([3, 0, 3, 7, 7, 7, 1, 0], device=DEV)
+    a, b = ops.LatentRows.apply(wt, wl, idx)
+    assert torch.equal(a, wt[idx]) and torch.equal(b, wl[idx])
+    ga, gb = torch.randn_like(a), torch.randn_like(b)
+    (a * ga).sum().backward(retain_graph=True)
+    (b * gb).sum().backward()
+    ref_t = torch.zeros_like(wt).index_add_(0, idx, ga)
+    ref_l = torch.zeros_like(wl).index_add_(0, idx, gb)
+    assert (wt.grad - ref_t).abs().max() <= 1e-6 and (wl.grad - ref_l).abs().max() <= 1e-6
+    assert wt.grad[2].abs().max() == 0 and wl.grad[8].abs().max() == 0

@@ -249,7 +249,57 @@ __global__ void eval_psnr_kernel(const float* __restrict__ partial, int blocks, 
   psnr[b] = -10.f * log10f(m);
 }
 
+// Latent rows of a training batch (model/nerf_adapt_st_gan.py:589-603: latent_vars_trans.weight[idx], latent_vars_light.weight[idx])
+// and their gradient.  torch's index backward is ~14 launches per table (sort, arange, index_put ...): 2 % of a C3 step.
+__global__ void latent_rows_kernel(const float* __restrict__ ta, int ca, const float* __restrict__ tb, int cb,
+                                   const long long* __restrict__ idx, int B, float* __restrict__ oa, float* __restrict__ ob) {
+  const int n = B * (ca + cb);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int b = i / (ca + cb), c = i - b * (ca + cb);
+    const long long r = idx[b];
+    if (c < ca) oa[b * ca + c] = ta[r * ca + c];
+    else ob[b * cb + c - ca] = tb[r * cb + c - ca];
+  }
+}
+// d_table[r, c] = sum over b with idx[b] == r of g[b, c], in ascending b (deterministic); rows no sample touches become zero
+__global__ void latent_rows_grad_kernel(const float* __restrict__ ga, int ca, long long ra, const float* __restrict__ gb, int cb,
+                                        long long rb, const long long* __restrict__ idx, int B, float* __restrict__ da,
+                                        float* __restrict__ db) {
+  const long long na = ra * ca, n = na + rb * cb;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const bool first = i < na;
+    const long long j = first ? i : i - na;
+    const int cols = first ? ca : cb;
+    const long long r = j / cols;
+    const int c = (int)(j - r * cols);
+    const float* g = first ? ga : gb;
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b)
+      if (idx[b] == r) acc += g[b * cols + c];
+    (first ? da : db)[j] = acc;
+  }
+}
+
 }  // namespace
+
+TP_API int tp_latent_rows(const float* table_a, int cols_a, const float* table_b, int cols_b, const int64_t* idx, int B,
+                          float* out_a, float* out_b, void* stream) {
+  if (!table_a || !table_b || !idx || !out_a || !out_b) return TP_ERR_BAD_ARG;
+  if (B < 0 || cols_a < 1 || cols_b < 1) return TP_ERR_BAD_SHAPE;
+  if (B == 0) return TP_OK;
+  latent_rows_kernel<<<tp_grid_for((long long)B * (cols_a + cols_b), 256, 2), 256, 0, (cudaStream_t)stream>>>(
+      table_a, cols_a, table_b, cols_b, reinterpret_cast<const long long*>(idx), B, out_a, out_b);
+  return tp_launch_status();
+}
+
+TP_API int tp_latent_rows_backward(const float* g_a, int cols_a, int64_t rows_a, const float* g_b, int cols_b, int64_t rows_b,
+                                   const int64_t* idx, int B, float* d_table_a, float* d_table_b, void* stream) {
+  if (!g_a || !g_b || !idx || !d_table_a || !d_table_b) return TP_ERR_BAD_ARG;
+  if (B < 0 || cols_a < 1 || cols_b < 1 || rows_a < 1 || rows_b < 1) return TP_ERR_BAD_SHAPE;
+  latent_rows_grad_kernel<<<tp_grid_for(rows_a * cols_a + rows_b * cols_b, 256, 4), 256, 0, (cudaStream_t)stream>>>(
+      g_a, cols_a, rows_a, g_b, cols_b, rows_b, reinterpret_cast<const long long*>(idx), B, d_table_a, d_table_b);
+  return tp_launch_status();
+}
 
 TP_API int64_t tp_eval_epilogue_workspace(int B) { return (int64_t)B * kEvalBlocksPerView; }
 

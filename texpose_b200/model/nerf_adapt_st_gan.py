@@ -132,8 +132,11 @@ class Graph(torch.nn.Module):
         """Latent rows of model/nerf_adapt_st_gan.py:589-603, one row per view (a single row is broadcast as the
         reference's `.expand(B, ...)` does, layers/nerf_static_transient_light.py:113,127)."""
         if mode == "train":
-            lat_trans = self.latent_vars_trans.weight[sample_idx]
-            lat_light = self.latent_vars_light.weight[sample_idx]
+            if self.latent_vars_trans.weight.is_cuda and sample_idx.dim() == 1:
+                lat_trans, lat_light = ops.LatentRows.apply(self.latent_vars_trans.weight, self.latent_vars_light.weight, sample_idx)
+            else:
+                lat_trans = self.latent_vars_trans.weight[sample_idx]
+                lat_light = self.latent_vars_light.weight[sample_idx]
         elif mode == "val":
             lat_trans = self.latent_vars_trans.weight[0][None]
             lat_light = self.latent_vars_light.weight[0][None]

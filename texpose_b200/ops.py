@@ -301,6 +301,34 @@ class PatchLoss(torch.autograd.Function):
         return g_rgb, g_unc, g_den, None, None, None, None
 
 
+class LatentRows(torch.autograd.Function):
+    """(latent_vars_trans.weight[idx], latent_vars_light.weight[idx]) of model/nerf_adapt_st_gan.py:589-603 in one launch, with
+    the dense table gradients formed by one deterministic kernel (torch's index backward: ~14 launches per table)."""
+
+    @staticmethod
+    def forward(ctx, table_a, table_b, idx):
+        _need_cuda(table_a, table_b, idx)
+        ta, tb = _f32(table_a.detach()), _f32(table_b.detach())
+        idx_c = idx.detach().to(torch.int64).reshape(-1).contiguous()
+        B = idx_c.numel()
+        oa = torch.empty(B, ta.shape[1], device=ta.device)
+        ob = torch.empty(B, tb.shape[1], device=tb.device)
+        _C.call("tp_latent_rows", _p(ta), ta.shape[1], _p(tb), tb.shape[1], _p(idx_c), B, _p(oa), _p(ob), _stream())
+        ctx.idx, ctx.shapes = idx_c, (ta.shape, tb.shape)
+        return oa, ob
+
+    @staticmethod
+    def backward(ctx, ga, gb):
+        (ra, ca), (rb, cb) = ctx.shapes
+        dev = ctx.idx.device
+        B = ctx.idx.numel()
+        ga = _f32(ga) if ga is not None else torch.zeros(B, ca, device=dev)
+        gb = _f32(gb) if gb is not None else torch.zeros(B, cb, device=dev)
+        da, db = torch.empty(ra, ca, device=dev), torch.empty(rb, cb, device=dev)
+        _C.call("tp_latent_rows_backward", _p(ga), ca, ra, _p(gb), cb, rb, _p(ctx.idx), B, _p(da), _p(db), _stream())
+        return da, db, None
+
+
 # ------------------------------------------------------------------------------------------------- fp32 MLP layers
 
 Seg = Tuple[Tensor, int, int]   # (tensor [rows, ld], group, cols)

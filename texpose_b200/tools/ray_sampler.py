@@ -22,13 +22,14 @@ class RaySampler(object):
 
     @staticmethod
     def get_bounds(opt, coords, z_near, z_far, H=None, W=None):
-        """tools/ray_sampler.py:23-37 -> ([B,h,w], [B,h,w]); both planes sampled in one launch."""
+        """tools/ray_sampler.py:23-37 -> ([B,h,w], [B,h,w]); one launch per plane straight from the caller's maps (a stacked copy
+        plus two strided views cost four launches)."""
         H, W = RaySampler._hw(opt, H, W)
         with torch.no_grad():
             B = coords.shape[0]
-            planes = torch.stack([z_near.reshape(B, H, W), z_far.reshape(B, H, W)], dim=1)
-            out = ops.grid_sample_bilinear(planes, coords)
-        return out[:, 0], out[:, 1]
+            zn = ops.grid_sample_bilinear(z_near.reshape(B, 1, H, W), coords)
+            zf = ops.grid_sample_bilinear(z_far.reshape(B, 1, H, W), coords)
+        return zn[:, 0], zf[:, 0]
 
     @staticmethod
     def get_rays(opt, intrinsics, coords, pose, H=None, W=None):
