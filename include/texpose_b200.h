@@ -340,6 +340,20 @@ int tp_patch_loss_backward(const float* g_losses, const float* image_sample, con
 
 /* ---- eval-frame epilogue --------------------------------------------------------------------------- */
 
+/* ---- K7: mesh depth / NOCS / colour rasteriser --------------------------------------------------------
+ * tools/mvrenderer.py:33-178 as compute_surfelinfo.py:114-116 calls it (pytorch3d MeshRasterizer, faces_per_pixel 1, blur 0,
+ * perspective-correct barycentrics; vertex-attribute shader; softmax_rgb_blend with sigma = gamma, black background).
+ * pytorch3d is absent and unpinned by the reference: its published rules are restated -- parity unpinned.
+ *   verts [V,3] object space; faces [F,3] int32; attr [V,C] per-vertex attributes (C <= 8: vertex colours, or the NOCS
+ *   coordinates of mvrenderer.py:695-722), may be NULL when out is NULL; pose [B,12] = [R | t] rows (OpenCV camera: x right,
+ *   y down, z forward), K [B,9] pixel intrinsics.
+ * Outputs (any may be NULL): out [B,C,H,W]; depth [B,H,W] = view depth of the nearest face, -1 where none (fragments.zbuf);
+ * pix_to_face [B,H,W] int32, -1 where none.  Deterministic (64-bit atomicMin on depth | face index). */
+int64_t tp_mesh_render_workspace(int B, int V, int H, int W);
+int tp_mesh_render(const float* verts, int V, const int32_t* faces, int F, const float* attr, int C, const float* pose,
+                   const float* K, int B, int H, int W, float sigma, float* out, float* depth, int32_t* pix_to_face,
+                   void* workspace, int64_t workspace_bytes, void* stream);
+
 /* Latent rows of a training batch (model/nerf_adapt_st_gan.py:589-603): out_a[b,:] = table_a[idx[b],:], out_b likewise -- both
  * embedding tables in one launch; idx DEVICE int64 [B].  The backward writes the dense table gradients: d_table[r,:] = sum of
  * g[b,:] over the b with idx[b] == r, in ascending b (deterministic); untouched rows are zero. */
