@@ -486,6 +486,20 @@ def run_ours(args, rank, world, local_rank):
                       executed_tflops=tf32, frac_of_sustained_tensor_peak=tf32 / pk["tf_sustained"],
                       note="fp32-parity mode: operands carried as hi + lo fp16, three tcgen05 passes per K step (executed FLOPs = 3 x "
                            "algorithmic); tolerance 1e-4 (tests/test_gpu_tc32.py)")
+    # depth + NOCS maps of a 20 480-face mesh at the frame size (tp_mesh_render: project, clear, raster, resolve)
+    raster = None
+    if world == 1:
+        from texpose_b200.tools import mvrenderer
+        mv, mf = [t.to(dev) for t in synth.icosphere(5, 0.6)]
+        nocs = mvrenderer.nocs_coordinates(mv)
+        rows8 = synth.poses(list(range(8))).reshape(8, 12).to(dev)
+        K8 = intr_d.expand(8, 3, 3).contiguous()
+        ms_r1, _ = timed(lambda: mvrenderer.render_mesh(mv, mf, nocs, rows8[:1], K8[:1], H, W), 20, 3)
+        ms_r8, _ = timed(lambda: mvrenderer.render_mesh(mv, mf, nocs, rows8, K8, H, W), 20, 3)
+        bytes_view = mv.numel() * 4 * 2 + mf.numel() * 4 + H * W * (8 + 8 + 4 + 12)
+        raster = dict(workload="depth + NOCS of a 20 480-face icosphere, 480x640", ms_per_view_b1=ms_r1, ms_per_view_b8=ms_r8 / 8,
+                      algorithmic_bytes_per_view=bytes_view, hbm_gbs_b8=8 * bytes_view / (ms_r8 * 1e-3) / 1e9, hbm_peak=pk["hbm"],
+                      note="10 MB per view: four launches in the launch-latency regime; views batch into the same four launches")
     value = samples_per_frame / (ms * 1e-3)
     e2e_value = samples_per_frame / (ms_e2e * 1e-3)
 
@@ -549,6 +563,8 @@ def run_ours(args, rank, world, local_rank):
         line["multi_kernel_frame"] = multi
     if parity:
         line["fp32_parity_frame"] = parity
+    if raster:
+        line["mesh_rasteriser"] = raster
     if weak:
         line["weak_views"] = weak
     if train:

@@ -240,22 +240,26 @@ int tp_render_fused_forward(const float* kinv, const float* pose_inv, int B, int
  *   image: n_slots x tp_tc32_slot_bytes() from tp_tc32_pack_weights; slot_desc: DEVICE int64 [n_slots,8] rows {W device
  *   pointer (0 = zeros), ld, row0, rows_valid, col0, cols_valid, kind (256: one K = 16 step of a 256-row layer, hi | lo;
  *   16: an output layer of <= 8 rows over K = 256, hi rows 0..7 / lo rows 8..15), 0} in consumption order;
- *   stages: HOST int32 [n_stages,6] rows {a_steps (0 | 16: K steps read from the activation tile), e_steps (0..4: K steps
+ *   stages: HOST int32 [n_stages,7] rows {a_steps (0 | 16: K steps read from the activation tile), e_steps (0..4: K steps
  *   read from the encoding tile [xyz, enc(xyz)], taken first), kind (0 hidden 256-wide + ReLU, 1 density: softplus of row 0,
  *   2 rgb: sigmoid of rows 0..2, 3 transient: sigmoid x3, softplus x2), bias kind (0 static: bias + bias_off, 1 per ray:
  *   raybias row, 2 per image: imgbias row), bias_off (floats, multiple of 4), flags (1 = reads the activation tile the previous
  *   hidden stage wrote, 2 = reads the parked trunk feature, 4 = its output is the trunk feature (parked), 8 = last stage that
- *   reads the encoding tile)}; the list is validated (TP_ERR_BAD_ARG / TP_ERR_BAD_SHAPE) before the launch;
+ *   reads the encoding tile), save slot (-1 = none)}; the list is validated (TP_ERR_BAD_ARG / TP_ERR_BAD_SHAPE) before the launch;
+ *   precision 0 = the split mode above; 1 = ONE pass with bf16 operands (image packed with precision 1): the bf16 forward for any
+ *   stage list (<= 1e-2; tp_tc_nerf_stl_forward stays the fast path of the yaml's architecture).  With precision 1, `save`
+ *   [ceil(S/128)][n_save][64 KB] receives the output of every hidden stage that names a save slot as a bf16 tile image
+ *   [32 k8][128 rows][8] -- the operands of the tensor-core backward (tp_tc_chain_backward, tp_tc_dw_gemm);
  *   bias: fp32 static biases; raybias [rays,256] from tp_tc_ray_bias, imgbias [images,256] from tp_tc_image_bias.
  * Outputs rgb [S,3,2], density [S,2], uncert [S] as tp_tc_nerf_stl_forward.  scratch >= tp_tc32_scratch_bytes(). */
 int64_t tp_tc32_slot_bytes(void);
 int64_t tp_tc32_scratch_bytes(void);
 int tp_tc32_max_stages(void);
-int tp_tc32_pack_weights(const int64_t* slot_desc, int n_slots, void* image, void* stream);
+int tp_tc32_pack_weights(const int64_t* slot_desc, int n_slots, int precision, void* image, void* stream);
 int tp_tc32_forward(const float* center, const float* ray, const float* depth, int64_t S, int N, int64_t per_image,
                     const void* image, int n_slots, const int32_t* stages, int n_stages, const float* bias,
                     const float* raybias, const float* imgbias, float* rgb, float* density, float* uncert, void* scratch,
-                    int64_t scratch_bytes, void* stream);
+                    int64_t scratch_bytes, int precision, void* save, int n_save, void* stream);
 
 /* One slot of the saved tile images -> row-major fp32 [S,256]. */
 int tp_tc_unpack_images(const void* images, int slot, int n_slots, int64_t S, float* out, void* stream);
@@ -339,6 +343,19 @@ int tp_patch_loss_backward(const float* g_losses, const float* image_sample, con
                            int64_t workspace_floats, void* stream);
 
 /* ---- eval-frame epilogue --------------------------------------------------------------------------- */
+
+/* dX chain of any stack of 256-wide ReLU layers on the tensor cores (csrc/mlp_tc_chain.cu; autograd of layers/nerf.py:61-99 for
+ * the plain model, whose trunk trains): per 128-sample tile and stage, dz_out = (dz_in W) * [saved activation > 0], every dz
+ * tile stored as a bf16 image for tp_tc_dw_gemm.  thin0 [S,cols0] / thin1 [S,cols1] (<= 8 fp32 columns; thin1 may be NULL):
+ * narrow gradients that enter the chain through one K = 16 step (the rgb output layer's dz, the raw-density gradient).
+ * packed_bwd: n_chunks x 16 KB transposed weight chunks (tp_tc_pack_weights, transpose flag).  stages: HOST int32 [n_stages,6]
+ * rows {thin operand (-1 | 0 | 1), its 8 KB chunk, first K = 32 chunk, number of K = 32 chunks (0 | 8, read against the previous
+ * stage's output), mask slot in `saved`, dz slot written}; the first stage reads only a thin operand.
+ * saved [tiles][n_saved][64 KB] from tp_tc32_forward (precision 1, save); dz_out [tiles][n_out][64 KB]. */
+int tp_tc_chain_max_stages(void);
+int tp_tc_chain_backward(const float* thin0, int cols0, const float* thin1, int cols1, int64_t S, const void* packed_bwd,
+                         int n_chunks, const int32_t* stages, int n_stages, const void* saved, int n_saved, void* dz_out,
+                         int n_out, void* stream);
 
 /* ---- K7: mesh depth / NOCS / colour rasteriser --------------------------------------------------------
  * tools/mvrenderer.py:33-178 as compute_surfelinfo.py:114-116 calls it (pytorch3d MeshRasterizer, faces_per_pixel 1, blur 0,

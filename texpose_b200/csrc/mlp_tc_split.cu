@@ -53,7 +53,7 @@ enum Flags : int {
   F_E_LAST = 8         // last stage of the tile that reads E: the next tile's encoding may be written once its MMAs retired
 };
 struct Stage {
-  int a_steps, e_steps, kind, bias_kind, bias_off, flags;
+  int a_steps, e_steps, kind, bias_kind, bias_off, flags, save_slot;      // save_slot: -1, or the tile-image slot the stage's output is kept in
 };
 struct Params {
   const float* center;       // [rays,3]
@@ -70,6 +70,8 @@ struct Params {
   float* density;            // [S,2]
   float* uncert;             // [S]
   uint8_t* scratch;          // gridDim.x x 128 KB (parked feature, hi | lo)
+  uint8_t* save;             // single-pass mode, training: [tiles][n_save][64 KB] bf16 tile images of the stages with a save slot
+  int n_save;
   int n_stages;
   Stage st[kMaxStages];
 };
@@ -97,6 +99,10 @@ __device__ __forceinline__ void umma3(uint32_t d, uint32_t ah, uint32_t al, uint
   umma_bf16_lohi(d, al, a_hi, bh, b_hi, idesc, 1u);
 }
 
+// kSingle = false: the fp32-parity mode (fp16 hi + lo, three passes).  kSingle = true: ONE pass with bf16 operands -- the general-
+// architecture bf16 forward (any stage list; <= 1e-2 like mlp_tc.cu, which stays the fast path for the yaml's architecture), whose
+// drain can also keep every hidden activation as a bf16 tile image for the tensor-core backward (training of layers/nerf.py).
+template <bool kSingle>
 __global__ void __launch_bounds__(kThreads, 1) nerf_forward_split_kernel(const Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
@@ -147,7 +153,7 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_forward_split_kernel(const P
         const Stage sg = p.st[L];
         const bool small = sg.kind != KIND_HIDDEN;
         const int n = small ? 1 : sg.e_steps + sg.a_steps;
-        const uint32_t bytes = small ? kHalfSlot : kSlotBytes;
+        const uint32_t bytes = (small || kSingle) ? kHalfSlot : kSlotBytes;      // single pass: only the hi half of a slot exists
         for (int j = 0; j < n; ++j, ++c) {
           mbar_wait(bar_empty(slot), phase ^ 1);
           if (elect_one_sync()) {
@@ -163,7 +169,8 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_forward_split_kernel(const P
   } else if (warp == kMmaWarp) {
     // ================================================================ MMA issuer
     uint32_t slot = 0, phase = 0, ready_ph = 0, reload_ph = 0, enc_ph = 0, out_ph = 0;
-    const uint32_t idesc256 = umma_idesc_f16(128, 256), idesc16 = umma_idesc_f16(128, 16);
+    const uint32_t idesc256 = kSingle ? umma_idesc(128, 256) : umma_idesc_f16(128, 256);
+    const uint32_t idesc16 = kSingle ? umma_idesc(128, 16) : umma_idesc_f16(128, 16);
     constexpr uint32_t kHi = (128u >> 4) | (1u << 14);      // SBO = 128 B, descriptor version 1
     bool first_tile = true;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -195,7 +202,8 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_forward_split_kernel(const P
               const uint32_t a0 = (from_e ? kOffEhi : kOffAhi) + (uint32_t)ks * 4096u;
               const uint32_t a1 = (from_e ? kOffElo : kOffAlo) + (uint32_t)ks * 4096u;
               const uint32_t ah = ((sbase + a0) >> 4) | ((2048u >> 4) << 16), al = ((sbase + a1) >> 4) | ((2048u >> 4) << 16);
-              umma3(d_tmem, ah, al, kHi, bh, bl, kHi, idesc256, step > 0 ? 1u : 0u);
+              if (kSingle) umma_bf16_lohi(d_tmem, ah, kHi, bh, kHi, idesc256, step > 0 ? 1u : 0u);
+              else umma3(d_tmem, ah, al, kHi, bh, bl, kHi, idesc256, step > 0 ? 1u : 0u);
               umma_commit(bar_empty(slot));
               if (step == n - 1) umma_commit(bar_acc(L & 1));
             }
@@ -220,11 +228,13 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_forward_split_kernel(const P
             __syncwarp();
           }
           if (elect_one_sync()) {
+            if (!kSingle) {
 #pragma unroll
-            for (int ks = 0; ks < 16; ++ks) {
-              const uint32_t al = ((sbase + kOffAlo + (uint32_t)ks * 4096u) >> 4) | ((2048u >> 4) << 16);
-              const uint32_t b = ((wsm + (uint32_t)ks * 512u) >> 4) | ((256u >> 4) << 16);
-              umma_bf16_lohi(d_tmem, al, kHi, b, kHi, idesc16, 1u);
+              for (int ks = 0; ks < 16; ++ks) {
+                const uint32_t al = ((sbase + kOffAlo + (uint32_t)ks * 4096u) >> 4) | ((2048u >> 4) << 16);
+                const uint32_t b = ((wsm + (uint32_t)ks * 512u) >> 4) | ((256u >> 4) << 16);
+                umma_bf16_lohi(d_tmem, al, kHi, b, kHi, idesc16, 1u);
+              }
             }
             umma_commit(bar_empty(slot));
             umma_commit(bar_acc(L & 1));
@@ -268,9 +278,12 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_forward_split_kernel(const P
       for (int k8 = 0; k8 < 8; ++k8) {
         uint32_t h[4], l[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) split2(v[k8 * 8 + 2 * e], v[k8 * 8 + 2 * e + 1], h[e], l[e]);
+        for (int e = 0; e < 4; ++e) {
+          if (kSingle) h[e] = pack_bf16(v[k8 * 8 + 2 * e], v[k8 * 8 + 2 * e + 1]);
+          else split2(v[k8 * 8 + 2 * e], v[k8 * 8 + 2 * e + 1], h[e], l[e]);
+        }
         st_shared_v4(sbase + kOffEhi + k8 * 2048 + row * 16, h[0], h[1], h[2], h[3]);
-        st_shared_v4(sbase + kOffElo + k8 * 2048 + row * 16, l[0], l[1], l[2], l[3]);
+        if (!kSingle) st_shared_v4(sbase + kOffElo + k8 * 2048 + row * 16, l[0], l[1], l[2], l[3]);
       }
       fence_proxy_async_smem();
       __syncwarp();
@@ -293,9 +306,9 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_forward_split_kernel(const P
           fence_proxy_async_all();
 #pragma unroll 1
           for (int g = 0; g < 8; ++g) {
-            mbar_expect_tx(bar_reload(g), 2 * kHalfSlot);
+            mbar_expect_tx(bar_reload(g), kSingle ? kHalfSlot : 2 * kHalfSlot);
             bulk_g2s(sbase + kOffAhi + g * kHalfSlot, park + g * kHalfSlot, kHalfSlot, bar_reload(g));
-            bulk_g2s(sbase + kOffAlo + g * kHalfSlot, park + kABytes + g * kHalfSlot, kHalfSlot, bar_reload(g));
+            if (!kSingle) bulk_g2s(sbase + kOffAlo + g * kHalfSlot, park + kABytes + g * kHalfSlot, kHalfSlot, bar_reload(g));
           }
         }
         if (sg.kind == KIND_HIDDEN) {
@@ -304,6 +317,7 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_forward_split_kernel(const P
                                                            : p.imgbias + (s / p.per_image) * 256) + half * 128;
           const uint32_t tmem_d = tmem_row + (uint32_t)(L & 1) * 256 + half * 128;
           const bool do_park = (sg.flags & F_PARK) != 0;
+          uint8_t* const g_save = (kSingle && p.save && sg.save_slot >= 0) ? p.save + ((size_t)tile * p.n_save + sg.save_slot) * kABytes : nullptr;
           // one 32-column slab: + bias, ReLU, hi / lo split, 4 core-matrix rows of A_hi and A_lo (and of the parked copy)
           auto slab = [&](const uint32_t (&v)[32], int j) {
 #pragma unroll
@@ -313,16 +327,19 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_forward_split_kernel(const P
               const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
               uint32_t h[4], l[4];
 #pragma unroll
-              for (int e = 0; e < 4; ++e)
-                split2(fmaxf(__uint_as_float(v[i * 8 + 2 * e]) + bb[2 * e], 0.f),
-                       fmaxf(__uint_as_float(v[i * 8 + 2 * e + 1]) + bb[2 * e + 1], 0.f), h[e], l[e]);
+              for (int e = 0; e < 4; ++e) {
+                const float x0 = __uint_as_float(v[i * 8 + 2 * e]) + bb[2 * e], x1 = __uint_as_float(v[i * 8 + 2 * e + 1]) + bb[2 * e + 1];
+                if (kSingle) h[e] = pack_relu_bf16(x0, x1);
+                else split2(fmaxf(x0, 0.f), fmaxf(x1, 0.f), h[e], l[e]);
+              }
               const uint32_t off = (uint32_t)(half * 16 + j * 4 + i) * 2048 + row * 16;
               st_shared_v4(sbase + kOffAhi + off, h[0], h[1], h[2], h[3]);
-              st_shared_v4(sbase + kOffAlo + off, l[0], l[1], l[2], l[3]);
+              if (!kSingle) st_shared_v4(sbase + kOffAlo + off, l[0], l[1], l[2], l[3]);
               if (do_park) {
                 st_global_v4(park + off, h[0], h[1], h[2], h[3]);
-                st_global_v4(park + kABytes + off, l[0], l[1], l[2], l[3]);
+                if (!kSingle) st_global_v4(park + kABytes + off, l[0], l[1], l[2], l[3]);
               }
+              if (g_save) st_global_cs_v4(g_save + off, h[0], h[1], h[2], h[3]);
             }
             if (do_park) __threadfence();      // the parked copy is read back through the async proxy (bulk load) four stages later
             fence_proxy_async_smem();
@@ -388,11 +405,13 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_forward_split_kernel(const P
 // slot_desc row: [W ptr, ld, row0, rows_valid, col0, cols_valid, kind (256 | 16), unused]
 //   kind 256: slot = [hi | lo], each [2 k8][256 rows][8]: element (n, kl) = W[row0 + n][col0 + kl], kl < 16
 //   kind 16:  first 8 KB = [32 k8][16 rows][8]: rows 0..7 hi, rows 8..15 lo of W[row0 + (n & 7)][col0 + kl], kl < 256
-__global__ void pack_split_kernel(const long long* __restrict__ desc, __half* __restrict__ out) {
+// bf16 != 0: the single-pass image -- bf16(W) in the hi half (the lo half stays zero and is never streamed); output layers keep
+// their hi / lo rows, as bf16
+__global__ void pack_split_kernel(const long long* __restrict__ desc, uint16_t* __restrict__ out, int bf16) {
   const long long* d = desc + (long long)blockIdx.x * 8;
   const float* W = reinterpret_cast<const float*>(d[0]);
   const long long ld = d[1], row0 = d[2], rows_valid = d[3], col0 = d[4], cols_valid = d[5], kind = d[6];
-  __half* o = out + (long long)blockIdx.x * (kSlotBytes / 2);
+  uint16_t* o = out + (long long)blockIdx.x * (kSlotBytes / 2);
   for (int e = threadIdx.x; e < (int)(kSlotBytes / 2); e += blockDim.x) {
     int n, kl;
     bool lo_part, in_layout = true;
@@ -410,8 +429,13 @@ __global__ void pack_split_kernel(const long long* __restrict__ desc, __half* __
     }
     float v = 0.f;
     if (in_layout && W && n < rows_valid && kl < cols_valid) v = W[(row0 + n) * ld + col0 + kl];
-    if (lo_part) v -= __half2float(__float2half_rn(v));
-    o[e] = __float2half_rn(v);
+    if (bf16) {
+      if (lo_part) v = kind == 256 ? 0.f : v - __bfloat162float(__float2bfloat16_rn(v));
+      o[e] = __bfloat16_as_ushort(__float2bfloat16_rn(v));
+    } else {
+      if (lo_part) v -= __half2float(__float2half_rn(v));
+      o[e] = __half_as_ushort(__float2half_rn(v));
+    }
   }
 }
 
@@ -421,20 +445,22 @@ TP_API int64_t tp_tc32_slot_bytes(void) { return tcs::kSlotBytes; }
 TP_API int64_t tp_tc32_scratch_bytes(void) { return (int64_t)tp_num_sms() * 2 * tc::kABytes; }
 TP_API int tp_tc32_max_stages(void) { return tcs::kMaxStages; }
 
-TP_API int tp_tc32_pack_weights(const int64_t* slot_desc, int n_slots, void* image, void* stream) {
+TP_API int tp_tc32_pack_weights(const int64_t* slot_desc, int n_slots, int precision, void* image, void* stream) {
   if (!slot_desc || !image) return TP_ERR_BAD_ARG;
   if (n_slots < 1) return TP_ERR_BAD_SHAPE;
+  if (precision != 0 && precision != 1) return TP_ERR_BAD_ARG;
   tcs::pack_split_kernel<<<n_slots, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const long long*>(slot_desc),
-                                                                   reinterpret_cast<__half*>(image));
+                                                                   reinterpret_cast<uint16_t*>(image), precision);
   return tp_launch_status();
 }
 
 TP_API int tp_tc32_forward(const float* center, const float* ray, const float* depth, int64_t S, int N, int64_t per_image,
                            const void* image, int n_slots, const int32_t* stages, int n_stages, const float* bias,
                            const float* raybias, const float* imgbias, float* rgb, float* density, float* uncert,
-                           void* scratch, int64_t scratch_bytes, void* stream) {
+                           void* scratch, int64_t scratch_bytes, int precision, void* save, int n_save, void* stream) {
   if (!center || !ray || !depth || !image || !stages || !bias || !rgb || !density || !uncert || !scratch) return TP_ERR_BAD_ARG;
   if (S < 0 || N < 1 || per_image < 1 || n_stages < 1 || n_stages > tcs::kMaxStages) return TP_ERR_BAD_SHAPE;
+  if ((precision != 0 && precision != 1) || (save && (precision != 1 || n_save < 1)) || ((uintptr_t)save & 15)) return TP_ERR_BAD_ARG;
   if (((uintptr_t)image & 15) || ((uintptr_t)scratch & 15) || ((uintptr_t)bias & 15) || ((uintptr_t)raybias & 15) ||
       ((uintptr_t)imgbias & 15) || ((uintptr_t)rgb & 7) || ((uintptr_t)density & 7))
     return TP_ERR_ALIGN;
@@ -445,8 +471,9 @@ TP_API int tp_tc32_forward(const float* center, const float* ray, const float* d
   bool parked = false;
   for (int L = 0; L < n_stages; ++L) {
     tcs::Stage& sg = p.st[L];
-    const int32_t* r = stages + L * 6;
-    sg.a_steps = r[0]; sg.e_steps = r[1]; sg.kind = r[2]; sg.bias_kind = r[3]; sg.bias_off = r[4]; sg.flags = r[5];
+    const int32_t* r = stages + L * 7;
+    sg.a_steps = r[0]; sg.e_steps = r[1]; sg.kind = r[2]; sg.bias_kind = r[3]; sg.bias_off = r[4]; sg.flags = r[5]; sg.save_slot = r[6];
+    if (sg.save_slot < -1 || (save && sg.save_slot >= n_save) || (sg.save_slot >= 0 && sg.kind != tcs::KIND_HIDDEN)) return TP_ERR_BAD_ARG;
     if (sg.kind < 0 || sg.kind > 3 || sg.bias_kind < 0 || sg.bias_kind > 2 || sg.bias_off < 0 || (sg.bias_off & 3)) return TP_ERR_BAD_ARG;
     if (sg.e_steps < 0 || sg.e_steps > 4 || (sg.a_steps != 0 && sg.a_steps != 16)) return TP_ERR_BAD_SHAPE;
     const bool hidden = sg.kind == tcs::KIND_HIDDEN, wait = sg.flags & tcs::F_WAIT_READY, reload = sg.flags & tcs::F_RELOAD;
@@ -484,8 +511,10 @@ TP_API int tp_tc32_forward(const float* center, const float* ray, const float* d
   p.image = reinterpret_cast<const uint8_t*>(image); p.bias = bias; p.raybias = raybias; p.imgbias = imgbias;
   p.rgb = rgb; p.density = density; p.uncert = uncert; p.scratch = reinterpret_cast<uint8_t*>(scratch);
   p.n_stages = n_stages;
-  cudaError_t e = cudaFuncSetAttribute(tcs::nerf_forward_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcs::kSmemBytes);
+  p.save = reinterpret_cast<uint8_t*>(save); p.n_save = n_save;
+  void (*kern)(const tcs::Params) = precision ? tcs::nerf_forward_split_kernel<true> : tcs::nerf_forward_split_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcs::kSmemBytes);
   if (e != cudaSuccess) return (int)e;
-  tcs::nerf_forward_split_kernel<<<grid, tcs::kThreads, tcs::kSmemBytes, (cudaStream_t)stream>>>(p);
+  kern<<<grid, tcs::kThreads, tcs::kSmemBytes, (cudaStream_t)stream>>>(p);
   return tp_launch_status();
 }

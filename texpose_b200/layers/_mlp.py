@@ -252,12 +252,20 @@ class NerfMLP(torch.autograd.Function):
         if cfg.precision == "auto" and cfg.stl and not trunk_grad and geom.get("mode") == "rays":
             from .. import mlp_tc
             use_tc = mlp_tc.supported(cfg, feat_p, rgb_p, trans_p)
-        use_tc32 = False
-        if not use_tc and sv is None and cfg.stl and cfg.fp32_tc and geom.get("mode") == "rays":
-            from .. import mlp_tc32
-            use_tc32 = mlp_tc32.supported(cfg, feat_p, rgb_p, trans_p)
+        use_tc32, single = False, 0
+        if sv is None and cfg.stl and geom.get("mode") == "rays":
+            from .. import mlp_tc, mlp_tc32
+            if cfg.precision == "fp32" or (cfg.precision == "auto" and not use_tc):
+                # the <= 1e-4 mode (and 'auto' on an architecture the bf16 kernels below do not cover) without gradients
+                use_tc32 = cfg.fp32_tc and mlp_tc32.supported(cfg, feat_p, rgb_p, trans_p)
+            if cfg.precision in ("bf16", "auto") and not mlp_tc.supported(cfg, feat_p, rgb_p, trans_p) \
+                    and mlp_tc32.supported(cfg, feat_p, rgb_p, trans_p):
+                # bf16 on an architecture the lock-step kernel is not specialised for: single-pass launch of the staged kernel
+                use_tc32, single, use_tc = True, 1, False
         if use_tc32:
-            rgb, density, uncert = mlp_tc32.forward(cfg, geom, lt, ll, feat_p, rgb_p, trans_p, static_only=cfg.static_only)
+            from .. import mlp_tc32
+            rgb, density, uncert = mlp_tc32.forward(cfg, geom, lt, ll, feat_p, rgb_p, trans_p, static_only=cfg.static_only,
+                                                    precision=single)
         elif use_tc:
             from .. import mlp_tc
             if sv is None:

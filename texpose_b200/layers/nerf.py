@@ -68,6 +68,9 @@ class NeRF(torch.nn.Module):
             return self._forward_tc(cfg, geom)
         if geom["S"] > 0 and self.uses_split_tensor_cores(opt):
             return self._forward_tc32(cfg, geom)
+        if geom["S"] > 0 and self.trains_on_tensor_cores(opt, cfg):
+            from .. import mlp_tc_plain
+            return mlp_tc_plain.PlainTC.apply(cfg, geom, len(self.mlp_feat), *_common.flat_params(self.mlp_feat, self.mlp_rgb))
         return run_mlp(cfg, geom, None, None, *_common.flat_params(self.mlp_feat, self.mlp_rgb))
 
     # ------------------------------------------------------------------ tensor-core rendering path
@@ -131,6 +134,16 @@ class NeRF(torch.nn.Module):
         none = torch.zeros(B, 0, device=dev)
         rgb, density, _ = mlp_tc.forward(stl, geom, none, none, feat_p, rgb_p, trans_p, static_only=True)
         return rgb.view(B, R, N, 3, 2)[..., 0].contiguous(), density.view(B, R, N, 2)[..., 0].contiguous()
+
+    def trains_on_tensor_cores(self, opt, cfg=None) -> bool:
+        """True when a gradient-recording forward_samples takes the tensor-core training path (mlp_tc_plain: single-pass bf16
+        forward with saved activations, staged dX chain, dW GEMMs): opt.b200.mlp 'bf16' / 'auto' and a supported architecture."""
+        if _common.mlp_precision(opt) == "fp32" or not torch.is_grad_enabled():
+            return False
+        from .. import mlp_tc_plain
+        cfg = cfg or self._config(opt, None)
+        pairs = [(l.weight, l.bias) for l in list(self.mlp_feat) + list(self.mlp_rgb)]
+        return mlp_tc_plain.supported(cfg, pairs[:len(self.mlp_feat)], pairs[len(self.mlp_feat):])
 
     # ------------------------------------------------------------------ fp32-parity rendering on the tensor cores
     def uses_split_tensor_cores(self, opt) -> bool:

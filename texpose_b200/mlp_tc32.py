@@ -42,9 +42,10 @@ def supported(cfg, feat_p, rgb_p, trans_p) -> bool:
     return n_stages <= _C.load().tp_tc32_max_stages()
 
 
-def build_tables(cfg, feat_p, rgb_p, trans_p, static_only=False):
+def build_tables(cfg, feat_p, rgb_p, trans_p, static_only=False, save=False):
     """-> (slot descriptor rows, stage rows, bias tensors).  Within a stage the K steps that read the encoding tile come first
-    (it is ready long before the previous drain finishes), then the sixteen K steps over the activation tile."""
+    (it is ready long before the previous drain finishes), then the sixteen K steps over the activation tile.  save: every hidden
+    stage gets a save slot, numbered in execution order (trunk layers, feature, rgb hidden layers, transient hidden layers)."""
     slots, stages, biases = [], [], []
     off = [0]
 
@@ -100,32 +101,40 @@ def build_tables(cfg, feat_p, rgb_p, trans_p, static_only=False):
         W, b = trans_p[-1]
         small(W, 0, 5)
         stages.append([16, 0, KIND_TRANS_OUT, BIAS_STATIC, add_bias(b), F_WAIT_READY])
+    n_hidden = 0
+    for st in stages:
+        hidden = st[2] == KIND_HIDDEN
+        st.append(n_hidden if (save and hidden) else -1)
+        n_hidden += hidden
     return slots, stages, biases
 
 
 class Packed:
-    __slots__ = ("key", "image", "n_slots", "stages", "bias", "keep")
+    __slots__ = ("key", "image", "n_slots", "stages", "bias", "keep", "n_save")
 
 
-def pack(cfg, holder, feat_p, rgb_p, trans_p, static_only=False) -> Packed:
+def pack(cfg, holder, feat_p, rgb_p, trans_p, static_only=False, precision=0, save=False) -> Packed:
+    """precision 0: split fp16 hi + lo image (three passes, <= 1e-4); 1: bf16 image for the single-pass launch (<= 1e-2)."""
     flat = [t for pair in (feat_p + rgb_p + trans_p) for t in pair]
-    key = (mlp_tc._version_key(flat), bool(static_only))
-    cache = getattr(holder, "_packed32", None) if holder is not None else None
+    key = (mlp_tc._version_key(flat), bool(static_only), int(precision), bool(save))
+    attr = "_packed32" if precision == 0 else "_packed16"
+    cache = getattr(holder, attr, None) if holder is not None else None
     if cache is not None and cache.key == key:
         return cache
-    slots, stages, biases = build_tables(cfg, feat_p, rgb_p, trans_p, static_only)
+    slots, stages, biases = build_tables(cfg, feat_p, rgb_p, trans_p, static_only, save)
     dev = feat_p[0][0].device
     desc = torch.tensor(slots, dtype=torch.int64, device=dev)
     image = torch.empty(len(slots) * _C.load().tp_tc32_slot_bytes(), dtype=torch.uint8, device=dev)
-    _C.call("tp_tc32_pack_weights", ops._p(desc), len(slots), ops._p(image), ops._stream())
+    _C.call("tp_tc32_pack_weights", ops._p(desc), len(slots), int(precision), ops._p(image), ops._stream())
     out = Packed()
     out.key, out.image, out.n_slots = key, image, len(slots)
     out.stages = torch.tensor(stages, dtype=torch.int32)           # host: the launch copies it into the kernel parameters
     out.bias = torch.cat([b.float() for b in biases]).contiguous()
     out.keep = desc
+    out.n_save = sum(1 for st in stages if st[6] >= 0)
     if holder is not None:
         try:
-            holder._packed32 = out
+            setattr(holder, attr, out)
         except AttributeError:
             pass
     return out
@@ -141,8 +150,9 @@ def _scratch_for(dev):
     return _scratch[k]
 
 
-def forward(cfg, geom, lat_trans, lat_light, feat_p, rgb_p, trans_p, static_only=False):
-    """NeRF.forward_samples (layers/nerf_static_transient_light.py:147-166) -> rgb [S,3,2], density [S,2], uncert [S]."""
+def forward(cfg, geom, lat_trans, lat_light, feat_p, rgb_p, trans_p, static_only=False, precision=0, save=False):
+    """NeRF.forward_samples (layers/nerf_static_transient_light.py:147-166) -> rgb [S,3,2], density [S,2], uncert [S]
+    (+ (images, n_save) with save: the bf16 tile images of every hidden activation, single-pass launch only)."""
     if geom.get("mode") != "rays":
         raise NotImplementedError("the tensor-core kernels are ray-parameterised (forward_samples)")
     if not supported(cfg, feat_p, rgb_p, trans_p):
@@ -151,7 +161,7 @@ def forward(cfg, geom, lat_trans, lat_light, feat_p, rgb_p, trans_p, static_only
     B, R, N = geom["shape"]
     S, per_image = geom["S"], geom["per_image"]
     dev = depth.device
-    pk = pack(cfg, cfg.packed, feat_p, rgb_p, trans_p, static_only)
+    pk = pack(cfg, cfg.packed, feat_p, rgb_p, trans_p, static_only, precision, save)
     W_r0 = rgb_p[0][0]
     img_r, img_t = mlp_tc.image_biases(cfg, B, lat_trans, lat_light, rgb_p, trans_p)
     raybias = torch.empty(B * R, _F, device=dev)
@@ -161,7 +171,14 @@ def forward(cfg, geom, lat_trans, lat_light, feat_p, rgb_p, trans_p, static_only
     density = torch.empty(S, 2, device=dev)
     uncert = torch.empty(S, device=dev)
     scratch = _scratch_for(dev)
+    images = None
+    if save:
+        assert precision == 1, "activations are saved by the single-pass (bf16) launch"
+        images = torch.empty(((S + 127) // 128) * pk.n_save * 65536, dtype=torch.uint8, device=dev)
     _C.call("tp_tc32_forward", ops._p(center), ops._p(ray), ops._p(depth), S, N, per_image, ops._p(pk.image), pk.n_slots,
             ops._p(pk.stages), pk.stages.shape[0], ops._p(pk.bias), ops._p(raybias), ops._p(img_t), ops._p(rgb),
-            ops._p(density), ops._p(uncert), ops._p(scratch), scratch.numel(), ops._stream())
+            ops._p(density), ops._p(uncert), ops._p(scratch), scratch.numel(), int(precision), ops._p(images), pk.n_save if save else 0,
+            ops._stream())
+    if save:
+        return rgb, density, uncert, (images, pk.n_save)
     return rgb, density, uncert

@@ -96,3 +96,28 @@ def ellipsoid_depth(pose: torch.Tensor, intr: torch.Tensor, H: int, W: int, radi
         tt = (-bq - disc.clamp(min=0).sqrt()) / (2 * a)
         out.append(torch.where((disc > 0) & (tt > 0), tt, torch.zeros_like(tt)).view(H, W))
     return torch.stack(out, 0).float()
+
+
+def icosphere(subdiv=2, radius=1.0):
+    """Synthetic CAD model for the rasteriser: icosphere vertices [V,3] float32 and faces [F,3] int32 (20 x 4^subdiv)."""
+    import numpy as np
+    t = (1.0 + 5 ** 0.5) / 2.0
+    v = [(-1, t, 0), (1, t, 0), (-1, -t, 0), (1, -t, 0), (0, -1, t), (0, 1, t), (0, -1, -t), (0, 1, -t), (t, 0, -1), (t, 0, 1),
+         (-t, 0, -1), (-t, 0, 1)]
+    f = [(0, 11, 5), (0, 5, 1), (0, 1, 7), (0, 7, 10), (0, 10, 11), (1, 5, 9), (5, 11, 4), (11, 10, 2), (10, 7, 6), (7, 1, 8),
+         (3, 9, 4), (3, 4, 2), (3, 2, 6), (3, 6, 8), (3, 8, 9), (4, 9, 5), (2, 4, 11), (6, 2, 10), (8, 6, 7), (9, 8, 1)]
+    v = [np.array(p, np.float64) / np.linalg.norm(p) for p in v]
+    for _ in range(subdiv):
+        cache, nf = {}, []
+        for a, b, c in f:
+            m = []
+            for i, j in ((a, b), (b, c), (c, a)):
+                k = (min(i, j), max(i, j))
+                if k not in cache:
+                    p = v[i] + v[j]
+                    v.append(p / np.linalg.norm(p))
+                    cache[k] = len(v) - 1
+                m.append(cache[k])
+            nf += [(a, m[0], m[2]), (b, m[1], m[0]), (c, m[2], m[1]), (m[0], m[1], m[2])]
+        f = nf
+    return torch.from_numpy((np.array(v) * radius).astype(np.float32)), torch.from_numpy(np.array(f, np.int32))
