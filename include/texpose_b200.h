@@ -249,7 +249,8 @@ int tp_render_fused_forward(const float* kinv, const float* pose_inv, int B, int
  *   precision 0 = the split mode above; 1 = ONE pass with bf16 operands (image packed with precision 1): the bf16 forward for any
  *   stage list (<= 1e-2; tp_tc_nerf_stl_forward stays the fast path of the yaml's architecture).  With precision 1, `save`
  *   [ceil(S/128)][n_save][64 KB] receives the output of every hidden stage that names a save slot as a bf16 tile image
- *   [32 k8][128 rows][8] -- the operands of the tensor-core backward (tp_tc_chain_backward, tp_tc_dw_gemm);
+ *   [32 k8][128 rows][8] -- the operands of the tensor-core backward (tp_tc_chain_backward, tp_tc_dw_gemm) -- and slot enc_slot
+ *   (-1 = none) the encoding tile [xyz, enc(xyz), 1, 0...]: dz^T of it = the encoding columns of a layer's dW and its bias sum;
  *   bias: fp32 static biases; raybias [rays,256] from tp_tc_ray_bias, imgbias [images,256] from tp_tc_image_bias.
  * Outputs rgb [S,3,2], density [S,2], uncert [S] as tp_tc_nerf_stl_forward.  scratch >= tp_tc32_scratch_bytes(). */
 int64_t tp_tc32_slot_bytes(void);
@@ -259,7 +260,7 @@ int tp_tc32_pack_weights(const int64_t* slot_desc, int n_slots, int precision, v
 int tp_tc32_forward(const float* center, const float* ray, const float* depth, int64_t S, int N, int64_t per_image,
                     const void* image, int n_slots, const int32_t* stages, int n_stages, const float* bias,
                     const float* raybias, const float* imgbias, float* rgb, float* density, float* uncert, void* scratch,
-                    int64_t scratch_bytes, int precision, void* save, int n_save, void* stream);
+                    int64_t scratch_bytes, int precision, void* save, int n_save, int enc_slot, void* stream);
 
 /* One slot of the saved tile images -> row-major fp32 [S,256]. */
 int tp_tc_unpack_images(const void* images, int slot, int n_slots, int64_t S, float* out, void* stream);
@@ -352,6 +353,12 @@ int tp_patch_loss_backward(const float* g_losses, const float* image_sample, con
  * rows {thin operand (-1 | 0 | 1), its 8 KB chunk, first K = 32 chunk, number of K = 32 chunks (0 | 8, read against the previous
  * stage's output), mask slot in `saved`, dz slot written}; the first stage reads only a thin operand.
  * saved [tiles][n_saved][64 KB] from tp_tc32_forward (precision 1, save); dz_out [tiles][n_out][64 KB]. */
+/* Column sums of tile images over all samples (bias gradients): sel DEVICE int32 [n_sel] slots; partial [blocks][n_sel][256]
+ * with blocks = tp_tc_images_colsum_blocks(), reduced by tp_reduce_partials(partial, blocks, n_sel * 256, out).  Rows of the last
+ * tile beyond S must be zero (the dz images of tp_tc_chain_backward are). */
+int tp_tc_images_colsum_blocks(void);
+int tp_tc_images_colsum(const void* images, int n_slots, int64_t S, const int32_t* sel, int n_sel, float* partial,
+                        int64_t partial_floats, void* stream);
 int tp_tc_chain_max_stages(void);
 int tp_tc_chain_backward(const float* thin0, int cols0, const float* thin1, int cols1, int64_t S, const void* packed_bwd,
                          int n_chunks, const int32_t* stages, int n_stages, const void* saved, int n_saved, void* dz_out,

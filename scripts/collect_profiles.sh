@@ -42,7 +42,7 @@ timeout -k 10 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__
     python scripts/train_profile.py 2 > /dev/null 2>&1
 # (6) sanitizers on smoke-sized launches of every hand-written synchronisation protocol (peer kernels: scripts/gpu_round2_n2.sh, two GPUs)
 for tool in memcheck racecheck synccheck; do
-  timeout -k 10 900 compute-sanitizer --tool $tool --print-limit 40 python scripts/sanitize_target.py render train split > gpurun_out/${T}_sanitizer_${tool}.log 2>&1
+  timeout -k 10 900 compute-sanitizer --tool $tool --print-limit 40 python scripts/sanitize_target.py render train split plain > gpurun_out/${T}_sanitizer_${tool}.log 2>&1
   echo "$tool rc=$?" | tee -a gpurun_out/${T}_rc.txt
 done
 cat gpurun_out/${T}_rc.txt; tail -4 gpurun_out/${T}_pytest.log; head -c 700 gpurun_out/${T}_bench_n1.json

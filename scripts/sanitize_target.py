@@ -2,7 +2,7 @@
 the fused forward kernel in its three launch kinds (render <1,17,3>, per-sample inference <1,17,1>, training <1,17,2> with the
 activation save), the static-only instantiations, the fused backward chain + dW GEMM kernels, the fused loss, and the peer-window
 exchange / barrier kernels with two "ranks" on one device.
-usage: compute-sanitizer --tool racecheck python scripts/sanitize_target.py [what ...]   (what: render train split peer; default render train split)"""
+usage: compute-sanitizer --tool racecheck python scripts/sanitize_target.py [what ...]   (what: render train split plain peer; default render train split plain)"""
 import os
 import sys
 
@@ -14,7 +14,7 @@ from texpose_b200.config import AttrDict, adapt_gan_opt  # noqa: E402
 from texpose_b200.model.base import summarize_loss  # noqa: E402
 from texpose_b200.model.nerf_adapt_st_gan import Graph  # noqa: E402
 
-what = set(sys.argv[1:]) or {"render", "train", "split"}      # "peer" needs concurrent kernels: the tool serialises launches of one process
+what = set(sys.argv[1:]) or {"render", "train", "split", "plain"}      # "peer" needs concurrent kernels: the tool serialises launches of one process
 dev = "cuda:0"
 H, W, N = 12, 64, 128            # 768 rays x 128 samples = 384 super-tiles: every CTA runs 2-3 of them
 opt = adapt_gan_opt(H=H, W=W, sample_intvs=N, device=dev)
@@ -48,6 +48,24 @@ if "split" in what:
         b = g.render(o33, pose[:1], intr=intr[:1], ray_idx=range(0, H * W - 5), depth_range=(dr[0][:1], dr[1][:1]), sample_idx=torch.tensor(0, device=dev), mode="eval")
     torch.cuda.synchronize()
     print("split ok", float(a.rgb.sum()), float(b.rgb_static.sum()))
+
+if "plain" in what:
+    # plain-model training on the tensor cores: single-pass forward with activation save, staged dX chain, dW GEMM; mesh rasteriser
+    from texpose_b200.config import env_opt
+    from texpose_b200.layers.nerf import NeRF as PlainNeRF
+    from texpose_b200.tools import mvrenderer
+    oe = env_opt(device=dev); oe.b200 = AttrDict(mlp="bf16")
+    pm = PlainNeRF(oe).to(dev)
+    gg = torch.Generator().manual_seed(0)
+    c_ = (torch.randn(2, 100, 3, generator=gg) * 0.02 + torch.tensor([0.3, 0.2, -0.8])).to(dev)
+    r_ = (torch.randn(2, 100, 3, generator=gg) * 0.1 + torch.tensor([0.0, 0.0, 1.0])).to(dev)
+    d_ = ((torch.rand(2, 100, 48, 1, generator=gg) + torch.arange(48)[None, None, :, None]) / 48 * 1.2 + 0.2).to(dev)
+    rgb_s, sig = pm.forward_samples(oe, c_, r_, d_, mode="train")
+    (rgb_s.square().mean() + sig.mean()).backward()
+    mv, mf = [t.to(dev) for t in synth.icosphere(3, 0.6)]
+    out, dep, _ = mvrenderer.render_mesh(mv, mf, mvrenderer.nocs_coordinates(mv), synth.poses([0, 1]).reshape(2, 12).to(dev), synth.intrinsics(2).to(dev) * torch.tensor([0.2, 0.2, 1.0], device=dev)[:, None], 96, 128)
+    torch.cuda.synchronize()
+    print("plain ok", float(pm.mlp_feat[0].weight.grad.abs().sum()), float(dep.max()))
 
 if "train" in what:
     B, P = 4, 16

@@ -154,7 +154,7 @@ def test_stage_list_is_validated():
         return lib.tp_tc32_forward(ops._p(dummy), ops._p(dummy), ops._p(dummy), 128, 32, 128, ops._p(img), n_slots, ops._p(st),
                                    len(rows), ops._p(dummy), ops._p(dummy), ops._p(dummy), ops._p(dummy), ops._p(dummy),
                                    ops._p(dummy), ops._p(torch.zeros(lib.tp_tc32_scratch_bytes(), dtype=torch.uint8, device=DEV)),
-                                   lib.tp_tc32_scratch_bytes(), 0, None, 0, ctypes.c_void_p(0))
+                                   lib.tp_tc32_scratch_bytes(), 0, None, 0, -1, ctypes.c_void_p(0))
 
     ok = [[0, 1, 0, 0, 0, 8, -1], [16, 0, 2, 0, 256, 1, -1]]
     assert run(ok, 2) == 0

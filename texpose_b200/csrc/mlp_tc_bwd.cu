@@ -676,7 +676,7 @@ constexpr uint32_t kDwSlots = 3;                     // ring of 64 KB image slot
 constexpr uint32_t kDwOffBar = kDwSlots * kABytes;
 constexpr uint32_t kDwSmemBytes = kDwOffBar + 128;
 
-constexpr int kDwMaxJobs = 8;
+constexpr int kDwMaxJobs = 12;      // (six head layers of the frozen-trunk model; up to 8 + the encoding jobs of the plain model)
 struct DwParams {
   const uint8_t* a_images; int a_nslots;             // dz  (M = n)
   const uint8_t* b_images; int b_nslots;             // x   (N = k)

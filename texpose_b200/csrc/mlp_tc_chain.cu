@@ -219,7 +219,59 @@ __global__ void __launch_bounds__(kThreads, 1) chain_backward_staged_kernel(cons
   }
 }
 
+// Column sums of tile images (bias gradients: db = sum over the samples of dz).  Block (x, y) walks the tiles x, x + gridDim.x, ...
+// of the y-th selected slot; a warp owns four k8 groups, lane = row (512 contiguous bytes per load), 32 fp32 accumulators per
+// thread over all its tiles, one warp reduction at the end -> partial[x][y][256].  Fixed order: deterministic.
+__global__ void __launch_bounds__(256) images_colsum_kernel(const uint8_t* __restrict__ images, int n_slots, long long n_tiles,
+                                                           const int* __restrict__ sel, float* __restrict__ partial) {
+  const int slot = sel[blockIdx.y], warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float acc[4][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[i][e] = 0.f;
+  for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const uint8_t* img = images + ((size_t)t * n_slots + slot) * kABytes;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint4 q = __ldcs(reinterpret_cast<const uint4*>(img + (warp * 4 + i) * 2048 + (j * 32 + lane) * 16));
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          acc[i][2 * e] += __uint_as_float(w[e] << 16);
+          acc[i][2 * e + 1] += __uint_as_float(w[e] & 0xffff0000u);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float v = acc[i][e];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) partial[((size_t)blockIdx.x * gridDim.y + blockIdx.y) * 256 + (warp * 4 + i) * 8 + e] = v;
+    }
+}
+
 }  // namespace tcc
+
+TP_API int tp_tc_images_colsum_blocks(void) { return 32; }
+
+/* out-of-place partials: partial [blocks][n_sel][256]; reduce with tp_reduce_partials(partial, blocks, n_sel * 256, out) */
+TP_API int tp_tc_images_colsum(const void* images, int n_slots, int64_t S, const int32_t* sel, int n_sel, float* partial,
+                               int64_t partial_floats, void* stream) {
+  if (!images || !sel || !partial) return TP_ERR_BAD_ARG;
+  if (n_slots < 1 || S < 1 || n_sel < 1 || n_sel > 64) return TP_ERR_BAD_SHAPE;
+  const int blocks = tp_tc_images_colsum_blocks();
+  if (partial_floats < (int64_t)blocks * n_sel * 256) return TP_ERR_WORKSPACE;
+  tcc::images_colsum_kernel<<<dim3(blocks, n_sel), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint8_t*>(images), n_slots,
+                                                                                  (S + 127) / 128, sel, partial);
+  return tp_launch_status();
+}
 
 TP_API int tp_tc_chain_max_stages(void) { return tcc::kMaxStages; }
 

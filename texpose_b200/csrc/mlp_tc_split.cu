@@ -72,6 +72,8 @@ struct Params {
   uint8_t* scratch;          // gridDim.x x 128 KB (parked feature, hi | lo)
   uint8_t* save;             // single-pass mode, training: [tiles][n_save][64 KB] bf16 tile images of the stages with a save slot
   int n_save;
+  int enc_slot;              // -1, or the save slot that receives the encoding tile [x, enc(x), 1] (zero beyond column 63): the B
+                             // operand of the weight-gradient GEMMs of the layers that read the encoding (column 63 = 1: their bias sums)
   int n_stages;
   Stage st[kMaxStages];
 };
@@ -273,7 +275,8 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_forward_split_kernel(const P
           v[3 + j * 2 * kEncL + kEncL + k] = cs;
         }
       }
-      v[63] = 0.f;
+      uint8_t* const g_enc = (kSingle && p.save && p.enc_slot >= 0) ? p.save + ((size_t)tile * p.n_save + p.enc_slot) * kABytes + row * 16 : nullptr;
+      v[63] = g_enc ? 1.f : 0.f;      // (no layer has a weight column 63: the packed images hold zeros there)
 #pragma unroll
       for (int k8 = 0; k8 < 8; ++k8) {
         uint32_t h[4], l[4];
@@ -284,6 +287,11 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_forward_split_kernel(const P
         }
         st_shared_v4(sbase + kOffEhi + k8 * 2048 + row * 16, h[0], h[1], h[2], h[3]);
         if (!kSingle) st_shared_v4(sbase + kOffElo + k8 * 2048 + row * 16, l[0], l[1], l[2], l[3]);
+        if (g_enc) st_global_cs_v4(g_enc + k8 * 2048, h[0], h[1], h[2], h[3]);
+      }
+      if (g_enc) {
+#pragma unroll 4
+        for (int k8 = 8; k8 < 32; ++k8) st_global_cs_v4(g_enc + k8 * 2048, 0u, 0u, 0u, 0u);
       }
       fence_proxy_async_smem();
       __syncwarp();
@@ -457,10 +465,11 @@ TP_API int tp_tc32_pack_weights(const int64_t* slot_desc, int n_slots, int preci
 TP_API int tp_tc32_forward(const float* center, const float* ray, const float* depth, int64_t S, int N, int64_t per_image,
                            const void* image, int n_slots, const int32_t* stages, int n_stages, const float* bias,
                            const float* raybias, const float* imgbias, float* rgb, float* density, float* uncert,
-                           void* scratch, int64_t scratch_bytes, int precision, void* save, int n_save, void* stream) {
+                           void* scratch, int64_t scratch_bytes, int precision, void* save, int n_save, int enc_slot, void* stream) {
   if (!center || !ray || !depth || !image || !stages || !bias || !rgb || !density || !uncert || !scratch) return TP_ERR_BAD_ARG;
   if (S < 0 || N < 1 || per_image < 1 || n_stages < 1 || n_stages > tcs::kMaxStages) return TP_ERR_BAD_SHAPE;
   if ((precision != 0 && precision != 1) || (save && (precision != 1 || n_save < 1)) || ((uintptr_t)save & 15)) return TP_ERR_BAD_ARG;
+  if (enc_slot < -1 || (enc_slot >= 0 && (!save || enc_slot >= n_save))) return TP_ERR_BAD_ARG;
   if (((uintptr_t)image & 15) || ((uintptr_t)scratch & 15) || ((uintptr_t)bias & 15) || ((uintptr_t)raybias & 15) ||
       ((uintptr_t)imgbias & 15) || ((uintptr_t)rgb & 7) || ((uintptr_t)density & 7))
     return TP_ERR_ALIGN;
@@ -474,6 +483,7 @@ TP_API int tp_tc32_forward(const float* center, const float* ray, const float* d
     const int32_t* r = stages + L * 7;
     sg.a_steps = r[0]; sg.e_steps = r[1]; sg.kind = r[2]; sg.bias_kind = r[3]; sg.bias_off = r[4]; sg.flags = r[5]; sg.save_slot = r[6];
     if (sg.save_slot < -1 || (save && sg.save_slot >= n_save) || (sg.save_slot >= 0 && sg.kind != tcs::KIND_HIDDEN)) return TP_ERR_BAD_ARG;
+    if (sg.save_slot >= 0 && sg.save_slot == enc_slot) return TP_ERR_BAD_ARG;
     if (sg.kind < 0 || sg.kind > 3 || sg.bias_kind < 0 || sg.bias_kind > 2 || sg.bias_off < 0 || (sg.bias_off & 3)) return TP_ERR_BAD_ARG;
     if (sg.e_steps < 0 || sg.e_steps > 4 || (sg.a_steps != 0 && sg.a_steps != 16)) return TP_ERR_BAD_SHAPE;
     const bool hidden = sg.kind == tcs::KIND_HIDDEN, wait = sg.flags & tcs::F_WAIT_READY, reload = sg.flags & tcs::F_RELOAD;
@@ -511,7 +521,7 @@ TP_API int tp_tc32_forward(const float* center, const float* ray, const float* d
   p.image = reinterpret_cast<const uint8_t*>(image); p.bias = bias; p.raybias = raybias; p.imgbias = imgbias;
   p.rgb = rgb; p.density = density; p.uncert = uncert; p.scratch = reinterpret_cast<uint8_t*>(scratch);
   p.n_stages = n_stages;
-  p.save = reinterpret_cast<uint8_t*>(save); p.n_save = n_save;
+  p.save = reinterpret_cast<uint8_t*>(save); p.n_save = n_save; p.enc_slot = save ? enc_slot : -1;
   void (*kern)(const tcs::Params) = precision ? tcs::nerf_forward_split_kernel<true> : tcs::nerf_forward_split_kernel<false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcs::kSmemBytes);
   if (e != cudaSuccess) return (int)e;

@@ -131,7 +131,7 @@ def pack(cfg, holder, feat_p, rgb_p, trans_p, static_only=False, precision=0, sa
     out.stages = torch.tensor(stages, dtype=torch.int32)           # host: the launch copies it into the kernel parameters
     out.bias = torch.cat([b.float() for b in biases]).contiguous()
     out.keep = desc
-    out.n_save = sum(1 for st in stages if st[6] >= 0)
+    out.n_save = sum(1 for st in stages if st[6] >= 0) + (1 if save else 0)      # + the encoding tile, in the last slot
     if holder is not None:
         try:
             setattr(holder, attr, out)
@@ -178,7 +178,7 @@ def forward(cfg, geom, lat_trans, lat_light, feat_p, rgb_p, trans_p, static_only
     _C.call("tp_tc32_forward", ops._p(center), ops._p(ray), ops._p(depth), S, N, per_image, ops._p(pk.image), pk.n_slots,
             ops._p(pk.stages), pk.stages.shape[0], ops._p(pk.bias), ops._p(raybias), ops._p(img_t), ops._p(rgb),
             ops._p(density), ops._p(uncert), ops._p(scratch), scratch.numel(), int(precision), ops._p(images), pk.n_save if save else 0,
-            ops._stream())
+            pk.n_save - 1 if save else -1, ops._stream())
     if save:
         return rgb, density, uncert, (images, pk.n_save)
     return rgb, density, uncert

@@ -72,6 +72,16 @@ def dw_gemm(a_images, a_nslots, b_images, b_nslots, pairs, S, flags=0):
     return reduce_partials(partial, splits, n * 65536).view(n, 256, 256)
 
 
+def images_colsum(images, n_slots, S, slots):
+    """[len(slots),256]: column sums over all samples of the selected image slots (bias gradients), one launch + one reduce."""
+    lib = _C.load()
+    blocks, n = lib.tp_tc_images_colsum_blocks(), len(slots)
+    sel = torch.tensor(list(slots), dtype=torch.int32, device=images.device)
+    partial = torch.empty(blocks * n * 256, device=images.device)
+    _C.call("tp_tc_images_colsum", ops._p(images), n_slots, S, ops._p(sel), n, ops._p(partial), partial.numel(), ops._stream())
+    return reduce_partials(partial, blocks, n * 256).view(n, 256)
+
+
 def image_ray_sums(images, slot, n_slots, S, N):
     out = torch.empty((S + N - 1) // N, 256, device=images.device)
     _C.call("tp_tc_image_ray_sums", ops._p(images), slot, n_slots, S, N, ops._p(out), ops._stream())

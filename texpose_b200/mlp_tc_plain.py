@@ -123,13 +123,18 @@ def backward(ctx, g_rgb, g_density, feat_p, rgb_p):
     st = torch.tensor(stages, dtype=torch.int32)
     _C.call("tp_tc_chain_backward", ops._p(dz_rgb), 3, ops._p(dz_sigma), 1, S, ops._p(packed), len(rows), ops._p(st), n_dz,
             ops._p(images), n_save, ops._p(dz), n_dz, ops._stream())
-    # ---- 256 x 256 weight gradients: (dz slot, saved activation slot) per layer, one launch
-    slot_feat, slot_rgb_h = nf - 1, nf
+    # ---- 256 x 256 weight gradients: (dz slot, saved activation slot) per layer; the layers that read the encoding (layer 0, skip
+    # layers) add a job against the saved encoding tile, whose column 63 is a constant 1: dz^T of it = [dW encoding columns | db]
+    slot_feat, slot_rgb_h, slot_enc = nf - 1, nf, n_save - 1
     dz_slot = lambda li: 2 + (nf - 2 - li) if li < nf - 1 else 1      # dz of trunk layer li's pre-activation (the last layer: its feature rows)
-    pairs = [(0, slot_feat), (1, nf - 2)] + [(dz_slot(li), li - 1) for li in range(nf - 2, 0, -1)]
-    big = mlp_tc_bwd.dw_gemm(dz, n_dz, images, n_save, pairs, S)
-    # ---- column sums of every dz image (bias gradients)
-    colsum = lambda slot: ops.group_colsum(mlp_tc_bwd.image_ray_sums(dz, slot, n_dz, S, N), B * R, B * R)[0]
+    enc_layers = [0] + sorted(set(cfg.skip))
+    pairs = [(0, slot_feat), (1, nf - 2)] + [(dz_slot(li), li - 1) for li in range(nf - 2, 0, -1)] + [(dz_slot(li), slot_enc) for li in enc_layers]
+    big = torch.cat([mlp_tc_bwd.dw_gemm(dz, n_dz, images, n_save, pairs[i:i + 12], S) for i in range(0, len(pairs), 12)], dim=0)      # one launch for <= 12 jobs
+    enc_grad = {li: big[nf + j] for j, li in enumerate(enc_layers)}       # [256, 256]: columns 0..62 encoding, 63 bias sum
+    # ---- column sums of the dz images whose bias gradient does not come out of an encoding job
+    want = [0, 1] + [dz_slot(li) for li in range(nf - 2, 0, -1) if li not in enc_grad]
+    sums = mlp_tc_bwd.images_colsum(dz, n_dz, S, want)
+    colsum = lambda slot: sums[want.index(slot)]
     # ---- thin pieces
     h = rgb_p[0][0].shape[0]
     dW_out = mlp_tc_bwd.thin_dw(dz_rgb, images, slot_rgb_h, n_save, S)[:, :h].contiguous()
@@ -140,25 +145,19 @@ def backward(ctx, g_rgb, g_density, feat_p, rgb_p):
     xyz = ops.points_from_depth(geom["center"], geom["ray"], geom["depth"]).view(S, 3)
     dW_xyz = mlp_tc_bwd.thin_dw(xyz, dz, 0, n_dz, S).t()                                                   # [256, 3]
     dW_r0 = torch.cat([big[0], dW_view, dW_xyz], dim=1)[:h].contiguous()
-    db_r0 = ops.group_colsum(ray_sums0, B * R, B * R)[0][:h].contiguous()
+    db_r0 = colsum(0)[:h].contiguous()
     g_rgb_layers = [(dW_r0, db_r0), (dW_out, db_out)]
     # ---- trunk
-    enc = geom["enc"]()
     ec = cfg.enc_cols
-
-    def enc_cols_grad(slot):            # dz^T enc for the 63 encoding columns of layer 0 / a skip layer
-        dY = mlp_tc_bwd.unpack(dz, slot, n_dz, S)
-        return ops.linear_backward_weight(dY, [(enc, 1, ec)], S, want_bias=False)[0]
-
     g_feat = [None] * nf
     dW_sigma = mlp_tc_bwd.thin_dw(dz_sigma, images, nf - 2, n_save, S)                          # [1,256]: row 0 of the last layer
     g_feat[nf - 1] = (torch.cat([dW_sigma, big[1]], dim=0), torch.cat([mlp_tc_bwd.thin_colsum(dz_sigma, S), colsum(1)]))
     for j, li in enumerate(range(nf - 2, 0, -1)):
-        dW = big[2 + j]
-        if li in set(cfg.skip):
-            dW = torch.cat([dW, enc_cols_grad(dz_slot(li))], dim=1)
-        g_feat[li] = (dW.contiguous(), colsum(dz_slot(li)))
-    g_feat[0] = (enc_cols_grad(dz_slot(0)), colsum(dz_slot(0)))
+        if li in enc_grad:
+            g_feat[li] = (torch.cat([big[2 + j], enc_grad[li][:, :ec]], dim=1), enc_grad[li][:, 63].contiguous())
+        else:
+            g_feat[li] = (big[2 + j], colsum(dz_slot(li)))
+    g_feat[0] = (enc_grad[0][:, :ec].contiguous(), enc_grad[0][:, 63].contiguous())
     return g_feat, g_rgb_layers
 
 
