@@ -664,6 +664,8 @@ def bench_train(args, g, opt, dev, world, timed, pk):
              bwd_bytes, "tensor + hbm"),
     ]
     out["entry_point_ms"] = {k: round(v, 4) for k, v in sorted(per.items(), key=lambda kv: -kv[1])}
+    if world == 1:
+        out["plain_model_train_step"] = bench_plain_train(dev, timed, samples)
     if world > 1:
         exchange.check()
         # the exchanged gradients must equal the NCCL allreduce of the same bucket: one more step, then both exchanges
@@ -690,6 +692,37 @@ def bench_train(args, g, opt, dev, world, timed, pk):
         exchange.close()
     g.eval()
     return out
+
+
+def bench_plain_train(dev, timed, samples):
+    """layers/nerf.py (options/nerf_lm_env.yaml) at the C3 shape: forward + composite + backward of every trunk / head parameter,
+    tensor-core path (single-pass staged forward with saved activations, staged dX chain, dW GEMMs) vs the SIMT fp32 kernels."""
+    import torch
+    from texpose_b200.config import AttrDict, env_opt
+    from texpose_b200.layers.nerf import NeRF as PlainNeRF
+    B, R, N = 16, 256, NS
+    g = torch.Generator().manual_seed(0)
+    center = (torch.randn(B, R, 3, generator=g) * 0.02 + torch.tensor([0.3, 0.2, -0.8])).to(dev)
+    ray = (torch.randn(B, R, 3, generator=g) * 0.1 + torch.tensor([0.0, 0.0, 1.0])).to(dev)
+    depth = ((torch.rand(B, R, N, 1, generator=g) + torch.arange(N)[None, None, :, None]) / N * 1.2 + 0.2).to(dev)
+    image = torch.rand(B, R, 3, generator=g).to(dev)
+    res = {}
+    for mode, steps in (("bf16", 10), ("fp32", 2)):
+        opt = env_opt(device=str(dev))
+        opt.b200 = AttrDict(mlp=mode)
+        torch.manual_seed(0)
+        m = PlainNeRF(opt).to(dev)
+
+        def step():
+            for p in m.parameters():
+                p.grad = None
+            rgb_s, sig = m.forward_samples(opt, center, ray, depth, mode="train")
+            ((m.composite(opt, ray, rgb_s, sig, depth)[0] - image) ** 2).mean().backward()
+
+        res[mode] = timed(step, steps, 2)[0]
+    return dict(workload="plain NeRF (8 x 256 trunk, 286 -> 128 -> 3 head), 4096 rays x 128 samples, fwd + composite + bwd of all parameters",
+                ms_per_step=res["bf16"], value=samples / (res["bf16"] * 1e-3), unit="samples/s", simt_fp32_ms_per_step=res["fp32"],
+                speedup_vs_simt=res["fp32"] / res["bf16"])
 
 
 def main():

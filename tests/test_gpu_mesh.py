@@ -156,3 +156,18 @@ def test_argument_errors():
     assert lib.tp_mesh_render(*args(C=9)) == -2
     assert lib.tp_mesh_render(*args(sigma=0.0)) == -2
     assert lib.tp_mesh_render(*args(ws=16)) == -5
+
+
+def test_empty_mesh_and_faces_behind_the_camera_render_background():
+    v, f = M.icosphere(1, 0.2)
+    vt, ft = torch.from_numpy(v).to(DEV), torch.from_numpy(f).to(DEV)
+    Kt = torch.tensor([[[100.0, 0, 32], [0, 100.0, 24], [0, 0, 1]]], device=DEV)
+    front = torch.tensor([[1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 2.0]], device=DEV)
+    behind = torch.tensor([[1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, -2.0]], device=DEV)
+    attr = torch.ones(v.shape[0], 3, device=DEV)
+    out, depth, p2f = mvrenderer.render_mesh(vt, ft[:0], attr, front, Kt, 48, 64, want_faces=True)      # no faces at all
+    assert bool((depth == -1).all()) and bool((p2f == -1).all()) and float(out.abs().max()) == 0
+    out, depth, p2f = mvrenderer.render_mesh(vt, ft, attr, behind, Kt, 48, 64, want_faces=True)
+    assert bool((depth == -1).all()) and bool((p2f == -1).all())
+    out, depth, _ = mvrenderer.render_mesh(vt, ft, attr, front, Kt, 48, 64)
+    assert int((depth > 0).sum()) > 200 and abs(float(out[0, 0][depth[0] > 0].min()) - 1) < 1e-6
