@@ -42,7 +42,9 @@ timeout -k 10 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__
     python scripts/train_profile.py 2 > /dev/null 2>&1
 # (6) sanitizers on smoke-sized launches of every hand-written synchronisation protocol (peer kernels: scripts/gpu_round2_n2.sh, two GPUs)
 for tool in memcheck racecheck synccheck; do
-  timeout -k 10 900 compute-sanitizer --tool $tool --print-limit 40 python scripts/sanitize_target.py render train split plain > gpurun_out/${T}_sanitizer_${tool}.log 2>&1
-  echo "$tool rc=$?" | tee -a gpurun_out/${T}_rc.txt
+  for what in render train split plain; do      # one process per target: a tool that aborts one target does not hide the others
+    timeout -k 10 600 compute-sanitizer --tool $tool --print-limit 20 python scripts/sanitize_target.py $what > gpurun_out/${T}_sanitizer_${tool}_${what}.log 2>&1
+    echo "$tool $what rc=$? $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' gpurun_out/${T}_sanitizer_${tool}_${what}.log | head -1)" | tee -a gpurun_out/${T}_rc.txt
+  done
 done
 cat gpurun_out/${T}_rc.txt; tail -4 gpurun_out/${T}_pytest.log; head -c 700 gpurun_out/${T}_bench_n1.json

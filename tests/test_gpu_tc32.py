@@ -218,3 +218,17 @@ def test_single_pass_bf16_covers_other_architectures():
         for k in ("rgb", "rgb_static", "rgb_transient", "depth", "opacity", "opacity_static", "opacity_transient"):
             assert 1e-6 < errs[k] <= 1e-2 or errs[k] <= 1e-2, (k, errs[k])
         assert errs["uncert"] <= 1.5e-2
+
+
+def test_c2_rays_split_kernel_vs_oracle():
+    """BASELINE configs[1] sampling: 1024 AABB-bounded rays of the 480 x 640 frame at 128 samples per ray (one ray per tile),
+    all eleven rendered outputs within 1e-4 of the oracle."""
+    center, ray, depth = _c1_inputs(R=1024, N=128)
+    lt, ll = synth.latents(1)
+    opt, m = _module("auto")
+    ref_s, ref = _oracle_render(m, center, ray, depth, lt, ll)
+    with torch.no_grad():
+        got_s = m.forward_samples(opt, center.to(DEV), ray.to(DEV), depth.to(DEV), lt.to(DEV), ll.to(DEV), mode="val")
+        got = m.composite(opt, ray.to(DEV), *got_s[:2], depth.to(DEV), got_s[2])
+    for k, a, b in zip(NAMES, got, ref):
+        assert (a.cpu() - b).abs().max() <= TOL, (k, float((a.cpu() - b).abs().max()))
