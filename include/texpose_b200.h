@@ -252,9 +252,12 @@ int tp_render_fused_forward(const float* kinv, const float* pose_inv, int B, int
  *   [32 k8][128 rows][8] -- the operands of the tensor-core backward (tp_tc_chain_backward, tp_tc_dw_gemm) -- and slot enc_slot
  *   (-1 = none) the encoding tile [xyz, enc(xyz), 1, 0...]: dz^T of it = the encoding columns of a layer's dW and its bias sum;
  *   bias: fp32 static biases; raybias [rays,256] from tp_tc_ray_bias, imgbias [images,256] from tp_tc_image_bias.
- * Outputs rgb [S,3,2], density [S,2], uncert [S] as tp_tc_nerf_stl_forward.  scratch >= tp_tc32_scratch_bytes(). */
+ * Outputs rgb [S,3,2], density [S,2], uncert [S] as tp_tc_nerf_stl_forward.  scratch >= tp_tc32_scratch_bytes().  Range of the
+ * split mode: |weights|, |hidden activations| < 65 504 (fp16 hi part); a violation is reported through the status word. */
 int64_t tp_tc32_slot_bytes(void);
 int64_t tp_tc32_scratch_bytes(void);
+int64_t tp_tc32_status_offset(void);      /* byte offset, inside scratch, of a 32-bit status word the caller zeroes once: the split
+                                           * mode sets bit 0 when a hidden activation exceeds the fp16 range (> 6e4) or is NaN */
 int tp_tc32_max_stages(void);
 int tp_tc32_pack_weights(const int64_t* slot_desc, int n_slots, int precision, void* image, void* stream);
 int tp_tc32_forward(const float* center, const float* ray, const float* depth, int64_t S, int N, int64_t per_image,

@@ -232,3 +232,19 @@ def test_c2_rays_split_kernel_vs_oracle():
         got = m.composite(opt, ray.to(DEV), *got_s[:2], depth.to(DEV), got_s[2])
     for k, a, b in zip(NAMES, got, ref):
         assert (a.cpu() - b).abs().max() <= TOL, (k, float((a.cpu() - b).abs().max()))
+
+
+def test_split_mode_reports_activations_outside_the_fp16_range():
+    from texpose_b200 import mlp_tc32
+    center, ray, depth = [t.to(DEV) for t in _c1_inputs(R=64, N=32)]
+    lt, ll = [t.to(DEV) for t in synth.latents(1)]
+    opt, m = _module("auto")
+    with torch.no_grad():
+        m.forward_samples(opt, center, ray, depth, lt, ll, mode="val")
+    mlp_tc32.check_range(torch.device(DEV))                 # a sane network: nothing to report
+    with torch.no_grad():
+        m.mlp_feat[2].weight.mul_(3e4)                      # hidden activations of ~1e5
+        m.forward_samples(opt, center, ray, depth, lt, ll, mode="val")
+    with pytest.raises(FloatingPointError):
+        mlp_tc32.check_range(torch.device(DEV))
+    mlp_tc32.check_range(torch.device(DEV))                 # the flag is cleared by the failed check

@@ -69,7 +69,9 @@ struct Params {
   float* rgb;                // [S,3,2]
   float* density;            // [S,2]
   float* uncert;             // [S]
-  uint8_t* scratch;          // gridDim.x x 128 KB (parked feature, hi | lo)
+  uint8_t* scratch;          // gridDim.x x 128 KB (parked feature, hi | lo), then one 32-bit status word
+  unsigned int* status;      // bit 0 is set when a hidden activation left the fp16 range of the split mode (the launch's results are
+                             // then not the <= 1e-4 ones): read back by the caller off the hot path (mlp_tc32.check_range)
   uint8_t* save;             // single-pass mode, training: [tiles][n_save][64 KB] bf16 tile images of the stages with a save slot
   int n_save;
   int enc_slot;              // -1, or the save slot that receives the encoding tile [x, enc(x), 1] (zero beyond column 63): the B
@@ -255,6 +257,7 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_forward_split_kernel(const P
     const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16);
     uint8_t* park = p.scratch + (size_t)blockIdx.x * 2 * kABytes;
     uint32_t acc_ph = 0;      // bit i: phase of bar_acc(i)
+    float act_max = 0.f;      // split mode: largest hidden activation this thread converted (fp16 hi saturates at 65 504)
 
     // fp32 encoding of one sample (layers/nerf_static_transient_light.py:217-234: the reference multiplies by fl(2^k pi) and
     // takes sin / cos of the ROUNDED product -- its own encoding differs from the exact one by up to 6e-5 at k = 9, so the
@@ -338,7 +341,10 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_forward_split_kernel(const P
               for (int e = 0; e < 4; ++e) {
                 const float x0 = __uint_as_float(v[i * 8 + 2 * e]) + bb[2 * e], x1 = __uint_as_float(v[i * 8 + 2 * e + 1]) + bb[2 * e + 1];
                 if (kSingle) h[e] = pack_relu_bf16(x0, x1);
-                else split2(fmaxf(x0, 0.f), fmaxf(x1, 0.f), h[e], l[e]);
+                else {
+                  split2(fmaxf(x0, 0.f), fmaxf(x1, 0.f), h[e], l[e]);
+                  act_max = fmaxf(act_max, fmaxf(x0, x1));
+                }
               }
               const uint32_t off = (uint32_t)(half * 16 + j * 4 + i) * 2048 + row * 16;
               st_shared_v4(sbase + kOffAhi + off, h[0], h[1], h[2], h[3]);
@@ -393,6 +399,7 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_forward_split_kernel(const P
           }
         }
       }
+      if (!kSingle && !(act_max <= 6.0e4f)) atomicOr(p.status, 1u);      // (also catches NaN)
       if (half == 0 && live) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) *reinterpret_cast<float2*>(p.rgb + s * 6 + c * 2) = make_float2(rgb_s[c], rgb_t[c]);
@@ -450,7 +457,8 @@ __global__ void pack_split_kernel(const long long* __restrict__ desc, uint16_t* 
 }  // namespace tcs
 
 TP_API int64_t tp_tc32_slot_bytes(void) { return tcs::kSlotBytes; }
-TP_API int64_t tp_tc32_scratch_bytes(void) { return (int64_t)tp_num_sms() * 2 * tc::kABytes; }
+TP_API int64_t tp_tc32_scratch_bytes(void) { return (int64_t)tp_num_sms() * 2 * tc::kABytes + 16; }
+TP_API int64_t tp_tc32_status_offset(void) { return (int64_t)tp_num_sms() * 2 * tc::kABytes; }
 TP_API int tp_tc32_max_stages(void) { return tcs::kMaxStages; }
 
 TP_API int tp_tc32_pack_weights(const int64_t* slot_desc, int n_slots, int precision, void* image, void* stream) {
@@ -516,10 +524,11 @@ TP_API int tp_tc32_forward(const float* center, const float* ray, const float* d
   const long long n_tiles = (S + 127) / 128;
   int grid = tp_num_sms();
   if (n_tiles < grid) grid = (int)n_tiles;
-  if (scratch_bytes < (int64_t)grid * 2 * tc::kABytes) return TP_ERR_WORKSPACE;
+  if (scratch_bytes < tp_tc32_scratch_bytes()) return TP_ERR_WORKSPACE;
   p.center = center; p.ray = ray; p.depth = depth; p.S = S; p.N = N; p.per_image = per_image;
   p.image = reinterpret_cast<const uint8_t*>(image); p.bias = bias; p.raybias = raybias; p.imgbias = imgbias;
   p.rgb = rgb; p.density = density; p.uncert = uncert; p.scratch = reinterpret_cast<uint8_t*>(scratch);
+  p.status = reinterpret_cast<unsigned int*>(p.scratch + tp_tc32_status_offset());
   p.n_stages = n_stages;
   p.save = reinterpret_cast<uint8_t*>(save); p.n_save = n_save; p.enc_slot = save ? enc_slot : -1;
   void (*kern)(const tcs::Params) = precision ? tcs::nerf_forward_split_kernel<true> : tcs::nerf_forward_split_kernel<false>;

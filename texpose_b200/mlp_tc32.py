@@ -146,8 +146,25 @@ _scratch = {}
 def _scratch_for(dev):
     k = (dev.type, dev.index)
     if k not in _scratch:
-        _scratch[k] = torch.empty(_C.load().tp_tc32_scratch_bytes(), dtype=torch.uint8, device=dev)
+        _scratch[k] = torch.zeros(_C.load().tp_tc32_scratch_bytes(), dtype=torch.uint8, device=dev)      # (status word starts at 0)
     return _scratch[k]
+
+
+def check_range(device=None):
+    """Off the hot path (one 4-byte read-back): raises if a split-mode launch on `device` saw a hidden activation outside the fp16
+    range (> 6e4, or NaN) since the last check -- its outputs are then not the <= 1e-4 ones; use opt.b200.fp32_engine = 'simt'."""
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    k = (dev.type, dev.index)
+    if k not in _scratch:
+        return
+    off = _C.load().tp_tc32_status_offset()
+    word = _scratch[k][off:off + 4]
+    bad = int(word.view(torch.int32).item())
+    if bad:
+        word.zero_()
+        raise FloatingPointError("tp_tc32_forward: a hidden activation left the fp16 range of the split-precision mode")
 
 
 def forward(cfg, geom, lat_trans, lat_light, feat_p, rgb_p, trans_p, static_only=False, precision=0, save=False):
