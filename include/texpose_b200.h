@@ -255,6 +255,7 @@ int tp_render_fused_forward(const float* kinv, const float* pose_inv, int B, int
  * Outputs rgb [S,3,2], density [S,2], uncert [S] as tp_tc_nerf_stl_forward.  scratch >= tp_tc32_scratch_bytes().  Range of the
  * split mode: |weights|, |hidden activations| < 65 504 (fp16 hi part); a violation is reported through the status word. */
 int64_t tp_tc32_slot_bytes(void);
+int64_t tp_tc32_save_bytes(int64_t S, int n_save);      /* save buffer: [tiles][n_save][64 KB] images + [tiles][n_save][4 KB] ReLU bitmasks */
 int64_t tp_tc32_scratch_bytes(void);
 int64_t tp_tc32_status_offset(void);      /* byte offset, inside scratch, of a 32-bit status word the caller zeroes once: the split
                                            * mode sets bit 0 when a hidden activation exceeds the fp16 range (> 6e4) or is NaN */
@@ -354,8 +355,9 @@ int tp_patch_loss_backward(const float* g_losses, const float* image_sample, con
  * narrow gradients that enter the chain through one K = 16 step (the rgb output layer's dz, the raw-density gradient).
  * packed_bwd: n_chunks x 16 KB transposed weight chunks (tp_tc_pack_weights, transpose flag).  stages: HOST int32 [n_stages,6]
  * rows {thin operand (-1 | 0 | 1), its 8 KB chunk, first K = 32 chunk, number of K = 32 chunks (0 | 8, read against the previous
- * stage's output), mask slot in `saved`, dz slot written}; the first stage reads only a thin operand.
- * saved [tiles][n_saved][64 KB] from tp_tc32_forward (precision 1, save); dz_out [tiles][n_out][64 KB]. */
+ * stage's output), mask slot, dz slot written}; the first stage reads only a thin operand, every later one reads the previous output.
+ * mask_bits [tiles][n_saved][8 planes][128 rows] uint32 = the ReLU bitmasks tp_tc32_forward (precision 1, save) writes behind its
+ * tile images (at byte offset tiles * n_save * 65536 of the save buffer); dz_out [tiles][n_out][64 KB]. */
 /* Column sums of tile images over all samples (bias gradients): sel DEVICE int32 [n_sel] slots; partial [blocks][n_sel][256]
  * with blocks = tp_tc_images_colsum_blocks(), reduced by tp_reduce_partials(partial, blocks, n_sel * 256, out).  Rows of the last
  * tile beyond S must be zero (the dz images of tp_tc_chain_backward are). */
@@ -364,7 +366,7 @@ int tp_tc_images_colsum(const void* images, int n_slots, int64_t S, const int32_
                         int64_t partial_floats, void* stream);
 int tp_tc_chain_max_stages(void);
 int tp_tc_chain_backward(const float* thin0, int cols0, const float* thin1, int cols1, int64_t S, const void* packed_bwd,
-                         int n_chunks, const int32_t* stages, int n_stages, const void* saved, int n_saved, void* dz_out,
+                         int n_chunks, const int32_t* stages, int n_stages, const void* mask_bits, int n_saved, void* dz_out,
                          int n_out, void* stream);
 
 /* ---- K7: mesh depth / NOCS / colour rasteriser --------------------------------------------------------

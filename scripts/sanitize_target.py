@@ -27,6 +27,13 @@ lo, hi = [t.to(dev) for t in synth.padded_aabb()]
 zn, zf = compute_box.box_range(pose, intr, lo, hi, H, W, *synth.BG_RANGE)
 dr = (zn[:, :, None], zf[:, :, None])
 
+if "render1" in what:      # the per-sample inference launch alone (multi-kernel path)
+    with torch.no_grad():
+        o2 = AttrDict(opt); o2.b200 = AttrDict(opt.b200); o2.b200.fused_render = False
+        b = g.render(o2, pose, intr=intr, ray_idx=range(0, H * W), depth_range=dr, mode="val")
+    torch.cuda.synchronize()
+    print("render1 ok", float(b.rgb.sum()))
+
 if "render" in what:
     with torch.no_grad():
         a = g.render(opt, pose, intr=intr, ray_idx=range(0, H * W), depth_range=dr, mode="val")                   # <1,17,3>

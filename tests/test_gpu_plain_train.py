@@ -95,7 +95,7 @@ def test_chain_stage_list_is_validated():
     from texpose_b200 import ops
     lib = _C.load()
     z = torch.zeros(1 << 16, device=DEV)
-    img = torch.zeros(2 * 65536, dtype=torch.uint8, device=DEV)
+    img = torch.zeros(9 * 16384, dtype=torch.uint8, device=DEV)
 
     def run(rows, thin1=None):
         st = torch.tensor(rows, dtype=torch.int32)

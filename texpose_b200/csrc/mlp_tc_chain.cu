@@ -3,15 +3,17 @@
 // mlp_tc_bwd.cu's fused chain is specialised for the two frozen-trunk heads of layers/nerf_static_transient_light.py.  The plain
 // model (layers/nerf.py:61-99) trains its trunk as well, so its backward walks head + trunk: autograd of
 //     h_l = relu(W_l h_{l-1} + b_l)      ->      dz_{l-1} = (dz_l W_l) * [h_{l-1} > 0]
-// per 128-sample tile, with the activations the single-pass forward saved (csrc/mlp_tc_split.cu, bf16 tile images) as masks and
+// per 128-sample tile, with the ReLU bitmasks of the activations the single-pass forward saved (csrc/mlp_tc_split.cu) as masks and
 // every dz tile stored as an image for the weight-gradient GEMMs (tp_tc_dw_gemm).  A stage may add one K = 16 step that reads a
 // THIN operand (<= 8 fp32 columns per sample, turned into a bf16 tile by the drain warps): the gradient of a narrow output layer
 // (dz_rgb: 3 columns) or of a single extra output row (the raw density, row 0 of the last trunk layer).
 //
 // Structure (one persistent 320-thread CTA per SM, one tile at a time): weights (transposed images, tp_tc_pack_weights) stream
-// through a 4 x 16 KB ring, tcgen05.mma M = 128 x N = 256 into one 256-column TMEM accumulator, 8 drain warps mask / convert /
-// write the next A operand in place and stream the dz image to HBM from their registers; the next stage's mask tile is
-// bulk-loaded while the MMAs run.  HBM per stage and tile: 64 KB mask in + 64 KB dz out.
+// through a 4 x 16 KB ring, tcgen05.mma M = 128 x N = 256 into TWO 256-column TMEM accumulators used alternately by the stages,
+// 8 drain warps mask / convert / write the next A operand in place -- published in eight 32-column groups, so the next stage's
+// MMAs overlap the drain -- and stream the dz image to HBM from their registers.  The ReLU masks are the 4 KB bitmasks the forward
+// wrote beside the tile images (a 64 KB mask tile per stage made the kernel HBM-bound at twice the traffic).  HBM per stage and
+// tile: 4 KB of mask bits in + 64 KB dz out.
 #include "tc_common.cuh"
 #include "../../include/texpose_b200.h"
 
@@ -20,23 +22,23 @@ using namespace tc;
 
 constexpr int kThreads = 320;        // warps 0-7 drain, warp 8 weight producer, warp 9 MMA issuer
 constexpr int kRing = 4;
-constexpr uint32_t kOffA = 0, kOffM = kABytes, kOffZ = 2 * kABytes;      // Z: two thin tiles [2 k8][128][8] (4 KB each)
+constexpr uint32_t kOffA = 0, kOffZ = kABytes;      // Z: two thin tiles [2 k8][128][8] (4 KB each)
 constexpr uint32_t kOffRing = kOffZ + 8192;
 constexpr uint32_t kOffBar = kOffRing + kRing * kChunkBytes;
-constexpr uint32_t kSmemBytes = kOffBar + 128;
+constexpr uint32_t kSmemBytes = kOffBar + 256;
 constexpr int kMaxStages = 16;
 
 struct Stage {
   int thin, thin_chunk;      // thin >= 0: a K = 16 step on thin tile `thin` with the 8 KB chunk `thin_chunk` comes first
   int chunk0, n_chunks;      // then n_chunks (0 | 8) K = 32 chunks from `chunk0` on, read against the A tile
-  int mask_slot, out_slot;   // slot of `saved` whose positive entries pass; dz image slot written
+  int mask_slot, out_slot;   // saved activation whose positive entries pass (its ReLU bitmask); dz image slot written
 };
 struct Params {
   const float* thin[2];
   int thin_cols[2];
   long long S;
   const uint8_t* packed;     // transposed weight chunks (16 KB each)
-  const uint8_t* saved;      // [tiles][n_saved][64 KB]
+  const uint32_t* bits;      // [tiles][n_saved][8 planes][128 rows] ReLU bitmasks of the saved activations
   int n_saved;
   uint8_t* dz_out;           // [tiles][n_out][64 KB]
   int n_out;
@@ -52,21 +54,27 @@ __global__ void __launch_bounds__(kThreads, 1) chain_backward_staged_kernel(cons
   const uint32_t bar0 = sbase + kOffBar;
   auto bar_full = [&](int s) { return bar0 + 8 * s; };
   auto bar_empty = [&](int s) { return bar0 + 8 * (kRing + s); };
-  const uint32_t bar_acc = bar0 + 8 * (2 * kRing), bar_ready = bar_acc + 8, bar_mask = bar_acc + 16;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBar + 8 * (2 * kRing + 3));
+  // Both 256-column accumulators serve the one tile, alternating by stage, and the drain publishes the next A operand in eight
+  // 32-column groups (= the eight K = 32 chunks of the next stage): the MMAs of stage s + 1 start after the first group and overlap
+  // the rest of the drain of stage s (the mechanism of csrc/mlp_tc_split.cu; this kernel has no thin accumulators in its way).
+  auto bar_acc = [&](int i) { return bar0 + 8 * (2 * kRing + i); };
+  auto bar_ready = [&](int g) { return bar0 + 8 * (2 * kRing + 2 + g); };
+  const uint32_t bar_thin = bar0 + 8 * (2 * kRing + 10);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBar + 8 * (2 * kRing + 12));
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kRing; ++s) {
       mbar_init(bar_full(s), 1);
       mbar_init(bar_empty(s), 1);
     }
-    mbar_init(bar_acc, 1);
-    mbar_init(bar_ready, 8);         // one arrive per drain warp
-    mbar_init(bar_mask, 1);
+    mbar_init(bar_acc(0), 1);
+    mbar_init(bar_acc(1), 1);
+    for (int g = 0; g < 8; ++g) mbar_init(bar_ready(g), 4);      // the four lane-quarter warps of the column half
+    mbar_init(bar_thin, 8);          // one arrive per drain warp: the tile's thin operands are in place, its last accumulator is read
     fence_barrier_init();
   }
   if (warp == 9) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -101,18 +109,20 @@ __global__ void __launch_bounds__(kThreads, 1) chain_backward_staged_kernel(cons
     }
   } else if (warp == 9) {
     // ================================================================ MMA issuer
-    uint32_t slot = 0, phase = 0, ready_ph = 0;
+    uint32_t slot = 0, phase = 0, ready_ph = 0, thin_ph = 0, g = 0;
     const uint32_t idesc = umma_idesc(128, 256);
     constexpr uint32_t kHi = (128u >> 4) | (1u << 14);
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      for (int s = 0; s < n_stages; ++s) {
+      mbar_wait(bar_thin, thin_ph);
+      thin_ph ^= 1;
+      for (int s = 0; s < n_stages; ++s, ++g) {
         const Stage sg = p.st[s];
         const int n = (sg.thin >= 0 ? 1 : 0) + sg.n_chunks;
-        mbar_wait(bar_ready, ready_ph);      // the A tile / thin tiles of this stage are written, the accumulator is drained
-        ready_ph ^= 1;
+        const uint32_t d_tmem = tmem_base + (g & 1u) * 256;
         for (int j = 0; j < n; ++j) {
           const bool thin = sg.thin >= 0 && j == 0;
           const int c = j - (sg.thin >= 0 ? 1 : 0);
+          if (!thin) mbar_wait(bar_ready(c), ready_ph);      // columns [32 c, 32 c + 32) of the A tile are written
           mbar_wait(bar_full(slot), phase);
           tc_fence_after();
           if (elect_one_sync()) {
@@ -120,31 +130,27 @@ __global__ void __launch_bounds__(kThreads, 1) chain_backward_staged_kernel(cons
             const uint32_t b_lo = (wsm >> 4) | ((4096u >> 4) << 16);
             if (thin) {
               const uint32_t a_lo = ((sbase + kOffZ + (uint32_t)sg.thin * 4096u) >> 4) | ((2048u >> 4) << 16);
-              umma_bf16_lohi(tmem_base, a_lo, kHi, b_lo, kHi, idesc, 0u);
+              umma_bf16_lohi(d_tmem, a_lo, kHi, b_lo, kHi, idesc, 0u);
             } else {
               const uint32_t a_lo = ((sbase + kOffA + (uint32_t)c * 4u * 2048u) >> 4) | ((2048u >> 4) << 16);
-              umma_bf16_lohi(tmem_base, a_lo, kHi, b_lo, kHi, idesc, j > 0 ? 1u : 0u);
-              umma_bf16_lohi(tmem_base, a_lo + (4096u >> 4), kHi, b_lo + (8192u >> 4), kHi, idesc, 1u);
+              umma_bf16_lohi(d_tmem, a_lo, kHi, b_lo, kHi, idesc, j > 0 ? 1u : 0u);
+              umma_bf16_lohi(d_tmem, a_lo + (4096u >> 4), kHi, b_lo + (8192u >> 4), kHi, idesc, 1u);
             }
-            if (j == n - 1) umma_commit(bar_acc);
+            if (j == n - 1) umma_commit(bar_acc(g & 1u));
             umma_commit(bar_empty(slot));
           }
           __syncwarp();
           if (++slot == kRing) { slot = 0; phase ^= 1; }
         }
+        if (sg.n_chunks) ready_ph ^= 1;
       }
     }
   } else {
     // ================================================================ drain warps: mask, convert, next A operand, dz image
     const int q = warp & 3, half = warp >> 2, row = q * 32 + lane;
-    const uint32_t a_smem = sbase + kOffA, m_smem = sbase + kOffM;
-    const uint32_t tmem_d = tmem_base + ((uint32_t)(q * 32) << 16) + half * 128;
-    uint32_t acc_ph = 0, mask_ph = 0;
-    if (threadIdx.x == 32 && (long long)blockIdx.x < n_tiles) {
-      mbar_expect_tx(bar_mask, kABytes);
-      bulk_g2s_hint(m_smem, p.saved + ((size_t)blockIdx.x * p.n_saved + p.st[0].mask_slot) * kABytes, kABytes, bar_mask,
-                    l2_policy_evict_first());
-    }
+    const uint32_t a_smem = sbase + kOffA;
+    const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16) + half * 128;
+    uint32_t acc_ph = 0, g = 0;      // acc_ph bit i: phase of bar_acc(i)
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       // thin tiles of this tile's samples: [2 k8][128 rows][8] bf16, columns beyond the operand's width are zero
       if (half < 2 && p.thin[half]) {
@@ -160,53 +166,54 @@ __global__ void __launch_bounds__(kThreads, 1) chain_backward_staged_kernel(cons
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_ready);
+      if (lane == 0) mbar_arrive(bar_thin);
 
-      for (int s = 0; s < n_stages; ++s) {
+      for (int s = 0; s < n_stages; ++s, ++g) {
         const Stage sg = p.st[s];
-        mbar_wait(bar_acc, acc_ph);
-        acc_ph ^= 1;
-        mbar_wait(bar_mask, mask_ph);
-        mask_ph ^= 1;
+        const bool last = s == n_stages - 1;
+        // ReLU bitmask words of this thread's four 32-column slabs, fetched before the accumulator wait
+        const uint32_t* bw = p.bits + ((size_t)tile * p.n_saved + sg.mask_slot) * 1024 + half * 4 * 128 + row;
+        const uint32_t words[4] = {__ldg(bw), __ldg(bw + 128), __ldg(bw + 256), __ldg(bw + 384)};
+        mbar_wait(bar_acc(g & 1u), (acc_ph >> (g & 1u)) & 1u);
+        acc_ph ^= 1u << (g & 1u);
         tc_fence_after();
+        const uint32_t tmem_d = tmem_row + (g & 1u) * 256;
         uint8_t* g_tile = p.dz_out + ((size_t)tile * p.n_out + sg.out_slot) * kABytes;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint32_t v[32];
-          TP_TMEM_LD32(tmem_d + j * 32, v);
-          TP_TMEM_WAIT32(v);
+        auto slab = [&](const uint32_t (&v)[32], int j) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const uint32_t off = (uint32_t)(half * 16 + j * 4 + i) * 2048 + row * 16;
-            const uint4 mk = ld_shared_v4(m_smem + off);
-            const uint32_t mw[4] = {mk.x, mk.y, mk.z, mk.w};
+            const uint32_t byte = (words[j] >> (i * 8)) & 0xffu;
             uint32_t o[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const float lo = (mw[e] & 0xffffu) ? __uint_as_float(v[i * 8 + 2 * e]) : 0.f;
-              const float hi = (mw[e] >> 16) ? __uint_as_float(v[i * 8 + 2 * e + 1]) : 0.f;
+              const float lo = (byte & (1u << (2 * e))) ? __uint_as_float(v[i * 8 + 2 * e]) : 0.f;
+              const float hi = (byte & (2u << (2 * e))) ? __uint_as_float(v[i * 8 + 2 * e + 1]) : 0.f;
               o[e] = pack_bf16(lo, hi);
             }
             st_shared_v4(a_smem + off, o[0], o[1], o[2], o[3]);
             st_global_cs_v4(g_tile + off, o[0], o[1], o[2], o[3]);
           }
-        }
-        fence_proxy_async_smem();
-        named_bar_sync(1, 256);           // every drain thread finished reading M (the next mask tile may land in it)
-        if (threadIdx.x == 32) {          // the next stage's mask tile (possibly of this CTA's next tile)
-          const bool last = s == n_stages - 1;
-          const long long nt = last ? tile + gridDim.x : tile;
-          if (nt < n_tiles) {
-            mbar_expect_tx(bar_mask, kABytes);
-            bulk_g2s_hint(m_smem, p.saved + ((size_t)nt * p.n_saved + p.st[last ? 0 : s + 1].mask_slot) * kABytes, kABytes, bar_mask,
-                          l2_policy_evict_first());
+          if (!last) {       // (the last stage's output feeds no MMA: its groups are not published)
+            fence_proxy_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_ready(half * 4 + j));
           }
-        }
-        if (s != n_stages - 1) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_ready);
-        }
+        };
+        uint32_t va[32], vb[32];
+        TP_TMEM_LD32(tmem_d, va);
+        TP_TMEM_WAIT32(va);
+        TP_TMEM_LD32(tmem_d + 32, vb);
+        slab(va, 0);
+        TP_TMEM_WAIT32(vb);
+        TP_TMEM_LD32(tmem_d + 64, va);
+        slab(vb, 1);
+        TP_TMEM_WAIT32(va);
+        TP_TMEM_LD32(tmem_d + 96, vb);
+        slab(va, 2);
+        TP_TMEM_WAIT32(vb);
+        slab(vb, 3);
       }
     }
   }
@@ -215,7 +222,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_backward_staged_kernel(cons
   __syncthreads();
   if (warp == 9) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
 
@@ -276,8 +283,9 @@ TP_API int tp_tc_images_colsum(const void* images, int n_slots, int64_t S, const
 TP_API int tp_tc_chain_max_stages(void) { return tcc::kMaxStages; }
 
 TP_API int tp_tc_chain_backward(const float* thin0, int cols0, const float* thin1, int cols1, int64_t S, const void* packed_bwd,
-                                int n_chunks, const int32_t* stages, int n_stages, const void* saved, int n_saved, void* dz_out,
+                                int n_chunks, const int32_t* stages, int n_stages, const void* mask_bits, int n_saved, void* dz_out,
                                 int n_out, void* stream) {
+  const void* saved = mask_bits;
   if (!thin0 || !packed_bwd || !stages || !saved || !dz_out) return TP_ERR_BAD_ARG;
   if (S < 0 || n_stages < 1 || n_stages > tcc::kMaxStages || n_saved < 1 || n_out < 1 || n_chunks < 1) return TP_ERR_BAD_SHAPE;
   if (cols0 < 1 || cols0 > 8 || (thin1 && (cols1 < 1 || cols1 > 8))) return TP_ERR_BAD_SHAPE;
@@ -292,13 +300,14 @@ TP_API int tp_tc_chain_backward(const float* thin0, int cols0, const float* thin
     if (sg.n_chunks != 0 && sg.n_chunks != 8) return TP_ERR_BAD_SHAPE;
     if (sg.thin < 0 && sg.n_chunks == 0) return TP_ERR_BAD_SHAPE;
     if (s == 0 && sg.n_chunks != 0) return TP_ERR_BAD_ARG;      // nothing has written the A tile yet
+    if (s > 0 && sg.n_chunks == 0) return TP_ERR_BAD_ARG;       // every later stage consumes the previous drain's column groups
     if (sg.thin >= 0 && (sg.thin_chunk < 0 || sg.thin_chunk >= n_chunks)) return TP_ERR_BAD_ARG;
     if (sg.n_chunks && (sg.chunk0 < 0 || sg.chunk0 + sg.n_chunks > n_chunks)) return TP_ERR_BAD_ARG;
     if (sg.mask_slot < 0 || sg.mask_slot >= n_saved || sg.out_slot < 0 || sg.out_slot >= n_out) return TP_ERR_BAD_ARG;
   }
   if (S == 0) return TP_OK;
   p.thin[0] = thin0; p.thin[1] = thin1; p.thin_cols[0] = cols0; p.thin_cols[1] = thin1 ? cols1 : 0;
-  p.S = S; p.packed = reinterpret_cast<const uint8_t*>(packed_bwd); p.saved = reinterpret_cast<const uint8_t*>(saved);
+  p.S = S; p.packed = reinterpret_cast<const uint8_t*>(packed_bwd); p.bits = reinterpret_cast<const uint32_t*>(saved);
   p.n_saved = n_saved; p.dz_out = reinterpret_cast<uint8_t*>(dz_out); p.n_out = n_out; p.n_stages = n_stages;
   const long long n_tiles = (S + 127) / 128;
   int grid = tp_num_sms();

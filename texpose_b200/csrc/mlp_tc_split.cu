@@ -74,6 +74,8 @@ struct Params {
                              // then not the <= 1e-4 ones): read back by the caller off the hot path (mlp_tc32.check_range)
   uint8_t* save;             // single-pass mode, training: [tiles][n_save][64 KB] bf16 tile images of the stages with a save slot
   int n_save;
+  uint32_t* save_bits;       // behind the images: [tiles][n_save][8 planes][128 rows] ReLU bitmasks (plane = 32-column slab, bit = column
+                             // is positive): what the backward chain masks with instead of re-reading the 64 KB tiles
   int enc_slot;              // -1, or the save slot that receives the encoding tile [x, enc(x), 1] (zero beyond column 63): the B
                              // operand of the weight-gradient GEMMs of the layers that read the encoding (column 63 = 1: their bias sums)
   int n_stages;
@@ -329,8 +331,10 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_forward_split_kernel(const P
           const uint32_t tmem_d = tmem_row + (uint32_t)(L & 1) * 256 + half * 128;
           const bool do_park = (sg.flags & F_PARK) != 0;
           uint8_t* const g_save = (kSingle && p.save && sg.save_slot >= 0) ? p.save + ((size_t)tile * p.n_save + sg.save_slot) * kABytes : nullptr;
+          uint32_t* const g_bits = g_save ? p.save_bits + ((size_t)tile * p.n_save + sg.save_slot) * 1024 + half * 4 * 128 + row : nullptr;
           // one 32-column slab: + bias, ReLU, hi / lo split, 4 core-matrix rows of A_hi and A_lo (and of the parked copy)
           auto slab = [&](const uint32_t (&v)[32], int j) {
+            uint32_t positive = 0u;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const float4 b0 = __ldg(reinterpret_cast<const float4*>(brow + j * 32 + i * 8));
@@ -340,8 +344,13 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_forward_split_kernel(const P
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const float x0 = __uint_as_float(v[i * 8 + 2 * e]) + bb[2 * e], x1 = __uint_as_float(v[i * 8 + 2 * e + 1]) + bb[2 * e + 1];
-                if (kSingle) h[e] = pack_relu_bf16(x0, x1);
-                else {
+                if (kSingle) {
+                  h[e] = pack_relu_bf16(x0, x1);
+                  if (g_save) {      // sign bits, first column shifted in first (one funnel shift per element; reversed below)
+                    positive = __funnelshift_l(__float_as_uint(x0), positive, 1);
+                    positive = __funnelshift_l(__float_as_uint(x1), positive, 1);
+                  }
+                } else {
                   split2(fmaxf(x0, 0.f), fmaxf(x1, 0.f), h[e], l[e]);
                   act_max = fmaxf(act_max, fmaxf(x0, x1));
                 }
@@ -355,6 +364,7 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_forward_split_kernel(const P
               }
               if (g_save) st_global_cs_v4(g_save + off, h[0], h[1], h[2], h[3]);
             }
+            if (g_bits) g_bits[j * 128] = __brev(~positive);      // bit c = column c of the slab is positive (sign bit clear)
             if (do_park) __threadfence();      // the parked copy is read back through the async proxy (bulk load) four stages later
             fence_proxy_async_smem();
             tc_fence_before();
@@ -457,6 +467,8 @@ __global__ void pack_split_kernel(const long long* __restrict__ desc, uint16_t* 
 }  // namespace tcs
 
 TP_API int64_t tp_tc32_slot_bytes(void) { return tcs::kSlotBytes; }
+/* bytes of the save buffer of a single-pass launch: [tiles][n_save][64 KB] tile images, then [tiles][n_save][4 KB] ReLU bitmasks */
+TP_API int64_t tp_tc32_save_bytes(int64_t S, int n_save) { return ((S + 127) / 128) * (int64_t)n_save * (tc::kABytes + 4096); }
 TP_API int64_t tp_tc32_scratch_bytes(void) { return (int64_t)tp_num_sms() * 2 * tc::kABytes + 16; }
 TP_API int64_t tp_tc32_status_offset(void) { return (int64_t)tp_num_sms() * 2 * tc::kABytes; }
 TP_API int tp_tc32_max_stages(void) { return tcs::kMaxStages; }
@@ -531,6 +543,7 @@ TP_API int tp_tc32_forward(const float* center, const float* ray, const float* d
   p.status = reinterpret_cast<unsigned int*>(p.scratch + tp_tc32_status_offset());
   p.n_stages = n_stages;
   p.save = reinterpret_cast<uint8_t*>(save); p.n_save = n_save; p.enc_slot = save ? enc_slot : -1;
+  p.save_bits = save ? reinterpret_cast<uint32_t*>(p.save + (size_t)((S + 127) / 128) * n_save * tc::kABytes) : nullptr;
   void (*kern)(const tcs::Params) = precision ? tcs::nerf_forward_split_kernel<true> : tcs::nerf_forward_split_kernel<false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcs::kSmemBytes);
   if (e != cudaSuccess) return (int)e;

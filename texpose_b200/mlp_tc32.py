@@ -191,7 +191,7 @@ def forward(cfg, geom, lat_trans, lat_light, feat_p, rgb_p, trans_p, static_only
     images = None
     if save:
         assert precision == 1, "activations are saved by the single-pass (bf16) launch"
-        images = torch.empty(((S + 127) // 128) * pk.n_save * 65536, dtype=torch.uint8, device=dev)
+        images = torch.empty(_C.load().tp_tc32_save_bytes(S, pk.n_save), dtype=torch.uint8, device=dev)      # tile images, then ReLU bitmasks
     _C.call("tp_tc32_forward", ops._p(center), ops._p(ray), ops._p(depth), S, N, per_image, ops._p(pk.image), pk.n_slots,
             ops._p(pk.stages), pk.stages.shape[0], ops._p(pk.bias), ops._p(raybias), ops._p(img_t), ops._p(rgb),
             ops._p(density), ops._p(uncert), ops._p(scratch), scratch.numel(), int(precision), ops._p(images), pk.n_save if save else 0,

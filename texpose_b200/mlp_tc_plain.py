@@ -121,8 +121,9 @@ def backward(ctx, g_rgb, g_density, feat_p, rgb_p):
     n_tiles = (S + 127) // 128
     dz = torch.empty(n_tiles * n_dz * 65536, dtype=torch.uint8, device=dev)
     st = torch.tensor(stages, dtype=torch.int32)
+    bits = images[n_tiles * n_save * 65536:]          # the ReLU bitmasks the forward wrote behind the tile images
     _C.call("tp_tc_chain_backward", ops._p(dz_rgb), 3, ops._p(dz_sigma), 1, S, ops._p(packed), len(rows), ops._p(st), n_dz,
-            ops._p(images), n_save, ops._p(dz), n_dz, ops._stream())
+            ops._p(bits), n_save, ops._p(dz), n_dz, ops._stream())
     # ---- 256 x 256 weight gradients: (dz slot, saved activation slot) per layer; the layers that read the encoding (layer 0, skip
     # layers) add a job against the saved encoding tile, whose column 63 is a constant 1: dz^T of it = [dW encoding columns | db]
     slot_feat, slot_rgb_h, slot_enc = nf - 1, nf, n_save - 1
