@@ -66,6 +66,17 @@ def so_sha16():
         return None
 
 
+def src_sha16():
+    """Hash of the kernel sources + the C-ABI header: identifies a build across recompilations (nvcc's output is not bit-reproducible)."""
+    from texpose_b200 import _C
+    h = hashlib.sha256()
+    files = sorted(os.path.join(_C.CSRC, f) for f in os.listdir(_C.CSRC) if f.endswith((".cu", ".cuh"))) + [_C.HEADER]
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
+
+
 # ---------------------------------------------------------------------------------------------- reference arm
 
 def frame_inputs(dev="cpu"):
@@ -534,10 +545,12 @@ def run_ours(args, rank, world, local_rank):
     if os.path.exists(tpath) and world == 1:
         try:
             tj = json.load(open(tpath))
-            if tj.get("so_sha16") == so_sha16():
-                traffic, traffic_note = tj.get("dram_bytes_per_launch"), f"ncu dram__bytes_read+write of this build ({tj.get('so_sha16')})"
+            if tj.get("so_sha16") == so_sha16() or (tj.get("src_sha16") and tj.get("src_sha16") == src_sha16()):
+                traffic, traffic_note = tj.get("dram_bytes_per_launch"), (f"ncu dram__bytes_read+write of this build (sources "
+                                                                          f"{tj.get('src_sha16')}, .so {tj.get('so_sha16')})")
             else:
-                traffic_note = f"profiles/r02_render_traffic.json was measured on build {tj.get('so_sha16')}, this is {so_sha16()}"
+                traffic_note = (f"profiles/r02_render_traffic.json was measured on sources {tj.get('src_sha16')} / .so {tj.get('so_sha16')}, "
+                                f"this is {src_sha16()} / {so_sha16()}")
         except Exception:
             pass
 
@@ -558,7 +571,7 @@ def run_ours(args, rank, world, local_rank):
                               kernel_ms=k_ms, kernel_share_of_step=k_ms / ms, peak_source=f"{pk['src']} bf16 sustained",
                               flop_per_sample=FLOP_PER_SAMPLE_FWD, samples_per_launch=local_samples),
                 e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=ms_e2e),
-                gpu_launches=launches, launches_per_step=per_step, clocks=clocks, so_sha16=so_sha16())
+                gpu_launches=launches, launches_per_step=per_step, clocks=clocks, so_sha16=so_sha16(), src_sha16=src_sha16())
     if multi:
         line["multi_kernel_frame"] = multi
     if parity:

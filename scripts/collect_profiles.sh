@@ -5,16 +5,8 @@ mkdir -p gpurun_out
 T=${TAG:-r02}
 # (1) the whole GPU suite
 timeout -k 10 1500 python -m pytest tests -m gpu -q --timeout=900 -s > gpurun_out/${T}_pytest.log 2>&1; echo "pytest rc=$?" | tee gpurun_out/${T}_rc.txt
-# (2) plain bench runs (ours, then the reference arm) with a clocks log beside them
-nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap --format=csv -lms 200 > gpurun_out/${T}_clocks_during_bench.csv &
-SMI=$!
-timeout -k 10 900 python bench.py --steps 10 --warmup 3 > gpurun_out/${T}_bench_n1.json 2> gpurun_out/${T}_bench.err; echo "bench rc=$?" | tee -a gpurun_out/${T}_rc.txt
-kill $SMI
-timeout -k 10 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${T}_bench_reference_n1.json 2>> gpurun_out/${T}_bench.err; echo "ref rc=$?" | tee -a gpurun_out/${T}_rc.txt
-# (3) launch list of the bench command (cold-cache, serialised: compare SHARES)
-timeout -k 10 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/${T}_launches_bench.csv \
-    python bench.py --steps 2 --warmup 1 --no-train --no-cpu-baseline > gpurun_out/${T}_bench_under_ncu.log 2>&1; echo "ncu launches rc=$?" | tee -a gpurun_out/${T}_rc.txt
-# (4) the fused render launch at full C2 size: DRAM traffic + tensor pipe; the traffic is keyed by the .so hash for bench.py
+# (1b) the fused render launch at full C2 size: DRAM traffic + tensor pipe, keyed by the source / .so hash -- BEFORE the plain bench,
+# whose JSON line then carries roofline.traffic of this very build
 timeout -k 10 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed,gpu__time_duration.sum,sm__cycles_elapsed.avg.per_second,lts__t_bytes.sum \
     --clock-control none -k regex:nerf_stl_forward -c 1 --csv --log-file gpurun_out/${T}_render_full_c2_metrics.csv \
     python bench.py --steps 1 --warmup 0 --no-train --no-cpu-baseline > /dev/null 2>&1; echo "ncu render rc=$?" | tee -a gpurun_out/${T}_rc.txt
@@ -24,13 +16,24 @@ rows = [r for r in csv.reader(open("gpurun_out/${T}_render_full_c2_metrics.csv")
 hdr = rows[0]; mi, vi = hdr.index("Metric Name"), hdr.index("Metric Value")
 m = {r[mi]: float(r[vi].replace(",", "")) for r in rows[1:]}
 sha = hashlib.sha256(open("texpose_b200/libtexpose_b200.so", "rb").read()).hexdigest()[:16]
-out = dict(so_sha16=sha, dram_bytes_per_launch=int(m["dram__bytes_read.sum"] + m["dram__bytes_write.sum"]), dram_read=int(m["dram__bytes_read.sum"]),
+import sys; sys.path.insert(0, "."); import bench
+out = dict(so_sha16=sha, src_sha16=bench.src_sha16(), dram_bytes_per_launch=int(m["dram__bytes_read.sum"] + m["dram__bytes_write.sum"]), dram_read=int(m["dram__bytes_read.sum"]),
            dram_write=int(m["dram__bytes_write.sum"]), kernel_ns=m.get("gpu__time_duration.sum"),
            tensor_pipe_active_pct=m.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"), l2_bytes=m.get("lts__t_bytes.sum"),
            source="ncu --clock-control none, one launch of the fused render kernel at C2 size (480x640x128), units as printed by ncu")
 json.dump(out, open("gpurun_out/${T}_render_traffic.json", "w"), indent=1)
+json.dump(out, open("profiles/r02_render_traffic.json", "w"), indent=1)
 print(out)
 PY
+# (2) plain bench runs (ours, then the reference arm) with a clocks log beside them
+nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap --format=csv -lms 200 > gpurun_out/${T}_clocks_during_bench.csv &
+SMI=$!
+timeout -k 10 900 python bench.py --steps 10 --warmup 3 > gpurun_out/${T}_bench_n1.json 2> gpurun_out/${T}_bench.err; echo "bench rc=$?" | tee -a gpurun_out/${T}_rc.txt
+kill $SMI
+timeout -k 10 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${T}_bench_reference_n1.json 2>> gpurun_out/${T}_bench.err; echo "ref rc=$?" | tee -a gpurun_out/${T}_rc.txt
+# (3) launch list of the bench command (cold-cache, serialised: compare SHARES)
+timeout -k 10 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/${T}_launches_bench.csv \
+    python bench.py --steps 2 --warmup 1 --no-train --no-cpu-baseline > gpurun_out/${T}_bench_under_ncu.log 2>&1; echo "ncu launches rc=$?" | tee -a gpurun_out/${T}_rc.txt
 # (4b) the split-fp16 kernel of the fp32-parity mode: one launch (2^21 samples of the C2 frame), tensor pipe + traffic
 timeout -k 10 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed,gpu__time_duration.sum,sm__cycles_elapsed.avg.per_second,lts__t_bytes.sum \
     --clock-control none -k regex:nerf_forward_split -s 2 -c 1 --csv --log-file gpurun_out/${T}_split_kernel_metrics.csv \
