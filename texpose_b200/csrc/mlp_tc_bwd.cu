@@ -336,7 +336,7 @@ __device__ __forceinline__ void write_tr_row(const FusedParams& p, long long s, 
   st_shared_v4(ti_row + 2048, 0u, 0u, 0u, 0u);
 }
 
-constexpr int kFEpiWarps = 16, kFEpiThreads = kFEpiWarps * 32, kFThreads = kFEpiThreads + 64;   // + producer warp + MMA warp
+constexpr int kFEpiWarps = 8, kFEpiThreads = kFEpiWarps * 32, kFThreads = kFEpiThreads + 64;   // + producer warp + MMA warp
 
 __global__ void __launch_bounds__(kFThreads, 1) backward_chain_fused_kernel(const FusedParams fp) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -483,10 +483,12 @@ __global__ void __launch_bounds__(kFThreads, 1) backward_chain_fused_kernel(cons
     __syncwarp();
   } else {
     // ================================================================ epilogue warps: mask, convert, store dz images, thin tiles
-    // warp -> (TMEM lane quarter q, column quarter cq): each thread converts 64 accumulator columns (two 32-column slabs)
+    // warp -> (TMEM lane quarter q, column half cq): each thread converts 128 accumulator columns (four 32-column slabs, the next
+    // slab's TMEM load in flight while the current one is converted).  Eight drain warps, not sixteen: same-box A/B 2.218 vs 2.235 ms
+    // per C3 step, and the narrower CTA leaves 168 registers per thread
     const int q = warp & 3, cq = warp >> 2, row = q * 32 + lane;
     const uint32_t a_smem = sbase + kOffA, m_smem = sbase + kOffM;
-    const uint32_t tmem_d = tmem_base + ((uint32_t)(q * 32) << 16) + cq * 64;
+    const uint32_t tmem_d = tmem_base + ((uint32_t)(q * 32) << 16) + cq * 128;
     uint32_t acc_ph = 0, mask_ph = 0;
     const long long img0 = (t0 * 128) / fp.per_image;
     // ReLU bitmasks of h1 / h2 (written by the forward behind the tile images): word planes [8][128 rows] per tile and slot
@@ -559,11 +561,13 @@ __global__ void __launch_bounds__(kFThreads, 1) backward_chain_fused_kernel(cons
 
       for (int s = 0; s < kNumStagesPerTile; ++s) {
         const bool tile_mask = s % 3 == 0;       // stages 0 / 3 mask with the h3 tile in M (it is also block O's operand)
-        uint32_t w0 = 0u, w1 = 0u;
-        if (!tile_mask) {                        // others: h2 / h1 bitmask words of this thread's 64 columns, fetched before the wait
-          const uint32_t* w = reinterpret_cast<const uint32_t*>(bits + ((size_t)tile * 4 + kBitSlot[s]) * 4096) + cq * 2 * 128 + row;
+        uint32_t w0 = 0u, w1 = 0u, w2 = 0u, w3 = 0u;
+        if (!tile_mask) {                        // others: h2 / h1 bitmask words of this thread's 128 columns, fetched before the wait
+          const uint32_t* w = reinterpret_cast<const uint32_t*>(bits + ((size_t)tile * 4 + kBitSlot[s]) * 4096) + cq * 4 * 128 + row;
           w0 = __ldg(w);
           w1 = __ldg(w + 128);
+          w2 = __ldg(w + 256);
+          w3 = __ldg(w + 384);
         }
         TP_PF(long long pe_a = clock64();)
         mbar_wait(bar_acc, acc_ph);
@@ -577,17 +581,23 @@ __global__ void __launch_bounds__(kFThreads, 1) backward_chain_fused_kernel(cons
         tc_fence_after();
         TP_PF(pe_a = clock64();)
         TP_PF(pe_mask += pe_a - pe_b;)
-        // (18 warps leave 96 registers per thread: one slab in flight per thread, four warps per scheduler hide the latency)
-        uint32_t va[32];
+        // (10 warps: up to 168 registers per thread -- the next slab's TMEM load is in flight while the current one is converted)
+        uint32_t va[32], vb[32];
         TP_TMEM_LD32(tmem_d, va);
         uint8_t* g_tile = p.dz_out + ((size_t)tile * kDzSlots + s) * kABytes;
         TP_PF(pe_b = clock64();)
         TP_PF(pe_store += pe_b - pe_a;)
         TP_TMEM_WAIT32(va);
-        convert_slab(va, cq * 8, tile_mask, w0, g_tile);
-        TP_TMEM_LD32(tmem_d + 32, va);
+        TP_TMEM_LD32(tmem_d + 32, vb);
+        convert_slab(va, cq * 16, tile_mask, w0, g_tile);
+        TP_TMEM_WAIT32(vb);
+        TP_TMEM_LD32(tmem_d + 64, va);
+        convert_slab(vb, cq * 16 + 4, tile_mask, w1, g_tile);
         TP_TMEM_WAIT32(va);
-        convert_slab(va, cq * 8 + 4, tile_mask, w1, g_tile);
+        TP_TMEM_LD32(tmem_d + 96, vb);
+        convert_slab(va, cq * 16 + 8, tile_mask, w2, g_tile);
+        TP_TMEM_WAIT32(vb);
+        convert_slab(vb, cq * 16 + 12, tile_mask, w3, g_tile);
         if (cq == 1 && s % 3 != 2) {       // the 1-column of block S for the dz tile just written: column = dz slot
           const uint32_t one = 0x3F80u << ((s & 1) * 16);
           const int w = s >> 1;
@@ -619,7 +629,7 @@ __global__ void __launch_bounds__(kFThreads, 1) backward_chain_fused_kernel(cons
     if (lane == 0) mbar_arrive(bar_ready);
     mbar_wait(bar_acc, acc_ph);
     tc_fence_after();
-    if (cq < 2) {                                 // column quarters 0 / 1 flush the accumulators of feature half 0 / 1
+    if (cq < 2) {                                 // column halves 0 / 1 flush the accumulators of feature half 0 / 1
       const int half = cq, n = half * 128 + row;
       float* P = fp.extras + (size_t)blockIdx.x * kXCols * 256 + n;
       const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
