@@ -107,3 +107,33 @@ def test_c3_backward_is_linear_in_the_upstream_gradient():
     for a, b in zip(g1, g2):
         assert torch.isfinite(a).all() and a.abs().max() > 0
         assert torch.equal(2 * a, b)
+
+
+def test_c2_full_frame_in_the_parity_mode_on_the_split_kernel():
+    """The whole 480 x 640 x 128 frame in the <= 1e-4 mode (split-fp16 tensor-core kernel, 19 launches of 2^21 samples): finite,
+    deterministic, row-block shards equal the frame bit for bit, and a strip of object rows equals the SIMT fp32 kernels to 1e-4."""
+    from texpose_b200 import _C
+    H, W, N = 480, 640, 128
+    opt, g, pose, intr, zn, zf = _setup(H, W, N, "fp32")
+    dr = (zn[:, :, None], zf[:, :, None])
+    _C.launch_counts.clear()
+    with torch.no_grad():
+        full = g.nerf_forward(opt, AttrDict(pose=pose, intr=intr, z_near=zn, z_far=zf, obj_mask=torch.ones(1, H, W, device=DEV),
+                                            idx=torch.zeros(1, dtype=torch.long, device=DEV)), mode="val")
+    assert _C.launch_counts.get("tp_tc32_forward", 0) >= 1 and "tp_linear_forward" not in _C.launch_counts
+    for k in ("rgb", "depth", "uncert", "opacity"):
+        assert torch.isfinite(full[k]).all(), k
+    assert (full.opacity - 1).abs().max() < 1e-4
+    b, e = parallel.shard_rays(H * W, 3, 8, align=W)
+    idx = torch.arange(b, e, device=DEV)[None]
+    opt_s = AttrDict(opt)
+    opt_s.b200 = AttrDict(mlp="fp32", fp32_engine="simt")
+    with torch.no_grad():
+        part = g.render(opt, pose, intr=intr, ray_idx=idx, depth_range=dr, mode="val")
+        part2 = g.render(opt, pose, intr=intr, ray_idx=idx, depth_range=dr, mode="val")
+        strip = torch.arange(b + 60 * W, b + 60 * W + 2048, device=DEV)[None]        # rows through the object
+        tc = g.render(opt, pose, intr=intr, ray_idx=strip, depth_range=dr, mode="val")
+        simt = g.render(opt_s, pose, intr=intr, ray_idx=strip, depth_range=dr, mode="val")
+    for k in ("rgb", "depth", "uncert", "opacity", "rgb_static"):
+        assert torch.equal(part[k], part2[k]) and torch.equal(part[k], full[k][:, b:e]), k
+        assert (tc[k] - simt[k]).abs().max() <= 1e-4, (k, float((tc[k] - simt[k]).abs().max()))

@@ -107,3 +107,30 @@ def test_chain_stage_list_is_validated():
     assert run([[0, 0, 0, 0, 0, 0], [-1, 0, 4, 8, 1, 1]]) == -1  # chunks beyond the image
     assert run([[0, 0, 0, 0, 2, 0]]) == -1                       # mask slot beyond the saved images
     torch.cuda.synchronize()
+
+
+def test_plain_training_step_at_the_c3_shape_matches_the_simt_step():
+    """16 x 256 rays x 128 samples (BASELINE C3 shape) of the plain model: tensor-core step against the fp32 SIMT step, every
+    gradient within the bf16 contract, and the step is deterministic."""
+    B, R, N = 16, 256, 128
+    g = torch.Generator().manual_seed(0)
+    center = (torch.randn(B, R, 3, generator=g) * 0.02 + torch.tensor([0.3, 0.2, -0.8])).to(DEV)
+    ray = (torch.randn(B, R, 3, generator=g) * 0.1 + torch.tensor([0.0, 0.0, 1.0])).to(DEV)
+    depth = ((torch.rand(B, R, N, 1, generator=g) + torch.arange(N)[None, None, :, None]) / N * 1.2 + 0.2).to(DEV)
+    image = torch.rand(B, R, 3, generator=g).to(DEV)
+    opt, m, _ = _models()
+    o32 = env_opt(device=DEV)
+    o32.b200 = AttrDict(mlp="fp32")
+
+    def grads(o):
+        for p in m.parameters():
+            p.grad = None
+        rgb_s, sig = m.forward_samples(o, center, ray, depth, mode="train")
+        comp = m.composite(o, ray, rgb_s, sig, depth)
+        (((comp[0] - image) ** 2).mean() + 0.1 * comp[1].mean() + 0.01 * sig.mean()).backward()
+        return [p.grad.clone() for p in m.parameters()]
+
+    a, a2, ref = grads(opt), grads(opt), grads(o32)
+    for (n, _), x, x2, y in zip(m.named_parameters(), a, a2, ref):
+        assert torch.equal(x, x2), n
+        assert (x - y).abs().max() <= TOL, (n, float((x - y).abs().max()), float(y.abs().max()))
