@@ -99,6 +99,8 @@ def test_mvrenderer_drop_in_and_surfel_normals():
     assert r(pose, K, mode="nocs", return_depth=False).shape == (1, 3, H, W)
     with pytest.raises(NotImplementedError):
         r(pose, K, mode="mask")
+    feat, _ = r(pose, K, mode="feature")                                           # vertex features: the same attribute path
+    assert torch.equal(feat, rgb)
     hit = depth[0] > 0
     assert 840 < int(hit.sum()) < 920 and abs(float(depth[0, 60, 80]) - 800.0) < 0.5
     n = compute_surfelinfo.normal_from_depth(pose, depth.clamp(min=0) / 1000.0, K, h=H, w=W)

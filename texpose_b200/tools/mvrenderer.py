@@ -3,7 +3,8 @@ NOCS maps of a CAD mesh under a batch of poses, on the rasteriser of csrc/raster
 
 pytorch3d is neither vendored nor pinned by the reference (README.md:16) and absent here, so the kernel restates its
 published rasterisation rules; parity with the real package is UNPINNED.  Modes 'color' and 'nocs' (the
-two compute_surfelinfo renders) are implemented; 'mask' (70 faces per pixel soft silhouette), 'normal' and 'feature' are not.
+two compute_surfelinfo renders) and 'feature' (vertex features of up to 8 channels) are implemented; 'mask' (70 faces per pixel
+soft silhouette) and 'normal' (tangent-space normal maps) are not.
 """
 from __future__ import annotations
 
@@ -19,7 +20,7 @@ class Mesh:
     def __init__(self, verts, faces, colors=None):
         self._verts = verts.reshape(-1, 3).float()
         self._faces = faces.reshape(-1, 3)
-        self._colors = None if colors is None else colors.reshape(-1, 3).float()
+        self._colors = None if colors is None else colors.reshape(self._verts.shape[0], -1).float()
         self.textures = self
         self.device = self._verts.device
 
@@ -81,7 +82,7 @@ class MVRenderer(torch.nn.Module):
         colors = mesh.textures.verts_features_packed() if getattr(mesh, "textures", None) is not None else None
         self.attrs = {"nocs": nocs_coordinates(self.verts).contiguous()}
         if colors is not None:
-            self.attrs["color"] = colors.float().to(self.device)[:self.verts.shape[0]].contiguous()
+            self.attrs["color"] = colors.float().to(self.device)[:self.verts.shape[0]].contiguous()      # [V, C]: colours or any vertex features
         if cam_K is None:
             cam_K = torch.eye(3)
         self.K = torch.as_tensor(cam_K, dtype=torch.float32).reshape(-1, 3, 3)[:1].to(self.device)
@@ -89,9 +90,11 @@ class MVRenderer(torch.nn.Module):
 
     def forward(self, pose, K=None, mode="feature", return_depth=True):
         """mvrenderer.py:152-178 -> rendered [B,3,H,W] (+ depth [B,H,W], -1 = background, from fragments.zbuf)."""
+        if mode == "feature" and "color" in self.attrs and self.attrs["color"].shape[1] <= 8:
+            mode = "color"      # SoftPhongFeatureShader (mvrenderer.py:929-956): the vertex features themselves, same blend
         if mode not in self.attrs:
-            raise NotImplementedError(f"MVRenderer mode {mode!r}: texpose_b200 implements 'color' and 'nocs' "
-                                      "(the renders of compute_surfelinfo.py:114-115)")
+            raise NotImplementedError(f"MVRenderer mode {mode!r}: texpose_b200 implements 'color' / 'feature' (vertex features, <= 8 "
+                                      "channels) and 'nocs' (compute_surfelinfo.py:114-115 renders 'color' and 'nocs')")
         if self.device.type != "cuda":
             raise RuntimeError("texpose_b200 has no CPU path: MVRenderer needs a CUDA mesh")
         rows = _pose_rows(pose).float().to(self.device).contiguous()
