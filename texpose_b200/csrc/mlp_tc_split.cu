@@ -333,12 +333,17 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_forward_split_kernel(const P
           uint8_t* const g_save = (kSingle && p.save && sg.save_slot >= 0) ? p.save + ((size_t)tile * p.n_save + sg.save_slot) * kABytes : nullptr;
           uint32_t* const g_bits = g_save ? p.save_bits + ((size_t)tile * p.n_save + sg.save_slot) * 1024 + half * 4 * 128 + row : nullptr;
           // one 32-column slab: + bias, ReLU, hi / lo split, 4 core-matrix rows of A_hi and A_lo (and of the parked copy)
-          auto slab = [&](const uint32_t (&v)[32], int j) {
+          // the slab's 32 bias values are fetched one slab ahead (beside the TMEM load): loads issued inside the conversion loop
+          // wait out their full latency behind the stores of the previous group (16 exposed load-use stalls per stage, ncu source page)
+          auto load_bias = [&](float4 (&bq)[8], int j) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) bq[i] = __ldg(reinterpret_cast<const float4*>(brow + j * 32 + i * 4));
+          };
+          auto slab = [&](const uint32_t (&v)[32], const float4 (&bq)[8], int j) {
             uint32_t positive = 0u;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(brow + j * 32 + i * 8));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(brow + j * 32 + i * 8 + 4));
+              const float4 b0 = bq[2 * i], b1 = bq[2 * i + 1];
               const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
               uint32_t h[4], l[4];
 #pragma unroll
@@ -372,18 +377,23 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_forward_split_kernel(const P
             if (lane == 0) mbar_arrive(bar_ready(half * 4 + j));
           };
           uint32_t va[32], vb[32];
+          float4 ba[8], bb2[8];
           TP_TMEM_LD32(tmem_d, va);
+          load_bias(ba, 0);
           TP_TMEM_WAIT32(va);
           TP_TMEM_LD32(tmem_d + 32, vb);
-          slab(va, 0);
+          load_bias(bb2, 1);
+          slab(va, ba, 0);
           TP_TMEM_WAIT32(vb);
           TP_TMEM_LD32(tmem_d + 64, va);
-          slab(vb, 1);
+          load_bias(ba, 2);
+          slab(vb, bb2, 1);
           TP_TMEM_WAIT32(va);
           TP_TMEM_LD32(tmem_d + 96, vb);
-          slab(va, 2);
+          load_bias(bb2, 3);
+          slab(va, ba, 2);
           TP_TMEM_WAIT32(vb);
-          slab(vb, 3);
+          slab(vb, bb2, 3);
           if ((sg.flags & F_E_LAST) && half == 1 && tile + gridDim.x < n_tiles) encode_tile(tile + gridDim.x);
         } else if (half == 0) {
           uint32_t v[16];
