@@ -75,3 +75,37 @@ def test_pixel_centres_are_half_integers_of_the_opencv_projection():
         assert abs(M.pix_to_ndc(W - 1 - c, W, H) + ((c + 0.5) - W / 2) / s) < 1e-6
     for r in (0, 7, H - 1):
         assert abs(M.pix_to_ndc(H - 1 - r, H, W) + ((r + 0.5) - H / 2) / s) < 1e-6
+
+
+def test_drop_in_host_helpers_on_cpu():
+    """tools.mvrenderer host side without a GPU: NOCS vertex attribute == the oracle's, every pose layout the reference passes
+    (Pose wrapper with .R / .t, [B,3,4], [B,4,4], the wrapper's flat [R(9) | t(3)] data) maps to the same [R | t] rows, the Mesh
+    holder answers what MVRenderer reads from a pytorch3d Meshes, and a CPU mesh is refused loudly (no CPU path)."""
+    import pytest
+    import torch
+    from texpose_b200.tools import mvrenderer as mv
+    v, f = M.icosphere(2, 0.3)
+    vt = torch.from_numpy(v) * torch.tensor([1.0, 2.0, 0.5])
+    assert np.abs(mv.nocs_coordinates(vt).numpy() - M.nocs_coordinates(vt.numpy())).max() < 1e-6
+    R = torch.tensor([[[0.0, -1, 0], [1, 0, 0], [0, 0, 1]]])
+    t = torch.tensor([[0.1, 0.2, 3.0]])
+    want = torch.cat([R, t[:, :, None]], dim=-1).reshape(1, 12)
+
+    class PoseLike:          # the reference's Pose wrapper exposes .R and .t (tools/mvrenderer.py:495-503)
+        def __init__(self, R, t):
+            self.R, self.t = R, t
+
+    T44 = torch.eye(4)[None].clone()
+    T44[:, :3, :3], T44[:, :3, 3] = R, t
+    flat = torch.cat([R.reshape(1, 9), t], dim=-1)
+    for pose in (PoseLike(R, t), torch.cat([R, t[:, :, None]], dim=-1), T44, flat):
+        assert torch.equal(mv._pose_rows(pose), want)
+    mesh = mv.Mesh(vt, torch.from_numpy(f.astype(np.int64)), torch.rand(len(v), 3))
+    assert mesh.verts_packed().shape == (len(v), 3) and mesh.faces_packed().shape == (len(f), 3)
+    assert mesh.textures.verts_features_packed().shape == (len(v), 3) and mesh.extend(4) is mesh
+    r = mv.MVRenderer(mesh, 48, 64, 1, None)
+    assert set(r.attrs) == {"nocs", "color"} and r.faces.dtype == torch.int32
+    with pytest.raises(RuntimeError):
+        r(torch.cat([R, t[:, :, None]], dim=-1), torch.eye(3)[None], mode="nocs")
+    with pytest.raises(NotImplementedError):
+        r(torch.cat([R, t[:, :, None]], dim=-1), torch.eye(3)[None], mode="mask")
