@@ -262,7 +262,19 @@ class NerfMLP(torch.autograd.Function):
                     and mlp_tc32.supported(cfg, feat_p, rgb_p, trans_p):
                 # bf16 on an architecture the lock-step kernel is not specialised for: single-pass launch of the staged kernel
                 use_tc32, single, use_tc = True, 1, False
-        if use_tc32:
+        staged_train = False
+        if sv is not None and cfg.stl and not trunk_grad and cfg.precision in ("bf16", "auto") and geom.get("mode") == "rays":
+            from .. import mlp_tc, mlp_tc32
+            # training on an architecture the lock-step kernel / fused backward are not specialised for: staged kernels
+            staged_train = (not mlp_tc.supported(cfg, feat_p, rgb_p, trans_p)) and mlp_tc32.supported(cfg, feat_p, rgb_p, trans_p) \
+                and (len(rgb_p) - 1) + (len(trans_p) - 1) + 1 <= 16
+        if staged_train:
+            from .. import mlp_tc32
+            rgb, density, uncert, (images, n_save) = mlp_tc32.forward(cfg, geom, lt, ll, feat_p, rgb_p, trans_p, precision=1,
+                                                                      save="heads")
+            sv.images, sv.n_save, sv.staged, sv.geom, sv.lat = images, n_save, True, geom, (lt, ll)
+            sv.rgb, sv.density, sv.uncert = rgb, density, uncert
+        elif use_tc32:
             from .. import mlp_tc32
             rgb, density, uncert = mlp_tc32.forward(cfg, geom, lt, ll, feat_p, rgb_p, trans_p, static_only=cfg.static_only,
                                                     precision=single)
@@ -297,11 +309,12 @@ class NerfMLP(torch.autograd.Function):
         need = ctx.needs_input_grad[4:]
         g = lambda t: t.contiguous().float() if t is not None else None
         if getattr(sv, "images", None) is not None:
-            # bf16 mode: tensor-core backward on the tile images the fused forward saved (csrc/mlp_tc_bwd.cu)
+            # bf16 mode: tensor-core backward on the tile images the fused forward saved (csrc/mlp_tc_bwd.cu), or -- architectures
+            # outside its fixed stage table -- the staged kernels (csrc/mlp_tc_chain.cu)
             from .. import mlp_tc_bwd
-            gr, gt, d_lt, d_ll = mlp_tc_bwd.heads_backward(cfg, sv, S, ctx.per_image, rgb_p, trans_p, g(g_rgb), g(g_density),
-                                                           g(g_uncert), bool(ctx.needs_input_grad[2]),
-                                                           bool(ctx.needs_input_grad[3]))
+            fn = mlp_tc_bwd.heads_backward_staged if getattr(sv, "staged", False) else mlp_tc_bwd.heads_backward
+            gr, gt, d_lt, d_ll = fn(cfg, sv, S, ctx.per_image, rgb_p, trans_p, g(g_rgb), g(g_density),
+                                    g(g_uncert), bool(ctx.needs_input_grad[2]), bool(ctx.needs_input_grad[3]))
             out = [None] * n_f
             for layers in (gr, gt):
                 for pair in layers:

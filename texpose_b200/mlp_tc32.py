@@ -101,10 +101,13 @@ def build_tables(cfg, feat_p, rgb_p, trans_p, static_only=False, save=False):
         W, b = trans_p[-1]
         small(W, 0, 5)
         stages.append([16, 0, KIND_TRANS_OUT, BIAS_STATIC, add_bias(b), F_WAIT_READY])
+    # save slots: 'all' / True = every hidden stage in execution order (trunk layers, feature, rgb hidden, transient hidden);
+    # 'heads' = from the feature stage on (frozen trunk: layers/nerf_static_transient_light.py:34,87 -- its activations are not needed)
+    first = (len(feat_p) - 1) if save == "heads" else 0      # index, among the hidden stages, of the first one that is kept
     n_hidden = 0
     for st in stages:
         hidden = st[2] == KIND_HIDDEN
-        st.append(n_hidden if (save and hidden) else -1)
+        st.append(n_hidden - first if (save and hidden and n_hidden >= first) else -1)
         n_hidden += hidden
     return slots, stages, biases
 
@@ -116,7 +119,7 @@ class Packed:
 def pack(cfg, holder, feat_p, rgb_p, trans_p, static_only=False, precision=0, save=False) -> Packed:
     """precision 0: split fp16 hi + lo image (three passes, <= 1e-4); 1: bf16 image for the single-pass launch (<= 1e-2)."""
     flat = [t for pair in (feat_p + rgb_p + trans_p) for t in pair]
-    key = (mlp_tc._version_key(flat), bool(static_only), int(precision), bool(save))
+    key = (mlp_tc._version_key(flat), bool(static_only), int(precision), str(save))
     attr = "_packed32" if precision == 0 else "_packed16"
     cache = getattr(holder, attr, None) if holder is not None else None
     if cache is not None and cache.key == key:

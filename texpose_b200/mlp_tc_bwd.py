@@ -201,3 +201,85 @@ def heads_backward_unfused(cfg, sv, S, per_image, rgb_p, trans_p, g_rgb, g_densi
     grads_t[0] = (torch.cat([big[5], dW_lt], dim=1), tot[5])
     d_lt = ops.linear_backward_input(g_timg, W_t0, B, cfg.n_latent_trans, None, w_col0=256) if need_lat_trans else None
     return grads_r, grads_t, d_lt, d_ll
+
+
+def heads_backward_staged(cfg, sv, S, per_image, rgb_p, trans_p, g_rgb, g_density, g_uncert, need_lat_trans, need_lat_light):
+    """The two heads' backward for ANY head depth (256-wide layers), on the staged kernels: the activations are the tile images /
+    ReLU bitmasks the single-pass staged forward saved (slots: feature, rgb hidden 1.., transient hidden 1.., encoding tile), the
+    dX chains are two tp_tc_chain_backward launches (one per head: its output layer's dz enters as the thin operand), the
+    256 x 256 weight gradients one tp_tc_dw_gemm launch, the thin pieces the helpers of the multi-kernel path.  Used when
+    tp_tc_heads_backward's fixed stage table (the yaml's 3 x 256 heads) does not describe the architecture."""
+    from . import mlp_tc32  # noqa: F401  (save layout)
+    dev = sv.rgb.device
+    geom = sv.geom
+    lt, ll = sv.lat
+    B, R, N = geom["shape"]
+    images, n_save = sv.images, sv.n_save
+    nr, nt = len(rgb_p), len(trans_p)
+    slot_feat = 0
+    slot_r = lambda i: i                  # rgb hidden activation h_i (output of rgb layer i-1), i = 1 .. nr-1
+    slot_t = lambda i: (nr - 1) + i       # transient hidden activation, i = 1 .. nt-1
+    lib = _C.load()
+    dz_rgb, dz_trans = torch.empty(S, 3, device=dev), torch.empty(S, 5, device=dev)
+    _C.call("tp_stl_output_grad", ops._p(sv.rgb), ops._p(sv.density), ops._p(sv.uncert), ops._p(g_rgb), ops._p(g_density),
+            ops._p(g_uncert), S, ops._p(dz_rgb), ops._p(dz_trans), None, ops._stream())
+    n_tiles = (S + 127) // 128
+    n_dz = (nr - 1) + (nt - 1)            # dz of every hidden layer's pre-activation: rgb nr-2 .. 0, then transient nt-2 .. 0
+    dz = torch.empty(n_tiles * n_dz * 65536, dtype=torch.uint8, device=dev)
+    bits = images[n_tiles * n_save * 65536:]
+    rows = []
+
+    def chain(layers, thin, slot_h, dz0):
+        """Stage list of one head: out layer (thin) -> hidden layers n-2 .. 1; dz slot dz0 + j holds the dz of layer n-2-j."""
+        n = len(layers)
+        W_out = layers[n - 1][0]
+        rows.append([W_out.data_ptr(), W_out.stride(0), 0, 256, 0, W_out.shape[0], 256, 0, -1, 1])
+        stages = [[0, len(rows) - 1, 0, 0, slot_h(n - 1), dz0]]
+        for j, li in enumerate(range(n - 2, 0, -1)):
+            c0 = len(rows)
+            W = layers[li][0]
+            for c in range(0, 256, 32):
+                rows.append([W.data_ptr(), W.stride(0), 0, 256, c, 32, 256, 0, -1, 1])
+            stages.append([-1, 0, c0, 8, slot_h(li), dz0 + 1 + j])
+        return thin, stages
+
+    jobs = [chain(rgb_p, dz_rgb, slot_r, 0), chain(trans_p, dz_trans, slot_t, nr - 1)]
+    desc = torch.tensor(rows, dtype=torch.int64, device=dev)
+    packed = torch.empty(len(rows) * lib.tp_tc_chunk_bytes(), dtype=torch.uint8, device=dev)
+    _C.call("tp_tc_pack_weights", ops._p(desc), len(rows), ops._p(packed), ops._stream())
+    for thin, stages in jobs:
+        st = torch.tensor(stages, dtype=torch.int32)
+        _C.call("tp_tc_chain_backward", ops._p(thin), thin.shape[1], None, 0, S, ops._p(packed), len(rows), ops._p(st), len(stages),
+                ops._p(bits), n_save, ops._p(dz), n_dz, ops._stream())
+    # dz slot of layer li's pre-activation (li = 0 .. n-2)
+    dzr = lambda li: (nr - 2) - li
+    dzt = lambda li: (nr - 1) + (nt - 2) - li
+    pairs = [(dzr(li), slot_r(li) if li else slot_feat) for li in range(nr - 2, -1, -1)] + \
+            [(dzt(li), slot_t(li) if li else slot_feat) for li in range(nt - 2, -1, -1)]
+    big = torch.cat([dw_gemm(dz, n_dz, images, n_save, pairs[i:i + 12], S) for i in range(0, len(pairs), 12)], dim=0)
+    big_r = {li: big[j] for j, li in enumerate(range(nr - 2, -1, -1))}
+    big_t = {li: big[(nr - 1) + j] for j, li in enumerate(range(nt - 2, -1, -1))}
+    sums = images_colsum(dz, n_dz, S, list(range(n_dz)))                                   # bias gradients of every hidden layer
+    grads_r, grads_t = [None] * nr, [None] * nt
+    grads_r[nr - 1] = (thin_dw(dz_rgb, images, slot_r(nr - 1), n_save, S), thin_colsum(dz_rgb, S))
+    grads_t[nt - 1] = (thin_dw(dz_trans, images, slot_t(nt - 1), n_save, S), thin_colsum(dz_trans, S))
+    for li in range(1, nr - 1):
+        grads_r[li] = (big_r[li], sums[dzr(li)])
+    for li in range(1, nt - 1):
+        grads_t[li] = (big_t[li], sums[dzt(li)])
+    # ---- layer 0 of each head: feature columns from the GEMM, per-ray view / per-sample xyz / per-image latent columns
+    W_r0, W_t0 = rgb_p[0][0], trans_p[0][0]
+    g_ray = image_ray_sums(dz, dzr(0), n_dz, S, N)                                         # [B*R,256]
+    g_img = ops.group_colsum(g_ray, B * R, R)                                              # [B,256]
+    g_timg = ops.group_colsum(image_ray_sums(dz, dzt(0), n_dz, S, N), B * R, R)
+    view_t, _, vc = geom["view_seg"]()
+    dW_view, _ = ops.linear_backward_weight(g_ray, [(view_t, 1, vc)], B * R, want_bias=False)
+    xyz = ops.points_from_depth(geom["center"], geom["ray"], geom["depth"]).view(S, 3)
+    dW_xyz = thin_dw(xyz, dz, dzr(0), n_dz, S).t().contiguous()
+    dW_light, _ = ops.linear_backward_weight(g_img, [(ll, 1, cfg.n_latent_light)], B, want_bias=False)
+    grads_r[0] = (torch.cat([big_r[0], dW_view, dW_xyz, dW_light], dim=1), sums[dzr(0)])
+    d_ll = ops.linear_backward_input(g_img, W_r0, B, cfg.n_latent_light, None, w_col0=256 + vc + 3) if need_lat_light else None
+    dW_lt, _ = ops.linear_backward_weight(g_timg, [(lt, 1, cfg.n_latent_trans)], B, want_bias=False)
+    grads_t[0] = (torch.cat([big_t[0], dW_lt], dim=1), sums[dzt(0)])
+    d_lt = ops.linear_backward_input(g_timg, W_t0, B, cfg.n_latent_trans, None, w_col0=256) if need_lat_trans else None
+    return grads_r, grads_t, d_lt, d_ll
