@@ -72,3 +72,21 @@ def test_plain_chain_stage_list():
     assert [s[4] for s in stages[3:]] == list(range(nf - 3, -1, -1))                 # h5 ... h0
     assert [s[5] for s in stages] == list(range(nf + 1))                             # dz slots in chain order
     assert all(s[3] == 8 for s in stages[1:]) and all(s[0] == -1 for s in stages[3:])
+
+
+def test_pretrain_graphs_host_logic():
+    """model/nerf_pretrain.py:505-511 against model/nerf_pretrain_env.py:484-485: pose selection; both Graphs build the plain model
+    (and a second one under nerf.fine_sampling, :454-455) with the reference's parameter names."""
+    import torch
+    from texpose_b200.config import AttrDict, env_opt
+    from texpose_b200.model import nerf_pretrain, nerf_pretrain_env
+    opt = env_opt()
+    var = AttrDict(pose=torch.zeros(2, 3, 4), pose_init=torch.ones(2, 3, 4))
+    assert nerf_pretrain.Graph.get_pose(opt, var, mode="train") is var.pose_init       # data.pose_source = predicted
+    assert nerf_pretrain.Graph.get_pose(opt, var, mode="val") is var.pose
+    assert nerf_pretrain_env.Graph.get_pose(opt, var, mode="train") is var.pose
+    g = nerf_pretrain_env.Graph(opt)
+    names = [n for n, _ in g.named_parameters()]
+    assert names[0] == "nerf.mlp_feat.0.weight" and names[-1] == "nerf.mlp_rgb.1.bias" and len(names) == 20
+    opt.nerf.fine_sampling = True
+    assert any(n.startswith("nerf_fine.") for n, _ in nerf_pretrain.Graph(opt).named_parameters())
