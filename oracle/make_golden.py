@@ -243,6 +243,64 @@ def case_plain(ns):
     return out
 
 
+def case_pretrain(ns):
+    """model/nerf_pretrain.py Graph end to end on CPU: forward(mode='train') (get_ray_idx -> render) + compute_loss + autograd,
+    and render_by_slices(mode='val') over a whole 96 x 128 frame.  The reference hard-codes `.cuda()` in ray_batch_sample (:462);
+    for this CPU run Tensor.cuda is the identity while the case runs (the reference itself is not modified)."""
+    import importlib
+    mod = importlib.import_module("model.nerf_pretrain")
+    H, W, N, B = 96, 128, 32, 2
+    opt = ref_import.load_yaml_opt("nerf_lm_env", H=H, W=W)
+    opt.nerf.sample_intvs, opt.nerf.rand_rays = N, 512
+    opt.loss_weight.update(render=0, mask=-1, depth=-1)
+    opt.data.erode_mask_loss = False
+    torch.manual_seed(0)
+    g = mod.Graph(opt)
+    pose = synth.poses([0, 1])
+    intr = synth.intrinsics(B).clone()
+    intr[:, :2] *= 0.2
+    c_full, r_full = ns.camera.get_center_and_ray(opt, pose, intr=intr)
+    lo, hi = synth.padded_aabb()
+    tn, tf, valid = ns.camera.aabb_ray_intersection(lo, hi, c_full, r_full)
+    z_near = torch.where(valid, tn, torch.full_like(tn, 7.0))
+    z_far = torch.where(valid, tf, torch.full_like(tf, 9.0))
+    gen = torch.Generator().manual_seed(3)
+    image = torch.rand(B, 3, H, W, generator=gen)
+    depth_gt = 7.5 + torch.rand(B, H, W, generator=gen)
+    obj_mask = valid.view(B, H, W).float()
+    from texpose_b200.config import AttrDict
+    var = AttrDict(idx=torch.arange(B), pose=pose, pose_init=pose, intr=intr, z_near=z_near, z_far=z_far, image=image,
+                   obj_mask=obj_mask, depth_gt=depth_gt)
+    cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        torch.manual_seed(21)
+        ray_idx = torch.randperm(H * W)[:opt.nerf.rand_rays // B].repeat(B, 1)
+        rand = torch.rand(B, opt.nerf.rand_rays // B, N, 1)
+        torch.manual_seed(21)
+        var = g.forward(opt, var, mode="train")
+        assert torch.equal(var.ray_idx, ray_idx)
+        loss = g.compute_loss(opt, var, mode="train")
+        total = sum(10 ** float(opt.loss_weight[k]) * loss[k] for k in loss)
+        total.backward()
+        out = dict(pose=pose, intr=intr, z_near=z_near, z_far=z_far, image=image, depth_gt=depth_gt, obj_mask=obj_mask, H=H, W=W,
+                   N=N, ray_idx=ray_idx, rand=rand, o_rgb=var.rgb, o_depth=var.depth, o_opacity=var.opacity, l_total=total)
+        out.update({"l_" + k: v for k, v in loss.items()})
+        for name, p in g.nerf.named_parameters():
+            out["g/" + name] = p.grad if p.grad.numel() <= 2048 else p.grad[:, ::8][::8].contiguous()
+            out["gsum/" + name] = p.grad.double().sum().item()
+            out["gabs/" + name] = p.grad.double().abs().sum().item()
+        opt.nerf.sample_stratified = False
+        with torch.no_grad():
+            val = g.render_by_slices(opt, pose[:1], intr=intr[:1], depth_range=(z_near[:1, :, None], z_far[:1, :, None]),
+                                     object_mask=obj_mask[:1], mode="val")
+        out.update(v_rgb=val.rgb, v_depth=val.depth, v_opacity=val.opacity)
+    finally:
+        torch.Tensor.cuda = cuda
+    out.update(weight_checksums(g.nerf))
+    return out
+
+
 def case_normals():
     box, surfel = ref_import.load_surfel()
     H, W = 120, 160
@@ -271,6 +329,7 @@ def main():
         plain=lambda: case_plain(ns),
         normals=case_normals,
         loss=lambda: case_loss(ns, opt128),
+        pretrain=lambda: case_pretrain(ns),
     )
     for name, fn in cases.items():
         d = _np(fn())
