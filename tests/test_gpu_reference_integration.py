@@ -6,6 +6,9 @@ leaves in baseline/_ref, which travels to the GPU box); the tests skip when neit
     Graph.render (model/nerf_adapt_st_gan.py:547-631, untouched Python) then runs on texpose_b200's kernels and must
     reproduce the unpatched reference on the same GPU (fp32 kernels <= 1e-4, bf16 tensor-core path <= 1e-2).
   * option A: texpose_b200's Graph (fused render launch) against the reference's Graph.render, same weights.
+  * the pre-training engine's Graph (model/nerf_pretrain.py): a training step (forward + compute_loss + backward) and a
+    validation frame of the unmodified reference on the GPU against option A (texpose_b200.model.nerf_pretrain.Graph) and
+    option B (the reference's Graph class with camera.* and NeRF patched), same seed -> same ray subset and jitter.
 """
 import pytest
 import torch
@@ -101,3 +104,89 @@ def test_option_a_fused_graph_matches_the_reference_graph():
               "alpha_transient"):
         assert errs[k] <= 1e-2, (k, errs[k])
     assert errs["uncert"] <= 1.5e-2
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the pre-training engine's Graph (model/nerf_pretrain.py:449-728), unmodified, on the same GPU
+
+def _pretrain_problem(precision):
+    import importlib
+    ns = ref_import.load()
+    mod = importlib.import_module("model.nerf_pretrain")
+    Hp, Wp, Np, B = 96, 128, 32, 2
+    opt = ref_import.load_yaml_opt("nerf_lm_env", Hp, Wp, device=DEV)
+    opt.nerf.sample_intvs, opt.nerf.rand_rays = Np, 512
+    opt.loss_weight.update(render=0, mask=-1, depth=-1)
+    opt.data.erode_mask_loss = False
+    opt.b200 = AttrDict(mlp=precision)
+    pose = synth.poses([0, 1]).to(DEV)
+    intr = synth.intrinsics(B).clone()
+    intr[:, :2] *= 0.2
+    intr = intr.to(DEV)
+    lo, hi = [t.to(DEV) for t in synth.padded_aabb()]
+    zn, zf = compute_box.box_range(pose, intr, lo, hi, Hp, Wp, 7.0, 9.0)
+    gen = torch.Generator().manual_seed(3)
+    var = dict(idx=torch.arange(B), pose=pose, pose_init=pose, intr=intr, z_near=zn, z_far=zf,
+               image=torch.rand(B, 3, Hp, Wp, generator=gen).to(DEV), obj_mask=(zf < 8.99).view(B, Hp, Wp).float(),
+               depth_gt=(7.5 + torch.rand(B, Hp, Wp, generator=gen)).to(DEV))
+    return ns, mod, opt, var
+
+
+def _pretrain_step(graph, opt, var):
+    """What Model.train_iteration does with the Graph (model/base.py:129-133): forward, compute_loss, weighted sum, backward."""
+    for p in graph.parameters():
+        p.grad = None
+    torch.manual_seed(21)                                    # the ray subset and the jitter come from the device generator
+    var = graph.forward(opt, AttrDict(var), mode="train")
+    loss = graph.compute_loss(opt, var, mode="train")
+    sum(10 ** float(opt.loss_weight[k]) * loss[k] for k in loss).backward()
+    with torch.no_grad():
+        stratified, opt.nerf.sample_stratified = opt.nerf.sample_stratified, False
+        val = graph.render_by_slices(opt, var.pose[:1], intr=var.intr[:1], depth_range=(var.z_near[:1, :, None], var.z_far[:1, :, None]),
+                                     object_mask=var.obj_mask[:1], mode="val")
+        opt.nerf.sample_stratified = stratified
+    out = {k: var[k] for k in ("ray_idx", "rgb", "depth", "opacity")}
+    out.update({"l_" + k: v.detach() for k, v in loss.items()})
+    out.update({"v_" + k: val[k] for k in ("rgb", "depth", "opacity")})
+    out.update({"g/" + n: p.grad for n, p in graph.nerf.named_parameters()})
+    return out
+
+
+def _compare(got, want, tol, label):
+    assert torch.equal(got["ray_idx"], want["ray_idx"])
+    errs = {k: float((got[k].detach() - want[k].detach()).abs().max()) for k in want if k != "ray_idx"}
+    worst_grad = max(v for k, v in errs.items() if k.startswith("g/"))
+    print(label, {k: f"{v:.1e}" for k, v in errs.items() if not k.startswith("g/")}, f"worst gradient {worst_grad:.1e}")
+    for k, e in errs.items():
+        assert got[k].shape == want[k].shape and e <= tol, (k, e)
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 1e-2)])
+def test_pretrain_graph_drop_in_and_monkeypatch_match_the_reference_graph(precision, tol):
+    ns, mod, opt, var = _pretrain_problem(precision)
+    torch.manual_seed(0)
+    g_ref = mod.Graph(opt).to(DEV)
+    want = _pretrain_step(g_ref, opt, var)
+    # ---- option A: texpose_b200's Graph in place of the class at model/nerf_pretrain.py:449
+    from texpose_b200.model import nerf_pretrain as BP
+    g_a = BP.Graph(opt).to(DEV)
+    g_a.load_state_dict(g_ref.state_dict())
+    _compare(_pretrain_step(g_a, opt, var), want, tol, f"pre-training Graph, option A ({precision}) vs the reference on the GPU:")
+    # ---- option B: the reference's own Graph class with the ray utilities and the NeRF module patched (INTEGRATION.md section 2)
+    import camera
+    import texpose_b200.layers.nerf as BN
+    saved = {name: getattr(camera, name) for name in ("get_center_and_ray", "get_3D_points_from_depth")}
+    saved_nerf = mod.NeRF
+    try:
+        for name in saved:
+            setattr(camera, name, getattr(bcam, name))
+        mod.NeRF = BN.NeRF
+        g_b = mod.Graph(opt).to(DEV)
+        assert type(g_b.nerf).__module__.startswith("texpose_b200") and type(g_b).__module__ == "model.nerf_pretrain"
+        g_b.load_state_dict(g_ref.state_dict())
+        got_b = _pretrain_step(g_b, opt, var)
+    finally:
+        for name, fn in saved.items():
+            setattr(camera, name, fn)
+        mod.NeRF = saved_nerf
+    _compare(got_b, want, tol, f"pre-training Graph, option B ({precision}) vs the reference on the GPU:")
