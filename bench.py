@@ -628,8 +628,13 @@ def bench_train(args, g, opt, dev, world, timed, pk):
     # bucket is timed beside it
     exchange = parallel.PeerGradExchange(params) if world > 1 else parallel.GradBucket(params)
     g.train()
+    # the engine's own optimizer (model/nerf_adapt_st_gan.py:62-69: torch.optim.Adam over nerf + the two latent tables, optim.lr 1e-3).
+    # It changes the weights every step, so every timed step also re-packs the bf16 weight images, as real training does.
+    optim = torch.optim.Adam([dict(params=g.nerf.parameters(), lr=1.e-3)])
+    optim.add_param_group(dict(params=g.latent_vars_light.parameters(), lr=1.e-3))
+    optim.add_param_group(dict(params=g.latent_vars_trans.parameters(), lr=1.e-3))
 
-    def make_step(bucket):
+    def make_step(bucket, optimizer=True):
         def step():
             for p in params:
                 p.grad = None
@@ -641,17 +646,24 @@ def bench_train(args, g, opt, dev, world, timed, pk):
             summarize_loss(opt_t, var, loss)["all"].backward()   # seeds formed on the device in the backward
             if bucket is not None:
                 bucket.allreduce_mean()
+            if optimizer:
+                optim.step()
         return step
 
     n_steps = max(10, args.steps)       # 2.4 ms each: enough steps for the max-over-ranks time to settle
     ms, _ = timed(make_step(exchange), n_steps, 3)
+    ms_fb, _ = timed(make_step(exchange, optimizer=False), n_steps, 2)      # forward + backward alone (weights unchanged: nothing re-packed)
     samples = B * P * P * NS
     tf = FLOP_PER_SAMPLE_FWD_BWD * samples / (ms * 1e-3) / 1e12
-    out = dict(workload="C3 train step fwd+bwd, 4096 rays x 128 samples per GPU, fused patch loss, bf16 tcgen05 fwd + bwd (dX chain with thin "
-                        "gradients, dW GEMMs), grad exchange",
+    tf_fb = FLOP_PER_SAMPLE_FWD_BWD * samples / (ms_fb * 1e-3) / 1e12
+    out = dict(workload="C3 train step: 4096 rays x 128 samples per GPU, fused patch loss, bf16 tcgen05 fwd + bwd (dX chain with thin "
+                        "gradients, dW GEMMs), grad exchange, Adam step of the engine (heads + latents) and the re-pack of the weight images",
                value=world * samples / (ms * 1e-3), unit="samples/s", ms_per_step=ms, grad_exchange_bytes=exchange.flat.numel() * 4,
                grad_exchange="none (1 GPU)" if world == 1 else "one-kernel rank-order mean over CUDA-IPC peer windows (NVLink)",
-               tflops_per_gpu=tf, flop_per_sample=FLOP_PER_SAMPLE_FWD_BWD, frac_of_sustained_bf16=tf / pk["tf_sustained"])
+               optimizer="torch.optim.Adam as model/nerf_adapt_st_gan.py:62-69 builds it, inside the timed step",
+               tflops_per_gpu=tf, flop_per_sample=FLOP_PER_SAMPLE_FWD_BWD, frac_of_sustained_bf16=tf / pk["tf_sustained"],
+               fwd_bwd_only=dict(ms_per_step=ms_fb, tflops_per_gpu=tf_fb, frac_of_sustained_bf16=tf_fb / pk["tf_sustained"],
+                                 note="same step without optimizer.step(): forward + loss + backward + exchange"))
     # per-entry-point device time of the step (CUDA events around every C-ABI call, a pass of its own) and the roofline of the
     # two calls that carry the work; algorithmic bytes per 128-sample tile from DESIGN.md section 4 (K2 / K2b)
     step = make_step(None)
@@ -726,14 +738,17 @@ def bench_plain_train(dev, timed, samples):
         torch.manual_seed(0)
         m = PlainNeRF(opt).to(dev)
 
+        optim = torch.optim.Adam([dict(params=m.parameters(), lr=1.e-3)])      # model/nerf_pretrain.py:59-62
+
         def step():
-            for p in m.parameters():
-                p.grad = None
+            optim.zero_grad()
             rgb_s, sig = m.forward_samples(opt, center, ray, depth, mode="train")
             ((m.composite(opt, ray, rgb_s, sig, depth)[0] - image) ** 2).mean().backward()
+            optim.step()
 
         res[mode] = timed(step, steps, 2)[0]
-    return dict(workload="plain NeRF (8 x 256 trunk, 286 -> 128 -> 3 head), 4096 rays x 128 samples, fwd + composite + bwd of all parameters",
+    return dict(workload="plain NeRF (8 x 256 trunk, 286 -> 128 -> 3 head), 4096 rays x 128 samples, fwd + composite + bwd of all parameters "
+                         "+ Adam step",
                 ms_per_step=res["bf16"], value=samples / (res["bf16"] * 1e-3), unit="samples/s", simt_fp32_ms_per_step=res["fp32"],
                 speedup_vs_simt=res["fp32"] / res["bf16"])
 

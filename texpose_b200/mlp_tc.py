@@ -105,7 +105,7 @@ def pack(cfg, holder, feat_p, rgb_p, trans_p, params_for_key) -> Packed:
     table, keep = _chunk_table(cfg, feat_p, rgb_p, trans_p)
     assert len(table) == n_chunks, (len(table), n_chunks)
     dev = feat_p[0][0].device
-    desc = torch.tensor(table, dtype=torch.int64, device=dev)
+    desc = ops.device_table(table, torch.int64, dev)
     weights = torch.empty(n_chunks * chunk_bytes, dtype=torch.uint8, device=dev)
     _C.call("tp_tc_pack_weights", ops._p(desc), n_chunks, ops._p(weights), ops._stream())
     fb = [b for _, b in feat_p]

@@ -126,7 +126,7 @@ def pack(cfg, holder, feat_p, rgb_p, trans_p, static_only=False, precision=0, sa
         return cache
     slots, stages, biases = build_tables(cfg, feat_p, rgb_p, trans_p, static_only, save)
     dev = feat_p[0][0].device
-    desc = torch.tensor(slots, dtype=torch.int64, device=dev)
+    desc = ops.device_table(slots, torch.int64, dev)
     image = torch.empty(len(slots) * _C.load().tp_tc32_slot_bytes(), dtype=torch.uint8, device=dev)
     _C.call("tp_tc32_pack_weights", ops._p(desc), len(slots), int(precision), ops._p(image), ops._stream())
     out = Packed()

@@ -39,7 +39,7 @@ def pack_bwd(holder, rgb_p, trans_p):
     table = _bwd_table(rgb_p, trans_p)
     assert len(table) == lib.tp_tc_bwd_num_chunks()
     dev = rgb_p[0][0].device
-    desc = torch.tensor(table, dtype=torch.int64, device=dev)
+    desc = ops.device_table(table, torch.int64, dev)
     img = torch.empty(len(table) * lib.tp_tc_chunk_bytes(), dtype=torch.uint8, device=dev)
     _C.call("tp_tc_pack_weights", ops._p(desc), len(table), ops._p(img), ops._stream())
     if holder is not None:
@@ -76,7 +76,7 @@ def images_colsum(images, n_slots, S, slots):
     """[len(slots),256]: column sums over all samples of the selected image slots (bias gradients), one launch + one reduce."""
     lib = _C.load()
     blocks, n = lib.tp_tc_images_colsum_blocks(), len(slots)
-    sel = torch.tensor(list(slots), dtype=torch.int32, device=images.device)
+    sel = ops.device_table(list(slots), torch.int32, images.device)
     partial = torch.empty(blocks * n * 256, device=images.device)
     _C.call("tp_tc_images_colsum", ops._p(images), n_slots, S, ops._p(sel), n, ops._p(partial), partial.numel(), ops._stream())
     return reduce_partials(partial, blocks, n * 256).view(n, 256)
@@ -244,7 +244,7 @@ def heads_backward_staged(cfg, sv, S, per_image, rgb_p, trans_p, g_rgb, g_densit
         return thin, stages
 
     jobs = [chain(rgb_p, dz_rgb, slot_r, 0), chain(trans_p, dz_trans, slot_t, nr - 1)]
-    desc = torch.tensor(rows, dtype=torch.int64, device=dev)
+    desc = ops.device_table(rows, torch.int64, dev)
     packed = torch.empty(len(rows) * lib.tp_tc_chunk_bytes(), dtype=torch.uint8, device=dev)
     _C.call("tp_tc_pack_weights", ops._p(desc), len(rows), ops._p(packed), ops._stream())
     for thin, stages in jobs:

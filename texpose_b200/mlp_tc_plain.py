@@ -33,15 +33,32 @@ def supported(cfg, feat_p, rgb_p) -> bool:
     return h <= _F and tuple(rgb_p[0][0].shape) == (h, _F + cfg.view_cols + 3) and tuple(rgb_p[1][0].shape) == (3, h)
 
 
+_PADDED = {}      # persistent padded-head buffers, one set per head (keyed by its parameters' storage): stable addresses, no per-step zero fills
+_DUMMY = {}       # the all-zero transient head the staged kernel's stage list carries for the plain model (never executed: static_only)
+
+
 def _padded_head(rgb_p):
     """rgb hidden layer zero-padded to 256 rows, output layer to 256 columns (exact: the padded units are relu(0) = 0)."""
     (W0, b0), (W1, b1) = rgb_p
     dev = W0.device
-    W0p, b0p = torch.zeros(_F, W0.shape[1], device=dev), torch.zeros(_F, device=dev)
+    key = (str(dev), W0.data_ptr(), W1.data_ptr(), tuple(W0.shape), tuple(W1.shape))
+    buf = _PADDED.get(key)
+    if buf is None:
+        if len(_PADDED) > 64:
+            _PADDED.clear()
+        buf = _PADDED[key] = (torch.zeros(_F, W0.shape[1], device=dev), torch.zeros(_F, device=dev), torch.zeros(3, _F, device=dev))
+    W0p, b0p, W1p = buf
     W0p[:W0.shape[0]], b0p[:b0.shape[0]] = W0, b0
-    W1p = torch.zeros(3, _F, device=dev)
     W1p[:, :W1.shape[1]] = W1
     return [(W0p, b0p), (W1p, b1.contiguous())]
+
+
+def _dummy_trans(dev):
+    k = str(dev)
+    if k not in _DUMMY:
+        z = lambda *shape: torch.zeros(*shape, device=dev)
+        _DUMMY[k] = ([(z(_F, _F), z(_F)), (z(5, _F), z(5))], z(1, 0))
+    return _DUMMY[k]
 
 
 def _stl_config(cfg, holder, n_feat):
@@ -58,11 +75,10 @@ def forward_train(cfg, geom, feat_p, rgb_p):
     dev = geom["depth"].device
     B, R, N = geom["shape"]
     rgb_pad = _padded_head(rgb_p)
-    z = lambda *shape: torch.zeros(*shape, device=dev)
-    trans_dummy = [(z(_F, _F), z(_F)), (z(5, _F), z(5))]
+    trans_dummy, none1 = _dummy_trans(dev)
     holder = _Holder()
     stl = _stl_config(cfg, holder, len(feat_p))
-    none = z(B, 0)
+    none = none1.expand(B, 0)
     rgb2, den2, _, (images, n_save) = mlp_tc32.forward(stl, geom, none, none, feat_p, rgb_pad, trans_dummy, static_only=True,
                                                        precision=1, save=True)
     rgb, density = rgb2[:, :, 0].contiguous(), den2[:, 0].contiguous()
@@ -114,7 +130,7 @@ def backward(ctx, g_rgb, g_density, feat_p, rgb_p):
     _C.call("tp_plain_output_grad", ops._p(ctx["rgb"]), ops._p(ctx["density"]), ops._p(ops._f32(g_rgb).reshape(S, 3)),
             ops._p(ops._f32(g_density).reshape(S)), S, ops._p(dz_rgb), ops._p(dz_sigma), ops._stream())
     rows, stages = _bwd_chunks(cfg, feat_p, rgb_pad)
-    desc = torch.tensor(rows, dtype=torch.int64, device=dev)
+    desc = ops.device_table(rows, torch.int64, dev)
     packed = torch.empty(len(rows) * lib.tp_tc_chunk_bytes(), dtype=torch.uint8, device=dev)
     _C.call("tp_tc_pack_weights", ops._p(desc), len(rows), ops._p(packed), ops._stream())
     n_dz = len(stages)

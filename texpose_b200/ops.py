@@ -5,6 +5,7 @@ hot path runs in libtexpose_b200.so.  CPU tensors are rejected (no CPU fallback)
 """
 from __future__ import annotations
 
+import collections
 import ctypes
 from typing import Optional, Sequence, Tuple
 
@@ -48,7 +49,28 @@ def _p(t: Optional[Tensor]):
 
 
 def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    """The caller's stream (torch's current stream on the current device) as a raw cudaStream_t.  The two C calls cost well
+    under a microsecond; `torch.cuda.current_stream()` builds a Stream object through several Python layers (~6 us per launch)."""
+    return ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice()))
+
+
+_TABLES = collections.OrderedDict()
+
+
+def device_table(rows, dtype, device) -> Tensor:
+    """Small integer table (weight-chunk descriptors, slot lists) as a device tensor, cached by content.  The rows hold pointers and
+    strides of parameters, which do not move between training steps, so a step re-uses the table it uploaded before: a fresh
+    `torch.tensor(rows, device=...)` is a pageable host-to-device copy, i.e. one stream synchronisation per call and step."""
+    flat = tuple(tuple(r) for r in rows) if rows and isinstance(rows[0], (list, tuple)) else tuple(rows)
+    key = (str(device), dtype, flat)
+    t = _TABLES.get(key)
+    if t is None:
+        t = _TABLES[key] = torch.tensor(rows, dtype=dtype, device=device)
+        if len(_TABLES) > 256:
+            _TABLES.popitem(last=False)
+    else:
+        _TABLES.move_to_end(key)
+    return t
 
 
 # ------------------------------------------------------------------------------------------------- rays
