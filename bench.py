@@ -691,6 +691,10 @@ def bench_train(args, g, opt, dev, world, timed, pk):
     out["entry_point_ms"] = {k: round(v, 4) for k, v in sorted(per.items(), key=lambda kv: -kv[1])}
     if world == 1:
         out["plain_model_train_step"] = bench_plain_train(dev, timed, samples)
+        try:
+            out["cuda_graph_step"] = bench_graphed_steps(g, dev, timed)
+        except Exception as e:  # noqa: BLE001  (an extra block; never fails the bench)
+            out["cuda_graph_step"] = dict(error=repr(e)[:300])
     if world > 1:
         exchange.check()
         # the exchanged gradients must equal the NCCL allreduce of the same bucket: one more step, then both exchanges
@@ -717,6 +721,63 @@ def bench_train(args, g, opt, dev, world, timed, pk):
         exchange.close()
     g.eval()
     return out
+
+
+def bench_graphed_steps(g, dev, timed):
+    """The whole training step -- render, fused loss, backward, Adam, weight re-pack -- captured once as a CUDA graph
+    (texpose_b200.train_graph.GraphedStep) beside the eager step, at BASELINE's C3 shape and at the step size of
+    options/nerf_lm_adapt_gan.yaml itself (8 patches x 256 rays x 64 samples), where Python cannot issue the launches as fast as the
+    GPU retires them."""
+    import torch
+    from texpose_b200 import compute_box, synth
+    from texpose_b200.config import AttrDict, adapt_gan_opt
+    from texpose_b200.model.base import summarize_loss
+    from texpose_b200.train_graph import GraphedStep
+    res = {}
+    for name, B, P, N in (("c3_16x256x128", 16, 16, NS), ("yaml_8x256x64", 8, 16, 64)):
+        o = adapt_gan_opt(H=128, W=128, sample_intvs=N, device=str(dev))
+        o.batch_size = B
+        o.b200 = AttrDict(mlp="bf16", rng="torch")       # torch.rand jitter: graph-safe (the Philox mode draws its seed on the host)
+        pose = synth.poses(list(range(B))).to(dev)
+        K = torch.tensor([[572.4114, 0, 64 - 572.4114 * 0.3 / 8], [0, 573.57043, 64 + 573.57043 * 0.2 / 8], [0, 0, 1]])
+        intr = K.repeat(B, 1, 1).to(dev)
+        lo, hi = [t.to(dev) for t in synth.padded_aabb()]
+        zn, zf = compute_box.box_range(pose, intr, lo, hi, 128, 128, *synth.BG_RANGE)
+        coords = synth.patch_coords(B, P, seed=2)[0].to(dev)
+        idx = torch.arange(B, device=dev) % 8
+        image = torch.rand(B, 3, 128, 128, device=dev)
+        mask = (torch.rand(B, 128, 128, device=dev) > 0.3).float()
+
+        def adam(capturable):
+            op = torch.optim.Adam([dict(params=g.nerf.parameters(), lr=1.e-3)], capturable=capturable)
+            op.add_param_group(dict(params=g.latent_vars_light.parameters(), lr=1.e-3))
+            op.add_param_group(dict(params=g.latent_vars_trans.parameters(), lr=1.e-3))
+            return op
+
+        def fwd_bwd():
+            ret = g.render(o, pose, intr=intr, ray_idx=coords, depth_range=(zn[:, :, None], zf[:, :, None]), sample_idx=idx, mode="train")
+            var = AttrDict(idx=idx, image=image, obj_mask=mask, ray_idx=coords)
+            var.update(ret)
+            total = summarize_loss(o, var, g.compute_loss(o, var, mode="train"))["all"]
+            total.backward()
+            return total
+
+        eager_optim = adam(False)
+
+        def eager():
+            eager_optim.zero_grad(set_to_none=True)
+            fwd_bwd()
+            eager_optim.step()
+
+        ms_eager, _ = timed(eager, 20, 3)
+        step = GraphedStep(fwd_bwd, adam(True), static=dict(coords=coords, image=image, mask=mask), warmup=3)
+        ms_graph, _ = timed(lambda: step(coords=coords, image=image), 20, 3)      # inputs copied into the static buffers every step
+        n = B * P * P * N
+        res[name] = dict(samples_per_step=n, eager_ms_per_step=ms_eager, graph_ms_per_step=ms_graph,
+                         graph_samples_per_s=n / (ms_graph * 1e-3), speedup=ms_eager / ms_graph)
+    res["note"] = ("whole step (render, fused loss, backward, Adam, weight re-pack) replayed as one CUDA graph; bit-identical to the eager "
+                   "run (tests/test_gpu_train_graph.py)")
+    return res
 
 
 def bench_plain_train(dev, timed, samples):
