@@ -87,8 +87,11 @@ def _chunk_table(cfg, feat_p, rgb_p, trans_p):
     return rows, keep
 
 
+_PAD7 = {}
+
+
 class Packed:
-    __slots__ = ("key", "weights", "wview", "biasbuf", "keep")
+    __slots__ = ("key", "weights", "wview", "biasbuf", "keep", "where")
 
 
 def _version_key(params):
@@ -102,25 +105,32 @@ def pack(cfg, holder, feat_p, rgb_p, trans_p, params_for_key) -> Packed:
         return cached
     lib = _C.load()
     n_chunks, chunk_bytes = lib.tp_tc_num_chunks(), lib.tp_tc_chunk_bytes()
-    table, keep = _chunk_table(cfg, feat_p, rgb_p, trans_p)
-    assert len(table) == n_chunks, (len(table), n_chunks)
     dev = feat_p[0][0].device
-    desc = ops.device_table(table, torch.int64, dev)
+    # the descriptor table holds addresses and strides only: while the parameters stay where they are (an optimizer updates them in
+    # place) the table of the previous step is re-used as it is, and only the pack kernel runs again
+    where = tuple((w.data_ptr(), w.stride(0), b.data_ptr()) for w, b in feat_p + rgb_p + trans_p)
+    if cached is not None and getattr(cached, "where", None) == where:
+        desc, keep = cached.keep
+    else:
+        table, keep = _chunk_table(cfg, feat_p, rgb_p, trans_p)
+        assert len(table) == n_chunks, (len(table), n_chunks)
+        desc = ops.device_table(table, torch.int64, dev)
     weights = torch.empty(n_chunks * chunk_bytes, dtype=torch.uint8, device=dev)
     _C.call("tp_tc_pack_weights", ops._p(desc), n_chunks, ops._p(weights), ops._stream())
     fb = [b for _, b in feat_p]
     rb = [b for _, b in rgb_p]
     tb = [b for _, b in trans_p]
-    biasbuf = torch.zeros(16, device=dev)      # fp32 biases of the three N=16 output stages
-    biasbuf[0] = fb[7][0]
-    biasbuf[1:4] = rb[3]
-    biasbuf[4:9] = tb[3]
+    pad = _PAD7.get(dev)
+    if pad is None:
+        pad = _PAD7[dev] = torch.zeros(7, device=dev)
+    biasbuf = torch.cat([fb[7][:1].float(), rb[3].float(), tb[3].float(), pad])      # fp32 biases of the three N=16 output stages (one launch)
     out = Packed()
     out.key, out.weights, out.biasbuf = key, weights, biasbuf
     # view-direction columns of mlp_rgb[0] ([unit dir, posenc]: layers/nerf_static_transient_light.py:111-117), transposed to
     # [3+6L, 256] so a warp of the render launch reads one input's 256 weights as two coalesced 512 B rows (a copy, no arithmetic)
     out.wview = rgb_p[0][0][:, 256:256 + cfg.view_cols].t().contiguous()
     out.keep = (desc, keep)
+    out.where = where
     if holder is not None:
         holder._packed = out
     return out

@@ -36,14 +36,19 @@ def pack_bwd(holder, rgb_p, trans_p):
     if cached is not None and cached[0] == key:
         return cached[1]
     lib = _C.load()
-    table = _bwd_table(rgb_p, trans_p)
-    assert len(table) == lib.tp_tc_bwd_num_chunks()
     dev = rgb_p[0][0].device
-    desc = ops.device_table(table, torch.int64, dev)
-    img = torch.empty(len(table) * lib.tp_tc_chunk_bytes(), dtype=torch.uint8, device=dev)
-    _C.call("tp_tc_pack_weights", ops._p(desc), len(table), ops._p(img), ops._stream())
+    where = tuple((p.data_ptr(), p.stride(0)) for p in params)
+    if cached is not None and len(cached) > 3 and cached[3] == where:      # same addresses: last step's descriptor table
+        desc = cached[2]
+    else:
+        table = _bwd_table(rgb_p, trans_p)
+        assert len(table) == lib.tp_tc_bwd_num_chunks()
+        desc = ops.device_table(table, torch.int64, dev)
+    n = lib.tp_tc_bwd_num_chunks()
+    img = torch.empty(n * lib.tp_tc_chunk_bytes(), dtype=torch.uint8, device=dev)
+    _C.call("tp_tc_pack_weights", ops._p(desc), n, ops._p(img), ops._stream())
     if holder is not None:
-        holder._packed_bwd = (key, img, desc)
+        holder._packed_bwd = (key, img, desc, where)
     return img
 
 
