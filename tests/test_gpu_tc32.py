@@ -8,7 +8,6 @@ from oracle import texpose_oracle as O
 from texpose_b200 import synth
 from texpose_b200.config import AttrDict, adapt_gan_opt
 from texpose_b200.layers.nerf_static_transient_light import NeRF
-from tests.conftest import layer_list
 from tests.test_gpu_tc import _c1_inputs
 
 pytestmark = pytest.mark.gpu

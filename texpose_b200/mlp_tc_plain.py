@@ -11,7 +11,7 @@ from __future__ import annotations
 
 import torch
 
-from . import _C, mlp_tc, mlp_tc32, mlp_tc_bwd, ops
+from . import _C, mlp_tc32, mlp_tc_bwd, ops
 from .layers._mlp import MLPConfig
 
 _F = 256
