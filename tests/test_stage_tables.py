@@ -90,3 +90,29 @@ def test_pretrain_graphs_host_logic():
     assert names[0] == "nerf.mlp_feat.0.weight" and names[-1] == "nerf.mlp_rgb.1.bias" and len(names) == 20
     opt.nerf.fine_sampling = True
     assert any(n.startswith("nerf_fine.") for n, _ in nerf_pretrain.Graph(opt).named_parameters())
+
+
+def test_descriptor_tables_are_cached_by_content_and_graphed_step_needs_cuda():
+    """Host logic of the launch-bound step sizes: `ops.device_table` hands the same tensor back for the same rows (no re-upload, hence
+    no stream synchronisation per training step) and a different one for different rows; `GraphedStep` refuses to run without CUDA
+    (no CPU path)."""
+    import pytest
+    import torch
+    from texpose_b200 import ops
+    from texpose_b200.train_graph import GraphedStep
+    rows = [[1, 2, 3], [4, 5, 6]]
+    a = ops.device_table(rows, torch.int64, "cpu")
+    b = ops.device_table([list(r) for r in rows], torch.int64, "cpu")
+    c = ops.device_table([[1, 2, 3], [4, 5, 7]], torch.int64, "cpu")
+    d = ops.device_table(rows, torch.int32, "cpu")
+    assert a is b and a is not c and a is not d and d.dtype == torch.int32
+    assert a.tolist() == rows and c.tolist()[1][2] == 7
+    flat = ops.device_table([3, 1, 2], torch.int32, "cpu")
+    assert flat.tolist() == [3, 1, 2] and ops.device_table((3, 1, 2), torch.int32, "cpu") is flat
+    for i in range(300):                                  # bounded: the oldest entries are dropped, the newest stay
+        ops.device_table([i, i + 1], torch.int64, "cpu")
+    assert len(ops._TABLES) <= 257
+    assert ops.device_table([299, 300], torch.int64, "cpu").tolist() == [299, 300]
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="CUDA"):
+            GraphedStep(lambda: None)
