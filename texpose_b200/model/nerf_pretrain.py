@@ -74,6 +74,8 @@ class Graph(torch.nn.Module):
         if opt.camera.ndc:
             raise NotImplementedError("camera.ndc is false in every reference yaml; not implemented")
         B = len(pose)
+        if ray_idx is None:         # the novel-view caller (:421-422) passes no ray list: the whole frame
+            ray_idx = range(0, opt.H * opt.W)
         if isinstance(ray_idx, range):
             ray_idx = torch.arange(ray_idx.start, ray_idx.stop, device=pose.device)[None].expand(B, -1)
         center, ray = camera.get_center_and_ray(opt, pose, intr=intr, ray_idx=ray_idx)
