@@ -1,0 +1,109 @@
+"""Host logic of `texpose_b200.model.nerf_adapt_st_gan.Graph` on the CPU: the kernel wrappers it calls are swapped for the oracle's
+restatements (test infrastructure standing in for the CUDA library, which has no CPU path), so that what runs is the drop-in's own
+orchestration -- nerf_forward's mode dispatch and depth-range packing, the patch-ray / bounds calls, the latent rows of the batch,
+the output dict of `render`, `compute_loss` + `summarize_loss`, FlexPatchSampler -- against the fixtures of the REAL reference
+(tests/golden/render_train.npz = Graph.render(mode='train'), model/nerf_adapt_st_gan.py:547-631; loss.npz = compute_loss +
+summarize_loss + autograd seeds, :712-763 and model/base.py:145-157)."""
+import pytest
+import torch
+
+from oracle import texpose_oracle as O
+from texpose_b200 import camera, ops
+from texpose_b200.config import AttrDict, adapt_gan_opt
+from texpose_b200.layers.nerf_static_transient_light import NeRF
+from texpose_b200.model import nerf_adapt_st_gan
+from texpose_b200.model.base import summarize_loss
+
+
+class _PatchLoss:
+    """ops.PatchLoss.apply with the oracle behind it: (losses [render, uncert, trans_reg, all], image_sample, mask_sample)."""
+
+    @staticmethod
+    def apply(rgb, uncert, density, image, obj_mask, coords, weights):
+        out = O.patch_losses(image, obj_mask, coords, rgb, uncert, density, *weights)
+        zero = rgb.sum() * 0
+        terms = [out.get(k, zero) for k in ("render", "uncert", "trans_reg")] + [out["all"]]
+        return torch.stack(terms), out["image_sample"], out["mask_sample"]
+
+
+@pytest.fixture
+def oracle_kernels(monkeypatch):
+    layers = lambda ml: [(l.weight, l.bias) for l in ml]
+
+    def forward_samples(self, opt, center, ray, depth_samples, latent_variable_trans=None, latent_variable_light=None, mode=None):
+        pts = O.points_from_depth(center, ray, depth_samples)
+        unit = torch.nn.functional.normalize(ray, dim=-1)[..., None, :].expand_as(pts)
+        return O.nerf_stl_forward(pts, unit, latent_variable_trans, latent_variable_light, layers(self.mlp_feat),
+                                  layers(self.mlp_rgb), layers(self.mlp_trans))
+
+    def composite(opt, ray, rgb, dens, depth, uncert):
+        return O.composite_stl(ray, rgb, dens, depth, uncert, opt.nerf.min_uncert)
+
+    monkeypatch.setattr(camera, "view_matrices", lambda pose, intr, one_launch=False: (intr, pose))       # handed through to patch_rays
+    monkeypatch.setattr(ops, "patch_rays", lambda intr, pose, coords, H, W: O.patch_rays(coords, pose, intr, H, W))
+    monkeypatch.setattr(ops, "grid_sample_bilinear",
+                        lambda img, coords: torch.nn.functional.grid_sample(img, coords, mode="bilinear", align_corners=True))
+    monkeypatch.setattr(ops, "sample_depth",
+                        lambda zn, zf, N, rand=None, stratified=True, seed=None: O.sample_depth(zn, zf, N, rand if stratified else None))
+    monkeypatch.setattr(NeRF, "forward_samples", forward_samples)
+    monkeypatch.setattr(NeRF, "composite", staticmethod(composite))
+    monkeypatch.setattr(ops, "PatchLoss", _PatchLoss)
+
+
+def close(a, b, tol=2e-6):
+    assert a.shape == b.shape and (a.double() - b.double()).abs().max().item() <= tol, (a.double() - b.double()).abs().max().item()
+
+
+def test_nerf_forward_train_matches_the_reference_fixture(golden, oracle_kernels):
+    g = golden("render_train")
+    opt = adapt_gan_opt(H=int(g.H), W=int(g.W))
+    torch.manual_seed(0)
+    graph = nerf_adapt_st_gan.Graph(opt, n_train_images=4)
+    torch.manual_seed(3)
+    torch.nn.init.normal_(graph.latent_vars_trans.weight)
+    torch.nn.init.normal_(graph.latent_vars_light.weight)
+    assert torch.equal(graph.latent_vars_trans.weight.detach(), g.emb_trans)
+    var = AttrDict(idx=g.sample_idx, pose=g.pose, pose_init=g.pose, intr=g.intr, z_near=g.z_near, z_far=g.z_far, ray_idx=g.coords)
+    torch.manual_seed(21)                     # the reference's seed: the same jitter draw
+    var = graph.nerf_forward(opt, var, mode="train")
+    keys = ("rgb", "rgb_static", "rgb_transient", "opacity", "opacity_static", "opacity_transient", "uncert", "depth", "alpha_static",
+            "alpha_transient", "density")
+    for k in keys:
+        close(var[k], g["o_" + k], 1e-5 if k == "depth" else 3e-6)
+
+
+def test_compute_loss_and_summarize_loss_match_the_reference_fixture(golden, oracle_kernels):
+    d = golden("loss")
+    B = d.image.shape[0]
+    opt = adapt_gan_opt(H=int(d.H), W=int(d.W))
+    opt.loss_weight = AttrDict(render=float(d.w_render), uncert=float(d.w_uncert), trans_reg=float(d.w_trans_reg))
+    graph = nerf_adapt_st_gan.Graph(opt)
+    rgb, unc, dens = [t.clone().requires_grad_(True) for t in (d.rgb, d.uncert, d.density)]
+    var = AttrDict(idx=torch.arange(B), image=d.image, obj_mask=d.obj_mask, ray_idx=d.coords, rgb=rgb, uncert=unc, density=dens)
+    loss = graph.compute_loss(opt, var, mode="train")
+    assert set(loss.keys()) == {"render", "uncert", "trans_reg"} and "all" not in loss        # what the reference's summarize_loss asserts
+    assert torch.equal(var.image_sample, d.image_sample) and torch.equal(var.mask_sample, d.mask_sample)
+    loss = summarize_loss(opt, var, loss)
+    for k in ("render", "uncert", "trans_reg", "all"):
+        ref = float(d["l_" + k])
+        assert abs(float(loss[k].detach()) - ref) <= 1e-6 * max(1.0, abs(ref)), k
+    loss["all"].backward()
+    close(rgb.grad, d.g_rgb, 1e-6 * float(d.g_rgb.abs().max()))
+    close(unc.grad, d.g_uncert, 1e-5 * float(d.g_uncert.abs().max()))
+    close(dens.grad, d.g_density, 1e-9)
+    # terms that the hot path does not own are refused, not silently dropped
+    opt.loss_weight.feat = -1
+    with pytest.raises(NotImplementedError):
+        graph.compute_loss(opt, var, mode="train")
+
+
+def test_patch_sampler_draws_and_anneal_match_the_reference(golden):
+    d = golden("loss")
+    opt = adapt_gan_opt(H=int(d.H), W=int(d.W))
+    opt.batch_size, opt.patch_size = d.flex_coords.shape[0], d.flex_coords.shape[1]
+    graph = nerf_adapt_st_gan.Graph(opt)
+    # the fixture was drawn without annealing (min_scale 0.25): the engine's anneal reaches that floor at large `iterations`
+    graph.patch_sampler.iterations = 10 ** 9
+    torch.manual_seed(int(d.flex_seed))
+    var = graph.get_ray_idx(opt, AttrDict())
+    assert torch.equal(var.ray_idx, d.flex_coords) and torch.equal(var.ray_scales, d.flex_scales)
