@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from oracle import texpose_oracle as O
-from texpose_b200 import camera, ops
+from texpose_b200 import camera, ops, synth
 from texpose_b200.config import AttrDict, adapt_gan_opt
 from texpose_b200.layers.nerf_static_transient_light import NeRF
 from texpose_b200.model import nerf_adapt_st_gan
@@ -39,6 +39,12 @@ def oracle_kernels(monkeypatch):
     def composite(opt, ray, rgb, dens, depth, uncert):
         return O.composite_stl(ray, rgb, dens, depth, uncert, opt.nerf.min_uncert)
 
+    def center_and_ray(opt, pose, intr=None, H=None, W=None, ray_idx=None):
+        c, r = O.get_center_and_ray(pose, intr, opt.H, opt.W)
+        return (c, r) if ray_idx is None else (O.gather_rays(c, ray_idx), O.gather_rays(r, ray_idx))
+
+    monkeypatch.setattr(camera, "get_center_and_ray", center_and_ray)
+    monkeypatch.setattr(ops, "gather_rows", lambda src, idx: O.gather_rays(src.float(), idx))
     monkeypatch.setattr(camera, "view_matrices", lambda pose, intr, one_launch=False: (intr, pose))       # handed through to patch_rays
     monkeypatch.setattr(ops, "patch_rays", lambda intr, pose, coords, H, W: O.patch_rays(coords, pose, intr, H, W))
     monkeypatch.setattr(ops, "grid_sample_bilinear",
@@ -107,3 +113,45 @@ def test_patch_sampler_draws_and_anneal_match_the_reference(golden):
     torch.manual_seed(int(d.flex_seed))
     var = graph.get_ray_idx(opt, AttrDict())
     assert torch.equal(var.ray_idx, d.flex_coords) and torch.equal(var.ray_scales, d.flex_scales)
+
+
+def test_val_and_eval_frames_slices_mask_prior_and_latent_pick(oracle_kernels):
+    """nerf_forward(mode='val' / 'eval...') (model/nerf_adapt_st_gan.py:464-514, :633-680): slices concatenated, latent row 0 broadcast
+    (val); only the object's pixels rendered, the defaults of :657-667 elsewhere, zero transient latent, the light latent of the
+    nearest anchor pose (eval).  The reference can only run these modes on CUDA (hard-coded .cuda()), so the expected values come from
+    the oracle's render of the same rays."""
+    H, W, N = 24, 32, 32
+    opt = adapt_gan_opt(H=H, W=W, sample_intvs=N)
+    opt.nerf.sample_stratified = False
+    opt.b200 = AttrDict(slice_rays=300, fused_render=False)       # several slices; the generic (multi-call) branch of render
+    torch.manual_seed(0)
+    graph = nerf_adapt_st_gan.Graph(opt, n_train_images=4)
+    pose, intr = synth.poses([0]), synth.intrinsics(1).clone()
+    intr[:, :2] *= 0.05
+    lo, hi = synth.padded_aabb()
+    c, r = O.get_center_and_ray(pose, intr, H, W)
+    tn, tf, v = O.aabb_ray_intersection(lo, hi, c, r)
+    zn, zf = O.box_bounds_to_range(tn, tf, v, *synth.BG_RANGE)
+    assert v.sum() > 20
+    var = AttrDict(pose=pose, intr=intr, z_near=zn, z_far=zf, obj_mask=v.view(1, H, W).float(), idx=torch.tensor([0]))
+    layers = lambda ml: [(l.weight.detach(), l.bias.detach()) for l in ml]
+    nets = (layers(graph.nerf.mlp_feat), layers(graph.nerf.mlp_rgb), layers(graph.nerf.mlp_trans))
+    lt, ll = graph.latent_vars_trans.weight.detach(), graph.latent_vars_light.weight.detach()
+    with torch.no_grad():
+        out = graph.nerf_forward(opt, AttrDict(var), mode="val")
+        ref = O.render_stl(c, r, zn, zf, None, N, lt[0][None], ll[0][None], *nets)
+    for k, want in ref.items():
+        close(out[k], want, 1e-5 if k == "depth" else 3e-6)
+    # ---- eval: anchors 3, 1, 0, 2 -> the nearest anchor of view 0 is row 2
+    var.pose_anchor = synth.poses([3, 1, 0, 2])
+    opt.render.N_candidate = 1
+    with torch.no_grad():
+        out = graph.nerf_forward(opt, AttrDict(var), mode="eval_noalign")
+        obj, bg = v[0].nonzero()[:, 0], (~v[0]).nonzero()[:, 0]
+        ref = O.render_stl(O.gather_rays(c, obj[None]), O.gather_rays(r, obj[None]), zn[:, obj], zf[:, obj], None, N,
+                           torch.zeros(1, 16), ll[2][None], *nets)
+    for k, want in ref.items():
+        assert out[k].shape[1] == H * W
+        close(out[k][:, obj], want, 1e-5 if k == "depth" else 3e-6)
+    assert (out["rgb"][:, bg] == 0).all() and (out["uncert"][:, bg] == 0.05).all() and (out["depth"][:, bg] == 0).all()
+    assert (out["density"][:, bg] == 1).all() and (out["alpha_static"][:, bg] == 1).all()
