@@ -13,47 +13,12 @@ from texpose_b200.config import AttrDict, adapt_gan_opt
 from texpose_b200.layers.nerf_static_transient_light import NeRF
 from texpose_b200.model import nerf_adapt_st_gan
 from texpose_b200.model.base import summarize_loss
-
-
-class _PatchLoss:
-    """ops.PatchLoss.apply with the oracle behind it: (losses [render, uncert, trans_reg, all], image_sample, mask_sample)."""
-
-    @staticmethod
-    def apply(rgb, uncert, density, image, obj_mask, coords, weights):
-        out = O.patch_losses(image, obj_mask, coords, rgb, uncert, density, *weights)
-        zero = rgb.sum() * 0
-        terms = [out.get(k, zero) for k in ("render", "uncert", "trans_reg")] + [out["all"]]
-        return torch.stack(terms), out["image_sample"], out["mask_sample"]
+from tests import oracle_swap
 
 
 @pytest.fixture
 def oracle_kernels(monkeypatch):
-    layers = lambda ml: [(l.weight, l.bias) for l in ml]
-
-    def forward_samples(self, opt, center, ray, depth_samples, latent_variable_trans=None, latent_variable_light=None, mode=None):
-        pts = O.points_from_depth(center, ray, depth_samples)
-        unit = torch.nn.functional.normalize(ray, dim=-1)[..., None, :].expand_as(pts)
-        return O.nerf_stl_forward(pts, unit, latent_variable_trans, latent_variable_light, layers(self.mlp_feat),
-                                  layers(self.mlp_rgb), layers(self.mlp_trans))
-
-    def composite(opt, ray, rgb, dens, depth, uncert):
-        return O.composite_stl(ray, rgb, dens, depth, uncert, opt.nerf.min_uncert)
-
-    def center_and_ray(opt, pose, intr=None, H=None, W=None, ray_idx=None):
-        c, r = O.get_center_and_ray(pose, intr, opt.H, opt.W)
-        return (c, r) if ray_idx is None else (O.gather_rays(c, ray_idx), O.gather_rays(r, ray_idx))
-
-    monkeypatch.setattr(camera, "get_center_and_ray", center_and_ray)
-    monkeypatch.setattr(ops, "gather_rows", lambda src, idx: O.gather_rays(src.float(), idx))
-    monkeypatch.setattr(camera, "view_matrices", lambda pose, intr, one_launch=False: (intr, pose))       # handed through to patch_rays
-    monkeypatch.setattr(ops, "patch_rays", lambda intr, pose, coords, H, W: O.patch_rays(coords, pose, intr, H, W))
-    monkeypatch.setattr(ops, "grid_sample_bilinear",
-                        lambda img, coords: torch.nn.functional.grid_sample(img, coords, mode="bilinear", align_corners=True))
-    monkeypatch.setattr(ops, "sample_depth",
-                        lambda zn, zf, N, rand=None, stratified=True, seed=None: O.sample_depth(zn, zf, N, rand if stratified else None))
-    monkeypatch.setattr(NeRF, "forward_samples", forward_samples)
-    monkeypatch.setattr(NeRF, "composite", staticmethod(composite))
-    monkeypatch.setattr(ops, "PatchLoss", _PatchLoss)
+    oracle_swap.install(monkeypatch.setattr)
 
 
 def close(a, b, tol=2e-6):
