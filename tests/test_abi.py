@@ -142,3 +142,17 @@ def test_product_never_imports_the_oracle_and_refuses_cpu_tensors():
         ops.gather_rows(torch.zeros(1, 4, 3), torch.zeros(1, 2, dtype=torch.long))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         ops.sample_depth(torch.zeros(1, 4), torch.ones(1, 4), 8, stratified=False)
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    """No CPU path behind the drop-ins: without the built .so every entry point raises (and says how to build it), nothing falls
+    back to torch or to the oracle."""
+    import pytest
+    monkeypatch.setattr(_C, "_lib", None)
+    monkeypatch.setattr(_C, "LIB_PATH", str(tmp_path / "libtexpose_b200.so"))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _C.load()
+    with pytest.raises(RuntimeError, match="g.build"):
+        _C.call("tp_version")
+    monkeypatch.undo()
+    assert _C.load().tp_version() == 100
